@@ -1,0 +1,85 @@
+// Common definitions for the bilby_b200 CUDA library (sm_100a).
+//
+// The per-sample "prologue" math is written as host+device inline functions so that the exact same
+// source can be exercised by a host-compiled unit test in the build container (tests/host_check.cpp,
+// test infrastructure only - the shipped library exposes no CPU execution path).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define BB_HD __host__ __device__ __forceinline__
+#else
+#define BB_HD inline
+#endif
+
+#define BB_MAX_DET 4
+#define BB_NPARAM 16
+
+// canonical per-sample parameter columns (row-major [n][BB_NPARAM] doubles); must match
+// include/bilby_b200.h and bilby_b200/gw/_params.py
+enum {
+    BB_P_MASS_1 = 0, BB_P_MASS_2, BB_P_CHI_1, BB_P_CHI_2, BB_P_DISTANCE, BB_P_THETA_JN, BB_P_PSI,
+    BB_P_PHASE, BB_P_RA, BB_P_DEC, BB_P_GEOCENT_TIME, BB_P_TIME_JITTER, BB_P_LAMBDA_1, BB_P_LAMBDA_2,
+    BB_P_SPARE_0, BB_P_SPARE_1
+};
+
+// physical constants: the reference mirrors LAL's values (bilby/core/utils/constants.py:3-7)
+#define BB_C_SI 299792458.0
+#define BB_PARSEC_SI 3.085677581491367e+16
+#define BB_MSUN_SI 1.988409870698050731911960804878414216e30
+#define BB_G_SI 6.6743e-11
+#define BB_PI 3.141592653589793238462643383279502884
+#define BB_EULER_GAMMA 0.5772156649015328606065120900824024
+
+// ---------------------------------------------------------------------------------------------
+// per-sample coefficient record (doubles).  Written by the prologue kernel, read by the
+// inner-product kernels.  All frequency dependence is expressed in Hz with the total-mass scaling
+// folded into the coefficients; all phase coefficients are in units of pi ("half turns") so that
+// the per-bin complex exponential is one sincospi().
+// ---------------------------------------------------------------------------------------------
+enum {
+    BC_A0 = 0,        // amplitude prefactor multiplying f^(-7/6)
+    BC_FA1, BC_FA2,   // amplitude region boundaries [Hz]
+    BC_AINS,          // 10 Horner coefficients in x = f^(1/3)
+    BC_AINT = BC_AINS + 10,   // 5 coefficients in xs = (f - f1) * invw
+    BC_AINT_F1 = BC_AINT + 5,
+    BC_AINT_INVW,
+    BC_MR_FRD, BC_MR_WL2, BC_MR_G, BC_MR_LAM,
+    BC_FP1, BC_FP2,   // phase region boundaries [Hz]
+    BC_PINS,          // 13: 1, x, x^2, f, f x, f x^2, f^2, 1/x, 1/x^2, 1/f, f^(-5/3), ln f, x ln f
+    BC_PINT = BC_PINS + 13,   // 4: 1, f, f^-3, ln f
+    BC_PMR = BC_PINT + 4,     // 7: 1, f, 1/f, f^(3/4), atan coefficient, f0, 1/fdamp
+    BC_KMIN = BC_PMR + 7,     // active bins [kmin, kmax) (stored as exact doubles)
+    BC_KMAX,
+    BC_DISTANCE,      // luminosity distance [Mpc] (distance marginalisation rescaling)
+    BC_STATUS,        // 0 = ok, 1 = waveform domain error (-> likelihood sentinel)
+    BC_JITTER,
+    BC_SPARE,
+    BC_DET,           // per detector 4: K_re, K_im, 2*dt_det [half turns / Hz], |K|^2
+    BC_NCOEF = BC_DET + 4 * BB_MAX_DET
+};
+
+struct BBNetwork {
+    int n_det;
+    int n_freq;           // bins of the full one-sided grid, N = round(T fs / 2) + 1
+    int k_lo, k_hi;       // bounding bin range of the union of detector masks, inclusive
+    double duration, sampling_frequency, start_time, df;
+    double detector_tensor[BB_MAX_DET][9];
+    double vertex[BB_MAX_DET][3];
+};
+
+struct BBWaveformConfig {
+    int approximant;      // 0 IMRPhenomD, 1 TaylorF2(+tides)
+    int add_jitter;       // time marginalisation with jitter: geocent_time += time_jitter (base.py:427-428)
+    double f_ref, f_min, f_max;
+};
+
+struct BBQnmTable {
+    const double* x;
+    const double* fring;
+    const double* fring_d2;
+    const double* fdamp;
+    const double* fdamp_d2;
+    int n;
+};

@@ -1,0 +1,162 @@
+// K4: time-marginalised likelihood, one CTA per sample (included by bb_kernels.cu).
+//
+//   series   X[k] = sum_det h_det[k] conj(d[k]) / S[k] (4/T folded into the tiles), k < N-1
+//            <- GravitationalWaveTransient.calculate_snrs, bilby/gw/likelihood/base.py:325-330
+//               (note h * conj(d), not conj(h) * d, and the dropped Nyquist bin)
+//   FFT      d_inner_h_tc_array[j] = sum_k X[k] exp(-2 pi i j k / (N-1))   (numpy.fft.fft), summed over
+//            detectors BEFORE the transform (linearity; the reference transforms per detector, base.py:439)
+//   weights  times[j] = start_time + (j+1) T/(N-1) (+ time_jitter), kept where inside the geocent_time
+//            prior; b = prior.prob * delta_tc                         <- base.py:794-806, 1027-1035
+//   reduce   logsumexp_j( lnl_j, b )  with lnl_j = plain | phase-marginalised | distance(-phase)-marginalised
+//            point likelihood                                          <- base.py:808-820
+//
+// The series lives in shared memory (16 B * nfft, 128 KB at 8 s / 2048 Hz); radix-2 decimation-in-time with
+// the bit-reversal folded into the store of X[k]; twiddles from a device table.
+#pragma once
+
+#define BB_TM_THREADS 256
+
+__device__ __forceinline__ unsigned bb_bitrev(unsigned v, int bits) { return __brev(v) >> (32 - bits); }
+
+template <int NDET>
+__global__ void __launch_bounds__(BB_TM_THREADS, 1)
+bb_time_marg_kernel(const double* __restrict__ coef, long n, BBTiles tiles, int n_freq, double df, int nfft,
+                    int log2n, const double2* __restrict__ twiddle, BBMarg marg, double start_time,
+                    double duration, double* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2* X = reinterpret_cast<double2*>(smem_raw);
+    double* c = reinterpret_cast<double*>(smem_raw + (size_t)nfft * sizeof(double2));
+    double* red = c + BC_NCOEF;      // [BB_TM_THREADS / 32 * 2]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (long s = blockIdx.x; s < n; s += gridDim.x) {
+        __syncthreads();
+        for (int i = tid; i < BC_NCOEF; i += BB_TM_THREADS) c[i] = coef[s * BC_NCOEF + i];
+        for (int i = tid; i < nfft; i += BB_TM_THREADS) X[i] = make_double2(0.0, 0.0);
+        __syncthreads();
+        if (c[BC_STATUS] != 0.0) {
+            if (tid == 0) out[s] = -DBL_MAX;
+            continue;
+        }
+        const int k0 = (int)c[BC_KMIN];
+        const int k1 = min((int)c[BC_KMAX], nfft);    // Nyquist bin dropped from the series, kept in <h|h>
+        const int k1h = (int)c[BC_KMAX];
+        double hh = 0.0;
+        for (int k = k0 + tid; k < k1h; k += BB_TM_THREADS) {
+            const double f = (double)k * df;
+            const double u = tiles.u[k], t = u * u, x = f * t * t;
+            const double A = bb_phenomd_amp(c, f, u, t, x);
+            const double ph = bb_phenomd_phase(c, f, t, x, tiles.lf[k], tiles.q34[k]);
+            double sn, cs;
+            sincospi(ph, &sn, &cs);
+            const double zr = A * cs, zi = A * sn;
+            const double A2 = A * A;
+            double vr = 0.0, vi = 0.0;
+#pragma unroll
+            for (int d = 0; d < NDET; ++d) {
+                double rs, rc;
+                sincospi(c[BC_DET + 4 * d + 2] * f, &rs, &rc);
+                const double wr = zr * rc - zi * rs, wi = zr * rs + zi * rc;
+                const double2 dd = tiles.ds[(size_t)d * n_freq + k];
+                const double pr = wr * dd.x - wi * dd.y, pi = wr * dd.y + wi * dd.x;   // conj(h/K) d/S
+                const double kr = c[BC_DET + 4 * d], ki = c[BC_DET + 4 * d + 1];
+                vr += kr * pr + ki * pi;       // conj(K) * p
+                vi += kr * pi - ki * pr;
+                hh += c[BC_DET + 4 * d + 3] * A2 * tiles.is[(size_t)d * n_freq + k];
+            }
+            if (k < k1) X[bb_bitrev((unsigned)k, log2n)] = make_double2(vr, -vi);   // h conj(d)/S = conj(conj(h) d/S)
+        }
+        // block-reduce <h|h>
+        hh = bb_warp_sum(hh);
+        if (lane == 0) red[warp] = hh;
+        __syncthreads();
+        hh = 0.0;
+        for (int w = 0; w < BB_TM_THREADS / 32; ++w) hh += red[w];
+        __syncthreads();
+
+        // in-place radix-2 DIT butterflies on the bit-reversed series
+        for (int stage = 0; stage < log2n; ++stage) {
+            const int half = 1 << stage;
+            const int tstep = nfft >> (stage + 1);
+            for (int b = tid; b < (nfft >> 1); b += BB_TM_THREADS) {
+                const int j = b & (half - 1);
+                const int i0 = ((b >> stage) << (stage + 1)) + j;
+                const int i1 = i0 + half;
+                const double2 w = twiddle[j * tstep];
+                const double2 a = X[i0], bb = X[i1];
+                const double tr = bb.x * w.x - bb.y * w.y, ti = bb.x * w.y + bb.y * w.x;
+                X[i0] = make_double2(a.x + tr, a.y + ti);
+                X[i1] = make_double2(a.x - tr, a.y - ti);
+            }
+            __syncthreads();
+        }
+
+        // weighted logsumexp over the times inside the prior
+        const double dtc = duration / (double)nfft;     // = 2 / sampling_frequency
+        const double jit = marg.jitter ? c[BC_JITTER] : 0.0;
+        const double bw = dtc / (marg.time_max - marg.time_min);
+        const double dist = c[BC_DISTANCE];
+        double mx = -INFINITY, sum = 0.0;
+        for (int j = tid; j < nfft; j += BB_TM_THREADS) {
+            // times = start_time + linspace(0, T, nfft + 1)[1:]  (+ jitter)
+            const double tj = (start_time + (double)(j + 1) * dtc) + jit;
+            if (tj < marg.time_min || tj > marg.time_max) continue;
+            const double2 v = X[j];
+            const double l = bb_point_lnl(marg, v.x, v.y, hh, dist);
+            if (l == -INFINITY) continue;
+            if (l > mx) { sum = sum * exp(mx - l) + bw; mx = l; }
+            else sum += bw * exp(l - mx);
+        }
+        double gmx = mx;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) gmx = fmax(gmx, __shfl_xor_sync(0xffffffffu, gmx, o));
+        if (lane == 0) red[warp] = gmx;
+        __syncthreads();
+        gmx = red[0];
+        for (int w = 1; w < BB_TM_THREADS / 32; ++w) gmx = fmax(gmx, red[w]);
+        __syncthreads();
+        double part = (mx == -INFINITY) ? 0.0 : sum * exp(mx - gmx);
+        part = bb_warp_sum(part);
+        if (lane == 0) red[warp] = part;
+        __syncthreads();
+        if (tid == 0) {
+            double tot = 0.0;
+            for (int w = 0; w < BB_TM_THREADS / 32; ++w) tot += red[w];
+            out[s] = (gmx == -INFINITY) ? -INFINITY : log(tot) + gmx;
+        }
+    }
+}
+
+template <int NDET>
+static int bb_launch_time_marg_t(bb_handle* h, long n, double* out, cudaStream_t st) {
+    const int nfft = h->nfft;
+    int log2n = 0;
+    while ((1 << log2n) < nfft) ++log2n;
+    const size_t smem = (size_t)nfft * sizeof(double2) + (BC_NCOEF + 32) * sizeof(double);
+    if (smem > 227 * 1024) return bb_fail("time marginalisation: series does not fit shared memory (nfft > 8192)");
+    BB_CUDA(cudaFuncSetAttribute(bb_time_marg_kernel<NDET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 4) per_sm = 4;
+    long grid = (long)h->sm_count * per_sm;
+    if (grid > n) grid = n;
+    bb_time_marg_kernel<NDET><<<(unsigned)grid, BB_TM_THREADS, smem, st>>>(
+        h->d_coef, n, bb_tiles(h), h->net.n_freq, h->net.df, nfft, log2n, h->d_twiddle, h->marg,
+        h->net.start_time, h->net.duration, out);
+    h->launches++;
+    BB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int bb_launch_time_marg(bb_handle* h, long n, double* out, cudaStream_t st) {
+    if (h->nfft == 0) return bb_fail("time marginalisation needs n_freq - 1 to be a power of two");
+    if (h->shard_lo != 0 || h->shard_hi != h->net.n_freq)
+        return bb_fail("time marginalisation cannot be frequency-sharded (SURVEY.md section 8e)");
+    switch (h->net.n_det) {
+        case 1: return bb_launch_time_marg_t<1>(h, n, out, st);
+        case 2: return bb_launch_time_marg_t<2>(h, n, out, st);
+        case 3: return bb_launch_time_marg_t<3>(h, n, out, st);
+        case 4: return bb_launch_time_marg_t<4>(h, n, out, st);
+    }
+    return bb_fail("bad n_det");
+}

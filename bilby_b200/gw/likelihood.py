@@ -1,0 +1,504 @@
+"""GravitationalWaveTransient on B200: the reference's likelihood API over the fused CUDA path.
+
+Mirrors bilby/gw/likelihood/base.py:
+  constructor + prior side effects            :150-229 (geocent_time -> start_time, time_jitter prior,
+                                               phase -> 0, luminosity_distance -> d_ref)
+  _check_set_duration_and_sampling_frequency  :239-258
+  noise_log_likelihood                        :402-417
+  log_likelihood_ratio                        :419-446  (scalar call == batch of one)
+  distance marginalisation set-up             :894-934, 994-1018 (table built on the device)
+  time marginalisation set-up                 :1027-1035
+  get_sky_frame_parameters                    :1091-1137 (sky frame / geocentre time reference)
+plus the batched entry point the reference lacks: ``log_likelihood_ratio_batch``.
+"""
+import copy
+import ctypes
+import os
+
+import numpy as np
+
+from .. import _lib
+from ..core.likelihood import Likelihood
+from ..core.prior import Prior, Uniform
+from ..core.utils import logger
+from . import _params
+from .detector import InterferometerList
+from .detector.calibration import CubicSpline
+
+
+class DeviceNetwork:
+    """Device-resident detector network: one bb_handle + helpers (interferometers -> tiles)."""
+
+    def __init__(self, interferometers, device=None):
+        import torch
+        self.torch = torch
+        self.ifos = list(interferometers)
+        self.handle = _lib.Handle(device)
+        self.lib = self.handle.lib
+        self.device = torch.device("cuda", self.handle.device)
+        self.version = None
+        self.upload()
+
+    @property
+    def ptr(self):
+        return self.handle.ptr
+
+    def upload(self):
+        ifos = self.ifos
+        n_det = len(ifos)
+        f = ifos[0].frequency_array
+        self.n_freq = n_freq = len(f)
+        self.n_det = n_det
+        tens = np.ascontiguousarray(np.stack([ifo.detector_tensor.ravel() for ifo in ifos]), dtype=np.float64)
+        vert = np.ascontiguousarray(np.stack([ifo.vertex for ifo in ifos]), dtype=np.float64)
+        strain = np.zeros((n_det, n_freq, 2), dtype=np.float64)
+        psd = np.zeros((n_det, n_freq), dtype=np.float64)
+        mask = np.zeros((n_det, n_freq), dtype=np.uint8)
+        for i, ifo in enumerate(ifos):
+            s = ifo.strain_data._frequency_domain_strain
+            if s is None:
+                s = np.zeros(n_freq, dtype=complex)
+            strain[i, :, 0] = s.real
+            strain[i, :, 1] = s.imag
+            psd[i] = ifo.power_spectral_density_array
+            mask[i] = ifo.frequency_mask
+        _lib.check(self.lib.bb_set_network(
+            self.ptr, n_det, n_freq, float(ifos[0].duration), float(ifos[0].sampling_frequency),
+            float(ifos[0].start_time), tens.ctypes.data, vert.ctypes.data, strain.ctypes.data, psd.ctypes.data,
+            mask.ctypes.data))
+
+    def _stream(self):
+        return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _rows(self, **kw):
+        rows = np.zeros((1, _params.NPARAM))
+        rows[0, _params.MASS_1] = rows[0, _params.MASS_2] = 1.0
+        rows[0, _params.LUMINOSITY_DISTANCE] = 1.0
+        for k, v in kw.items():
+            rows[0, getattr(_params, k.upper())] = v
+        return self.torch.from_numpy(rows).to(self.device)
+
+    def antenna(self, ra, dec, time, psi):
+        rows = self._rows(ra=ra, dec=dec, geocent_time=time, psi=psi)
+        out = self.torch.empty((1, self.n_det, 3), dtype=self.torch.float64, device=self.device)
+        _lib.check(self.lib.bb_antenna_response_device(self.ptr, rows.data_ptr(), 1, out.data_ptr(), self._stream()))
+        return out[0].cpu().numpy()
+
+    def _complex_to_dev(self, arr):
+        arr = np.asarray(arr, dtype=complex)
+        buf = np.empty((len(arr), 2))
+        buf[:, 0] = arr.real
+        buf[:, 1] = arr.imag
+        return self.torch.from_numpy(buf).to(self.device)
+
+    def project(self, pols, parameters, det):
+        unknown = set(pols) - {"plus", "cross"}
+        if unknown:
+            raise NotImplementedError(f"polarisation modes {sorted(unknown)} are outside the hot path")
+        zero = np.zeros(self.n_freq, dtype=complex)
+        plus = self._complex_to_dev(pols.get("plus", zero))
+        cross = self._complex_to_dev(pols.get("cross", zero))
+        ifo = self.ifos[det]
+        if isinstance(ifo.calibration_model, CubicSpline):
+            raise NotImplementedError("calibration of injected signals is not supported")
+        rows = self._rows(ra=parameters["ra"], dec=parameters["dec"], psi=parameters["psi"],
+                          geocent_time=parameters["geocent_time"])
+        if ifo.reference_time is not None:
+            raise NotImplementedError("Interferometer.reference_time is not supported on the device path")
+        out = self.torch.empty((self.n_freq, 2), dtype=self.torch.float64, device=self.device)
+        _lib.check(self.lib.bb_project_polarizations_device(self.ptr, det, plus.data_ptr(), cross.data_ptr(),
+                                                            rows.data_ptr(), out.data_ptr(), self._stream()))
+        o = out.cpu().numpy()
+        return o[:, 0] + 1j * o[:, 1]
+
+    def inner_product_arrays(self, det, a, b):
+        a_d = self._complex_to_dev(a)
+        b_d = self._complex_to_dev(b) if b is not None else None
+        out = self.torch.empty(2, dtype=self.torch.float64, device=self.device)
+        _lib.check(self.lib.bb_noise_weighted_inner_product_device(
+            self.ptr, det, a_d.data_ptr(), b_d.data_ptr() if b_d is not None else None, out.data_ptr(),
+            self._stream()))
+        o = out.cpu().numpy()
+        return complex(o[0], o[1])
+
+
+class GravitationalWaveTransient(Likelihood):
+    def __init__(self, interferometers, waveform_generator, time_marginalization=False,
+                 distance_marginalization=False, phase_marginalization=False, calibration_marginalization=False,
+                 priors=None, distance_marginalization_lookup_table=None, calibration_lookup_table=None,
+                 number_of_response_curves=1000, starting_index=0, jitter_time=True, reference_frame="sky",
+                 time_reference="geocenter", device=None):
+        super().__init__()
+        if calibration_marginalization:
+            raise NotImplementedError("calibration marginalisation is a 'next' row (SURVEY.md section 8f)")
+        if reference_frame != "sky" or "geocent" not in time_reference:
+            raise NotImplementedError("only reference_frame='sky', time_reference='geocenter' are implemented")
+        self.waveform_generator = waveform_generator
+        self.interferometers = InterferometerList(interferometers)
+        self.time_marginalization = time_marginalization
+        self.distance_marginalization = distance_marginalization
+        self.phase_marginalization = phase_marginalization
+        self.calibration_marginalization = False
+        self.priors = priors
+        self._check_set_duration_and_sampling_frequency_of_waveform_generator()
+        self._noise_log_likelihood_value = None
+        self.jitter_time = jitter_time
+        self.reference_frame = reference_frame
+        self.time_reference = "geocent"
+        self._device_index = device
+        self._net = None
+        self._net_versions = None
+        priors = self.priors
+
+        if self.time_marginalization:
+            self._check_marginalized_prior_is_set(key="geocent_time")
+            self._time_prior = self.priors["geocent_time"]
+            self._setup_time_marginalization()
+            priors["geocent_time"] = float(self.interferometers.start_time)
+            if self.jitter_time:
+                priors["time_jitter"] = Uniform(minimum=-self._delta_tc / 2, maximum=self._delta_tc / 2,
+                                                boundary="periodic", name="time_jitter", latex_label="$t_j$")
+            self._marginalized_parameters.append("geocent_time")
+        elif self.jitter_time:
+            self.jitter_time = False
+
+        if self.phase_marginalization:
+            self._check_marginalized_prior_is_set(key="phase")
+            priors["phase"] = float(0)
+            self._marginalized_parameters.append("phase")
+
+        if self.distance_marginalization:
+            self._lookup_table_filename = None
+            self._check_marginalized_prior_is_set(key="luminosity_distance")
+            self._distance_array = np.linspace(self.priors["luminosity_distance"].minimum,
+                                               self.priors["luminosity_distance"].maximum, int(1e4))
+            self.distance_prior_array = np.array([self.priors["luminosity_distance"].prob(distance)
+                                                  for distance in self._distance_array])
+            self._ref_dist = self.priors["luminosity_distance"].rescale(0.5)
+            self._setup_distance_marginalization(distance_marginalization_lookup_table)
+            for key in ["redshift", "comoving_distance"]:
+                if key in priors:
+                    del priors[key]
+            priors["luminosity_distance"] = float(self._ref_dist)
+            self._marginalized_parameters.append("luminosity_distance")
+
+    def __repr__(self):
+        return (f"{self.__class__.__name__}(interferometers={self.interferometers},\n\twaveform_generator="
+                f"{self.waveform_generator},\n\ttime_marginalization={self.time_marginalization}, "
+                f"distance_marginalization={self.distance_marginalization}, phase_marginalization="
+                f"{self.phase_marginalization}, calibration_marginalization=False, priors={self.priors})")
+
+    # ---- set-up --------------------------------------------------------------------------------
+    @property
+    def priors(self):
+        return self._prior
+
+    @priors.setter
+    def priors(self, priors):
+        if priors is not None:
+            self._prior = priors.copy()
+        elif any([self.time_marginalization, self.phase_marginalization, self.distance_marginalization]):
+            raise ValueError("You can't use a marginalized likelihood without specifying a priors")
+        else:
+            self._prior = None
+
+    def _check_set_duration_and_sampling_frequency_of_waveform_generator(self):
+        for attribute in ["duration", "sampling_frequency", "start_time"]:
+            setattr(self.waveform_generator, attribute, getattr(self.interferometers, attribute))
+
+    def _check_marginalized_prior_is_set(self, key):
+        """base.py:356-388 (cosmological / default-BBH-prior branches need astropy: out of scope)."""
+        if key in self.priors and getattr(self.priors[key], "is_fixed", False):
+            raise ValueError("Cannot use marginalized likelihood for {}: prior is fixed".format(key))
+        if key not in self.priors or not isinstance(self.priors[key], Prior):
+            if key == "geocent_time":
+                logger.warning("Prior not provided for geocent time, using the full segment.")
+                self.priors[key] = Uniform(self.interferometers.start_time,
+                                           self.interferometers.start_time + self.interferometers.duration)
+            else:
+                raise ValueError(f"Prior not provided for {key}: the reference would fall back to BBHPriorDict "
+                                 "(astropy); supply the prior explicitly")
+
+    def _setup_time_marginalization(self):
+        self._delta_tc = 2 / self.waveform_generator.sampling_frequency
+        self._times = self.interferometers.start_time + np.linspace(
+            0, self.interferometers.duration,
+            int(self.interferometers.duration / 2 * self.waveform_generator.sampling_frequency + 1))[1:]
+        self.time_prior_array = self.priors["geocent_time"].prob(self._times) * self._delta_tc
+
+    @property
+    def _delta_distance(self):
+        return self._distance_array[1] - self._distance_array[0]
+
+    @property
+    def _optimal_snr_squared_ref_array(self):
+        return np.logspace(-5, 10, self._dist_margd_loglikelihood_array.shape[0])
+
+    @property
+    def _d_inner_h_ref_array(self):
+        if self.phase_marginalization:
+            return np.logspace(-5, 10, self._dist_margd_loglikelihood_array.shape[1])
+        n_negative = self._dist_margd_loglikelihood_array.shape[1] // 2
+        n_positive = self._dist_margd_loglikelihood_array.shape[1] - n_negative
+        return np.hstack((-np.logspace(3, -3, n_negative), np.logspace(-3, 10, n_positive)))
+
+    @property
+    def cached_lookup_table_filename(self):
+        if self._lookup_table_filename is None:
+            self._lookup_table_filename = ".distance_marginalization_lookup.npz"
+        return self._lookup_table_filename
+
+    @cached_lookup_table_filename.setter
+    def cached_lookup_table_filename(self, filename):
+        if isinstance(filename, str) and filename[-4:] != ".npz":
+            filename += ".npz"
+        self._lookup_table_filename = filename
+
+    def _setup_distance_marginalization(self, lookup_table=None):
+        """base.py:916-934: same .npz cache format as the reference (:979-992)."""
+        table = None
+        if isinstance(lookup_table, str) or lookup_table is None:
+            self.cached_lookup_table_filename = lookup_table
+            lookup_table = self.load_lookup_table(self.cached_lookup_table_filename)
+        if isinstance(lookup_table, dict) and self._test_cached_lookup_table(lookup_table)[0]:
+            table = lookup_table["lookup_table"]
+        if table is None:
+            self._create_lookup_table()
+        else:
+            self._dist_margd_loglikelihood_array = np.asarray(table)
+        from scipy.interpolate import RectBivariateSpline
+        x, y = self._d_inner_h_ref_array, self._optimal_snr_squared_ref_array
+        spl = RectBivariateSpline(x, y, self._dist_margd_loglikelihood_array.T, kx=3, ky=3, s=0)
+        tx, ty, c = spl.tck
+        self._dist_spline = dict(tx=np.ascontiguousarray(tx), ty=np.ascontiguousarray(ty),
+                                 c=np.ascontiguousarray(c), bbox=(x.min(), x.max(), y.min(), y.max()))
+
+    def load_lookup_table(self, filename):
+        if filename is not None and os.path.exists(filename):
+            loaded = dict(np.load(filename))
+            match, failure = self._test_cached_lookup_table(loaded)
+            if match:
+                return loaded
+            logger.info("Loaded distance marginalisation lookup table does not match for {}.".format(failure))
+        return None
+
+    def cache_lookup_table(self):
+        np.savez(self.cached_lookup_table_filename, distance_array=self._distance_array,
+                 prior_array=self.distance_prior_array, lookup_table=self._dist_margd_loglikelihood_array,
+                 reference_distance=self._ref_dist, phase_marginalization=self.phase_marginalization)
+
+    def _test_cached_lookup_table(self, loaded_file):
+        pairs = dict(distance_array=self._distance_array, prior_array=self.distance_prior_array,
+                     reference_distance=self._ref_dist, phase_marginalization=self.phase_marginalization)
+        for key in pairs:
+            if key not in loaded_file:
+                return False, key
+            if not np.allclose(np.atleast_1d(loaded_file[key]), np.atleast_1d(pairs[key]), rtol=1e-15):
+                return False, key
+        return True, None
+
+    def _create_lookup_table(self):
+        """base.py:994-1018 on the device (bb_build_distance_table)."""
+        self._dist_margd_loglikelihood_array = np.zeros((400, 800))
+        x = np.ascontiguousarray(self._d_inner_h_ref_array)
+        y = np.ascontiguousarray(self._optimal_snr_squared_ref_array)
+        dist = np.ascontiguousarray(self._distance_array)
+        prior = np.ascontiguousarray(self.distance_prior_array)
+        table = np.zeros((400, 800))
+        h = _lib.Handle(self._device_index)
+        _lib.check(h.lib.bb_build_distance_table(h.ptr, x.ctypes.data, len(x), y.ctypes.data, len(y),
+                                                 dist.ctypes.data, prior.ctypes.data, len(dist),
+                                                 float(self._ref_dist), int(self.phase_marginalization),
+                                                 table.ctypes.data))
+        self._dist_margd_loglikelihood_array = table
+        if self._lookup_table_filename is not None or True:
+            try:
+                self.cache_lookup_table()
+            except OSError:  # pragma: no cover
+                pass
+
+    # ---- device state --------------------------------------------------------------------------
+    def _versions(self):
+        return tuple(ifo._data_version for ifo in self.interferometers)
+
+    @property
+    def device_network(self):
+        if self._net is None or self._net_versions != self._versions():
+            for ifo in self.interferometers:
+                if isinstance(ifo.calibration_model, CubicSpline):
+                    raise NotImplementedError("CubicSpline calibration inside the likelihood is not built yet")
+            self._net = DeviceNetwork(self.interferometers, self._device_index)
+            self._net_versions = self._versions()
+            self._configure()
+        return self._net
+
+    def _configure(self):
+        net = self._net
+        approx, f_ref, f_min, f_max = self.waveform_generator.approximant_config()
+        _lib.check(net.lib.bb_set_waveform(net.ptr, approx, f_ref, f_min, f_max))
+        flags = 0
+        if self.phase_marginalization:
+            flags |= _params.MARG_PHASE
+        if self.distance_marginalization:
+            flags |= _params.MARG_DISTANCE
+        if self.time_marginalization:
+            flags |= _params.MARG_TIME
+        tmin = tmax = 0.0
+        if self.time_marginalization:
+            tmin, tmax = float(self._time_prior.minimum), float(self._time_prior.maximum)
+        if self.distance_marginalization:
+            s = self._dist_spline
+            _lib.check(net.lib.bb_set_marginalization(
+                net.ptr, flags, float(self._ref_dist), s["tx"].ctypes.data, len(s["tx"]), s["ty"].ctypes.data,
+                len(s["ty"]), s["c"].ctypes.data, *[float(v) for v in s["bbox"]], tmin, tmax,
+                int(bool(self.jitter_time))))
+        else:
+            _lib.check(net.lib.bb_set_marginalization(net.ptr, flags, 1.0, None, 0, None, 0, None, 0.0, 0.0, 0.0,
+                                                      0.0, tmin, tmax, int(bool(self.jitter_time))))
+
+    # ---- evaluation ----------------------------------------------------------------------------
+    def get_sky_frame_parameters(self, parameters):
+        """base.py:1091-1137 for reference_frame='sky', time_reference='geocent'."""
+        return dict(ra=parameters["ra"], dec=parameters["dec"], geocent_time=parameters["geocent_time"])
+
+    def _rows_from_parameters(self, parameters, n, xp, device=None):
+        converted = self.waveform_generator.convert(parameters)
+        return _params.pack_rows(converted, n, xp, device=device)
+
+    def log_likelihood_ratio(self, parameters):
+        """base.py:419-446: one parameter dict in, one float out (a batch of one through the same kernels)."""
+        parameters = copy.deepcopy(parameters)
+        parameters.update(self.get_sky_frame_parameters(parameters))
+        rows = np.ascontiguousarray(self._rows_from_parameters(parameters, 1, np))
+        out = np.empty(1)
+        net = self.device_network
+        _lib.check(net.lib.bb_log_likelihood_ratio_host(net.ptr, rows.ctypes.data, 1, out.ctypes.data))
+        return float(out[0])
+
+    def log_likelihood_ratio_batch(self, parameters):
+        """NEW (no reference equivalent): evaluate a batch.
+
+        parameters: dict of equal-length numpy arrays (host path: one pinned H2D copy, kernels, D2H copy;
+        returns a numpy array) or dict of CUDA torch tensors / an [n, 16] CUDA float64 tensor of packed
+        rows (device path: asynchronous on the current stream; returns a CUDA tensor)."""
+        net = self.device_network
+        torch = net.torch
+        if isinstance(parameters, torch.Tensor):
+            rows = parameters
+            if rows.dtype != torch.float64 or rows.dim() != 2 or rows.shape[1] != _params.NPARAM or not rows.is_cuda:
+                raise ValueError("packed rows must be a CUDA float64 tensor of shape [n, 16]")
+            rows = rows.contiguous()
+            return self._evaluate_device(rows)
+        n = None
+        on_device = False
+        for v in parameters.values():
+            if isinstance(v, torch.Tensor):
+                on_device = on_device or v.is_cuda
+                if v.dim() > 0:
+                    n = v.shape[0]
+            elif isinstance(v, np.ndarray) and v.ndim > 0:
+                n = v.shape[0]
+        if n is None:
+            raise ValueError("log_likelihood_ratio_batch needs at least one array-valued parameter")
+        if on_device:
+            rows = self._rows_from_parameters(parameters, n, torch, device=net.device)
+            return self._evaluate_device(rows)
+        rows = np.ascontiguousarray(self._rows_from_parameters(parameters, n, np))
+        return self.log_likelihood_ratio_rows_host(rows)
+
+    def log_likelihood_ratio_rows_host(self, rows):
+        """Host rows [n,16] (numpy float64, C order) -> numpy lnL; the C ABI's end-to-end entry point."""
+        net = self.device_network
+        rows = np.ascontiguousarray(rows, dtype=np.float64)
+        out = np.empty(rows.shape[0])
+        _lib.check(net.lib.bb_log_likelihood_ratio_host(net.ptr, rows.ctypes.data, rows.shape[0], out.ctypes.data))
+        return out
+
+    def _evaluate_device(self, rows):
+        net = self.device_network
+        torch = net.torch
+        out = torch.empty(rows.shape[0], dtype=torch.float64, device=rows.device)
+        _lib.check(net.lib.bb_log_likelihood_ratio_device(net.ptr, rows.data_ptr(), rows.shape[0], out.data_ptr(),
+                                                          net._stream()))
+        return out
+
+    def inner_products_batch(self, rows):
+        """[n,16] CUDA rows -> [n, n_det, 3] (Re<h|d>, Im<h|d>, <h|h>) per detector (base.py:260-354)."""
+        net = self.device_network
+        torch = net.torch
+        out = torch.empty((rows.shape[0], net.n_det, 3), dtype=torch.float64, device=rows.device)
+        _lib.check(net.lib.bb_inner_products_device(net.ptr, rows.data_ptr(), rows.shape[0], out.data_ptr(),
+                                                    net._stream()))
+        return out
+
+    def likelihood_from_inner_products(self, rows, snrs):
+        net = self.device_network
+        torch = net.torch
+        out = torch.empty(rows.shape[0], dtype=torch.float64, device=rows.device)
+        _lib.check(net.lib.bb_likelihood_from_inner_products_device(
+            net.ptr, rows.data_ptr(), snrs.data_ptr(), rows.shape[0], out.data_ptr(), net._stream()))
+        return out
+
+    def pack(self, parameters, n=None, device=None):
+        """dict of arrays / tensors -> packed rows (numpy, or CUDA tensor if device is given)."""
+        if device is None:
+            if n is None:
+                n = max(np.size(v) for v in parameters.values())
+            return self._rows_from_parameters(parameters, n, np)
+        torch = self.device_network.torch
+        if n is None:
+            n = max((v.shape[0] for v in parameters.values() if hasattr(v, "shape") and len(v.shape)), default=1)
+        return self._rows_from_parameters(parameters, n, torch, device=device)
+
+    def calculate_snrs(self, parameters):
+        """Per-detector (d_inner_h, optimal_snr_squared, complex_matched_filter_snr) for one dict
+        (base.py:260-354, scalar quantities)."""
+        net = self.device_network
+        rows = net.torch.from_numpy(np.ascontiguousarray(self._rows_from_parameters(parameters, 1, np))).to(net.device)
+        s = self.inner_products_batch(rows)[0].cpu().numpy()
+        out = []
+        for d in range(net.n_det):
+            dih = complex(s[d, 0], s[d, 1])
+            out.append(dict(d_inner_h=dih, optimal_snr_squared=s[d, 2],
+                            complex_matched_filter_snr=dih / s[d, 2] ** 0.5))
+        return out
+
+    def _calculate_noise_log_likelihood(self):
+        """base.py:402-411 through the device inner-product kernel."""
+        log_l = 0.0
+        net = self.device_network
+        for i, ifo in enumerate(self.interferometers):
+            d = ifo.frequency_domain_strain
+            log_l -= abs(net.inner_product_arrays(i, d, None) / 2)
+        return log_l
+
+    def noise_log_likelihood(self):
+        if self._noise_log_likelihood_value is None:
+            self._noise_log_likelihood_value = self._calculate_noise_log_likelihood()
+        return self._noise_log_likelihood_value
+
+    def log_likelihood(self, parameters):
+        return self.log_likelihood_ratio(parameters=parameters) + self.noise_log_likelihood()
+
+    @property
+    def meta_data(self):
+        """base.py:1163-1183."""
+        return dict(interferometers=self.interferometers.meta_data,
+                    time_marginalization=self.time_marginalization,
+                    phase_marginalization=self.phase_marginalization,
+                    distance_marginalization=self.distance_marginalization,
+                    calibration_marginalization=self.calibration_marginalization,
+                    waveform_generator_class=self.waveform_generator.__class__,
+                    waveform_arguments=self.waveform_generator.waveform_arguments,
+                    frequency_domain_source_model=self.waveform_generator.frequency_domain_source_model,
+                    time_domain_source_model=None,
+                    parameter_conversion=self.waveform_generator.parameter_conversion,
+                    sampling_frequency=self.waveform_generator.sampling_frequency,
+                    duration=self.waveform_generator.duration,
+                    start_time=self.waveform_generator.start_time,
+                    time_reference=self.time_reference,
+                    reference_frame=self.reference_frame)
+
+    @meta_data.setter
+    def meta_data(self, value):
+        pass

@@ -1,0 +1,172 @@
+/*
+ * bilby_b200 - C ABI of the B200-native compact-binary likelihood hot path.
+ *
+ * Drop-in boundary for bilby's  parameters -> log_likelihood_ratio  path.  The reference (bilby,
+ * pure Python) has no FFI of its own; each entry point below names the reference interface it
+ * replaces (file:line relative to the bilby source tree).  Plain pointers and sizes only - no
+ * torch / numpy types.  "dev" pointers are CUDA device pointers on the handle's device, "host"
+ * pointers are ordinary host memory.  All functions return 0 on success, non-zero on failure;
+ * bb_last_error() describes the most recent failure of the calling thread.
+ *
+ * There is NO CPU execution path in this library: every compute entry point launches sm_100a
+ * kernels and fails if no CUDA device is usable.
+ */
+#ifndef BILBY_B200_H
+#define BILBY_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BB_ABI_VERSION 1
+#define BB_MAX_DET 4
+#define BB_NPARAM 16
+
+/* Column order of the per-sample parameter matrix, row-major double[n][BB_NPARAM].
+ * These are the *converted* source-model parameters, i.e. what
+ * bilby/gw/waveform_generator.py:260-269 (_format_parameters -> parameter_conversion,
+ * bilby/gw/conversion.py:182-283) hands to bilby/gw/source.py:269-348 (lal_binary_black_hole) plus
+ * the extrinsic parameters bilby/gw/detector/interferometer.py:303-368 reads.
+ * chi_i is the aligned spin component a_i*cos(tilt_i) (conversion.py:146-153). */
+enum bb_param {
+    BB_MASS_1 = 0,            /* solar masses */
+    BB_MASS_2 = 1,
+    BB_CHI_1 = 2,
+    BB_CHI_2 = 3,
+    BB_LUMINOSITY_DISTANCE = 4, /* Mpc */
+    BB_THETA_JN = 5,
+    BB_PSI = 6,
+    BB_PHASE = 7,
+    BB_RA = 8,
+    BB_DEC = 9,
+    BB_GEOCENT_TIME = 10,     /* GPS s; with time marginalisation: start_time (+ jitter added on device) */
+    BB_TIME_JITTER = 11,
+    BB_LAMBDA_1 = 12,
+    BB_LAMBDA_2 = 13
+};
+
+enum bb_approximant { BB_IMRPHENOMD = 0, BB_TAYLORF2 = 1 };
+
+enum bb_marginalization {
+    BB_MARG_PHASE = 1,    /* bilby/gw/likelihood/base.py:786-792 */
+    BB_MARG_DISTANCE = 2, /* base.py:775-784, 879-885 */
+    BB_MARG_TIME = 4      /* base.py:794-820 */
+};
+
+typedef struct bb_handle bb_handle;
+
+const char* bb_last_error(void);
+int bb_abi_version(void);
+
+/* One handle per (process, device): owns the device-resident tiles and scratch. */
+int bb_create(int device, bb_handle** out);
+void bb_destroy(bb_handle* h);
+
+/* Upload the detector network and data: replaces what GravitationalWaveTransient reads from
+ * InterferometerList on every call (base.py:432-439; interferometer.py:551-564 PSD array,
+ * strain_data.py:142-159 frequency_mask, :212-233 frequency_domain_strain,
+ * detector/geometry.py detector_tensor & vertex).
+ *   detector_tensors host double[n_det][9], vertices host double[n_det][3] (metres),
+ *   strain host double[n_det][n_freq][2] (re, im), psd host double[n_det][n_freq] (+inf allowed),
+ *   mask host uint8[n_det][n_freq].  n_freq = round(duration*sampling_frequency/2)+1. */
+int bb_set_network(bb_handle* h, int n_det, int n_freq, double duration, double sampling_frequency,
+                   double start_time, const double* detector_tensors, const double* vertices,
+                   const double* strain, const double* psd, const unsigned char* mask);
+
+/* Source model selection: replaces WaveformGenerator(frequency_domain_source_model=lal_binary_black_hole /
+ * lal_binary_neutron_star, waveform_arguments={waveform_approximant, reference_frequency,
+ * minimum_frequency, maximum_frequency}) - source.py:338-342, 422-426.  maximum_frequency <= 0 means
+ * "last bin of the grid" (source.py default frequency_array[-1]). */
+int bb_set_waveform(bb_handle* h, int approximant, double reference_frequency, double minimum_frequency,
+                    double maximum_frequency);
+
+/* Marginalisation state: replaces GravitationalWaveTransient.__init__ set-up (base.py:183-223).
+ *   flags: OR of bb_marginalization.
+ *   distance table = the FITPACK representation (tx, ty, c) of base.py:929-934's
+ *   BoundedRectBivariateSpline over (_d_inner_h_ref_array, _optimal_snr_squared_ref_array), with its
+ *   bounding box; ref_dist = priors['luminosity_distance'].rescale(0.5) (base.py:216).
+ *   time prior: Uniform [time_min, time_max] (base.py:799-806); jitter = base.py:189-197. */
+int bb_set_marginalization(bb_handle* h, int flags, double ref_dist,
+                           const double* tx, int nx, const double* ty, int ny, const double* c,
+                           double xmin, double xmax, double ymin, double ymax,
+                           double time_min, double time_max, int jitter_time);
+
+/* Batched log-likelihood ratio: replaces GravitationalWaveTransient.log_likelihood_ratio
+ * (base.py:419-446) evaluated for n parameter rows.  Invalid waveform domains give the reference's
+ * sentinel np.nan_to_num(-inf) = -DBL_MAX (base.py:424-425).
+ * _device: params/out are device pointers, asynchronous on `stream` (a cudaStream_t, may be NULL).
+ * _host:   params/out are host pointers; copies host->device, computes, copies back, synchronises. */
+int bb_log_likelihood_ratio_device(bb_handle* h, const double* params_dev, long n, double* out_dev,
+                                   void* stream);
+int bb_log_likelihood_ratio_host(bb_handle* h, const double* params_host, long n, double* out_host);
+
+/* Per-detector inner products: replaces GravitationalWaveTransient.calculate_snrs (base.py:260-354)
+ * / Interferometer.inner_product + optimal_snr_squared (interferometer.py:607-640).
+ * out double[n][n_det][3] = (Re <h|d>, Im <h|d>, <h|h>) with the reference's 4/T normalisation
+ * (gw/utils.py:118-138).  With a frequency-sharded network (bb_set_frequency_shard) these are the
+ * rank-local partial sums to be all-reduced. */
+int bb_inner_products_device(bb_handle* h, const double* params_dev, long n, double* out_dev, void* stream);
+
+/* Likelihood from (all-reduced) inner products: replaces compute_log_likelihood_from_snrs
+ * (base.py:448-477) for the phase / distance marginalised and plain cases.
+ * snrs double[n][n_det][3] as produced by bb_inner_products_device. */
+int bb_likelihood_from_inner_products_device(bb_handle* h, const double* params_dev, const double* snrs_dev,
+                                             long n, double* out_dev, void* stream);
+
+/* Restrict this handle to the contiguous bin range [k_begin, k_end) (frequency sharding of long
+ * signals across GPUs).  Pass (0, n_freq) to undo. */
+int bb_set_frequency_shard(bb_handle* h, int k_begin, int k_end);
+
+/* Polarisations on the full frequency grid: replaces WaveformGenerator.frequency_domain_strain
+ * (waveform_generator.py:113-141) for injections and tests.
+ * out double[n][2][n_freq][2]: [plus|cross][bin][re|im]. */
+int bb_frequency_domain_strain_device(bb_handle* h, const double* params_dev, long n, double* out_dev,
+                                      void* stream);
+
+/* Detector-frame strain: replaces Interferometer.get_detector_response (interferometer.py:303-368).
+ * out double[n][n_det][n_freq][2]. */
+int bb_detector_response_device(bb_handle* h, const double* params_dev, long n, double* out_dev, void* stream);
+
+/* Distance-marginalisation lookup table: replaces _create_lookup_table (base.py:994-1018).
+ * x_ref host double[nx] (_d_inner_h_ref_array), y_ref host double[ny] (_optimal_snr_squared_ref_array),
+ * distance / prior host double[nd]; table_out host double[ny][nx]. */
+int bb_build_distance_table(bb_handle* h, const double* x_ref, int nx, const double* y_ref, int ny,
+                            const double* distance, const double* prior, int nd, double ref_dist,
+                            int phase_marginalization, double* table_out);
+
+/* Antenna patterns and delays (tests / diagnostics): replaces Interferometer.antenna_response
+ * (interferometer.py:267-301) and time_delay_from_geocenter (:571-590).
+ * out double[n][n_det][3] = (F+, Fx, delay). */
+int bb_antenna_response_device(bb_handle* h, const double* params_dev, long n, double* out_dev, void* stream);
+
+/* ln I0 (gw/utils.py:1006-1022), elementwise on device arrays. */
+int bb_ln_i0_device(bb_handle* h, const double* x_dev, long n, double* out_dev, void* stream);
+
+/* Interferometer.get_detector_response for caller-supplied polarisation arrays
+ * (interferometer.py:303-368; injection path).  plus/cross: device complex double[n_freq][2];
+ * params_dev: ONE parameter row; det: detector index; out: device double[n_freq][2]. */
+int bb_project_polarizations_device(bb_handle* h, int det, const double* plus_dev, const double* cross_dev,
+                                    const double* params_dev, double* out_dev, void* stream);
+
+/* noise_weighted_inner_product over a detector's mask (gw/utils.py:118-138 via
+ * interferometer.py:607-640): sum conj(a) b / S * 4/T.  a, b: device complex double[n_freq][2];
+ * b == NULL means the detector's own data (Interferometer.inner_product).  out: device double[2]. */
+int bb_noise_weighted_inner_product_device(bb_handle* h, int det, const double* a_dev, const double* b_dev,
+                                           double* out_dev, void* stream);
+
+/* Measurement hooks (bench.py).  With profiling enabled the handle brackets every launch of the
+ * dominant kernel (K1, the fused inner-product kernel) with CUDA events on the launching stream;
+ * bb_profile_read synchronises and returns the summed duration and the number of launches since the
+ * last read.  bb_fp64_peak runs a register-resident DFMA stream kernel and returns the achieved
+ * TFLOP/s - the FP64 roofline denominator MEASURED_PEAKS.json does not provide. */
+int bb_profile_enable(bb_handle* h, int on);
+int bb_profile_read(bb_handle* h, double* k1_ms, long* k1_launches);
+int bb_fp64_peak(bb_handle* h, double* tflops);
+
+/* Number of kernel launches issued through this handle so far (bench.py's gpu_launches claim). */
+long bb_launch_count(bb_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BILBY_B200_H */

@@ -364,6 +364,17 @@ class OraclePowerLaw:
                              / (self.maximum ** (1 + self.alpha) - self.minimum ** (1 + self.alpha))) * inside
 
 
+def _lookup_rows(rows, ref_dist, distance_array, x_ref, y_ref, phase_marginalization, prior_term):
+    scaling = ref_dist / distance_array
+    d_full = np.outer(x_ref, scaling)
+    if phase_marginalization:
+        d_full = ln_i0(abs(d_full))
+    out = np.zeros((len(rows), len(x_ref)))
+    for n, ii in enumerate(rows):
+        out[n] = logsumexp(d_full - (y_ref[ii] * scaling ** 2) / 2, b=prior_term, axis=1)
+    return out
+
+
 class OracleLikelihood:
     """Restates GravitationalWaveTransient (bilby/gw/likelihood/base.py:150-229, 260-354, 419-477,
     775-820, 879-914, 994-1035) for sky reference frame, geocenter time reference, no calibration
@@ -372,7 +383,7 @@ class OracleLikelihood:
     def __init__(self, interferometers, source_model=lal_binary_black_hole, waveform_arguments=None,
                  parameter_conversion=convert_to_lal_binary_black_hole_parameters,
                  time_marginalization=False, distance_marginalization=False, phase_marginalization=False,
-                 distance_prior=None, time_prior=None, jitter_time=True, lookup_table=None):
+                 distance_prior=None, time_prior=None, jitter_time=True, lookup_table=None, table_processes=1):
         self.ifos = list(interferometers)
         self.duration = self.ifos[0].duration
         self.sampling_frequency = self.ifos[0].sampling_frequency
@@ -396,7 +407,7 @@ class OracleLikelihood:
             self.distance_prior_array = np.array([distance_prior.prob(d) for d in self._distance_array])
             self._ref_dist = distance_prior.rescale(0.5)
             if lookup_table is None:
-                lookup_table = self.create_lookup_table()
+                lookup_table = self.create_lookup_table(processes=table_processes)
             self._dist_margd_loglikelihood_array = lookup_table
             self._interp = RectBivariateSpline(self._d_inner_h_ref_array, self._optimal_snr_squared_ref_array,
                                                lookup_table.T, kx=3, ky=3, s=0)
@@ -412,18 +423,23 @@ class OracleLikelihood:
             return np.logspace(-5, 10, 800)
         return np.hstack((-np.logspace(3, -3, 400), np.logspace(-3, 10, 400)))
 
-    def create_lookup_table(self, rows=None):
-        """base.py:994-1018; ``rows`` restricts to a subset of optimal-SNR rows (tests)."""
+    def create_lookup_table(self, rows=None, processes=1):
+        """base.py:994-1018; ``rows`` restricts to a subset of optimal-SNR rows (tests); ``processes`` > 1
+        spreads the rows over a multiprocessing pool (same arithmetic per entry)."""
         table = np.zeros((400, 800))
-        scaling = self._ref_dist / self._distance_array
-        d_full = np.outer(self._d_inner_h_ref_array, scaling)
-        h_full = np.outer(self._optimal_snr_squared_ref_array, scaling ** 2)
-        if self.phase_marginalization:
-            d_full = ln_i0(abs(d_full))
+        idx = list(range(400)) if rows is None else list(rows)
         prior_term = self.distance_prior_array * (self._distance_array[1] - self._distance_array[0])
-        idx = range(400) if rows is None else rows
-        for ii in idx:
-            table[ii] = logsumexp(d_full - h_full[ii] / 2, b=prior_term, axis=1)
+        args = (self._ref_dist, self._distance_array, self._d_inner_h_ref_array,
+                self._optimal_snr_squared_ref_array, self.phase_marginalization, prior_term)
+        if processes > 1:
+            import multiprocessing
+            chunks = [idx[i::processes] for i in range(processes)]
+            with multiprocessing.get_context("fork").Pool(processes) as pool:
+                parts = pool.starmap(_lookup_rows, [(c,) + args for c in chunks])
+            for c, part in zip(chunks, parts):
+                table[c] = part
+        else:
+            table[idx] = _lookup_rows(idx, *args)
         log_norm = logsumexp(0 / self._distance_array, b=prior_term)
         table -= log_norm
         return table

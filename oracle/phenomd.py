@@ -300,8 +300,10 @@ class PhenomDCoefficients:
         self.finspin = final_spin_0815(eta, chi1, chi2)
         ring, damp = qnm_splines()
         erad = e_rad_0815(eta, chi1, chi2)
-        self.fRD = float(ring(self.finspin)) / (1.0 - erad)
-        self.fDM = float(damp(self.finspin)) / (1.0 - erad)
+        # the QNM table spans |a| <= 0.9999; clamp (upstream's GSL spline errors outside its table)
+        a_f = min(max(self.finspin, ring.x[0]), ring.x[-1])
+        self.fRD = float(ring(a_f)) / (1.0 - erad)
+        self.fDM = float(damp(a_f)) / (1.0 - erad)
         for name in FIT_ORDER:
             setattr(self, name, _fit(name, eta, xi))
         # ---- amplitude inspiral prefactors (init_amp_ins_prefactors)
