@@ -284,6 +284,31 @@ def lal_binary_black_hole(frequency_array, mass_1, mass_2, luminosity_distance, 
     return dict(plus=hp * bounds, cross=hc * bounds)
 
 
+def lal_binary_neutron_star(frequency_array, mass_1, mass_2, luminosity_distance, a_1, tilt_1, phi_12,
+                            a_2, tilt_2, phi_jl, theta_jn, phase, lambda_1, lambda_2, **kwargs):
+    """bilby-signature BNS source model (source.py:351-432) backed by the restated TaylorF2 (+tides)."""
+    from . import taylorf2 as _tf2
+    wa = dict(waveform_approximant="TaylorF2", reference_frequency=50.0, minimum_frequency=20.0,
+              maximum_frequency=frequency_array[-1], catch_waveform_errors=False)
+    wa.update(kwargs)
+    if wa["waveform_approximant"] != "TaylorF2":
+        raise ValueError("oracle restates TaylorF2 only for lal_binary_neutron_star")
+    s1z = a_1 * np.cos(tilt_1)
+    s2z = a_2 * np.cos(tilt_2)
+    delta_f = frequency_array[1] - frequency_array[0]
+    bounds = (frequency_array >= wa["minimum_frequency"]) * (frequency_array <= wa["maximum_frequency"])
+    try:
+        hp, hc = _tf2.choose_fd_waveform_taylorf2(
+            np.arange(len(frequency_array)) * delta_f, mass_1, mass_2, s1z, s2z, lambda_1, lambda_2,
+            luminosity_distance * 1e6 * _pd.PARSEC, theta_jn, phase,
+            wa["minimum_frequency"], wa["maximum_frequency"], wa["reference_frequency"], delta_f)
+    except _pd.WaveformDomainError:
+        if wa["catch_waveform_errors"]:
+            return None
+        raise
+    return dict(plus=hp * bounds, cross=hc * bounds)
+
+
 def convert_to_lal_binary_black_hole_parameters(parameters):
     """Subset of bilby/gw/conversion.py:182-283 used by the benchmark priors:
     (chirp_mass, mass_ratio) -> (mass_1, mass_2); chi_i -> (a_i, cos_tilt_i); cos_theta_jn;
@@ -459,9 +484,9 @@ class OracleLikelihood:
         """waveform_generator.py:178-209, 260-269."""
         p = self.parameter_conversion(parameters)
         args = {k: p[k] for k in SOURCE_ARGS if k in p}
-        for k in ("lambda_1", "lambda_2"):
-            if k in p and "neutron" in getattr(self.source_model, "__name__", ""):
-                args[k] = p[k]
+        if "neutron" in getattr(self.source_model, "__name__", ""):
+            for k in ("lambda_1", "lambda_2"):
+                args[k] = p.get(k, 0.0)
         return self.source_model(self.frequency_array, **args, **self.waveform_arguments)
 
     def calculate_snrs(self, pols, ifo, parameters):
