@@ -21,6 +21,7 @@
 #include "bb_common.cuh"
 #include "bb_geometry.cuh"
 #include "bb_phenomd.cuh"
+#include "bb_taylorf2.cuh"
 #include "bb_special.cuh"
 
 #include "qnm_table.inc"
@@ -82,6 +83,20 @@ struct bb_handle {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> k1_events;
 };
 
+// per-bin waveform evaluation, selected at compile time
+template <int APPROX>
+__device__ __forceinline__ void bb_wave(const double* c, double f, double u, double lf, double q34, double* A, double* ph) {
+    const double t = u * u;
+    const double x = f * t * t;
+    if (APPROX == BB_IMRPHENOMD) {
+        *A = bb_phenomd_amp(c, f, u, t, x);
+        *ph = bb_phenomd_phase(c, f, t, x, lf, q34);
+    } else {
+        *A = bb_taylorf2_amp(c, u, t);
+        *ph = bb_taylorf2_phase(c, f, t, x, lf);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K0: prologue
 // ------------------------------------------------------------------------------------------------
@@ -94,7 +109,8 @@ __global__ void bb_prologue_kernel(const double* __restrict__ params, long n, BB
     for (int k = 0; k < BB_NPARAM; ++k) p[k] = params[i * BB_NPARAM + k];
     BBQnmTable qnm = {bb_qnm_x, bb_qnm_fring, bb_qnm_fring_d2, bb_qnm_fdamp, bb_qnm_fdamp_d2, BB_QNM_N};
     double c[BC_NCOEF];
-    bb_phenomd_prologue(p, net, wf, qnm, bb_phenomd_fit, c);
+    if (wf.approximant == BB_IMRPHENOMD) bb_phenomd_prologue(p, net, wf, qnm, bb_phenomd_fit, c);
+    else bb_taylorf2_prologue(p, net, wf, c);
     double* dst = coef + i * BC_NCOEF;
     for (int k = 0; k < BC_NCOEF; ++k) dst[k] = c[k];
 }
@@ -125,7 +141,7 @@ __device__ __forceinline__ double bb_warp_sum(double v) {
     return v;
 }
 
-template <int NDET>
+template <int NDET, int APPROX>
 __global__ void __launch_bounds__(BB_K1_THREADS, 2)
 bb_inner_product_kernel(const double* __restrict__ coef, long n, BBTiles tiles, int n_freq, double df,
                         int shard_lo, int shard_hi, double* __restrict__ out) {
@@ -187,11 +203,8 @@ bb_inner_product_kernel(const double* __restrict__ coef, long n, BBTiles tiles, 
                 for (int k = lo + lane; k < hi; k += 32) {
                     const int i = k - c0;
                     const double f = (double)k * df;
-                    const double u = sm.u[i];
-                    const double t = u * u;
-                    const double x = f * t * t;
-                    const double A = bb_phenomd_amp(c, f, u, t, x);
-                    const double ph = bb_phenomd_phase(c, f, t, x, sm.lf[i], sm.q34[i]);
+                    double A, ph;
+                    bb_wave<APPROX>(c, f, sm.u[i], sm.lf[i], sm.q34[i], &A, &ph);
                     double sn, cs;
                     sincospi(ph, &sn, &cs);
                     const double zr = A * cs, zi = A * sn;    // A e^{+i Phi} = conj(h22 incl. geocentric shift)
@@ -322,7 +335,7 @@ __global__ void bb_distance_table_kernel(const double* __restrict__ xref, int nx
 // KW: strain on the full grid (injection / tests): polarisations or detector response
 // ------------------------------------------------------------------------------------------------
 __global__ void bb_strain_kernel(const double* __restrict__ coef, long n, BBTiles tiles, int n_freq, double df,
-                                 int n_det, int mode /*0 polarisations, 1 detector response*/,
+                                 int n_det, int approx, int mode /*0 polarisations, 1 detector response*/,
                                  const double* __restrict__ params, const unsigned char* __restrict__ mask,
                                  double start_time, double* __restrict__ out) {
     const long s = blockIdx.y;
@@ -335,9 +348,9 @@ __global__ void bb_strain_kernel(const double* __restrict__ coef, long n, BBTile
     double hr = 0.0, hi = 0.0;
     const double f = (double)k * df;
     if (active) {
-        const double u = tiles.u[k], t = u * u, x = f * t * t;
-        const double A = bb_phenomd_amp(c, f, u, t, x);
-        double ph = bb_phenomd_phase(c, f, t, x, tiles.lf[k], tiles.q34[k]);
+        double A, ph;
+        if (approx == BB_IMRPHENOMD) bb_wave<BB_IMRPHENOMD>(c, f, tiles.u[k], tiles.lf[k], tiles.q34[k], &A, &ph);
+        else bb_wave<BB_TAYLORF2>(c, f, tiles.u[k], tiles.lf[k], tiles.q34[k], &A, &ph);
         if (mode == 0) {
             // remove the geocentric time shift folded into the record: Phi - 2 f dt0
             const double dt0 = params[s * BB_NPARAM + BB_P_GEOCENT_TIME] - start_time;
@@ -657,7 +670,6 @@ extern "C" int bb_set_marginalization(bb_handle* h, int flags, double ref_dist, 
 }
 
 static int bb_launch_prologue(bb_handle* h, const double* params_dev, long n, cudaStream_t st) {
-    if (h->wf.approximant != BB_IMRPHENOMD) return bb_fail("approximant not implemented in this build");
     BBWaveformConfig wf = h->wf;
     if (!(wf.f_max > 0.0)) wf.f_max = h->net.df * (h->net.n_freq - 1);
     wf.add_jitter = ((h->marg.flags & BB_MARG_TIME) && h->marg.jitter) ? 1 : 0;
@@ -668,14 +680,10 @@ static int bb_launch_prologue(bb_handle* h, const double* params_dev, long n, cu
     return 0;
 }
 
-template <int NDET>
+template <int NDET, int APPROX>
 static int bb_launch_inner_t(bb_handle* h, long n, double* out, cudaStream_t st) {
     const size_t smem = sizeof(K1Smem<NDET>);
-    static bool configured[BB_MAX_DET + 1] = {false};
-    if (!configured[NDET]) {
-        BB_CUDA(cudaFuncSetAttribute(bb_inner_product_kernel<NDET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[NDET] = true;
-    }
+    BB_CUDA(cudaFuncSetAttribute(bb_inner_product_kernel<NDET, APPROX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long n_blocks = (n + BB_K1_SB - 1) / BB_K1_SB;
     long grid = (long)h->sm_count * 2;
     if (grid > n_blocks) grid = n_blocks;
@@ -685,7 +693,7 @@ static int bb_launch_inner_t(bb_handle* h, long n, double* out, cudaStream_t st)
         BB_CUDA(cudaEventCreate(&e1));
         BB_CUDA(cudaEventRecord(e0, st));
     }
-    bb_inner_product_kernel<NDET><<<(unsigned)grid, BB_K1_THREADS, smem, st>>>(
+    bb_inner_product_kernel<NDET, APPROX><<<(unsigned)grid, BB_K1_THREADS, smem, st>>>(
         h->d_coef, n, bb_tiles(h), h->net.n_freq, h->net.df, h->shard_lo, h->shard_hi, out);
     if (h->profile) {
         BB_CUDA(cudaEventRecord(e1, st));
@@ -697,11 +705,12 @@ static int bb_launch_inner_t(bb_handle* h, long n, double* out, cudaStream_t st)
 }
 
 static int bb_launch_inner(bb_handle* h, long n, double* out, cudaStream_t st) {
+    const bool pd = h->wf.approximant == BB_IMRPHENOMD;
     switch (h->net.n_det) {
-        case 1: return bb_launch_inner_t<1>(h, n, out, st);
-        case 2: return bb_launch_inner_t<2>(h, n, out, st);
-        case 3: return bb_launch_inner_t<3>(h, n, out, st);
-        case 4: return bb_launch_inner_t<4>(h, n, out, st);
+        case 1: return pd ? bb_launch_inner_t<1, BB_IMRPHENOMD>(h, n, out, st) : bb_launch_inner_t<1, BB_TAYLORF2>(h, n, out, st);
+        case 2: return pd ? bb_launch_inner_t<2, BB_IMRPHENOMD>(h, n, out, st) : bb_launch_inner_t<2, BB_TAYLORF2>(h, n, out, st);
+        case 3: return pd ? bb_launch_inner_t<3, BB_IMRPHENOMD>(h, n, out, st) : bb_launch_inner_t<3, BB_TAYLORF2>(h, n, out, st);
+        case 4: return pd ? bb_launch_inner_t<4, BB_IMRPHENOMD>(h, n, out, st) : bb_launch_inner_t<4, BB_TAYLORF2>(h, n, out, st);
     }
     return bb_fail("bad n_det");
 }
@@ -794,7 +803,7 @@ static int bb_strain_common(bb_handle* h, const double* params_dev, long n, doub
     if (bb_launch_prologue(h, params_dev, n, st)) return 1;
     // the record folds dt0 = t_c - start_time into the phase; mode 0 undoes it with start_time
     dim3 grid((h->net.n_freq + 127) / 128, (unsigned)n);
-    bb_strain_kernel<<<grid, 128, 0, st>>>(h->d_coef, n, bb_tiles(h), h->net.n_freq, h->net.df, h->net.n_det, mode,
+    bb_strain_kernel<<<grid, 128, 0, st>>>(h->d_coef, n, bb_tiles(h), h->net.n_freq, h->net.df, h->net.n_det, h->wf.approximant, mode,
                                           params_dev, h->d_mask, h->net.start_time, out_dev);
     h->launches++;
     BB_CUDA(cudaGetLastError());

@@ -18,7 +18,7 @@
 
 __device__ __forceinline__ unsigned bb_bitrev(unsigned v, int bits) { return __brev(v) >> (32 - bits); }
 
-template <int NDET>
+template <int NDET, int APPROX>
 __global__ void __launch_bounds__(BB_TM_THREADS, 1)
 bb_time_marg_kernel(const double* __restrict__ coef, long n, BBTiles tiles, int n_freq, double df, int nfft,
                     int log2n, const double2* __restrict__ twiddle, BBMarg marg, double start_time,
@@ -44,9 +44,8 @@ bb_time_marg_kernel(const double* __restrict__ coef, long n, BBTiles tiles, int 
         double hh = 0.0;
         for (int k = k0 + tid; k < k1h; k += BB_TM_THREADS) {
             const double f = (double)k * df;
-            const double u = tiles.u[k], t = u * u, x = f * t * t;
-            const double A = bb_phenomd_amp(c, f, u, t, x);
-            const double ph = bb_phenomd_phase(c, f, t, x, tiles.lf[k], tiles.q34[k]);
+            double A, ph;
+            bb_wave<APPROX>(c, f, tiles.u[k], tiles.lf[k], tiles.q34[k], &A, &ph);
             double sn, cs;
             sincospi(ph, &sn, &cs);
             const double zr = A * cs, zi = A * sn;
@@ -127,20 +126,20 @@ bb_time_marg_kernel(const double* __restrict__ coef, long n, BBTiles tiles, int 
     }
 }
 
-template <int NDET>
+template <int NDET, int APPROX>
 static int bb_launch_time_marg_t(bb_handle* h, long n, double* out, cudaStream_t st) {
     const int nfft = h->nfft;
     int log2n = 0;
     while ((1 << log2n) < nfft) ++log2n;
     const size_t smem = (size_t)nfft * sizeof(double2) + (BC_NCOEF + 32) * sizeof(double);
     if (smem > 227 * 1024) return bb_fail("time marginalisation: series does not fit shared memory (nfft > 8192)");
-    BB_CUDA(cudaFuncSetAttribute(bb_time_marg_kernel<NDET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BB_CUDA(cudaFuncSetAttribute(bb_time_marg_kernel<NDET, APPROX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = (int)((227 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 4) per_sm = 4;
     long grid = (long)h->sm_count * per_sm;
     if (grid > n) grid = n;
-    bb_time_marg_kernel<NDET><<<(unsigned)grid, BB_TM_THREADS, smem, st>>>(
+    bb_time_marg_kernel<NDET, APPROX><<<(unsigned)grid, BB_TM_THREADS, smem, st>>>(
         h->d_coef, n, bb_tiles(h), h->net.n_freq, h->net.df, nfft, log2n, h->d_twiddle, h->marg,
         h->net.start_time, h->net.duration, out);
     h->launches++;
@@ -152,11 +151,12 @@ static int bb_launch_time_marg(bb_handle* h, long n, double* out, cudaStream_t s
     if (h->nfft == 0) return bb_fail("time marginalisation needs n_freq - 1 to be a power of two");
     if (h->shard_lo != 0 || h->shard_hi != h->net.n_freq)
         return bb_fail("time marginalisation cannot be frequency-sharded (SURVEY.md section 8e)");
+    const bool pd = h->wf.approximant == BB_IMRPHENOMD;
     switch (h->net.n_det) {
-        case 1: return bb_launch_time_marg_t<1>(h, n, out, st);
-        case 2: return bb_launch_time_marg_t<2>(h, n, out, st);
-        case 3: return bb_launch_time_marg_t<3>(h, n, out, st);
-        case 4: return bb_launch_time_marg_t<4>(h, n, out, st);
+        case 1: return pd ? bb_launch_time_marg_t<1, BB_IMRPHENOMD>(h, n, out, st) : bb_launch_time_marg_t<1, BB_TAYLORF2>(h, n, out, st);
+        case 2: return pd ? bb_launch_time_marg_t<2, BB_IMRPHENOMD>(h, n, out, st) : bb_launch_time_marg_t<2, BB_TAYLORF2>(h, n, out, st);
+        case 3: return pd ? bb_launch_time_marg_t<3, BB_IMRPHENOMD>(h, n, out, st) : bb_launch_time_marg_t<3, BB_TAYLORF2>(h, n, out, st);
+        case 4: return pd ? bb_launch_time_marg_t<4, BB_IMRPHENOMD>(h, n, out, st) : bb_launch_time_marg_t<4, BB_TAYLORF2>(h, n, out, st);
     }
     return bb_fail("bad n_det");
 }
