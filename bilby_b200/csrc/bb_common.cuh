@@ -56,9 +56,14 @@ enum {
     BC_STATUS,        // 0 = ok, 1 = waveform domain error (-> likelihood sentinel)
     BC_JITTER,
     BC_SPARE,
-    BC_DET,           // per detector 4: K_re, K_im, 2*dt_det [half turns / Hz], |K|^2
-    BC_NCOEF = BC_DET + 4 * BB_MAX_DET
+    BC_KA1, BC_KA2,   // first bin of the amplitude intermediate / merger-ringdown regions (exact doubles)
+    BC_KP1, BC_KP2,   // first bin of the phase intermediate / merger-ringdown regions
+    BC_DET,           // per detector BC_DSTRIDE: K_re, K_im, 2*dt_det [half turns / Hz], |K|^2,
+                      // Re/Im of exp(+i pi * 2 dt_det * 32 df) (phase-ramp step over one row of 32 bins)
+    BC_DSTRIDE = 6,
+    BC_NCOEF = BC_DET + BC_DSTRIDE * BB_MAX_DET
 };
+#define BB_ROW 32     // bins per row: lane l of a warp owns bins k = 32 r + l
 
 struct BBNetwork {
     int n_det;

@@ -1,0 +1,386 @@
+// K1: fused waveform -> detector projection -> <h|d>, <h|h>   (included by bb_kernels.cu)
+//
+// Replaces, per sample, bilby/gw/source.py:552-690 (waveform on the grid), bilby/gw/detector/
+// interferometer.py:303-368 (projection, phase ramp) and :607-640 -> bilby/gw/utils.py:118-138 (inner
+// products) without ever materialising h(f).
+//
+// Mapping: one CTA of 16 warps per SM; each warp owns one sample of the block's 16; lane l owns the bins
+// k = 32 r + l of row r.  Data tiles (u = f^-1/6, ln f, f^3/4, d/S, 1/S per detector; 96 B per bin for
+// three detectors) are streamed through shared memory in chunks of 512 bins with 1-D TMA bulk copies
+// (cp.async.bulk + mbarrier, SASS UBLKCP), double buffered, and reused by the 16 samples of the block.
+// Samples arrive sorted by active-bin count, so the 16 warps of a block run in step and whole chunks
+// above the block's cut-off frequency are never loaded.  Per sample and detector the phase ramp
+// exp(2 pi i f dt_det) is advanced row to row by one complex multiplication (anchored with sincospi once
+// per sample); rows that lie inside one (amplitude, phase) region of IMRPhenomD run a loop specialised
+// for that region with its coefficients in registers, rows that straddle a region boundary take the
+// generic per-lane path.  Partial sums stay in registers; one warp-shuffle reduction per sample.
+#pragma once
+
+#define BB_K1_THREADS 512
+#define BB_K1_WARPS (BB_K1_THREADS / 32)
+#define BB_K1_SB BB_K1_WARPS               // samples per block (one per warp)
+#define BB_K1_CHUNK 512                    // bins per tile
+#define BB_K1_ROWS (BB_K1_CHUNK / BB_ROW)
+
+template <int NDET>
+struct K1Tile {
+    double u[BB_K1_CHUNK];
+    double lf[BB_K1_CHUNK];
+    double q34[BB_K1_CHUNK];
+    double2 ds[NDET][BB_K1_CHUNK];
+    double is[NDET][BB_K1_CHUNK];
+};
+
+template <int NDET>
+struct K1Smem {
+    K1Tile<NDET> tile[2];
+    double coef[BB_K1_SB][BC_NCOEF];
+    unsigned long long bar[2];
+    int krange[2];
+};
+
+// ---- mbarrier / bulk-copy primitives (PTX; sm_90+)
+__device__ __forceinline__ unsigned bb_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bb_mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bb_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void bb_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bb_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bb_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(bb_smem_u32(dst)), "l"(src), "r"(bytes), "r"(bb_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bb_mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "BB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra BB_DONE;\n"
+        "bra BB_WAIT;\n"
+        "BB_DONE:\n"
+        "}" ::"r"(bb_smem_u32(bar)), "r"(parity) : "memory");
+}
+
+template <int NDET>
+__device__ __forceinline__ void bb_k1_issue_tile(K1Tile<NDET>& t, unsigned long long* bar, const BBTiles& g, int c0) {
+    bb_mbar_expect_tx(bar, (unsigned)sizeof(K1Tile<NDET>));
+    bb_bulk_g2s(t.u, g.u + c0, BB_K1_CHUNK * 8, bar);
+    bb_bulk_g2s(t.lf, g.lf + c0, BB_K1_CHUNK * 8, bar);
+    bb_bulk_g2s(t.q34, g.q34 + c0, BB_K1_CHUNK * 8, bar);
+#pragma unroll
+    for (int d = 0; d < NDET; ++d) {
+        bb_bulk_g2s(t.ds[d], g.ds + (size_t)d * g.n_pad + c0, BB_K1_CHUNK * 16, bar);
+        bb_bulk_g2s(t.is[d], g.is + (size_t)d * g.n_pad + c0, BB_K1_CHUNK * 8, bar);
+    }
+}
+
+// ---- region-specialised pieces of IMRPhenomD (coefficients already in registers)
+struct K1AmpIns { double k[10]; };
+struct K1AmpInt { double k[5], f1, invw; };
+struct K1AmpMr { double frd, wl2, g, lam; };
+struct K1PhIns { double q[13]; };
+struct K1PhInt { double q[4]; };
+struct K1PhMr { double q[7]; };
+
+template <int AR>
+struct K1Amp;
+template <>
+struct K1Amp<0> {
+    K1AmpIns c;
+    __device__ __forceinline__ void load(const double* r) {
+#pragma unroll
+        for (int i = 0; i < 10; ++i) c.k[i] = r[BC_AINS + i];
+    }
+    __device__ __forceinline__ double eval(double f, double x) const {
+        double a = c.k[9];
+#pragma unroll
+        for (int i = 8; i >= 0; --i) a = a * x + c.k[i];
+        return a;
+    }
+};
+template <>
+struct K1Amp<1> {
+    K1AmpInt c;
+    __device__ __forceinline__ void load(const double* r) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) c.k[i] = r[BC_AINT + i];
+        c.f1 = r[BC_AINT_F1];
+        c.invw = r[BC_AINT_INVW];
+    }
+    __device__ __forceinline__ double eval(double f, double x) const {
+        const double xs = (f - c.f1) * c.invw;
+        double a = c.k[4];
+#pragma unroll
+        for (int i = 3; i >= 0; --i) a = a * xs + c.k[i];
+        return a;
+    }
+};
+template <>
+struct K1Amp<2> {
+    K1AmpMr c;
+    __device__ __forceinline__ void load(const double* r) {
+        c.frd = r[BC_MR_FRD];
+        c.wl2 = r[BC_MR_WL2];
+        c.g = r[BC_MR_G];
+        c.lam = r[BC_MR_LAM];
+    }
+    __device__ __forceinline__ double eval(double f, double x) const {
+        const double d = f - c.frd;
+        return c.g * exp(-c.lam * d) / (d * d + c.wl2);
+    }
+};
+
+template <int PR>
+struct K1Ph;
+template <>
+struct K1Ph<0> {
+    K1PhIns c;
+    __device__ __forceinline__ void load(const double* r) {
+#pragma unroll
+        for (int i = 0; i < 13; ++i) c.q[i] = r[BC_PINS + i];
+    }
+    __device__ __forceinline__ double eval(double f, double t, double x, double lf, double q34) const {
+        const double* q = c.q;
+        double pos = q[6];
+        pos = pos * x + q[5]; pos = pos * x + q[4]; pos = pos * x + q[3]; pos = pos * x + q[2]; pos = pos * x + q[1];
+        double neg = q[10] * t * t + q[9];
+        neg = neg * t + q[8]; neg = neg * t + q[7];
+        return q[0] + pos * x + neg * t + lf * (q[11] + q[12] * x);
+    }
+};
+template <>
+struct K1Ph<1> {
+    K1PhInt c;
+    __device__ __forceinline__ void load(const double* r) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) c.q[i] = r[BC_PINT + i];
+    }
+    __device__ __forceinline__ double eval(double f, double t, double x, double lf, double q34) const {
+        const double t3 = t * t * t;
+        return c.q[0] + c.q[1] * f + c.q[2] * (t3 * t3 * t3) + c.q[3] * lf;
+    }
+};
+template <>
+struct K1Ph<2> {
+    K1PhMr c;
+    __device__ __forceinline__ void load(const double* r) {
+#pragma unroll
+        for (int i = 0; i < 7; ++i) c.q[i] = r[BC_PMR + i];
+    }
+    __device__ __forceinline__ double eval(double f, double t, double x, double lf, double q34) const {
+        return c.q[0] + c.q[1] * f + c.q[2] * (t * t * t) + c.q[3] * q34 + c.q[4] * atan((f - c.q[5]) * c.q[6]);
+    }
+};
+
+// per-warp running state of one sample
+template <int NDET>
+struct K1State {
+    double acc[NDET][3];     // sum conj(h/K) d/S (re, im), sum A^2 / S
+    double ramp[NDET][2];    // exp(+2 pi i f dt_d) at this lane's bin of the current row
+    double step[NDET][2];    // its advance over one row
+};
+
+template <int NDET>
+__device__ __forceinline__ void bb_k1_accumulate(K1State<NDET>& st, const K1Tile<NDET>& tile, int i, bool act,
+                                                 double A, double ph) {
+    double sn, cs;
+    sincospi(act ? ph : 0.0, &sn, &cs);
+    A = act ? A : 0.0;
+    const double zr = A * cs, zi = A * sn;      // A e^{+i Phi} = conj(h22 incl. geocentric shift)
+    const double A2 = A * A;
+#pragma unroll
+    for (int d = 0; d < NDET; ++d) {
+        const double rc = st.ramp[d][0], rs = st.ramp[d][1];
+        const double wr = zr * rc - zi * rs, wi = zr * rs + zi * rc;
+        const double2 dd = tile.ds[d][i];
+        st.acc[d][0] += wr * dd.x - wi * dd.y;
+        st.acc[d][1] += wr * dd.y + wi * dd.x;
+        st.acc[d][2] += A2 * tile.is[d][i];
+        // advance the ramp to the next row
+        st.ramp[d][0] = rc * st.step[d][0] - rs * st.step[d][1];
+        st.ramp[d][1] = rc * st.step[d][1] + rs * st.step[d][0];
+    }
+}
+
+// rows [r0, r1) of one chunk, all inside amplitude region AR and phase region PR
+template <int NDET, int AR, int PR>
+__device__ __forceinline__ void bb_k1_rows_pd(K1State<NDET>& st, const K1Tile<NDET>& tile, const double* rec, int r0,
+                                              int r1, int c0, int lane, int kmin, int kmax, double df) {
+    K1Amp<AR> amp;
+    K1Ph<PR> phs;
+    amp.load(rec);
+    phs.load(rec);
+    const double a0 = rec[BC_A0];
+    for (int r = r0; r < r1; ++r) {
+        const int k = r * BB_ROW + lane, i = k - c0;
+        const bool act = (k >= kmin) && (k < kmax);
+        const double f = (double)k * df;
+        const double u = tile.u[i], t = u * u, x = f * t * t;
+        const double A = amp.eval(f, x) * a0 * (u * (t * t * t));
+        const double ph = phs.eval(f, t, x, tile.lf[i], tile.q34[i]);
+        bb_k1_accumulate<NDET>(st, tile, i, act, A, ph);
+    }
+}
+
+// generic rows: per-lane region selection (rows straddling a region boundary) or TaylorF2
+template <int NDET, int APPROX>
+__device__ __forceinline__ void bb_k1_rows_generic(K1State<NDET>& st, const K1Tile<NDET>& tile, const double* rec,
+                                                   int r0, int r1, int c0, int lane, int kmin, int kmax, double df) {
+    for (int r = r0; r < r1; ++r) {
+        const int k = r * BB_ROW + lane, i = k - c0;
+        const bool act = (k >= kmin) && (k < kmax);
+        const double f = (double)k * df;
+        double A, ph;
+        bb_wave<APPROX>(rec, f, tile.u[i], tile.lf[i], tile.q34[i], &A, &ph);
+        bb_k1_accumulate<NDET>(st, tile, i, act, A, ph);
+    }
+}
+
+template <int NDET>
+__device__ __forceinline__ void bb_k1_dispatch_pd(K1State<NDET>& st, const K1Tile<NDET>& tile, const double* rec,
+                                                  int r0, int r1, int c0, int lane, int kmin, int kmax, double df,
+                                                  int ar, int pr) {
+    const int combo = ar * 3 + pr;
+    switch (combo) {
+        case 0: bb_k1_rows_pd<NDET, 0, 0>(st, tile, rec, r0, r1, c0, lane, kmin, kmax, df); break;
+        case 3: bb_k1_rows_pd<NDET, 1, 0>(st, tile, rec, r0, r1, c0, lane, kmin, kmax, df); break;
+        case 4: bb_k1_rows_pd<NDET, 1, 1>(st, tile, rec, r0, r1, c0, lane, kmin, kmax, df); break;
+        case 5: bb_k1_rows_pd<NDET, 1, 2>(st, tile, rec, r0, r1, c0, lane, kmin, kmax, df); break;
+        case 8: bb_k1_rows_pd<NDET, 2, 2>(st, tile, rec, r0, r1, c0, lane, kmin, kmax, df); break;
+        default: bb_k1_rows_generic<NDET, BB_IMRPHENOMD>(st, tile, rec, r0, r1, c0, lane, kmin, kmax, df); break;
+    }
+}
+
+template <int NDET, int APPROX>
+__global__ void __launch_bounds__(BB_K1_THREADS, 1)
+bb_inner_product_kernel(const double* __restrict__ coef, const unsigned* __restrict__ perm, long n, BBTiles tiles,
+                        double df, int shard_lo, int shard_hi, double* __restrict__ out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    K1Smem<NDET>& sm = *reinterpret_cast<K1Smem<NDET>*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long n_blocks = (n + BB_K1_SB - 1) / BB_K1_SB;
+
+    if (tid == 0) {
+        bb_mbar_init(&sm.bar[0], 1);
+        bb_mbar_init(&sm.bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    unsigned phase0 = 0, phase1 = 0;      // parity of the next completion of each stage's barrier
+    int issued = 0;                       // tiles issued so far by this CTA (stage = issued & 1), uniform
+
+    for (long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+        const long p0 = blk * BB_K1_SB;
+        const int ns = (int)min((long)BB_K1_SB, n - p0);
+        if (tid == 0) { sm.krange[0] = INT_MAX; sm.krange[1] = 0; }
+        // coefficient records of this block's samples (sorted order -> sample index through perm)
+        for (int i = tid; i < ns * BC_NCOEF; i += BB_K1_THREADS) {
+            const int sl = i / BC_NCOEF, j = i - sl * BC_NCOEF;
+            const long s = perm ? (long)perm[p0 + sl] : p0 + sl;
+            sm.coef[sl][j] = coef[s * BC_NCOEF + j];
+        }
+        __syncthreads();
+        if (tid < ns) {
+            const int k0 = max((int)sm.coef[tid][BC_KMIN], shard_lo), k1 = min((int)sm.coef[tid][BC_KMAX], shard_hi);
+            if (k1 > k0) {
+                atomicMin(&sm.krange[0], k0);
+                atomicMax(&sm.krange[1], k1);
+            }
+        }
+        __syncthreads();
+        const int kb0 = sm.krange[0], kb1 = sm.krange[1];
+        const int cb0 = kb0 / BB_K1_CHUNK, cb1 = (kb1 + BB_K1_CHUNK - 1) / BB_K1_CHUNK;   // chunk index range
+
+        // ---- per-warp sample set-up
+        const bool have = warp < ns;
+        const double* rec = sm.coef[have ? warp : 0];
+        int kmin = 0, kmax = 0;
+        if (have) {
+            kmin = max((int)rec[BC_KMIN], shard_lo);
+            kmax = min((int)rec[BC_KMAX], shard_hi);
+            if (kmax < kmin) kmax = kmin;
+        }
+        const int row_first = kmin / BB_ROW, row_last = (kmax + BB_ROW - 1) / BB_ROW;   // [row_first, row_last)
+        K1State<NDET> st;
+#pragma unroll
+        for (int d = 0; d < NDET; ++d) {
+            st.acc[d][0] = st.acc[d][1] = st.acc[d][2] = 0.0;
+            const double f0 = (double)(row_first * BB_ROW + lane) * df;
+            sincospi(rec[BC_DET + BC_DSTRIDE * d + 2] * f0, &st.ramp[d][1], &st.ramp[d][0]);
+            st.step[d][0] = rec[BC_DET + BC_DSTRIDE * d + 4];
+            st.step[d][1] = rec[BC_DET + BC_DSTRIDE * d + 5];
+        }
+        int ka1 = 0, ka2 = 0, kp1 = 0, kp2 = 0;
+        if (APPROX == BB_IMRPHENOMD) {
+            ka1 = (int)rec[BC_KA1]; ka2 = (int)rec[BC_KA2]; kp1 = (int)rec[BC_KP1]; kp2 = (int)rec[BC_KP2];
+        }
+
+        // ---- stream the tiles
+        if (cb1 > cb0 && tid == 0) {
+            bb_k1_issue_tile<NDET>(sm.tile[issued & 1], &sm.bar[issued & 1], tiles, cb0 * BB_K1_CHUNK);
+        }
+        for (int cb = cb0; cb < cb1; ++cb) {
+            const int stage = issued & 1;
+            if (cb + 1 < cb1 && tid == 0) {
+                // the other stage was released by the __syncthreads that ended the previous iteration
+                bb_k1_issue_tile<NDET>(sm.tile[stage ^ 1], &sm.bar[stage ^ 1], tiles, (cb + 1) * BB_K1_CHUNK);
+            }
+            if (stage == 0) { bb_mbar_wait(&sm.bar[0], phase0); phase0 ^= 1; }
+            else { bb_mbar_wait(&sm.bar[1], phase1); phase1 ^= 1; }
+            ++issued;
+            const K1Tile<NDET>& tile = sm.tile[stage];
+            const int c0 = cb * BB_K1_CHUNK;
+            int r = max(row_first, c0 / BB_ROW);
+            const int rend = min(row_last, (c0 + BB_K1_CHUNK) / BB_ROW);
+            if (have && r < rend) {
+                if (APPROX == BB_IMRPHENOMD) {
+                    // split [r, rend) at the rows that contain a region boundary
+                    while (r < rend) {
+                        const int kf = r * BB_ROW;                 // first bin of row r
+                        const int ar = kf < ka1 ? 0 : (kf < ka2 ? 1 : 2);
+                        const int pr = kf < kp1 ? 0 : (kf < kp2 ? 1 : 2);
+                        // next boundary strictly above kf
+                        int nb = INT_MAX;
+                        if (ka1 > kf) nb = min(nb, ka1);
+                        if (ka2 > kf) nb = min(nb, ka2);
+                        if (kp1 > kf) nb = min(nb, kp1);
+                        if (kp2 > kf) nb = min(nb, kp2);
+                        if (nb < kf + BB_ROW) {
+                            // a boundary falls inside this row: generic per-lane path for one row
+                            bb_k1_rows_generic<NDET, BB_IMRPHENOMD>(st, tile, rec, r, r + 1, c0, lane, kmin, kmax, df);
+                            r += 1;
+                        } else {
+                            const int rstop = (nb == INT_MAX) ? rend : min(rend, nb / BB_ROW);
+                            bb_k1_dispatch_pd<NDET>(st, tile, rec, r, rstop, c0, lane, kmin, kmax, df, ar, pr);
+                            r = rstop;
+                        }
+                    }
+                } else {
+                    bb_k1_rows_generic<NDET, APPROX>(st, tile, rec, r, rend, c0, lane, kmin, kmax, df);
+                }
+            }
+            __syncthreads();     // everyone is done with this stage before it is refilled
+        }
+
+        // ---- reduce over lanes and write (Re<h|d>, Im<h|d>, <h|h>) per detector
+        if (have) {
+            const long s = perm ? (long)perm[p0 + warp] : p0 + warp;
+#pragma unroll
+            for (int d = 0; d < NDET; ++d) {
+                const double sr = bb_warp_sum(st.acc[d][0]);
+                const double si = bb_warp_sum(st.acc[d][1]);
+                const double sh = bb_warp_sum(st.acc[d][2]);
+                if (lane == 0) {
+                    const double kr = rec[BC_DET + BC_DSTRIDE * d], ki = rec[BC_DET + BC_DSTRIDE * d + 1];
+                    double* o = out + (s * NDET + d) * 3;
+                    o[0] = kr * sr + ki * si;        // <h|d> = conj(K) * sum
+                    o[1] = kr * si - ki * sr;
+                    o[2] = (rec[BC_STATUS] != 0.0) ? nan("") : rec[BC_DET + BC_DSTRIDE * d + 3] * sh;
+                }
+            }
+        }
+        __syncthreads();         // records are overwritten by the next block iteration
+    }
+}

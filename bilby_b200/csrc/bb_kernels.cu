@@ -10,6 +10,7 @@
 //   KT bb_distance_table_kernel  lookup table build
 //   KW bb_strain_kernel          polarisations / detector response on the full grid (injection, tests)
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 #include <float.h>
 #include <stdio.h>
 #include <string.h>
@@ -44,8 +45,9 @@ struct BBTiles {
     const double* u;      // f^(-1/6)            [n_freq]
     const double* lf;     // ln f                [n_freq]
     const double* q34;    // f^(3/4)             [n_freq]
-    const double2* ds;    // (4/T) d/S  complex  [n_det][n_freq]
-    const double* is;     // (4/T) / S           [n_det][n_freq]
+    const double2* ds;    // (4/T) d/S  complex  [n_det][n_pad]
+    const double* is;     // (4/T) / S           [n_det][n_pad]
+    int n_pad;            // n_freq rounded up to a whole number of K1 tiles (zero padded)
 };
 
 struct BBMarg {
@@ -73,6 +75,11 @@ struct bb_handle {
     size_t coef_cap = 0;                   // samples
     double* d_snr = nullptr;
     size_t snr_cap = 0;
+    unsigned *d_keys = nullptr, *d_keys_out = nullptr, *d_index = nullptr, *d_perm = nullptr;
+    void* d_sort_tmp = nullptr;
+    size_t sort_tmp_bytes = 0;
+    int n_pad = 0;
+    bool perm_valid = false;
     double *d_params = nullptr, *d_out = nullptr;   // staging for the host entry point
     size_t stage_cap = 0;
     double *h_params = nullptr, *h_out = nullptr;   // pinned
@@ -101,7 +108,8 @@ __device__ __forceinline__ void bb_wave(const double* c, double f, double u, dou
 // K0: prologue
 // ------------------------------------------------------------------------------------------------
 __global__ void bb_prologue_kernel(const double* __restrict__ params, long n, BBNetwork net,
-                                   BBWaveformConfig wf, double* __restrict__ coef) {
+                                   BBWaveformConfig wf, double* __restrict__ coef, unsigned* __restrict__ keys,
+                                   unsigned* __restrict__ index) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double p[BB_NPARAM];
@@ -113,138 +121,24 @@ __global__ void bb_prologue_kernel(const double* __restrict__ params, long n, BB
     else bb_taylorf2_prologue(p, net, wf, c);
     double* dst = coef + i * BC_NCOEF;
     for (int k = 0; k < BC_NCOEF; ++k) dst[k] = c[k];
+    if (keys) {
+        // descending active-bin count: blocks of K1 then hold samples of equal length, longest first
+        const unsigned count = (unsigned)(c[BC_KMAX] - c[BC_KMIN]);
+        keys[i] = (1u << 24) - min(count, (1u << 24) - 1u);
+        index[i] = (unsigned)i;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1: fused waveform -> projection -> <h|d>, <h|h>
+// K1: fused waveform -> projection -> <h|d>, <h|h>   (bb_k1.cuh)
 // ------------------------------------------------------------------------------------------------
-#define BB_K1_THREADS 256
-#define BB_K1_WARPS (BB_K1_THREADS / 32)
-#define BB_K1_SPW 2                       // samples per warp per block
-#define BB_K1_SB (BB_K1_WARPS * BB_K1_SPW) // samples per block
-#define BB_K1_CHUNK 512                   // frequency bins staged per tile
-
-template <int NDET>
-struct K1Smem {
-    double u[BB_K1_CHUNK];
-    double lf[BB_K1_CHUNK];
-    double q34[BB_K1_CHUNK];
-    double2 ds[NDET][BB_K1_CHUNK];
-    double is[NDET][BB_K1_CHUNK];
-    double coef[BB_K1_SB][BC_NCOEF];
-    int krange[2];
-};
-
 __device__ __forceinline__ double bb_warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
 
-template <int NDET, int APPROX>
-__global__ void __launch_bounds__(BB_K1_THREADS, 2)
-bb_inner_product_kernel(const double* __restrict__ coef, long n, BBTiles tiles, int n_freq, double df,
-                        int shard_lo, int shard_hi, double* __restrict__ out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    K1Smem<NDET>& sm = *reinterpret_cast<K1Smem<NDET>*>(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long n_blocks = (n + BB_K1_SB - 1) / BB_K1_SB;
-
-    for (long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
-        const long s0 = blk * BB_K1_SB;
-        const int ns = (int)min((long)BB_K1_SB, n - s0);
-        __syncthreads();   // previous iteration done with smem
-        if (tid == 0) { sm.krange[0] = INT_MAX; sm.krange[1] = 0; }
-        // coefficient records of this block's samples (coalesced)
-        for (int i = tid; i < ns * BC_NCOEF; i += BB_K1_THREADS)
-            (&sm.coef[0][0])[i] = coef[s0 * BC_NCOEF + i];
-        __syncthreads();
-        if (tid < ns) {
-            int k0 = (int)sm.coef[tid][BC_KMIN], k1 = (int)sm.coef[tid][BC_KMAX];
-            k0 = max(k0, shard_lo);
-            k1 = min(k1, shard_hi);
-            if (k1 > k0) {
-                atomicMin(&sm.krange[0], k0);
-                atomicMax(&sm.krange[1], k1);
-            }
-        }
-        __syncthreads();
-        const int kb0 = sm.krange[0], kb1 = sm.krange[1];
-
-        double acc[BB_K1_SPW][NDET][3];
-#pragma unroll
-        for (int s = 0; s < BB_K1_SPW; ++s)
-#pragma unroll
-            for (int d = 0; d < NDET; ++d) acc[s][d][0] = acc[s][d][1] = acc[s][d][2] = 0.0;
-
-        for (int c0 = (kb0 / BB_K1_CHUNK) * BB_K1_CHUNK; c0 < kb1; c0 += BB_K1_CHUNK) {
-            __syncthreads();
-            // stage this chunk's tiles
-            for (int i = tid; i < BB_K1_CHUNK; i += BB_K1_THREADS) {
-                const int k = c0 + i;
-                const bool ok = k < n_freq;
-                sm.u[i] = ok ? tiles.u[k] : 0.0;
-                sm.lf[i] = ok ? tiles.lf[k] : 0.0;
-                sm.q34[i] = ok ? tiles.q34[k] : 0.0;
-#pragma unroll
-                for (int d = 0; d < NDET; ++d) {
-                    sm.ds[d][i] = ok ? tiles.ds[(size_t)d * n_freq + k] : make_double2(0.0, 0.0);
-                    sm.is[d][i] = ok ? tiles.is[(size_t)d * n_freq + k] : 0.0;
-                }
-            }
-            __syncthreads();
-#pragma unroll
-            for (int s = 0; s < BB_K1_SPW; ++s) {
-                const int sl = warp * BB_K1_SPW + s;
-                if (sl >= ns) continue;
-                const double* c = sm.coef[sl];
-                const int lo = max(max((int)c[BC_KMIN], shard_lo), c0);
-                const int hi = min(min((int)c[BC_KMAX], shard_hi), c0 + BB_K1_CHUNK);
-                for (int k = lo + lane; k < hi; k += 32) {
-                    const int i = k - c0;
-                    const double f = (double)k * df;
-                    double A, ph;
-                    bb_wave<APPROX>(c, f, sm.u[i], sm.lf[i], sm.q34[i], &A, &ph);
-                    double sn, cs;
-                    sincospi(ph, &sn, &cs);
-                    const double zr = A * cs, zi = A * sn;    // A e^{+i Phi} = conj(h22 incl. geocentric shift)
-                    const double A2 = A * A;
-#pragma unroll
-                    for (int d = 0; d < NDET; ++d) {
-                        double rs, rc;
-                        sincospi(c[BC_DET + 4 * d + 2] * f, &rs, &rc);   // e^{+2 pi i f dt_d}
-                        const double wr = zr * rc - zi * rs, wi = zr * rs + zi * rc;
-                        const double2 dd = sm.ds[d][i];
-                        acc[s][d][0] += wr * dd.x - wi * dd.y;
-                        acc[s][d][1] += wr * dd.y + wi * dd.x;
-                        acc[s][d][2] += A2 * sm.is[d][i];
-                    }
-                }
-            }
-        }
-        // reduce over lanes and write (Re<h|d>, Im<h|d>, <h|h>) per detector
-#pragma unroll
-        for (int s = 0; s < BB_K1_SPW; ++s) {
-            const int sl = warp * BB_K1_SPW + s;
-            if (sl >= ns) continue;    // warp-uniform
-            const double* c = sm.coef[sl];
-#pragma unroll
-            for (int d = 0; d < NDET; ++d) {
-                const double sr = bb_warp_sum(acc[s][d][0]);
-                const double si = bb_warp_sum(acc[s][d][1]);
-                const double sh = bb_warp_sum(acc[s][d][2]);
-                if (lane == 0) {
-                    const double kr = c[BC_DET + 4 * d], ki = c[BC_DET + 4 * d + 1];
-                    // <h|d> = conj(K) * sum
-                    double* o = out + ((s0 + sl) * NDET + d) * 3;
-                    o[0] = kr * sr + ki * si;
-                    o[1] = kr * si - ki * sr;
-                    o[2] = (c[BC_STATUS] != 0.0) ? nan("") : c[BC_DET + 4 * d + 3] * sh;
-                }
-            }
-        }
-    }
-}
+#include "bb_k1.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // K3: epilogue (compute_log_likelihood_from_snrs, base.py:448-477 without time marginalisation)
@@ -373,9 +267,9 @@ __global__ void bb_strain_kernel(const double* __restrict__ coef, long n, BBTile
     } else {
         for (int d = 0; d < n_det; ++d) {
             double rs, rc;
-            sincospi(c[BC_DET + 4 * d + 2] * f, &rs, &rc);
+            sincospi(c[BC_DET + BC_DSTRIDE * d + 2] * f, &rs, &rc);
             // h_det = K h22 e^{-2 pi i f dt_d}
-            const double kr = c[BC_DET + 4 * d], ki = c[BC_DET + 4 * d + 1];
+            const double kr = c[BC_DET + BC_DSTRIDE * d], ki = c[BC_DET + BC_DSTRIDE * d + 1];
             const double ar = hr * rc + hi * rs, ai = hi * rc - hr * rs;
             const bool m = mask[(size_t)d * n_freq + k] != 0;
             double* o = out + (((size_t)s * n_det + d) * n_freq + k) * 2;
@@ -462,6 +356,7 @@ __global__ void bb_ln_i0_kernel(const double* __restrict__ x, long n, double* __
 // host side
 // ================================================================================================
 static int bb_ensure_scratch(bb_handle* h, size_t n) {
+    if (n >= (size_t)1 << 31) return bb_fail("at most 2^31-1 samples per call");
     if (n > h->coef_cap) {
         if (h->d_coef) cudaFree(h->d_coef);
         if (h->d_snr) cudaFree(h->d_snr);
@@ -470,6 +365,17 @@ static int bb_ensure_scratch(bb_handle* h, size_t n) {
         size_t cap = n < 4096 ? 4096 : n;
         BB_CUDA(cudaMalloc(&h->d_coef, cap * BC_NCOEF * sizeof(double)));
         BB_CUDA(cudaMalloc(&h->d_snr, cap * BB_MAX_DET * 3 * sizeof(double)));
+        cudaFree(h->d_keys); cudaFree(h->d_keys_out); cudaFree(h->d_index); cudaFree(h->d_perm); cudaFree(h->d_sort_tmp);
+        h->d_keys = h->d_keys_out = h->d_index = h->d_perm = nullptr;
+        h->d_sort_tmp = nullptr;
+        BB_CUDA(cudaMalloc(&h->d_keys, cap * sizeof(unsigned)));
+        BB_CUDA(cudaMalloc(&h->d_keys_out, cap * sizeof(unsigned)));
+        BB_CUDA(cudaMalloc(&h->d_index, cap * sizeof(unsigned)));
+        BB_CUDA(cudaMalloc(&h->d_perm, cap * sizeof(unsigned)));
+        size_t tmp = 0;
+        BB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, h->d_keys, h->d_keys_out, h->d_index, h->d_perm, (int)cap, 0, 25));
+        BB_CUDA(cudaMalloc(&h->d_sort_tmp, tmp));
+        h->sort_tmp_bytes = tmp;
         h->coef_cap = cap;
         h->snr_cap = cap;
     }
@@ -483,6 +389,7 @@ static BBTiles bb_tiles(const bb_handle* h) {
     t.q34 = h->d_q34;
     t.ds = h->d_ds;
     t.is = h->d_is;
+    t.n_pad = h->n_pad;
     return t;
 }
 
@@ -524,6 +431,7 @@ extern "C" void bb_destroy(bb_handle* h) {
     cudaFree(h->d_tx); cudaFree(h->d_ty); cudaFree(h->d_c);
     cudaFree(h->d_coef); cudaFree(h->d_snr); cudaFree(h->d_params); cudaFree(h->d_out);
     cudaFree(h->d_mask); cudaFree(h->d_twiddle);
+    cudaFree(h->d_keys); cudaFree(h->d_keys_out); cudaFree(h->d_index); cudaFree(h->d_perm); cudaFree(h->d_sort_tmp);
     if (h->h_params) cudaFreeHost(h->h_params);
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -551,8 +459,10 @@ extern "C" int bb_set_network(bb_handle* h, int n_det, int n_freq, double durati
         memcpy(net.detector_tensor[d], detector_tensors + 9 * d, 9 * sizeof(double));
         memcpy(net.vertex[d], vertices + 3 * d, 3 * sizeof(double));
     }
-    std::vector<double> u(n_freq), lf(n_freq), q34(n_freq), is((size_t)n_det * n_freq);
-    std::vector<double2> ds((size_t)n_det * n_freq);
+    const int n_pad = ((n_freq + BB_K1_CHUNK - 1) / BB_K1_CHUNK) * BB_K1_CHUNK;
+    h->n_pad = n_pad;
+    std::vector<double> u(n_pad, 0.0), lf(n_pad, 0.0), q34(n_pad, 0.0), is((size_t)n_det * n_pad, 0.0);
+    std::vector<double2> ds((size_t)n_det * n_pad, make_double2(0.0, 0.0));
     for (int k = 0; k < n_freq; ++k) {
         const double f = (double)k * net.df;
         u[k] = k ? pow(f, -1.0 / 6.0) : 0.0;
@@ -563,14 +473,14 @@ extern "C" int bb_set_network(bb_handle* h, int n_det, int n_freq, double durati
     const double norm = 4.0 / duration;
     for (int d = 0; d < n_det; ++d)
         for (int k = 0; k < n_freq; ++k) {
-            const size_t i = (size_t)d * n_freq + k;
+            const size_t i = (size_t)d * n_freq + k, o = (size_t)d * n_pad + k;
             const double S = psd[i];
             const bool m = mask[i] != 0;
             if (m) { if (k < k_lo) k_lo = k; if (k > k_hi) k_hi = k; }
             const bool live = m && isfinite(S) && S > 0.0;
             // +inf PSD outside the curve's range contributes exactly zero (psd.py:240-243)
-            is[i] = live ? norm / S : 0.0;
-            ds[i] = live ? make_double2(norm * strain[2 * i] / S, norm * strain[2 * i + 1] / S) : make_double2(0.0, 0.0);
+            is[o] = live ? norm / S : 0.0;
+            ds[o] = live ? make_double2(norm * strain[2 * i] / S, norm * strain[2 * i + 1] / S) : make_double2(0.0, 0.0);
         }
     if (k_hi < k_lo) { k_lo = 0; k_hi = -1; }
     net.k_lo = k_lo;
@@ -578,14 +488,14 @@ extern "C" int bb_set_network(bb_handle* h, int n_det, int n_freq, double durati
     cudaFree(h->d_u); cudaFree(h->d_lf); cudaFree(h->d_q34); cudaFree(h->d_is); cudaFree(h->d_ds);
     h->d_u = h->d_lf = h->d_q34 = h->d_is = nullptr;
     h->d_ds = nullptr;
-    BB_CUDA(cudaMalloc(&h->d_u, n_freq * sizeof(double)));
-    BB_CUDA(cudaMalloc(&h->d_lf, n_freq * sizeof(double)));
-    BB_CUDA(cudaMalloc(&h->d_q34, n_freq * sizeof(double)));
-    BB_CUDA(cudaMalloc(&h->d_is, (size_t)n_det * n_freq * sizeof(double)));
-    BB_CUDA(cudaMalloc(&h->d_ds, (size_t)n_det * n_freq * sizeof(double2)));
-    BB_CUDA(cudaMemcpy(h->d_u, u.data(), n_freq * sizeof(double), cudaMemcpyHostToDevice));
-    BB_CUDA(cudaMemcpy(h->d_lf, lf.data(), n_freq * sizeof(double), cudaMemcpyHostToDevice));
-    BB_CUDA(cudaMemcpy(h->d_q34, q34.data(), n_freq * sizeof(double), cudaMemcpyHostToDevice));
+    BB_CUDA(cudaMalloc(&h->d_u, n_pad * sizeof(double)));
+    BB_CUDA(cudaMalloc(&h->d_lf, n_pad * sizeof(double)));
+    BB_CUDA(cudaMalloc(&h->d_q34, n_pad * sizeof(double)));
+    BB_CUDA(cudaMalloc(&h->d_is, (size_t)n_det * n_pad * sizeof(double)));
+    BB_CUDA(cudaMalloc(&h->d_ds, (size_t)n_det * n_pad * sizeof(double2)));
+    BB_CUDA(cudaMemcpy(h->d_u, u.data(), n_pad * sizeof(double), cudaMemcpyHostToDevice));
+    BB_CUDA(cudaMemcpy(h->d_lf, lf.data(), n_pad * sizeof(double), cudaMemcpyHostToDevice));
+    BB_CUDA(cudaMemcpy(h->d_q34, q34.data(), n_pad * sizeof(double), cudaMemcpyHostToDevice));
     BB_CUDA(cudaMemcpy(h->d_is, is.data(), is.size() * sizeof(double), cudaMemcpyHostToDevice));
     BB_CUDA(cudaMemcpy(h->d_ds, ds.data(), ds.size() * sizeof(double2), cudaMemcpyHostToDevice));
     // keep the mask for detector-response output
@@ -674,9 +584,19 @@ static int bb_launch_prologue(bb_handle* h, const double* params_dev, long n, cu
     if (!(wf.f_max > 0.0)) wf.f_max = h->net.df * (h->net.n_freq - 1);
     wf.add_jitter = ((h->marg.flags & BB_MARG_TIME) && h->marg.jitter) ? 1 : 0;
     const int threads = 128;
-    bb_prologue_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(params_dev, n, h->net, wf, h->d_coef);
+    const bool sort = n > BB_K1_SB;
+    bb_prologue_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(
+        params_dev, n, h->net, wf, h->d_coef, sort ? h->d_keys : nullptr, h->d_index);
     h->launches++;
     BB_CUDA(cudaGetLastError());
+    h->perm_valid = false;
+    if (sort) {
+        size_t tmp = h->sort_tmp_bytes;
+        BB_CUDA(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp, tmp, h->d_keys, h->d_keys_out, h->d_index, h->d_perm,
+                                                (int)n, 0, 25, st));
+        h->launches += 3;     // CUB radix sort: histogram + onesweep passes
+        h->perm_valid = true;
+    }
     return 0;
 }
 
@@ -685,7 +605,7 @@ static int bb_launch_inner_t(bb_handle* h, long n, double* out, cudaStream_t st)
     const size_t smem = sizeof(K1Smem<NDET>);
     BB_CUDA(cudaFuncSetAttribute(bb_inner_product_kernel<NDET, APPROX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long n_blocks = (n + BB_K1_SB - 1) / BB_K1_SB;
-    long grid = (long)h->sm_count * 2;
+    long grid = (long)h->sm_count;
     if (grid > n_blocks) grid = n_blocks;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->profile) {
@@ -694,7 +614,7 @@ static int bb_launch_inner_t(bb_handle* h, long n, double* out, cudaStream_t st)
         BB_CUDA(cudaEventRecord(e0, st));
     }
     bb_inner_product_kernel<NDET, APPROX><<<(unsigned)grid, BB_K1_THREADS, smem, st>>>(
-        h->d_coef, n, bb_tiles(h), h->net.n_freq, h->net.df, h->shard_lo, h->shard_hi, out);
+        h->d_coef, h->perm_valid ? h->d_perm : nullptr, n, bb_tiles(h), h->net.df, h->shard_lo, h->shard_hi, out);
     if (h->profile) {
         BB_CUDA(cudaEventRecord(e1, st));
         h->k1_events.emplace_back(e0, e1);
@@ -883,7 +803,7 @@ extern "C" int bb_noise_weighted_inner_product_device(bb_handle* h, int det, con
     if (!h || !h->have_network) return bb_fail("bb_noise_weighted_inner_product_device: network not set");
     if (det < 0 || det >= h->net.n_det) return bb_fail("bb_noise_weighted_inner_product_device: bad detector index");
     BB_CUDA(cudaSetDevice(h->device));
-    const size_t off = (size_t)det * h->net.n_freq;
+    const size_t off = (size_t)det * h->n_pad;
     bb_nwip_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>((const double2*)a_dev, (const double2*)b_dev, h->d_ds + off,
                                                         h->d_is + off, h->net.n_freq, out_dev);
     h->launches++;

@@ -226,7 +226,7 @@ BB_HD double bb_detector_prologue(const double* p, const BBNetwork& net, int add
     const double cfac = cos(p[BB_P_THETA_JN]);
     const double pfac = 0.5 * (1.0 + cfac * cfac);
     for (int d = 0; d < BB_MAX_DET; ++d) {
-        double* cd = coef + BC_DET + 4 * d;
+        double* cd = coef + BC_DET + BC_DSTRIDE * d;
         if (d < net.n_det) {
             double fp, fc;
             bb_antenna(net.detector_tensor[d], p[BB_P_RA], p[BB_P_DEC], p[BB_P_PSI], gmst, &fp, &fc);
@@ -236,8 +236,14 @@ BB_HD double bb_detector_prologue(const double* p, const BBNetwork& net, int add
             cd[1] = -fc * cfac;
             cd[2] = 2.0 * delay;
             cd[3] = cd[0] * cd[0] + cd[1] * cd[1];
+            // ramp step over one row: exp(+i pi * cd[2] * 32 df); sincospi is device-only, and pi*x with
+            // |x| < 1 keeps sin/cos argument error at the 1e-17 level
+            const double a = cd[2] * (double)BB_ROW * net.df;
+            const double r = a - 2.0 * floor(0.5 * a + 0.5);     // a mod 2 in [-1, 1)
+            cd[4] = cos(BB_PI * r);
+            cd[5] = sin(BB_PI * r);
         } else {
-            cd[0] = cd[1] = cd[2] = cd[3] = 0.0;
+            for (int i = 0; i < BC_DSTRIDE; ++i) cd[i] = 0.0;
         }
     }
     return tc - net.start_time;
@@ -456,6 +462,15 @@ BB_HD void bb_phenomd_prologue(const double* p, const BBNetwork& net, const BBWa
     q[6] = Ms / s.fDM;
 
     bb_bin_range(net, wf, f_max_prime, coef);
+    // first bin of each region, consistent with the (f < boundary) tests of the per-bin functions
+    const int slots[4] = {BC_KA1, BC_KA2, BC_KP1, BC_KP2};
+    const double bounds[4] = {coef[BC_FA1], coef[BC_FA2], coef[BC_FP1], coef[BC_FP2]};
+    for (int i = 0; i < 4; ++i) {
+        double k = ceil(bounds[i] / net.df);
+        while ((k - 1.0) * net.df >= bounds[i]) k -= 1.0;
+        while (k * net.df < bounds[i]) k += 1.0;
+        coef[slots[i]] = k;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

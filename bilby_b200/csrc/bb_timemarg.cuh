@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(BB_TM_THREADS, 1)
 bb_time_marg_kernel(const double* __restrict__ coef, long n, BBTiles tiles, int n_freq, double df, int nfft,
                     int log2n, const double2* __restrict__ twiddle, BBMarg marg, double start_time,
                     double duration, double* __restrict__ out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     double2* X = reinterpret_cast<double2*>(smem_raw);
     double* c = reinterpret_cast<double*>(smem_raw + (size_t)nfft * sizeof(double2));
     double* red = c + BC_NCOEF;      // [BB_TM_THREADS / 32 * 2]
@@ -54,14 +54,14 @@ bb_time_marg_kernel(const double* __restrict__ coef, long n, BBTiles tiles, int 
 #pragma unroll
             for (int d = 0; d < NDET; ++d) {
                 double rs, rc;
-                sincospi(c[BC_DET + 4 * d + 2] * f, &rs, &rc);
+                sincospi(c[BC_DET + BC_DSTRIDE * d + 2] * f, &rs, &rc);
                 const double wr = zr * rc - zi * rs, wi = zr * rs + zi * rc;
-                const double2 dd = tiles.ds[(size_t)d * n_freq + k];
+                const double2 dd = tiles.ds[(size_t)d * tiles.n_pad + k];
                 const double pr = wr * dd.x - wi * dd.y, pi = wr * dd.y + wi * dd.x;   // conj(h/K) d/S
-                const double kr = c[BC_DET + 4 * d], ki = c[BC_DET + 4 * d + 1];
+                const double kr = c[BC_DET + BC_DSTRIDE * d], ki = c[BC_DET + BC_DSTRIDE * d + 1];
                 vr += kr * pr + ki * pi;       // conj(K) * p
                 vi += kr * pi - ki * pr;
-                hh += c[BC_DET + 4 * d + 3] * A2 * tiles.is[(size_t)d * n_freq + k];
+                hh += c[BC_DET + BC_DSTRIDE * d + 3] * A2 * tiles.is[(size_t)d * tiles.n_pad + k];
             }
             if (k < k1) X[bb_bitrev((unsigned)k, log2n)] = make_double2(vr, -vi);   // h conj(d)/S = conj(conj(h) d/S)
         }

@@ -62,10 +62,11 @@ int main(int argc, char** argv) {
         for (int d = 0; d < net.n_det; ++d) for (int i = 0; i < 9; ++i) net.detector_tensor[d][i] = in[o++];
         for (int d = 0; d < net.n_det; ++d) for (int i = 0; i < 3; ++i) net.vertex[d][i] = in[o++];
         BBQnmTable qnm = {bb_qnm_x, bb_qnm_fring, bb_qnm_fring_d2, bb_qnm_fdamp, bb_qnm_fdamp_d2, BB_QNM_N};
-        // out: per sample coef[BC_NCOEF] then (A, Phi) per bin
-        out.assign((size_t)n * (BC_NCOEF + 2 * (size_t)net.n_freq), 0.0);
+        // out: layout header [BC_NCOEF, BC_DET, BC_DSTRIDE, BC_KMIN], then per sample coef[BC_NCOEF] and (A, Phi) per bin
+        out.assign(4 + (size_t)n * (BC_NCOEF + 2 * (size_t)net.n_freq), 0.0);
+        out[0] = BC_NCOEF; out[1] = BC_DET; out[2] = BC_DSTRIDE; out[3] = BC_KMIN;
         for (long s = 0; s < n; ++s) {
-            double* c = &out[(size_t)s * (BC_NCOEF + 2 * (size_t)net.n_freq)];
+            double* c = &out[4 + (size_t)s * (BC_NCOEF + 2 * (size_t)net.n_freq)];
             const double* p = &in[o + s * BB_NPARAM];
             if (wf.approximant == 0) bb_phenomd_prologue(p, net, wf, qnm, bb_phenomd_fit, c);
 #ifdef BB_HAVE_TAYLORF2

@@ -11,7 +11,6 @@ from oracle import cbc_likelihood as ocl
 
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-NC = 72
 
 
 @pytest.fixture(scope="module")
@@ -44,7 +43,9 @@ def test_phenomd_prologue_and_bins_vs_oracle(host_check):
     hdr = [n, 3, nf, 4.0, 2048.0, st, 0, 50.0, 20.0, 1024.0, 80, 4096]
     blob = np.concatenate([hdr] + [i.detector_tensor.ravel() for i in ifos] + [i.vertex for i in ifos]
                           + [params.ravel()])
-    out = host_check("wave", blob).reshape(n, -1)
+    raw = host_check("wave", blob)
+    NC, DET, DS = int(raw[0]), int(raw[1]), int(raw[2])
+    out = raw[4:].reshape(n, -1)
     assert out.shape[1] == NC + 2 * nf
     f = ifos[0].frequency_array
     worst = 0.0
@@ -55,8 +56,8 @@ def test_phenomd_prologue_and_bins_vs_oracle(host_check):
             waveform_approximant="IMRPhenomD", reference_frequency=50.0, minimum_frequency=20.0))
         for d, ifo in enumerate(ifos):
             ref = ifo.get_detector_response(pols, p)
-            K = coef[NC - 16 + 4 * d] + 1j * coef[NC - 16 + 4 * d + 1]
-            mine = K * ap[:, 0] * np.exp(-1j * np.pi * (ap[:, 1] + coef[NC - 16 + 4 * d + 2] * f)) * ifo.frequency_mask
+            K = coef[DET + DS * d] + 1j * coef[DET + DS * d + 1]
+            mine = K * ap[:, 0] * np.exp(-1j * np.pi * (ap[:, 1] + coef[DET + DS * d + 2] * f)) * ifo.frequency_mask
             worst = max(worst, np.max(np.abs(mine - ref)) / np.max(np.abs(ref)))
     assert worst < 1e-10, worst
 
@@ -125,7 +126,9 @@ def test_taylorf2_prologue_and_bins_vs_oracle(host_check):
     hdr = [n, 3, nf, 128.0, 4096.0, st, 1, 50.0, 20.0, 2048.0, k_lo, k_hi]
     blob = np.concatenate([hdr] + [i.detector_tensor.ravel() for i in ifos] + [i.vertex for i in ifos]
                           + [params.ravel()])
-    out = host_check("wave", blob).reshape(n, -1)
+    raw = host_check("wave", blob)
+    NC, DET, DS = int(raw[0]), int(raw[1]), int(raw[2])
+    out = raw[4:].reshape(n, -1)
     f = ifos[0].frequency_array
     worst = 0.0
     for i in range(n):
@@ -139,8 +142,8 @@ def test_taylorf2_prologue_and_bins_vs_oracle(host_check):
         ext = dict(ra=params[i, 8], dec=params[i, 9], psi=params[i, 6], geocent_time=params[i, 10])
         for d, ifo in enumerate(ifos):
             ref = ifo.get_detector_response(pols, ext)
-            K = coef[NC - 16 + 4 * d] + 1j * coef[NC - 16 + 4 * d + 1]
-            mine = K * ap[:, 0] * np.exp(-1j * np.pi * (ap[:, 1] + coef[NC - 16 + 4 * d + 2] * f)) * ifo.frequency_mask
+            K = coef[DET + DS * d] + 1j * coef[DET + DS * d + 1]
+            mine = K * ap[:, 0] * np.exp(-1j * np.pi * (ap[:, 1] + coef[DET + DS * d + 2] * f)) * ifo.frequency_mask
             worst = max(worst, np.max(np.abs(mine - ref)) / np.max(np.abs(ref)))
     # phases reach ~1e6 rad (126 s time shift at 2 kHz): double rounding of the argument alone is ~1e-10
     assert worst < 5e-9, worst
