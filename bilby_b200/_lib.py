@@ -35,6 +35,10 @@ def load():
         "bb_log_likelihood_ratio_device": (i, [vp, vp, lng, vp, vp]),
         "bb_log_likelihood_ratio_host": (i, [vp, vp, lng, vp]),
         "bb_inner_products_device": (i, [vp, vp, lng, vp, vp]),
+        "bb_set_calibration": (i, [vp, i, vp, vp, vp]),
+        "bb_log_likelihood_ratio_cal_device": (i, [vp, vp, vp, lng, vp, vp]),
+        "bb_log_likelihood_ratio_cal_host": (i, [vp, vp, vp, lng, vp]),
+        "bb_inner_products_cal_device": (i, [vp, vp, vp, lng, vp, vp]),
         "bb_likelihood_from_inner_products_device": (i, [vp, vp, vp, lng, vp, vp]),
         "bb_set_frequency_shard": (i, [vp, i, i]),
         "bb_frequency_domain_strain_device": (i, [vp, vp, lng, vp, vp]),
@@ -60,7 +64,8 @@ def load():
 EXPORTED_SYMBOLS = (
     "bb_last_error", "bb_abi_version", "bb_create", "bb_destroy", "bb_set_network", "bb_set_waveform",
     "bb_set_marginalization", "bb_log_likelihood_ratio_device", "bb_log_likelihood_ratio_host",
-    "bb_inner_products_device", "bb_likelihood_from_inner_products_device", "bb_set_frequency_shard",
+    "bb_inner_products_device", "bb_set_calibration", "bb_log_likelihood_ratio_cal_device",
+    "bb_log_likelihood_ratio_cal_host", "bb_inner_products_cal_device", "bb_likelihood_from_inner_products_device", "bb_set_frequency_shard",
     "bb_frequency_domain_strain_device", "bb_detector_response_device", "bb_build_distance_table",
     "bb_antenna_response_device", "bb_ln_i0_device", "bb_project_polarizations_device",
     "bb_noise_weighted_inner_product_device", "bb_profile_enable", "bb_profile_read", "bb_fp64_peak",

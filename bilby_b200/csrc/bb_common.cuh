@@ -80,6 +80,32 @@ struct BBWaveformConfig {
     double f_ref, f_min, f_max;
 };
 
+// cubic-spline calibration grid (bilby/gw/detector/calibration.py:257-384): per detector the spline nodes are
+// linspace(log10 fmin, log10 fmax, n_points)
+#define BB_NCAL_MAX 32
+struct BBCalGrid {
+    int n_points;                    // 0 = no calibration model
+    double l0[BB_MAX_DET];           // log10 of the first node
+    double inv_delta[BB_MAX_DET];    // 1 / node spacing in log10 f
+};
+
+// calibration factor C = (1 + dA) (2 + i dphi) / (2 - i dphi) = amp1 * (cr + i ci), |cr + i ci| = 1.
+// rec: [4][n] = node amplitudes, their spline coefficients, node phases, their spline coefficients
+BB_HD void bb_cal_factor(const double* rec, int n, double l0, double inv_delta, double lf, double* amp1,
+                         double* cr, double* ci) {
+    const double x = (lf * 0.43429448190325182765 - l0) * inv_delta;       // log10 f = ln f / ln 10
+    int j = (int)x;                                                         // astype(int): truncation
+    j = j < 0 ? 0 : (j > n - 2 ? n - 2 : j);
+    const double b = x - (double)j, a = 1.0 - b;
+    const double c = (a * a * a - a) / 6.0, d = (b * b * b - b) / 6.0;
+    const double dA = a * rec[j] + b * rec[j + 1] + c * rec[n + j] + d * rec[n + j + 1];
+    const double dP = a * rec[2 * n + j] + b * rec[2 * n + j + 1] + c * rec[3 * n + j] + d * rec[3 * n + j + 1];
+    const double den = 1.0 / (4.0 + dP * dP);
+    *amp1 = 1.0 + dA;
+    *cr = (4.0 - dP * dP) * den;
+    *ci = 4.0 * dP * den;
+}
+
 struct BBQnmTable {
     const double* x;
     const double* fring;

@@ -180,9 +180,11 @@ struct K1State {
     double acc[NDET][3];     // sum conj(h/K) d/S (re, im), sum A^2 / S
     double ramp[NDET][2];    // exp(+2 pi i f dt_d) at this lane's bin of the current row
     double step[NDET][2];    // its advance over one row
+    const double* cal;       // CAL: this sample's calibration record [NDET][4][n_points] (shared memory)
+    BBCalGrid grid;
 };
 
-template <int NDET>
+template <int NDET, bool CAL>
 __device__ __forceinline__ void bb_k1_accumulate(K1State<NDET>& st, const K1Tile<NDET>& tile, int i, bool act,
                                                  double A, double ph) {
     double sn, cs;
@@ -193,11 +195,22 @@ __device__ __forceinline__ void bb_k1_accumulate(K1State<NDET>& st, const K1Tile
 #pragma unroll
     for (int d = 0; d < NDET; ++d) {
         const double rc = st.ramp[d][0], rs = st.ramp[d][1];
-        const double wr = zr * rc - zi * rs, wi = zr * rs + zi * rc;
+        double wr = zr * rc - zi * rs, wi = zr * rs + zi * rc;
+        double hw = A2;
+        if (CAL) {
+            // h_det *= C(f)  =>  conj(h) picks up amp1 (cr - i ci), |h|^2 picks up amp1^2
+            double amp1, cr, ci;
+            bb_cal_factor(st.cal + d * 4 * st.grid.n_points, st.grid.n_points, st.grid.l0[d], st.grid.inv_delta[d],
+                          tile.lf[i], &amp1, &cr, &ci);
+            const double tr = amp1 * (wr * cr + wi * ci), ti = amp1 * (wi * cr - wr * ci);
+            wr = tr;
+            wi = ti;
+            hw = A2 * amp1 * amp1;
+        }
         const double2 dd = tile.ds[d][i];
         st.acc[d][0] += wr * dd.x - wi * dd.y;
         st.acc[d][1] += wr * dd.y + wi * dd.x;
-        st.acc[d][2] += A2 * tile.is[d][i];
+        st.acc[d][2] += hw * tile.is[d][i];
         // advance the ramp to the next row
         st.ramp[d][0] = rc * st.step[d][0] - rs * st.step[d][1];
         st.ramp[d][1] = rc * st.step[d][1] + rs * st.step[d][0];
@@ -205,7 +218,7 @@ __device__ __forceinline__ void bb_k1_accumulate(K1State<NDET>& st, const K1Tile
 }
 
 // rows [r0, r1) of one chunk, all inside amplitude region AR and phase region PR
-template <int NDET, int AR, int PR>
+template <int NDET, int AR, int PR, bool CAL>
 __device__ __forceinline__ void bb_k1_rows_pd(K1State<NDET>& st, const K1Tile<NDET>& tile, const double* rec, int r0,
                                               int r1, int c0, int lane, int kmin, int kmax, double df) {
     K1Amp<AR> amp;
@@ -220,12 +233,12 @@ __device__ __forceinline__ void bb_k1_rows_pd(K1State<NDET>& st, const K1Tile<ND
         const double u = tile.u[i], t = u * u, x = f * t * t;
         const double A = amp.eval(f, x) * a0 * (u * (t * t * t));
         const double ph = phs.eval(f, t, x, tile.lf[i], tile.q34[i]);
-        bb_k1_accumulate<NDET>(st, tile, i, act, A, ph);
+        bb_k1_accumulate<NDET, CAL>(st, tile, i, act, A, ph);
     }
 }
 
 // generic rows: per-lane region selection (rows straddling a region boundary) or TaylorF2
-template <int NDET, int APPROX>
+template <int NDET, int APPROX, bool CAL>
 __device__ __forceinline__ void bb_k1_rows_generic(K1State<NDET>& st, const K1Tile<NDET>& tile, const double* rec,
                                                    int r0, int r1, int c0, int lane, int kmin, int kmax, double df) {
     for (int r = r0; r < r1; ++r) {
@@ -234,31 +247,34 @@ __device__ __forceinline__ void bb_k1_rows_generic(K1State<NDET>& st, const K1Ti
         const double f = (double)k * df;
         double A, ph;
         bb_wave<APPROX>(rec, f, tile.u[i], tile.lf[i], tile.q34[i], &A, &ph);
-        bb_k1_accumulate<NDET>(st, tile, i, act, A, ph);
+        bb_k1_accumulate<NDET, CAL>(st, tile, i, act, A, ph);
     }
 }
 
-template <int NDET>
+template <int NDET, bool CAL>
 __device__ __forceinline__ void bb_k1_dispatch_pd(K1State<NDET>& st, const K1Tile<NDET>& tile, const double* rec,
                                                   int r0, int r1, int c0, int lane, int kmin, int kmax, double df,
                                                   int ar, int pr) {
     const int combo = ar * 3 + pr;
     switch (combo) {
-        case 0: bb_k1_rows_pd<NDET, 0, 0>(st, tile, rec, r0, r1, c0, lane, kmin, kmax, df); break;
-        case 3: bb_k1_rows_pd<NDET, 1, 0>(st, tile, rec, r0, r1, c0, lane, kmin, kmax, df); break;
-        case 4: bb_k1_rows_pd<NDET, 1, 1>(st, tile, rec, r0, r1, c0, lane, kmin, kmax, df); break;
-        case 5: bb_k1_rows_pd<NDET, 1, 2>(st, tile, rec, r0, r1, c0, lane, kmin, kmax, df); break;
-        case 8: bb_k1_rows_pd<NDET, 2, 2>(st, tile, rec, r0, r1, c0, lane, kmin, kmax, df); break;
-        default: bb_k1_rows_generic<NDET, BB_IMRPHENOMD>(st, tile, rec, r0, r1, c0, lane, kmin, kmax, df); break;
+        case 0: bb_k1_rows_pd<NDET, 0, 0, CAL>(st, tile, rec, r0, r1, c0, lane, kmin, kmax, df); break;
+        case 3: bb_k1_rows_pd<NDET, 1, 0, CAL>(st, tile, rec, r0, r1, c0, lane, kmin, kmax, df); break;
+        case 4: bb_k1_rows_pd<NDET, 1, 1, CAL>(st, tile, rec, r0, r1, c0, lane, kmin, kmax, df); break;
+        case 5: bb_k1_rows_pd<NDET, 1, 2, CAL>(st, tile, rec, r0, r1, c0, lane, kmin, kmax, df); break;
+        case 8: bb_k1_rows_pd<NDET, 2, 2, CAL>(st, tile, rec, r0, r1, c0, lane, kmin, kmax, df); break;
+        default: bb_k1_rows_generic<NDET, BB_IMRPHENOMD, CAL>(st, tile, rec, r0, r1, c0, lane, kmin, kmax, df); break;
     }
 }
 
-template <int NDET, int APPROX>
+template <int NDET, int APPROX, bool CAL>
 __global__ void __launch_bounds__(BB_K1_THREADS, 1)
 bb_inner_product_kernel(const double* __restrict__ coef, const unsigned* __restrict__ perm, long n, BBTiles tiles,
-                        double df, int shard_lo, int shard_hi, double* __restrict__ out) {
+                        double df, int shard_lo, int shard_hi, const double* __restrict__ calrec, BBCalGrid grid,
+                        double* __restrict__ out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     K1Smem<NDET>& sm = *reinterpret_cast<K1Smem<NDET>*>(smem_raw);
+    double* sm_cal = reinterpret_cast<double*>(smem_raw + sizeof(K1Smem<NDET>));   // [SB][NDET*4*n_points] (CAL)
+    const int cal_len = CAL ? NDET * 4 * grid.n_points : 0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long n_blocks = (n + BB_K1_SB - 1) / BB_K1_SB;
 
@@ -280,6 +296,13 @@ bb_inner_product_kernel(const double* __restrict__ coef, const unsigned* __restr
             const int sl = i / BC_NCOEF, j = i - sl * BC_NCOEF;
             const long s = perm ? (long)perm[p0 + sl] : p0 + sl;
             sm.coef[sl][j] = coef[s * BC_NCOEF + j];
+        }
+        if (CAL) {
+            for (int i = tid; i < ns * cal_len; i += BB_K1_THREADS) {
+                const int sl = i / cal_len, j = i - sl * cal_len;
+                const long s = perm ? (long)perm[p0 + sl] : p0 + sl;
+                sm_cal[sl * cal_len + j] = calrec[s * cal_len + j];
+            }
         }
         __syncthreads();
         if (tid < ns) {
@@ -304,6 +327,8 @@ bb_inner_product_kernel(const double* __restrict__ coef, const unsigned* __restr
         }
         const int row_first = kmin / BB_ROW, row_last = (kmax + BB_ROW - 1) / BB_ROW;   // [row_first, row_last)
         K1State<NDET> st;
+        st.cal = sm_cal + (have ? warp : 0) * cal_len;
+        st.grid = grid;
 #pragma unroll
         for (int d = 0; d < NDET; ++d) {
             st.acc[d][0] = st.acc[d][1] = st.acc[d][2] = 0.0;
@@ -349,16 +374,16 @@ bb_inner_product_kernel(const double* __restrict__ coef, const unsigned* __restr
                         if (kp2 > kf) nb = min(nb, kp2);
                         if (nb < kf + BB_ROW) {
                             // a boundary falls inside this row: generic per-lane path for one row
-                            bb_k1_rows_generic<NDET, BB_IMRPHENOMD>(st, tile, rec, r, r + 1, c0, lane, kmin, kmax, df);
+                            bb_k1_rows_generic<NDET, BB_IMRPHENOMD, CAL>(st, tile, rec, r, r + 1, c0, lane, kmin, kmax, df);
                             r += 1;
                         } else {
                             const int rstop = (nb == INT_MAX) ? rend : min(rend, nb / BB_ROW);
-                            bb_k1_dispatch_pd<NDET>(st, tile, rec, r, rstop, c0, lane, kmin, kmax, df, ar, pr);
+                            bb_k1_dispatch_pd<NDET, CAL>(st, tile, rec, r, rstop, c0, lane, kmin, kmax, df, ar, pr);
                             r = rstop;
                         }
                     }
                 } else {
-                    bb_k1_rows_generic<NDET, APPROX>(st, tile, rec, r, rend, c0, lane, kmin, kmax, df);
+                    bb_k1_rows_generic<NDET, APPROX, CAL>(st, tile, rec, r, rend, c0, lane, kmin, kmax, df);
                 }
             }
             __syncthreads();     // everyone is done with this stage before it is refilled

@@ -79,6 +79,13 @@ struct bb_handle {
     void* d_sort_tmp = nullptr;
     size_t sort_tmp_bytes = 0;
     int n_pad = 0;
+    BBCalGrid cal{};
+    double* d_calM = nullptr;      // nodes_to_spline_coefficients [n][n]
+    double* d_calrec = nullptr;    // [cap][n_det][4][n_points]
+    size_t calrec_cap = 0;
+    double* d_calpar = nullptr;    // staging for the host entry point
+    size_t calpar_cap = 0;
+    const double* cal_params = nullptr;   // calibration parameters of the evaluation in flight (device)
     bool perm_valid = false;
     double *d_params = nullptr, *d_out = nullptr;   // staging for the host entry point
     size_t stage_cap = 0;
@@ -139,6 +146,25 @@ __device__ __forceinline__ double bb_warp_sum(double v) {
 }
 
 #include "bb_k1.cuh"
+
+// calibration prologue: node values -> (values, spline coefficients) per (sample, detector, amplitude|phase)
+// calibration.py:335-347: spline_coefficients = nodes_to_spline_coefficients . parameters
+__global__ void bb_cal_prologue_kernel(const double* __restrict__ calpar, long n, int n_det, int np,
+                                       const double* __restrict__ M, double* __restrict__ calrec) {
+    // one thread per (sample, detector, kind); calpar [n][n_det][2][np] -> calrec [n][n_det][4][np]
+    const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * n_det * 2) return;
+    const long sd = t >> 1;
+    const int kind = (int)(t & 1);
+    const double* p = calpar + (sd * 2 + kind) * np;
+    double* o = calrec + (sd * 4 + 2 * kind) * np;
+    for (int i = 0; i < np; ++i) {
+        o[i] = p[i];
+        double acc = 0.0;
+        for (int j = 0; j < np; ++j) acc += M[i * np + j] * p[j];
+        o[np + i] = acc;
+    }
+}
 
 // ------------------------------------------------------------------------------------------------
 // K3: epilogue (compute_log_likelihood_from_snrs, base.py:448-477 without time marginalisation)
@@ -365,7 +391,8 @@ static int bb_ensure_scratch(bb_handle* h, size_t n) {
         size_t cap = n < 4096 ? 4096 : n;
         BB_CUDA(cudaMalloc(&h->d_coef, cap * BC_NCOEF * sizeof(double)));
         BB_CUDA(cudaMalloc(&h->d_snr, cap * BB_MAX_DET * 3 * sizeof(double)));
-        cudaFree(h->d_keys); cudaFree(h->d_keys_out); cudaFree(h->d_index); cudaFree(h->d_perm); cudaFree(h->d_sort_tmp);
+        cudaFree(h->d_calM); cudaFree(h->d_calrec); cudaFree(h->d_calpar);
+    cudaFree(h->d_keys); cudaFree(h->d_keys_out); cudaFree(h->d_index); cudaFree(h->d_perm); cudaFree(h->d_sort_tmp);
         h->d_keys = h->d_keys_out = h->d_index = h->d_perm = nullptr;
         h->d_sort_tmp = nullptr;
         BB_CUDA(cudaMalloc(&h->d_keys, cap * sizeof(unsigned)));
@@ -589,6 +616,22 @@ static int bb_launch_prologue(bb_handle* h, const double* params_dev, long n, cu
         params_dev, n, h->net, wf, h->d_coef, sort ? h->d_keys : nullptr, h->d_index);
     h->launches++;
     BB_CUDA(cudaGetLastError());
+    if (h->cal_params) {
+        const int np = h->cal.n_points;
+        if (np < 4) return bb_fail("calibration parameters given but bb_set_calibration was not called");
+        if ((size_t)n > h->calrec_cap) {
+            cudaFree(h->d_calrec);
+            h->d_calrec = nullptr;
+            const size_t cap = n < 4096 ? 4096 : (size_t)n;
+            BB_CUDA(cudaMalloc(&h->d_calrec, cap * h->net.n_det * 4 * np * sizeof(double)));
+            h->calrec_cap = cap;
+        }
+        const long nt = n * h->net.n_det * 2;
+        bb_cal_prologue_kernel<<<(unsigned)((nt + 127) / 128), 128, 0, st>>>(h->cal_params, n, h->net.n_det, np,
+                                                                            h->d_calM, h->d_calrec);
+        h->launches++;
+        BB_CUDA(cudaGetLastError());
+    }
     h->perm_valid = false;
     if (sort) {
         size_t tmp = h->sort_tmp_bytes;
@@ -600,10 +643,11 @@ static int bb_launch_prologue(bb_handle* h, const double* params_dev, long n, cu
     return 0;
 }
 
-template <int NDET, int APPROX>
+template <int NDET, int APPROX, bool CAL>
 static int bb_launch_inner_t(bb_handle* h, long n, double* out, cudaStream_t st) {
-    const size_t smem = sizeof(K1Smem<NDET>);
-    BB_CUDA(cudaFuncSetAttribute(bb_inner_product_kernel<NDET, APPROX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = sizeof(K1Smem<NDET>) + (CAL ? (size_t)BB_K1_SB * NDET * 4 * h->cal.n_points * sizeof(double) : 0);
+    if (smem > 227 * 1024) return bb_fail("K1: shared memory budget exceeded (too many calibration nodes)");
+    BB_CUDA(cudaFuncSetAttribute(bb_inner_product_kernel<NDET, APPROX, CAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long n_blocks = (n + BB_K1_SB - 1) / BB_K1_SB;
     long grid = (long)h->sm_count;
     if (grid > n_blocks) grid = n_blocks;
@@ -613,8 +657,9 @@ static int bb_launch_inner_t(bb_handle* h, long n, double* out, cudaStream_t st)
         BB_CUDA(cudaEventCreate(&e1));
         BB_CUDA(cudaEventRecord(e0, st));
     }
-    bb_inner_product_kernel<NDET, APPROX><<<(unsigned)grid, BB_K1_THREADS, smem, st>>>(
-        h->d_coef, h->perm_valid ? h->d_perm : nullptr, n, bb_tiles(h), h->net.df, h->shard_lo, h->shard_hi, out);
+    bb_inner_product_kernel<NDET, APPROX, CAL><<<(unsigned)grid, BB_K1_THREADS, smem, st>>>(
+        h->d_coef, h->perm_valid ? h->d_perm : nullptr, n, bb_tiles(h), h->net.df, h->shard_lo, h->shard_hi,
+        h->d_calrec, h->cal, out);
     if (h->profile) {
         BB_CUDA(cudaEventRecord(e1, st));
         h->k1_events.emplace_back(e0, e1);
@@ -624,13 +669,22 @@ static int bb_launch_inner_t(bb_handle* h, long n, double* out, cudaStream_t st)
     return 0;
 }
 
-static int bb_launch_inner(bb_handle* h, long n, double* out, cudaStream_t st) {
+template <int NDET>
+static int bb_launch_inner_n(bb_handle* h, long n, double* out, cudaStream_t st) {
     const bool pd = h->wf.approximant == BB_IMRPHENOMD;
+    const bool cal = h->cal_params != nullptr;
+    if (cal) return pd ? bb_launch_inner_t<NDET, BB_IMRPHENOMD, true>(h, n, out, st)
+                       : bb_launch_inner_t<NDET, BB_TAYLORF2, true>(h, n, out, st);
+    return pd ? bb_launch_inner_t<NDET, BB_IMRPHENOMD, false>(h, n, out, st)
+              : bb_launch_inner_t<NDET, BB_TAYLORF2, false>(h, n, out, st);
+}
+
+static int bb_launch_inner(bb_handle* h, long n, double* out, cudaStream_t st) {
     switch (h->net.n_det) {
-        case 1: return pd ? bb_launch_inner_t<1, BB_IMRPHENOMD>(h, n, out, st) : bb_launch_inner_t<1, BB_TAYLORF2>(h, n, out, st);
-        case 2: return pd ? bb_launch_inner_t<2, BB_IMRPHENOMD>(h, n, out, st) : bb_launch_inner_t<2, BB_TAYLORF2>(h, n, out, st);
-        case 3: return pd ? bb_launch_inner_t<3, BB_IMRPHENOMD>(h, n, out, st) : bb_launch_inner_t<3, BB_TAYLORF2>(h, n, out, st);
-        case 4: return pd ? bb_launch_inner_t<4, BB_IMRPHENOMD>(h, n, out, st) : bb_launch_inner_t<4, BB_TAYLORF2>(h, n, out, st);
+        case 1: return bb_launch_inner_n<1>(h, n, out, st);
+        case 2: return bb_launch_inner_n<2>(h, n, out, st);
+        case 3: return bb_launch_inner_n<3>(h, n, out, st);
+        case 4: return bb_launch_inner_n<4>(h, n, out, st);
     }
     return bb_fail("bad n_det");
 }
@@ -809,6 +863,63 @@ extern "C" int bb_noise_weighted_inner_product_device(bb_handle* h, int det, con
     h->launches++;
     BB_CUDA(cudaGetLastError());
     return 0;
+}
+
+extern "C" int bb_set_calibration(bb_handle* h, int n_points, const double* log10_fmin, const double* log10_fmax,
+                                  const double* nodes_to_spline_coefficients) {
+    if (!h || !h->have_network) return bb_fail("bb_set_calibration: network not set");
+    if (n_points == 0) { h->cal.n_points = 0; return 0; }
+    if (n_points < 4 || n_points > BB_NCAL_MAX) return bb_fail("bb_set_calibration: n_points must be in [4, 32]");
+    BB_CUDA(cudaSetDevice(h->device));
+    h->cal.n_points = n_points;
+    for (int d = 0; d < h->net.n_det; ++d) {
+        h->cal.l0[d] = log10_fmin[d];
+        h->cal.inv_delta[d] = (double)(n_points - 1) / (log10_fmax[d] - log10_fmin[d]);
+    }
+    cudaFree(h->d_calM);
+    h->d_calM = nullptr;
+    BB_CUDA(cudaMalloc(&h->d_calM, (size_t)n_points * n_points * sizeof(double)));
+    BB_CUDA(cudaMemcpy(h->d_calM, nodes_to_spline_coefficients, (size_t)n_points * n_points * sizeof(double),
+                       cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int bb_log_likelihood_ratio_cal_device(bb_handle* h, const double* params_dev, const double* cal_params_dev,
+                                                  long n, double* out_dev, void* stream) {
+    if (!h) return bb_fail("bb_log_likelihood_ratio_cal_device: null handle");
+    h->cal_params = cal_params_dev;
+    const int rc = bb_log_likelihood_ratio_device(h, params_dev, n, out_dev, stream);
+    h->cal_params = nullptr;
+    return rc;
+}
+
+extern "C" int bb_inner_products_cal_device(bb_handle* h, const double* params_dev, const double* cal_params_dev,
+                                            long n, double* out_dev, void* stream) {
+    if (!h) return bb_fail("bb_inner_products_cal_device: null handle");
+    h->cal_params = cal_params_dev;
+    const int rc = bb_inner_products_device(h, params_dev, n, out_dev, stream);
+    h->cal_params = nullptr;
+    return rc;
+}
+
+extern "C" int bb_log_likelihood_ratio_cal_host(bb_handle* h, const double* params_host, const double* cal_params_host,
+                                                long n, double* out_host) {
+    if (!h || !h->have_network) return bb_fail("bb_log_likelihood_ratio_cal_host: network not set");
+    if (n <= 0) return 0;
+    BB_CUDA(cudaSetDevice(h->device));
+    const size_t per = (size_t)h->net.n_det * 2 * h->cal.n_points;
+    if ((size_t)n > h->calpar_cap) {
+        cudaFree(h->d_calpar);
+        h->d_calpar = nullptr;
+        const size_t cap = n < 4096 ? 4096 : (size_t)n;
+        BB_CUDA(cudaMalloc(&h->d_calpar, cap * per * sizeof(double)));
+        h->calpar_cap = cap;
+    }
+    BB_CUDA(cudaMemcpyAsync(h->d_calpar, cal_params_host, (size_t)n * per * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    h->cal_params = h->d_calpar;
+    const int rc = bb_log_likelihood_ratio_host(h, params_host, n, out_host);
+    h->cal_params = nullptr;
+    return rc;
 }
 
 extern "C" int bb_profile_enable(bb_handle* h, int on) {

@@ -18,21 +18,24 @@
 
 __device__ __forceinline__ unsigned bb_bitrev(unsigned v, int bits) { return __brev(v) >> (32 - bits); }
 
-template <int NDET, int APPROX>
+template <int NDET, int APPROX, bool CAL>
 __global__ void __launch_bounds__(BB_TM_THREADS, 1)
 bb_time_marg_kernel(const double* __restrict__ coef, long n, BBTiles tiles, int n_freq, double df, int nfft,
                     int log2n, const double2* __restrict__ twiddle, BBMarg marg, double start_time,
-                    double duration, double* __restrict__ out) {
+                    double duration, const double* __restrict__ calrec, BBCalGrid grid, double* __restrict__ out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double2* X = reinterpret_cast<double2*>(smem_raw);
     double* c = reinterpret_cast<double*>(smem_raw + (size_t)nfft * sizeof(double2));
-    double* red = c + BC_NCOEF;      // [BB_TM_THREADS / 32 * 2]
+    double* red = c + BC_NCOEF;      // [32]
+    double* cal = red + 32;          // CAL: [NDET][4][n_points]
+    const int cal_len = CAL ? NDET * 4 * grid.n_points : 0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     for (long s = blockIdx.x; s < n; s += gridDim.x) {
         __syncthreads();
         for (int i = tid; i < BC_NCOEF; i += BB_TM_THREADS) c[i] = coef[s * BC_NCOEF + i];
         for (int i = tid; i < nfft; i += BB_TM_THREADS) X[i] = make_double2(0.0, 0.0);
+        if (CAL) for (int i = tid; i < cal_len; i += BB_TM_THREADS) cal[i] = calrec[s * cal_len + i];
         __syncthreads();
         if (c[BC_STATUS] != 0.0) {
             if (tid == 0) out[s] = -DBL_MAX;
@@ -55,13 +58,23 @@ bb_time_marg_kernel(const double* __restrict__ coef, long n, BBTiles tiles, int 
             for (int d = 0; d < NDET; ++d) {
                 double rs, rc;
                 sincospi(c[BC_DET + BC_DSTRIDE * d + 2] * f, &rs, &rc);
-                const double wr = zr * rc - zi * rs, wi = zr * rs + zi * rc;
+                double wr = zr * rc - zi * rs, wi = zr * rs + zi * rc;
+                double hw = A2;
+                if (CAL) {
+                    double amp1, cr, ci;
+                    bb_cal_factor(cal + d * 4 * grid.n_points, grid.n_points, grid.l0[d], grid.inv_delta[d],
+                                  tiles.lf[k], &amp1, &cr, &ci);
+                    const double tr = amp1 * (wr * cr + wi * ci), ti = amp1 * (wi * cr - wr * ci);
+                    wr = tr;
+                    wi = ti;
+                    hw = A2 * amp1 * amp1;
+                }
                 const double2 dd = tiles.ds[(size_t)d * tiles.n_pad + k];
                 const double pr = wr * dd.x - wi * dd.y, pi = wr * dd.y + wi * dd.x;   // conj(h/K) d/S
                 const double kr = c[BC_DET + BC_DSTRIDE * d], ki = c[BC_DET + BC_DSTRIDE * d + 1];
                 vr += kr * pr + ki * pi;       // conj(K) * p
                 vi += kr * pi - ki * pr;
-                hh += c[BC_DET + BC_DSTRIDE * d + 3] * A2 * tiles.is[(size_t)d * tiles.n_pad + k];
+                hh += c[BC_DET + BC_DSTRIDE * d + 3] * hw * tiles.is[(size_t)d * tiles.n_pad + k];
             }
             if (k < k1) X[bb_bitrev((unsigned)k, log2n)] = make_double2(vr, -vi);   // h conj(d)/S = conj(conj(h) d/S)
         }
@@ -126,22 +139,22 @@ bb_time_marg_kernel(const double* __restrict__ coef, long n, BBTiles tiles, int 
     }
 }
 
-template <int NDET, int APPROX>
+template <int NDET, int APPROX, bool CAL>
 static int bb_launch_time_marg_t(bb_handle* h, long n, double* out, cudaStream_t st) {
     const int nfft = h->nfft;
     int log2n = 0;
     while ((1 << log2n) < nfft) ++log2n;
-    const size_t smem = (size_t)nfft * sizeof(double2) + (BC_NCOEF + 32) * sizeof(double);
+    const size_t smem = (size_t)nfft * sizeof(double2) + (BC_NCOEF + 32 + (CAL ? NDET * 4 * h->cal.n_points : 0)) * sizeof(double);
     if (smem > 227 * 1024) return bb_fail("time marginalisation: series does not fit shared memory (nfft > 8192)");
-    BB_CUDA(cudaFuncSetAttribute(bb_time_marg_kernel<NDET, APPROX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BB_CUDA(cudaFuncSetAttribute(bb_time_marg_kernel<NDET, APPROX, CAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = (int)((227 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 4) per_sm = 4;
     long grid = (long)h->sm_count * per_sm;
     if (grid > n) grid = n;
-    bb_time_marg_kernel<NDET, APPROX><<<(unsigned)grid, BB_TM_THREADS, smem, st>>>(
+    bb_time_marg_kernel<NDET, APPROX, CAL><<<(unsigned)grid, BB_TM_THREADS, smem, st>>>(
         h->d_coef, n, bb_tiles(h), h->net.n_freq, h->net.df, nfft, log2n, h->d_twiddle, h->marg,
-        h->net.start_time, h->net.duration, out);
+        h->net.start_time, h->net.duration, h->d_calrec, h->cal, out);
     h->launches++;
     BB_CUDA(cudaGetLastError());
     return 0;
@@ -152,11 +165,19 @@ static int bb_launch_time_marg(bb_handle* h, long n, double* out, cudaStream_t s
     if (h->shard_lo != 0 || h->shard_hi != h->net.n_freq)
         return bb_fail("time marginalisation cannot be frequency-sharded (SURVEY.md section 8e)");
     const bool pd = h->wf.approximant == BB_IMRPHENOMD;
+    const bool cal = h->cal_params != nullptr;
+#define BB_TM_CASE(N)                                                                                          \
+    case N:                                                                                                    \
+        if (cal) return pd ? bb_launch_time_marg_t<N, BB_IMRPHENOMD, true>(h, n, out, st)                      \
+                           : bb_launch_time_marg_t<N, BB_TAYLORF2, true>(h, n, out, st);                       \
+        return pd ? bb_launch_time_marg_t<N, BB_IMRPHENOMD, false>(h, n, out, st)                              \
+                  : bb_launch_time_marg_t<N, BB_TAYLORF2, false>(h, n, out, st);
     switch (h->net.n_det) {
-        case 1: return pd ? bb_launch_time_marg_t<1, BB_IMRPHENOMD>(h, n, out, st) : bb_launch_time_marg_t<1, BB_TAYLORF2>(h, n, out, st);
-        case 2: return pd ? bb_launch_time_marg_t<2, BB_IMRPHENOMD>(h, n, out, st) : bb_launch_time_marg_t<2, BB_TAYLORF2>(h, n, out, st);
-        case 3: return pd ? bb_launch_time_marg_t<3, BB_IMRPHENOMD>(h, n, out, st) : bb_launch_time_marg_t<3, BB_TAYLORF2>(h, n, out, st);
-        case 4: return pd ? bb_launch_time_marg_t<4, BB_IMRPHENOMD>(h, n, out, st) : bb_launch_time_marg_t<4, BB_TAYLORF2>(h, n, out, st);
+        BB_TM_CASE(1)
+        BB_TM_CASE(2)
+        BB_TM_CASE(3)
+        BB_TM_CASE(4)
     }
+#undef BB_TM_CASE
     return bb_fail("bad n_det");
 }

@@ -95,12 +95,12 @@ class Interferometer:
         self.geometry = InterferometerGeometry(length, latitude, longitude, elevation, xarm_azimuth, yarm_azimuth,
                                                xarm_tilt, yarm_tilt)
         self.power_spectral_density = power_spectral_density
-        self.calibration_model = Recalibrate() if calibration_model is None else calibration_model
+        self._calibration_model = Recalibrate() if calibration_model is None else calibration_model
         self.strain_data = _StrainData(minimum_frequency, maximum_frequency)
         self.meta_data = dict(name=name)
+        self._data_version = 0
         self.reference_time = None
         self._handle = None
-        self._data_version = 0
 
     def __repr__(self):
         return f"Interferometer(name='{self.name}', minimum_frequency={self.minimum_frequency}, " \
@@ -114,6 +114,15 @@ class Interferometer:
     time_array = property(lambda self: self.strain_data.time_array)
     frequency_mask = property(lambda self: self.strain_data.frequency_mask)
     frequency_domain_strain = property(lambda self: self.strain_data.frequency_domain_strain)
+
+    @property
+    def calibration_model(self):
+        return self._calibration_model
+
+    @calibration_model.setter
+    def calibration_model(self, model):
+        self._calibration_model = model
+        self._data_version += 1
 
     @property
     def minimum_frequency(self):

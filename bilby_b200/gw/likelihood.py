@@ -148,6 +148,7 @@ class GravitationalWaveTransient(Likelihood):
         self._device_index = device
         self._net = None
         self._net_versions = None
+        self._cal_points = 0
         priors = self.priors
 
         if self.time_marginalization:
@@ -324,9 +325,6 @@ class GravitationalWaveTransient(Likelihood):
     @property
     def device_network(self):
         if self._net is None or self._net_versions != self._versions():
-            for ifo in self.interferometers:
-                if isinstance(ifo.calibration_model, CubicSpline):
-                    raise NotImplementedError("CubicSpline calibration inside the likelihood is not built yet")
             self._net = DeviceNetwork(self.interferometers, self._device_index)
             self._net_versions = self._versions()
             self._configure()
@@ -336,6 +334,20 @@ class GravitationalWaveTransient(Likelihood):
         net = self._net
         approx, f_ref, f_min, f_max = self.waveform_generator.approximant_config()
         _lib.check(net.lib.bb_set_waveform(net.ptr, approx, f_ref, f_min, f_max))
+        # calibration model (interferometer.py:364 -> calibration.py:349-384)
+        models = [ifo.calibration_model for ifo in self.interferometers]
+        self._cal_points = 0
+        if any(isinstance(m, CubicSpline) for m in models):
+            if not all(isinstance(m, CubicSpline) for m in models) or len({m.n_points for m in models}) != 1:
+                raise NotImplementedError("all interferometers must use CubicSpline models with equal n_points")
+            npts = models[0].n_points
+            lo = np.array([m.log_spline_points[0] for m in models], dtype=np.float64)
+            hi = np.array([m.log_spline_points[-1] for m in models], dtype=np.float64)
+            mat = np.ascontiguousarray(models[0].nodes_to_spline_coefficients, dtype=np.float64)
+            _lib.check(net.lib.bb_set_calibration(net.ptr, npts, lo.ctypes.data, hi.ctypes.data, mat.ctypes.data))
+            self._cal_points = npts
+        else:
+            _lib.check(net.lib.bb_set_calibration(net.ptr, 0, None, None, None))
         flags = 0
         if self.phase_marginalization:
             flags |= _params.MARG_PHASE
@@ -365,15 +377,31 @@ class GravitationalWaveTransient(Likelihood):
         converted = self.waveform_generator.convert(parameters)
         return _params.pack_rows(converted, n, xp, device=device)
 
+    def _cal_from_parameters(self, parameters, n, xp, device=None):
+        """[n, n_det, 2, n_points] calibration parameters recalib_{IFO}_{amplitude,phase}_{i}
+        (calibration.py:248-251 prefix convention), or None without a calibration model."""
+        self.device_network
+        npts = self._cal_points
+        if not npts:
+            return None
+        n_det = len(self.interferometers)
+        if xp is np:
+            out = np.zeros((n, n_det, 2, npts), dtype=np.float64)
+        else:
+            out = xp.zeros((n, n_det, 2, npts), dtype=xp.float64, device=device)
+        for d, ifo in enumerate(self.interferometers):
+            for k, kind in enumerate(("amplitude", "phase")):
+                for i in range(npts):
+                    v = parameters[f"recalib_{ifo.name}_{kind}_{i}"]
+                    out[:, d, k, i] = v if xp is np else xp.as_tensor(v, dtype=xp.float64, device=device)
+        return out
+
     def log_likelihood_ratio(self, parameters):
         """base.py:419-446: one parameter dict in, one float out (a batch of one through the same kernels)."""
         parameters = copy.deepcopy(parameters)
         parameters.update(self.get_sky_frame_parameters(parameters))
         rows = np.ascontiguousarray(self._rows_from_parameters(parameters, 1, np))
-        out = np.empty(1)
-        net = self.device_network
-        _lib.check(net.lib.bb_log_likelihood_ratio_host(net.ptr, rows.ctypes.data, 1, out.ctypes.data))
-        return float(out[0])
+        return float(self.log_likelihood_ratio_rows_host(rows, self._cal_from_parameters(parameters, 1, np))[0])
 
     def log_likelihood_ratio_batch(self, parameters):
         """NEW (no reference equivalent): evaluate a batch.
@@ -388,6 +416,8 @@ class GravitationalWaveTransient(Likelihood):
             if rows.dtype != torch.float64 or rows.dim() != 2 or rows.shape[1] != _params.NPARAM or not rows.is_cuda:
                 raise ValueError("packed rows must be a CUDA float64 tensor of shape [n, 16]")
             rows = rows.contiguous()
+            if self.device_network and self._cal_points:
+                raise ValueError("packed rows need calibration parameters: use _evaluate_device(rows, cal)")
             return self._evaluate_device(rows)
         n = None
         on_device = False
@@ -402,33 +432,55 @@ class GravitationalWaveTransient(Likelihood):
             raise ValueError("log_likelihood_ratio_batch needs at least one array-valued parameter")
         if on_device:
             rows = self._rows_from_parameters(parameters, n, torch, device=net.device)
-            return self._evaluate_device(rows)
+            return self._evaluate_device(rows, self._cal_from_parameters(parameters, n, torch, device=net.device))
         rows = np.ascontiguousarray(self._rows_from_parameters(parameters, n, np))
-        return self.log_likelihood_ratio_rows_host(rows)
+        return self.log_likelihood_ratio_rows_host(rows, self._cal_from_parameters(parameters, n, np))
 
-    def log_likelihood_ratio_rows_host(self, rows):
-        """Host rows [n,16] (numpy float64, C order) -> numpy lnL; the C ABI's end-to-end entry point."""
+    def log_likelihood_ratio_rows_host(self, rows, cal=None):
+        """Host rows [n,16] (numpy float64, C order) [+ calibration parameters [n,n_det,2,n_points]] -> numpy
+        lnL; the C ABI's end-to-end entry point."""
         net = self.device_network
         rows = np.ascontiguousarray(rows, dtype=np.float64)
         out = np.empty(rows.shape[0])
-        _lib.check(net.lib.bb_log_likelihood_ratio_host(net.ptr, rows.ctypes.data, rows.shape[0], out.ctypes.data))
+        if self._cal_points:
+            if cal is None:
+                raise ValueError("this likelihood has a calibration model: calibration parameters are required")
+            cal = np.ascontiguousarray(cal, dtype=np.float64)
+            _lib.check(net.lib.bb_log_likelihood_ratio_cal_host(net.ptr, rows.ctypes.data, cal.ctypes.data,
+                                                                rows.shape[0], out.ctypes.data))
+        else:
+            _lib.check(net.lib.bb_log_likelihood_ratio_host(net.ptr, rows.ctypes.data, rows.shape[0], out.ctypes.data))
         return out
 
-    def _evaluate_device(self, rows):
+    def _evaluate_device(self, rows, cal=None):
         net = self.device_network
         torch = net.torch
         out = torch.empty(rows.shape[0], dtype=torch.float64, device=rows.device)
-        _lib.check(net.lib.bb_log_likelihood_ratio_device(net.ptr, rows.data_ptr(), rows.shape[0], out.data_ptr(),
-                                                          net._stream()))
+        if self._cal_points:
+            if cal is None:
+                raise ValueError("this likelihood has a calibration model: calibration parameters are required")
+            cal = cal.contiguous()
+            _lib.check(net.lib.bb_log_likelihood_ratio_cal_device(net.ptr, rows.data_ptr(), cal.data_ptr(),
+                                                                  rows.shape[0], out.data_ptr(), net._stream()))
+        else:
+            _lib.check(net.lib.bb_log_likelihood_ratio_device(net.ptr, rows.data_ptr(), rows.shape[0], out.data_ptr(),
+                                                              net._stream()))
         return out
 
-    def inner_products_batch(self, rows):
+    def inner_products_batch(self, rows, cal=None):
         """[n,16] CUDA rows -> [n, n_det, 3] (Re<h|d>, Im<h|d>, <h|h>) per detector (base.py:260-354)."""
         net = self.device_network
         torch = net.torch
         out = torch.empty((rows.shape[0], net.n_det, 3), dtype=torch.float64, device=rows.device)
-        _lib.check(net.lib.bb_inner_products_device(net.ptr, rows.data_ptr(), rows.shape[0], out.data_ptr(),
-                                                    net._stream()))
+        if self._cal_points:
+            if cal is None:
+                raise ValueError("this likelihood has a calibration model: calibration parameters are required")
+            cal = cal.contiguous()
+            _lib.check(net.lib.bb_inner_products_cal_device(net.ptr, rows.data_ptr(), cal.data_ptr(), rows.shape[0],
+                                                            out.data_ptr(), net._stream()))
+        else:
+            _lib.check(net.lib.bb_inner_products_device(net.ptr, rows.data_ptr(), rows.shape[0], out.data_ptr(),
+                                                        net._stream()))
         return out
 
     def likelihood_from_inner_products(self, rows, snrs):

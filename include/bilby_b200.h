@@ -100,6 +100,21 @@ int bb_log_likelihood_ratio_device(bb_handle* h, const double* params_dev, long 
                                    void* stream);
 int bb_log_likelihood_ratio_host(bb_handle* h, const double* params_host, long n, double* out_host);
 
+/* Cubic-spline calibration (bilby/gw/detector/calibration.py:257-384, applied in
+ * interferometer.py:364).  bb_set_calibration describes the model once: n_points spline nodes per
+ * detector at linspace(log10_fmin[d], log10_fmax[d], n_points) and the n_points x n_points matrix
+ * CubicSpline.nodes_to_spline_coefficients (calibration.py:302-325, row-major, host).  n_points = 0
+ * removes the model.  The *_cal_* entry points take, next to the parameter rows, the calibration
+ * parameters double[n][n_det][2][n_points] = recalib_{IFO}_amplitude_i, recalib_{IFO}_phase_i. */
+int bb_set_calibration(bb_handle* h, int n_points, const double* log10_fmin, const double* log10_fmax,
+                       const double* nodes_to_spline_coefficients);
+int bb_log_likelihood_ratio_cal_device(bb_handle* h, const double* params_dev, const double* cal_params_dev,
+                                       long n, double* out_dev, void* stream);
+int bb_log_likelihood_ratio_cal_host(bb_handle* h, const double* params_host, const double* cal_params_host,
+                                     long n, double* out_host);
+int bb_inner_products_cal_device(bb_handle* h, const double* params_dev, const double* cal_params_dev, long n,
+                                 double* out_dev, void* stream);
+
 /* Per-detector inner products: replaces GravitationalWaveTransient.calculate_snrs (base.py:260-354)
  * / Interferometer.inner_product + optimal_snr_squared (interferometer.py:607-640).
  * out double[n][n_det][3] = (Re <h|d>, Im <h|d>, <h|h>) with the reference's 4/T normalisation

@@ -280,3 +280,52 @@ def test_full_size_batch_properties():
     s2 = like.inner_products_batch(dev2).cpu().numpy()
     assert np.array_equal(s2[..., :2] * 2.0, s1[..., :2])
     assert np.array_equal(s2[..., 2] * 4.0, s1[..., 2])
+
+
+def _build_cal(**kw):
+    import bilby_b200 as bb
+    from bilby_b200.gw.detector import InterferometerList
+    from bilby_b200.gw.detector.calibration import CubicSpline
+    from bilby_b200.gw.source import lal_binary_black_hole
+    g = np.load(os.path.join(GOLDEN, "bbh_8s_cal_H1L1V1.npz"))
+    ifos = InterferometerList([str(x) for x in g["detectors"]])
+    for ifo in ifos:
+        ifo.minimum_frequency = 20.0
+        ifo.maximum_frequency = 1024.0
+        ifo.set_strain_data_from_frequency_domain_strain(
+            g[f"strain_{ifo.name}"], sampling_frequency=2048.0, duration=8.0, start_time=float(g["start_time"]))
+        ifo.calibration_model = CubicSpline(f"recalib_{ifo.name}_", 20.0, 1024.0, 10)
+    wfg = bb.gw.WaveformGenerator(
+        duration=8.0, sampling_frequency=2048.0, frequency_domain_source_model=lal_binary_black_hole,
+        waveform_arguments=dict(waveform_approximant="IMRPhenomD", reference_frequency=50.0, minimum_frequency=20.0))
+    like = bb.gw.GravitationalWaveTransient(ifos, wfg, **kw)
+    draws = {k[6:]: g[k] for k in g.files if k.startswith("param_")}
+    return g, like, draws
+
+
+def test_calibration_spline_plain_vs_reference():
+    """configs[2] ingredients: 8 s, CubicSpline calibration folded into the fused inner-product kernel."""
+    g, like, draws = _build_cal()
+    d = {k: v for k, v in draws.items() if k != "time_jitter"}
+    lnl = like.log_likelihood_ratio_batch(d)
+    err = np.abs(lnl - g["lnl_none"]) / _scale(g, g["lnl_none"])
+    assert err.max() < RTOL, err.max()
+    one = like.log_likelihood_ratio({k: float(v[2]) for k, v in d.items()})
+    assert abs(one - lnl[2]) < 1e-10 * max(1.0, abs(lnl[2]))
+    import torch
+    dt = {k: torch.from_numpy(v).cuda() for k, v in d.items()}
+    dev = like.log_likelihood_ratio_batch(dt).cpu().numpy()
+    assert np.max(np.abs(dev - lnl) / _scale(g, lnl)) < 1e-10
+
+
+@pytest.mark.parametrize("mode", ["time", "time_phase"])
+def test_calibration_spline_time_marginalised_vs_reference(mode):
+    """configs[2]: BBH 8 s H1L1V1, time marginalisation (8192-point FFT) + calibration splines."""
+    g, like, draws = _build_cal(time_marginalization=True, jitter_time=True, phase_marginalization="phase" in mode,
+                                priors=_priors(phase="phase" in mode, geocent_time=True))
+    d = dict(draws)
+    d["geocent_time"] = np.full(len(d["chirp_mass"]), float(g["start_time"]))
+    lnl = like.log_likelihood_ratio_batch(d)
+    ref = g["lnl_" + mode]
+    err = np.abs(lnl - ref) / _scale(g, ref)
+    assert err.max() < RTOL, err.max()

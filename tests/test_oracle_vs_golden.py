@@ -158,3 +158,22 @@ def test_phenomd_sanity():
         pd.phenomd_h22(np.arange(10.0), 3000.0, 2500.0, 0, 0, 1e25, 0, 50, 20, 1024, 1.0)
     with pytest.raises(pd.WaveformDomainError):
         pd.phenomd_h22(np.arange(10.0), 30.0, 25.0, 1.5, 0, 1e25, 0, 50, 20, 1024, 1.0)
+
+
+def test_calibration_spline_path_vs_reference():
+    """configs[2]: 8 s H1L1V1, CubicSpline calibration (interferometer.py:364), plain + time(+phase) marginalised."""
+    g = np.load(os.path.join(GOLDEN, "bbh_8s_cal_H1L1V1.npz"))
+    names = [str(x) for x in g["detectors"]]
+    ifos = [ocl.OracleInterferometer(n, 2048.0, 8.0, float(g["start_time"])) for n in names]
+    for ifo in ifos:
+        ifo.frequency_domain_strain = g[f"strain_{ifo.name}"]
+        ifo.calibration = ocl.OracleCubicSpline(f"recalib_{ifo.name}_", 20.0, 1024.0, 10)
+    draws = {k[6:]: g[k] for k in g.files if k.startswith("param_")}
+    n = 12
+    like = ocl.OracleLikelihood(ifos, waveform_arguments=WA)
+    assert np.allclose(_eval(like, draws, n), g["lnl_none"][:n], rtol=1e-12, atol=1e-12)
+    tp = ocl.OracleUniform(ocl.INJECTION["geocent_time"] - 0.1, ocl.INJECTION["geocent_time"] + 0.1)
+    for mode, kw in (("time", {}), ("time_phase", dict(phase_marginalization=True))):
+        like = ocl.OracleLikelihood(ifos, waveform_arguments=WA, time_marginalization=True, time_prior=tp, **kw)
+        got = _eval(like, draws, n, skip=(), geocent_time=float(g["start_time"]))
+        assert np.allclose(got, g["lnl_" + mode][:n], rtol=1e-11, atol=1e-11)
