@@ -391,8 +391,7 @@ static int bb_ensure_scratch(bb_handle* h, size_t n) {
         size_t cap = n < 4096 ? 4096 : n;
         BB_CUDA(cudaMalloc(&h->d_coef, cap * BC_NCOEF * sizeof(double)));
         BB_CUDA(cudaMalloc(&h->d_snr, cap * BB_MAX_DET * 3 * sizeof(double)));
-        cudaFree(h->d_calM); cudaFree(h->d_calrec); cudaFree(h->d_calpar);
-    cudaFree(h->d_keys); cudaFree(h->d_keys_out); cudaFree(h->d_index); cudaFree(h->d_perm); cudaFree(h->d_sort_tmp);
+        cudaFree(h->d_keys); cudaFree(h->d_keys_out); cudaFree(h->d_index); cudaFree(h->d_perm); cudaFree(h->d_sort_tmp);
         h->d_keys = h->d_keys_out = h->d_index = h->d_perm = nullptr;
         h->d_sort_tmp = nullptr;
         BB_CUDA(cudaMalloc(&h->d_keys, cap * sizeof(unsigned)));
@@ -458,6 +457,7 @@ extern "C" void bb_destroy(bb_handle* h) {
     cudaFree(h->d_tx); cudaFree(h->d_ty); cudaFree(h->d_c);
     cudaFree(h->d_coef); cudaFree(h->d_snr); cudaFree(h->d_params); cudaFree(h->d_out);
     cudaFree(h->d_mask); cudaFree(h->d_twiddle);
+    cudaFree(h->d_calM); cudaFree(h->d_calrec); cudaFree(h->d_calpar);
     cudaFree(h->d_keys); cudaFree(h->d_keys_out); cudaFree(h->d_index); cudaFree(h->d_perm); cudaFree(h->d_sort_tmp);
     if (h->h_params) cudaFreeHost(h->h_params);
     if (h->h_out) cudaFreeHost(h->h_out);
