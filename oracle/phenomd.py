@@ -517,10 +517,16 @@ class WaveformDomainError(Exception):
     ``None`` -> likelihood sentinel (bilby/gw/source.py:644-662)."""
 
 
-def phenomd_h22(frequencies, m1, m2, chi1, chi2, distance_m, phi_ref, f_ref, f_min, f_max, delta_f=None):
+def phenomd_h22(frequencies, m1, m2, chi1, chi2, distance_m, phi_ref, f_ref, f_min, f_max, delta_f=None,
+                sequence=False):
     """h22-like strain htilde(f) (before the inclination factors), complex128 array on
     ``frequencies`` (Hz, uniform grid starting at 0 when ``delta_f`` is given - then upstream's
     index rule  i in [int(f_min/df), int(f_max'/df))  decides which bins are filled).
+
+    ``sequence=True`` restates the frequency-sequence entry point (SimInspiralChooseFDWaveformSequence ->
+    IMRPhenomDFrequencySequence, called from bilby/gw/source.py:1124-1128): f_min is the first frequency
+    of the sequence, f_max is ignored and EVERY frequency of the sequence is evaluated with the ansatz
+    (no f_min / f_CUT zeroing); the (fCut <= f_min) domain check still applies.
 
     Restates IMRPhenomDGenerateFD."""
     if m1 <= 0 or m2 <= 0 or distance_m <= 0:
@@ -531,6 +537,9 @@ def phenomd_h22(frequencies, m1, m2, chi1, chi2, distance_m, phi_ref, f_ref, f_m
     M = m1 + m2
     M_sec = M * MTSUN_SI
     f_cut = F_CUT / M_sec
+    frequencies = np.asarray(frequencies, dtype=float)
+    if sequence:
+        f_min, f_max = float(frequencies[0]), 0.0
     if f_ref == 0.0:
         f_ref = f_min
     f_max_prime = f_cut if f_max == 0 else min(f_max, f_cut)
@@ -539,7 +548,9 @@ def phenomd_h22(frequencies, m1, m2, chi1, chi2, distance_m, phi_ref, f_ref, f_m
     amp0 = 2.0 * np.sqrt(5.0 / (64.0 * np.pi)) * M * MRSUN_SI * M * MTSUN_SI / distance_m
     frequencies = np.asarray(frequencies, dtype=float)
     out = np.zeros(len(frequencies), dtype=complex)
-    if delta_f is not None:
+    if sequence:
+        sel = np.ones(len(frequencies), dtype=bool)
+    elif delta_f is not None:
         ind_min = int(f_min / delta_f)
         ind_max = int(f_max_prime / delta_f)
         sel = np.zeros(len(frequencies), dtype=bool)
@@ -557,9 +568,9 @@ def phenomd_h22(frequencies, m1, m2, chi1, chi2, distance_m, phi_ref, f_ref, f_m
 
 
 def choose_fd_waveform_phenomd(frequencies, m1, m2, s1z, s2z, distance_m, inclination, phi_ref,
-                               f_min, f_max, f_ref, delta_f=None):
-    """(hplus, hcross) as SimInspiralChooseFDWaveform assembles them for IMRPhenomD."""
-    h = phenomd_h22(frequencies, m1, m2, s1z, s2z, distance_m, phi_ref, f_ref, f_min, f_max, delta_f)
+                               f_min, f_max, f_ref, delta_f=None, sequence=False):
+    """(hplus, hcross) as SimInspiralChooseFDWaveform[Sequence] assembles them for IMRPhenomD."""
+    h = phenomd_h22(frequencies, m1, m2, s1z, s2z, distance_m, phi_ref, f_ref, f_min, f_max, delta_f, sequence)
     cfac = np.cos(inclination)
     pfac = 0.5 * (1.0 + cfac * cfac)
     return pfac * h, -1j * cfac * h

@@ -50,9 +50,11 @@ def taylorf2_series(v, pv, pvl, tidal):
 
 
 def taylorf2_h(frequencies, m1, m2, chi1, chi2, lambda1, lambda2, distance_m, phi_ref, f_ref, f_min, f_max,
-               delta_f=None):
+               delta_f=None, sequence=False):
     """htilde(f) before the inclination factors (XLALSimInspiralTaylorF2Core).  m1 >= m2 is NOT required by
-    upstream; the PN coefficient routine is symmetric up to the (m1-m2) sign conventions it uses itself."""
+    upstream; the PN coefficient routine is symmetric up to the (m1-m2) sign conventions it uses itself.
+    ``sequence=True``: the frequency-sequence entry point (bilby/gw/source.py:1124-1128) - every frequency
+    of the sequence is evaluated, no f_min / f_ISCO cut and no time shift."""
     if m1 <= 0 or m2 <= 0 or distance_m <= 0:
         raise _pd.WaveformDomainError("masses and distance must be positive")
     M = m1 + m2
@@ -61,14 +63,16 @@ def taylorf2_h(frequencies, m1, m2, chi1, chi2, lambda1, lambda2, distance_m, ph
     piM = np.pi * m_sec
     f_isco = (1.0 / np.sqrt(6.0)) ** 3 / piM
     f_end = f_isco if f_max == 0 else f_max
-    if f_end <= f_min:
+    if not sequence and f_end <= f_min:
         raise _pd.WaveformDomainError("f_max <= f_min")
     pv, pvl = _pd.taylorf2_aligned_phasing(m1, m2, chi1, chi2)
     tidal = tidal_coefficients(m1 / M, m2 / M, lambda1, lambda2, eta)
     amp0 = -4.0 * m1 * m2 / distance_m * _pd.MRSUN_SI * _pd.MTSUN_SI * np.sqrt(np.pi / 12.0)
     frequencies = np.asarray(frequencies, dtype=float)
     out = np.zeros(len(frequencies), dtype=complex)
-    if delta_f is not None:
+    if sequence:
+        sel = frequencies > 0
+    elif delta_f is not None:
         i_start = int(np.ceil(f_min / delta_f))
         n = int(f_end / delta_f + 1)
         sel = np.zeros(len(frequencies), dtype=bool)
@@ -88,9 +92,9 @@ def taylorf2_h(frequencies, m1, m2, chi1, chi2, lambda1, lambda2, distance_m, ph
 
 
 def choose_fd_waveform_taylorf2(frequencies, m1, m2, s1z, s2z, lambda1, lambda2, distance_m, inclination,
-                                phi_ref, f_min, f_max, f_ref, delta_f=None):
+                                phi_ref, f_min, f_max, f_ref, delta_f=None, sequence=False):
     h = taylorf2_h(frequencies, m1, m2, s1z, s2z, lambda1, lambda2, distance_m, phi_ref, f_ref, f_min, f_max,
-                   delta_f)
+                   delta_f, sequence)
     cfac = np.cos(inclination)
     pfac = 0.5 * (1.0 + cfac * cfac)
     return pfac * h, -1j * cfac * h
