@@ -42,6 +42,9 @@ def load():
         "bb_likelihood_from_inner_products_device": (i, [vp, vp, vp, lng, vp, vp]),
         "bb_set_frequency_shard": (i, [vp, i, i]),
         "bb_frequency_domain_strain_device": (i, [vp, vp, lng, vp, vp]),
+        "bb_frequency_sequence_strain_device": (i, [vp, vp, lng, vp, i, d, vp, vp]),
+        "bb_set_relative_binning": (i, [vp, i, vp, vp, vp, vp, vp]),
+        "bb_set_roq": (i, [vp, i, vp, i, vp, i, lng, d, vp, vp, i, d, d, d]),
         "bb_detector_response_device": (i, [vp, vp, lng, vp, vp]),
         "bb_build_distance_table": (i, [vp, vp, i, vp, i, vp, vp, i, d, i, vp]),
         "bb_antenna_response_device": (i, [vp, vp, lng, vp, vp]),
@@ -66,7 +69,8 @@ EXPORTED_SYMBOLS = (
     "bb_set_marginalization", "bb_log_likelihood_ratio_device", "bb_log_likelihood_ratio_host",
     "bb_inner_products_device", "bb_set_calibration", "bb_log_likelihood_ratio_cal_device",
     "bb_log_likelihood_ratio_cal_host", "bb_inner_products_cal_device", "bb_likelihood_from_inner_products_device", "bb_set_frequency_shard",
-    "bb_frequency_domain_strain_device", "bb_detector_response_device", "bb_build_distance_table",
+    "bb_frequency_domain_strain_device", "bb_frequency_sequence_strain_device", "bb_set_relative_binning",
+    "bb_set_roq", "bb_detector_response_device", "bb_build_distance_table",
     "bb_antenna_response_device", "bb_ln_i0_device", "bb_project_polarizations_device",
     "bb_noise_weighted_inner_product_device", "bb_profile_enable", "bb_profile_read", "bb_fp64_peak",
     "bb_launch_count")

@@ -55,7 +55,7 @@ enum {
     BC_DISTANCE,      // luminosity distance [Mpc] (distance marginalisation rescaling)
     BC_STATUS,        // 0 = ok, 1 = waveform domain error (-> likelihood sentinel)
     BC_JITTER,
-    BC_SPARE,
+    BC_DT0,           // t_c - t_start [s] (reduced-order kernels add it to the per-detector delay themselves)
     BC_KA1, BC_KA2,   // first bin of the amplitude intermediate / merger-ringdown regions (exact doubles)
     BC_KP1, BC_KP2,   // first bin of the phase intermediate / merger-ringdown regions
     BC_DET,           // per detector BC_DSTRIDE: K_re, K_im, 2*dt_det [half turns / Hz], |K|^2,
@@ -78,6 +78,12 @@ struct BBWaveformConfig {
     int approximant;      // 0 IMRPhenomD, 1 TaylorF2(+tides)
     int add_jitter;       // time marginalisation with jitter: geocent_time += time_jitter (base.py:427-428)
     double f_ref, f_min, f_max;
+    // frequency-sequence semantics (source.py:1068-1140, ROQ nodes / relative-binning edges): every node is
+    // evaluated, f_min = first node for the IMRPhenomD domain check, no f_end check for TaylorF2
+    int sequence;
+    int no_time_shift;    // ROQ: the waveform carries no exp(-2 pi i f (t_c - t_start)) (roq.py:486-502)
+    int fixed_antenna_time;   // ROQ time marginalisation: antenna response / delay at antenna_time (roq.py:478-481)
+    double antenna_time;
 };
 
 // cubic-spline calibration grid (bilby/gw/detector/calibration.py:257-384): per detector the spline nodes are

@@ -10,6 +10,7 @@
 //   KT bb_distance_table_kernel  lookup table build
 //   KW bb_strain_kernel          polarisations / detector response on the full grid (injection, tests)
 #include <cuda_runtime.h>
+#include <cublas_v2.h>
 #include <cub/device/device_radix_sort.cuh>
 #include <float.h>
 #include <stdio.h>
@@ -56,7 +57,11 @@ struct BBMarg {
     BBSpline2D spl;
     double time_min, time_max;
     int jitter;
+    double roq_dtc;       // ROQ time marginalisation: the likelihood's own delta_tc (roq.py:320-331)
 };
+
+struct BBRelbinDev;
+struct BBRoqDev;
 
 struct bb_handle {
     int device = 0;
@@ -90,6 +95,17 @@ struct bb_handle {
     double *d_params = nullptr, *d_out = nullptr;   // staging for the host entry point
     size_t stage_cap = 0;
     double *h_params = nullptr, *h_out = nullptr;   // pinned
+    // reduced-order likelihoods (bb_reduced.cuh): 0 full grid, 1 relative binning, 2 ROQ
+    int kind = 0;
+    std::vector<void*> red_bufs;           // device allocations owned by the current reduced-order set-up
+    BBRelbinDev* rb = nullptr;             // host copies of the kernel argument structs
+    BBRoqDev* rq = nullptr;
+    double roq_ref_time = 0.0;
+    double roq_fmin = 0.0, rb_fmin = 0.0;
+    double2 *d_roq_V = nullptr, *d_roq_Y = nullptr;
+    double* d_roq_hh = nullptr;
+    size_t roq_chunk = 0;
+    cublasHandle_t cublas = nullptr;
     cudaStream_t stream = nullptr;
     int sm_count = 148;
     long launches = 0;
@@ -170,6 +186,9 @@ __global__ void bb_cal_prologue_kernel(const double* __restrict__ calpar, long n
 // K3: epilogue (compute_log_likelihood_from_snrs, base.py:448-477 without time marginalisation)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double bb_point_lnl(const BBMarg& m, double dre, double dim, double hh, double dist) {
+    // ROQ outside its time window: d_inner_h = -inf + i y (roq.py:532-533).  The reference's complex
+    // arithmetic turns that into nan once |d_inner_h| is taken (phase marginalisation), -inf otherwise.
+    if (dre == -INFINITY) return (m.flags & BB_MARG_PHASE) ? nan("") : -INFINITY;
     if (m.flags & BB_MARG_DISTANCE) {
         const double scale = dist / m.ref_dist;
         const double hh_ref = hh * dist * dist / (m.ref_dist * m.ref_dist);
@@ -305,6 +324,36 @@ __global__ void bb_strain_kernel(const double* __restrict__ coef, long n, BBTile
     }
 }
 
+// polarisations on a caller-supplied frequency sequence (source.py:1068-1140 semantics: every node evaluated)
+__global__ void bb_sequence_strain_kernel(const double* __restrict__ coef, long n, const double* __restrict__ freqs,
+                                          int n_nodes, int approx, const double* __restrict__ params,
+                                          double* __restrict__ out) {
+    const long s = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n || j >= n_nodes) return;
+    const double* c = coef + s * BC_NCOEF;
+    const double f = freqs[j];
+    double hr = 0.0, hi = 0.0;
+    if (c[BC_STATUS] == 0.0 && f > 0.0) {
+        const double u = pow(f, -1.0 / 6.0), lf = log(f), q34 = pow(f, 0.75);
+        double A, ph;
+        if (approx == BB_IMRPHENOMD) bb_wave<BB_IMRPHENOMD>(c, f, u, lf, q34, &A, &ph);
+        else bb_wave<BB_TAYLORF2>(c, f, u, lf, q34, &A, &ph);
+        double sn, cs;
+        sincospi(ph, &sn, &cs);
+        hr = A * cs;
+        hi = -A * sn;
+    }
+    const double cfac = cos(params[s * BB_NPARAM + BB_P_THETA_JN]);
+    const double pfac = 0.5 * (1.0 + cfac * cfac);
+    double* o = out + ((size_t)s * 2 * n_nodes + j) * 2;
+    o[0] = pfac * hr;
+    o[1] = pfac * hi;
+    double* oc = o + (size_t)n_nodes * 2;
+    oc[0] = cfac * hi;
+    oc[1] = -cfac * hr;
+}
+
 __global__ void bb_antenna_kernel(const double* __restrict__ params, long n, BBNetwork net, double* __restrict__ out) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -420,6 +469,8 @@ static BBTiles bb_tiles(const bb_handle* h) {
 }
 
 #include "bb_timemarg.cuh"
+#include "bb_reduced.cuh"
+#include "bb_reduced_host.cuh"
 
 extern "C" const char* bb_last_error(void) { return g_last_error.c_str(); }
 extern "C" int bb_abi_version(void) { return BB_ABI_VERSION; }
@@ -458,6 +509,8 @@ extern "C" void bb_destroy(bb_handle* h) {
     cudaFree(h->d_coef); cudaFree(h->d_snr); cudaFree(h->d_params); cudaFree(h->d_out);
     cudaFree(h->d_mask); cudaFree(h->d_twiddle);
     cudaFree(h->d_calM); cudaFree(h->d_calrec); cudaFree(h->d_calpar);
+    bb_reduced_clear(h);
+    if (h->cublas) cublasDestroy(h->cublas);
     cudaFree(h->d_keys); cudaFree(h->d_keys_out); cudaFree(h->d_index); cudaFree(h->d_perm); cudaFree(h->d_sort_tmp);
     if (h->h_params) cudaFreeHost(h->h_params);
     if (h->h_out) cudaFreeHost(h->h_out);
@@ -472,6 +525,7 @@ extern "C" int bb_set_network(bb_handle* h, int n_det, int n_freq, double durati
     if (n_det < 1 || n_det > BB_MAX_DET) return bb_fail("bb_set_network: n_det must be in [1, BB_MAX_DET]");
     if (n_freq < 2) return bb_fail("bb_set_network: n_freq too small");
     BB_CUDA(cudaSetDevice(h->device));
+    bb_reduced_clear(h);          // reduced-order set-ups refer to the previous network's data
     BBNetwork& net = h->net;
     net.n_det = n_det;
     net.n_freq = n_freq;
@@ -610,8 +664,22 @@ static int bb_launch_prologue(bb_handle* h, const double* params_dev, long n, cu
     BBWaveformConfig wf = h->wf;
     if (!(wf.f_max > 0.0)) wf.f_max = h->net.df * (h->net.n_freq - 1);
     wf.add_jitter = ((h->marg.flags & BB_MARG_TIME) && h->marg.jitter) ? 1 : 0;
+    if (h->kind == 1) {
+        wf.sequence = 1;
+        wf.f_min = h->rb_fmin;
+    } else if (h->kind == 2) {
+        wf.sequence = 1;
+        wf.f_min = h->roq_fmin;
+        wf.no_time_shift = 1;
+        if (h->marg.flags & BB_MARG_TIME) {
+            // roq.py:478-481: antenna response and delays at the beam-pattern reference time; the jitter enters
+            // the detector times in K7, not geocent_time's sky geometry
+            wf.fixed_antenna_time = 1;
+            wf.antenna_time = h->roq_ref_time;
+        }
+    }
     const int threads = 128;
-    const bool sort = n > BB_K1_SB;
+    const bool sort = n > BB_K1_SB && h->kind == 0;
     bb_prologue_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(
         params_dev, n, h->net, wf, h->d_coef, sort ? h->d_keys : nullptr, h->d_index);
     h->launches++;
@@ -696,6 +764,7 @@ extern "C" int bb_inner_products_device(bb_handle* h, const double* params_dev, 
     cudaStream_t st = (cudaStream_t)stream;
     if (bb_ensure_scratch(h, (size_t)n)) return 1;
     if (bb_launch_prologue(h, params_dev, n, st)) return 1;
+    if (h->kind != 0) return bb_launch_reduced(h, n, out_dev, st, 0);
     return bb_launch_inner(h, n, out_dev, st);
 }
 
@@ -721,8 +790,13 @@ extern "C" int bb_log_likelihood_ratio_device(bb_handle* h, const double* params
     cudaStream_t st = (cudaStream_t)stream;
     if (bb_ensure_scratch(h, (size_t)n)) return 1;
     if (bb_launch_prologue(h, params_dev, n, st)) return 1;
-    if (h->marg.flags & BB_MARG_TIME) return bb_launch_time_marg(h, n, out_dev, st);
-    if (bb_launch_inner(h, n, h->d_snr, st)) return 1;
+    if (h->kind != 0) {
+        if (h->marg.flags & BB_MARG_TIME) return bb_launch_reduced(h, n, out_dev, st, 1);
+        if (bb_launch_reduced(h, n, h->d_snr, st, 0)) return 1;
+    } else {
+        if (h->marg.flags & BB_MARG_TIME) return bb_launch_time_marg(h, n, out_dev, st);
+        if (bb_launch_inner(h, n, h->d_snr, st)) return 1;
+    }
     const int threads = 128;
     bb_epilogue_coef_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(
         h->d_coef, h->d_snr, n, h->net.n_det, h->marg, out_dev);
@@ -779,6 +853,30 @@ static int bb_strain_common(bb_handle* h, const double* params_dev, long n, doub
     dim3 grid((h->net.n_freq + 127) / 128, (unsigned)n);
     bb_strain_kernel<<<grid, 128, 0, st>>>(h->d_coef, n, bb_tiles(h), h->net.n_freq, h->net.df, h->net.n_det, h->wf.approximant, mode,
                                           params_dev, h->d_mask, h->net.start_time, out_dev);
+    h->launches++;
+    BB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int bb_frequency_sequence_strain_device(bb_handle* h, const double* params_dev, long n,
+                                                   const double* frequencies_dev, int n_nodes, double first_frequency,
+                                                   double* out_dev, void* stream) {
+    if (!h || !h->have_network) return bb_fail("bb_frequency_sequence_strain_device: network not set");
+    if (n <= 0 || n_nodes <= 0) return 0;
+    if (n > 65535) return bb_fail("sequence strain: at most 65535 samples per call");
+    BB_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (bb_ensure_scratch(h, (size_t)n)) return 1;
+    BBWaveformConfig wf = h->wf;
+    wf.sequence = 1;
+    wf.no_time_shift = 1;
+    wf.f_min = first_frequency;
+    wf.add_jitter = 0;
+    bb_prologue_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(params_dev, n, h->net, wf, h->d_coef, nullptr, nullptr);
+    h->launches++;
+    h->perm_valid = false;
+    dim3 grid((n_nodes + 127) / 128, (unsigned)n);
+    bb_sequence_strain_kernel<<<grid, 128, 0, st>>>(h->d_coef, n, frequencies_dev, n_nodes, h->wf.approximant, params_dev, out_dev);
     h->launches++;
     BB_CUDA(cudaGetLastError());
     return 0;

@@ -220,9 +220,9 @@ BB_HD void bb_solve5(double a[5][5], double* b) {
 // sky / detector part of the record, shared by all approximants.
 // interferometer.py:303-368: antenna response at geocent_time, dt = (t_c - t_start) + delay.
 // Returns dt0 = t_c - t_start (folded into the waveform phase by the caller).
-BB_HD double bb_detector_prologue(const double* p, const BBNetwork& net, int add_jitter, double* coef) {
-    const double tc = add_jitter ? p[BB_P_GEOCENT_TIME] + p[BB_P_TIME_JITTER] : p[BB_P_GEOCENT_TIME];
-    const double gmst = bb_wrap_2pi(bb_gmst(tc));
+BB_HD double bb_detector_prologue(const double* p, const BBNetwork& net, const BBWaveformConfig& wf, double* coef) {
+    const double tc = wf.add_jitter ? p[BB_P_GEOCENT_TIME] + p[BB_P_TIME_JITTER] : p[BB_P_GEOCENT_TIME];
+    const double gmst = bb_wrap_2pi(bb_gmst(wf.fixed_antenna_time ? wf.antenna_time : tc));
     const double cfac = cos(p[BB_P_THETA_JN]);
     const double pfac = 0.5 * (1.0 + cfac * cfac);
     for (int d = 0; d < BB_MAX_DET; ++d) {
@@ -246,7 +246,8 @@ BB_HD double bb_detector_prologue(const double* p, const BBNetwork& net, int add
             for (int i = 0; i < BC_DSTRIDE; ++i) cd[i] = 0.0;
         }
     }
-    return tc - net.start_time;
+    coef[BC_DT0] = tc - net.start_time;
+    return wf.no_time_shift ? 0.0 : tc - net.start_time;
 }
 
 // active bin range shared by the approximants: upstream fills i in [int(f_min/df), int(f_max'/df)),
@@ -274,7 +275,7 @@ BB_HD void bb_phenomd_prologue(const double* p, const BBNetwork& net, const BBWa
     const double dist_mpc = p[BB_P_DISTANCE];
     coef[BC_DISTANCE] = dist_mpc;
     coef[BC_JITTER] = p[BB_P_TIME_JITTER];
-    const double dt0 = bb_detector_prologue(p, net, wf.add_jitter, coef);
+    const double dt0 = bb_detector_prologue(p, net, wf, coef);
 
     const double M = m1 + m2;
     const double MTSUN = BB_G_SI * BB_MSUN_SI / (BB_C_SI * BB_C_SI * BB_C_SI);
@@ -282,7 +283,7 @@ BB_HD void bb_phenomd_prologue(const double* p, const BBNetwork& net, const BBWa
     const double Ms = M * MTSUN;
     const double f_cut = 0.2 / Ms;
     const double f_ref = (wf.f_ref == 0.0) ? wf.f_min : wf.f_ref;
-    const double f_max_prime = (wf.f_max == 0.0) ? f_cut : (wf.f_max < f_cut ? wf.f_max : f_cut);
+    const double f_max_prime = (wf.f_max == 0.0 || wf.sequence) ? f_cut : (wf.f_max < f_cut ? wf.f_max : f_cut);
     const bool bad = !(m1 > 0.0) || !(m2 > 0.0) || !(dist_mpc > 0.0) || fabs(chi1) > 1.0 || fabs(chi2) > 1.0
                      || !(f_max_prime > wf.f_min) || !isfinite(M) || !isfinite(dist_mpc);
     if (bad) {

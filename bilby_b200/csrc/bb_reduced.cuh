@@ -1,0 +1,467 @@
+// Reduced-order likelihood kernels (included by bb_kernels.cu).
+//
+//   K5 bb_relbin_kernel        relative binning  <- bilby/gw/likelihood/relative.py:365-430
+//   K6 bb_roq_kernel           ROQ, one coalescence time per sample  <- bilby/gw/likelihood/roq.py:467-602
+//   K7 bb_roq_hlinear_kernel + ZGEMM + bb_roq_time_marg_kernel   ROQ time marginalisation  <- roq.py:535-651
+//
+// All three evaluate the source model on a frequency SEQUENCE (bin edges / ROQ nodes), the device form of
+// bilby/gw/source.py:1068-1140: every node is evaluated with the per-sample coefficient record written by
+// K0 (no f_min / f_max masking).  One warp owns one sample; lanes stride over the nodes; the node tables
+// (f, f^-1/6, ln f, f^3/4) and the per-node data are read through L1/L2 (they are a few hundred KB and shared
+// by every sample); partial sums stay in registers; one warp-shuffle reduction per sample.
+#pragma once
+
+#define BB_RED_THREADS 256
+#define BB_RED_WARPS (BB_RED_THREADS / 32)
+
+struct BBNodes {
+    const double* f;
+    const double* u;      // f^(-1/6)
+    const double* lf;     // ln f
+    const double* q34;    // f^(3/4)
+    int n;
+};
+
+struct BBRelbinDev {
+    BBNodes edges;            // bin edges (relative.py:233 frequency_bin_edges)
+    const double2* ginv;      // [n_det][n_edges]  1 / per_detector_fiducial_waveform_points
+    const double2* a0;        // [n_det][n_bins]   summary data (relative.py:339-361)
+    const double2* a1;
+    const double* b0;         // [n_det][n_bins]   (real: <h0|h0> pieces)
+    const double* b1;
+    const double* inv_width;  // [n_bins] 1 / bin_widths
+    // time marginalisation (relative.py:380-421): P_d[k] = (4/T) h0_d[k] conj(d_d[k]) / S_d[k], bin of grid bin k
+    const double2* pgrid;     // [n_det][n_freq]
+    const int* bin_of_k;      // [n_freq], -1 outside [bin_inds[0], bin_inds[-1]]
+    const double* centre;     // [n_bins] bin_centers
+};
+
+struct BBRoqDev {
+    BBNodes lin, quad;
+    const double2* W;         // [n_det][n_time][n_lin]
+    const double* wq;         // [n_det][n_quad]
+    int n_time;
+    long time_start_index;    // time_samples[i] = (time_start_index + i) * time_step   (roq.py:766)
+    double time_step;
+    int n_marg;               // time marginalisation grid (roq.py:320-331)
+    double marg_start, marg_dtc;
+};
+
+// load one sample's coefficient record (and calibration record) into this warp's shared-memory slot
+template <bool CAL>
+__device__ __forceinline__ void bb_red_load(double* rec, double* cal, const double* coef, const double* calrec,
+                                            long s, int cal_len, int lane) {
+    __syncwarp();
+    for (int i = lane; i < BC_NCOEF; i += 32) rec[i] = coef[s * BC_NCOEF + i];
+    if (CAL) for (int i = lane; i < cal_len; i += 32) cal[i] = calrec[s * cal_len + i];
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: relative binning
+//   r(f_j) = h_det(f_j) / h0_det(f_j) at the bin edges; r0 = mean, r1 = slope over each bin;
+//   <d|h> = sum a0 conj(r0) + a1 conj(r1),  <h|h> = sum b0 |r0|^2 + 2 b1 Re(r0 conj(r1))
+// Lane l of row r owns edge j = 32 r + l and the bin whose RIGHT edge it is; the left edge's ratio comes
+// from the neighbouring lane (or from lane 31 of the previous row).
+// STORE: also keep (r0, r1) of every (bin, detector) in shared memory for the time-marginalised variant.
+// ------------------------------------------------------------------------------------------------
+template <int NDET, int APPROX, bool CAL, bool STORE>
+__device__ __forceinline__ void bb_relbin_sample(const double* rec, const double* cal, const BBCalGrid& grid,
+                                                 const BBRelbinDev& rb, int lane, double (*acc)[3],
+                                                 double2* r01 /* [n_bins][NDET][2] */) {
+    const int ne = rb.edges.n, nb = ne - 1;
+    double2 carry[NDET];
+#pragma unroll
+    for (int d = 0; d < NDET; ++d) carry[d] = make_double2(0.0, 0.0);
+    for (int base = 0; base < ne; base += 32) {
+        const int j = base + lane;
+        const bool act = j < ne;
+        const int jj = act ? j : ne - 1;
+        const double f = rb.edges.f[jj];
+        double A, ph;
+        bb_wave<APPROX>(rec, f, rb.edges.u[jj], rb.edges.lf[jj], rb.edges.q34[jj], &A, &ph);
+        const int b = j - 1;                               // bin whose right edge is j
+        const bool have_bin = act && b >= 0;
+        const double iw = have_bin ? rb.inv_width[b] : 0.0;
+#pragma unroll
+        for (int d = 0; d < NDET; ++d) {
+            const double* cd = rec + BC_DET + BC_DSTRIDE * d;
+            double sn, cs;
+            sincospi(ph + cd[2] * f, &sn, &cs);            // h22 e^{-2 pi i f (dt0 + delay)} = A (cs - i sn)
+            double hr = A * (cd[0] * cs + cd[1] * sn), hi = A * (cd[1] * cs - cd[0] * sn);   // K h
+            if (CAL) {
+                double amp1, cr, ci;
+                bb_cal_factor(cal + d * 4 * grid.n_points, grid.n_points, grid.l0[d], grid.inv_delta[d],
+                              rb.edges.lf[jj], &amp1, &cr, &ci);
+                const double tr = amp1 * (hr * cr - hi * ci), ti = amp1 * (hr * ci + hi * cr);
+                hr = tr;
+                hi = ti;
+            }
+            const double2 g = rb.ginv[(size_t)d * ne + jj];
+            const double rr = hr * g.x - hi * g.y, ri = hr * g.y + hi * g.x;        // ratio at edge j
+            double lr = __shfl_up_sync(0xffffffffu, rr, 1), li = __shfl_up_sync(0xffffffffu, ri, 1);
+            if (lane == 0) { lr = carry[d].x; li = carry[d].y; }
+            carry[d].x = __shfl_sync(0xffffffffu, rr, 31);
+            carry[d].y = __shfl_sync(0xffffffffu, ri, 31);
+            if (have_bin) {
+                const double r0r = 0.5 * (rr + lr), r0i = 0.5 * (ri + li);
+                const double r1r = (rr - lr) * iw, r1i = (ri - li) * iw;
+                const double2 a0 = rb.a0[(size_t)d * nb + b], a1 = rb.a1[(size_t)d * nb + b];
+                // a conj(r) = (ax rr + ay ri) + i (ay rr - ax ri)
+                acc[d][0] += (a0.x * r0r + a0.y * r0i) + (a1.x * r1r + a1.y * r1i);
+                acc[d][1] += (a0.y * r0r - a0.x * r0i) + (a1.y * r1r - a1.x * r1i);
+                acc[d][2] += rb.b0[(size_t)d * nb + b] * (r0r * r0r + r0i * r0i)
+                             + 2.0 * rb.b1[(size_t)d * nb + b] * (r0r * r1r + r0i * r1i);
+                if (STORE) {
+                    r01[((size_t)b * NDET + d) * 2] = make_double2(r0r, r0i);
+                    r01[((size_t)b * NDET + d) * 2 + 1] = make_double2(r1r, r1i);
+                }
+            }
+        }
+    }
+}
+
+template <int NDET, int APPROX, bool CAL>
+__global__ void __launch_bounds__(BB_RED_THREADS)
+bb_relbin_kernel(const double* __restrict__ coef, long n, BBRelbinDev rb, const double* __restrict__ calrec,
+                 BBCalGrid grid, double* __restrict__ out) {
+    extern __shared__ __align__(16) double red_smem[];
+    const int cal_len = CAL ? NDET * 4 * grid.n_points : 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* rec = red_smem + (size_t)warp * (BC_NCOEF + cal_len);
+    double* cal = rec + BC_NCOEF;
+    for (long s = (long)blockIdx.x * BB_RED_WARPS + warp; s < n; s += (long)gridDim.x * BB_RED_WARPS) {
+        bb_red_load<CAL>(rec, cal, coef, calrec, s, cal_len, lane);
+        double acc[NDET][3];
+#pragma unroll
+        for (int d = 0; d < NDET; ++d) acc[d][0] = acc[d][1] = acc[d][2] = 0.0;
+        bb_relbin_sample<NDET, APPROX, CAL, false>(rec, cal, grid, rb, lane, acc, nullptr);
+#pragma unroll
+        for (int d = 0; d < NDET; ++d) {
+            const double sr = bb_warp_sum(acc[d][0]), si = bb_warp_sum(acc[d][1]), sh = bb_warp_sum(acc[d][2]);
+            if (lane == 0) {
+                double* o = out + (s * NDET + d) * 3;
+                o[0] = sr;
+                o[1] = si;
+                o[2] = (rec[BC_STATUS] != 0.0) ? nan("") : sh;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6: ROQ at one coalescence time per sample (roq.py:467-549)
+// ------------------------------------------------------------------------------------------------
+// <h|h>_d = |K_d|^2 sum_j |h22(f_j)|^2 |C_d(f_j)|^2 w_d[j] over the quadratic nodes (roq.py:504-507)
+template <int NDET, int APPROX, bool CAL>
+__device__ __forceinline__ void bb_roq_quadratic(const double* rec, const double* cal, const BBCalGrid& grid,
+                                                 const BBRoqDev& rq, int lane, double* hq) {
+#pragma unroll
+    for (int d = 0; d < NDET; ++d) hq[d] = 0.0;
+    const int nq = rq.quad.n;
+    for (int j = lane; j < nq; j += 32) {
+        const double f = rq.quad.f[j];
+        double A, ph;
+        bb_wave<APPROX>(rec, f, rq.quad.u[j], rq.quad.lf[j], rq.quad.q34[j], &A, &ph);
+        const double A2 = A * A;
+#pragma unroll
+        for (int d = 0; d < NDET; ++d) {
+            double w = A2 * rq.wq[(size_t)d * nq + j];
+            if (CAL) {
+                double amp1, cr, ci;
+                bb_cal_factor(cal + d * 4 * grid.n_points, grid.n_points, grid.l0[d], grid.inv_delta[d],
+                              rq.quad.lf[j], &amp1, &cr, &ci);
+                w *= amp1 * amp1;
+            }
+            hq[d] += w;
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < NDET; ++d) hq[d] = bb_warp_sum(hq[d]) * rec[BC_DET + BC_DSTRIDE * d + 3];
+}
+
+// the cubic interpolation through five neighbouring ROQ times (roq.py:576-602 / 644-651, LIGO-T2100224)
+__device__ __forceinline__ double2 bb_interp5(const double2* v, double a) {
+    const double b = 1.0 - a;
+    const double c = (a * a * a - a) / 6.0, d = (b * b * b - b) / 6.0;
+    double2 o;
+    {
+        const double r1 = (-v[0].x + 8.0 * v[1].x - 14.0 * v[2].x + 8.0 * v[3].x - v[4].x) / 4.0;
+        const double r2 = v[2].x - 2.0 * v[3].x + v[4].x;
+        o.x = a * v[2].x + b * v[3].x + c * r1 + d * r2;
+    }
+    {
+        const double r1 = (-v[0].y + 8.0 * v[1].y - 14.0 * v[2].y + 8.0 * v[3].y - v[4].y) / 4.0;
+        const double r2 = v[2].y - 2.0 * v[3].y + v[4].y;
+        o.y = a * v[2].y + b * v[3].y + c * r1 + d * r2;
+    }
+    return o;
+}
+
+template <int NDET, int APPROX, bool CAL>
+__global__ void __launch_bounds__(BB_RED_THREADS)
+bb_roq_kernel(const double* __restrict__ coef, long n, BBRoqDev rq, const double* __restrict__ calrec,
+              BBCalGrid grid, double* __restrict__ out) {
+    extern __shared__ __align__(16) double red_smem[];
+    const int cal_len = CAL ? NDET * 4 * grid.n_points : 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* rec = red_smem + (size_t)warp * (BC_NCOEF + cal_len);
+    double* cal = rec + BC_NCOEF;
+    const int nl = rq.lin.n;
+    const double ts0 = (double)rq.time_start_index * rq.time_step;
+    const double ts1 = (double)(rq.time_start_index + 1) * rq.time_step;
+    const double space = ts1 - ts0;                          // samples[1] - samples[0] (roq.py:571)
+    for (long s = (long)blockIdx.x * BB_RED_WARPS + warp; s < n; s += (long)gridDim.x * BB_RED_WARPS) {
+        bb_red_load<CAL>(rec, cal, coef, calrec, s, cal_len, lane);
+        double hq[NDET];
+        bb_roq_quadratic<NDET, APPROX, CAL>(rec, cal, grid, rq, lane, hq);
+        // five neighbouring ROQ times per detector (roq.py:509-516, 551-574)
+        int idx[NDET][5];
+        bool inb[NDET];
+        double ifo_time[NDET];
+#pragma unroll
+        for (int d = 0; d < NDET; ++d) {
+            ifo_time[d] = rec[BC_DT0] + 0.5 * rec[BC_DET + BC_DSTRIDE * d + 2];
+            const double q = floor((ifo_time[d] - ts0) / space);
+            const long closest = (long)fmin(fmax(q, -1.0e9), 1.0e9);
+            inb[d] = (closest - 2 >= 0) && (closest + 2 < (long)rq.n_time);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                long i = closest + k - 2;
+                i = i < 0 ? 0 : (i > rq.n_time - 1 ? rq.n_time - 1 : i);
+                idx[d][k] = (int)i;
+            }
+        }
+        double2 acc[NDET][5];
+#pragma unroll
+        for (int d = 0; d < NDET; ++d)
+#pragma unroll
+            for (int k = 0; k < 5; ++k) acc[d][k] = make_double2(0.0, 0.0);
+        for (int j = lane; j < nl; j += 32) {
+            const double f = rq.lin.f[j];
+            double A, ph;
+            bb_wave<APPROX>(rec, f, rq.lin.u[j], rq.lin.lf[j], rq.lin.q34[j], &A, &ph);
+            double sn, cs;
+            sincospi(ph, &sn, &cs);
+            const double zr0 = A * cs, zi0 = A * sn;        // conj(h22) = A e^{+i Phi}
+#pragma unroll
+            for (int d = 0; d < NDET; ++d) {
+                double zr = zr0, zi = zi0;
+                if (CAL) {
+                    double amp1, cr, ci;                    // conj(h C) = conj(h) amp1 (cr - i ci)
+                    bb_cal_factor(cal + d * 4 * grid.n_points, grid.n_points, grid.l0[d], grid.inv_delta[d],
+                                  rq.lin.lf[j], &amp1, &cr, &ci);
+                    const double tr = amp1 * (zr * cr + zi * ci), ti = amp1 * (zi * cr - zr * ci);
+                    zr = tr;
+                    zi = ti;
+                }
+                const double2* Wd = rq.W + (size_t)d * rq.n_time * nl;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    const double2 w = Wd[(size_t)idx[d][k] * nl + j];
+                    acc[d][k].x += zr * w.x - zi * w.y;
+                    acc[d][k].y += zr * w.y + zi * w.x;
+                }
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < NDET; ++d) {
+            double2 v[5];
+            const double kr = rec[BC_DET + BC_DSTRIDE * d], ki = rec[BC_DET + BC_DSTRIDE * d + 1];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const double sr = bb_warp_sum(acc[d][k].x), si = bb_warp_sum(acc[d][k].y);
+                v[k] = make_double2(kr * sr + ki * si, kr * si - ki * sr);      // conj(K) * sum
+            }
+            if (lane == 0) {
+                // a = (time_samples[3] - time) / max(time_samples[1] - time_samples[0], 1e-12) on the CLIPPED indices
+                const double t3 = (double)(rq.time_start_index + idx[d][3]) * rq.time_step;
+                const double t1 = (double)(rq.time_start_index + idx[d][1]) * rq.time_step;
+                const double t0 = (double)(rq.time_start_index + idx[d][0]) * rq.time_step;
+                const double a = (t3 - ifo_time[d]) / fmax(t1 - t0, 1e-12);
+                const double2 dh = bb_interp5(v, a);
+                double* o = out + (s * NDET + d) * 3;
+                // out of the ROQ time window: d_inner_h += log(False) (roq.py:532-533)
+                o[0] = inb[d] ? dh.x : -INFINITY;
+                o[1] = dh.y;
+                o[2] = (rec[BC_STATUS] != 0.0) ? nan("") : hq[d];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7: ROQ time marginalisation (roq.py:535-549, 604-651; base.py:794-820)
+//   (a) bb_roq_hlinear_kernel : V_d[s][i] = conj(h_linear_d[i]) for every sample, <h|h> per sample
+//   (b) ZGEMM per detector    : Y_d[s][t] = sum_i W_d[t][i] V_d[s][i]      (the dense all-times contraction)
+//   (c) bb_roq_time_marg_kernel: five-sample interpolation at the likelihood's time grid, sum over detectors,
+//                                point likelihood, logsumexp with the time prior
+// ------------------------------------------------------------------------------------------------
+template <int NDET, int APPROX, bool CAL>
+__global__ void __launch_bounds__(BB_RED_THREADS)
+bb_roq_hlinear_kernel(const double* __restrict__ coef, long s_begin, long n, BBRoqDev rq,
+                      const double* __restrict__ calrec, BBCalGrid grid, double2* __restrict__ V /* [NDET][n][nl] */,
+                      double* __restrict__ hh /* [n] */) {
+    extern __shared__ __align__(16) double red_smem[];
+    const int cal_len = CAL ? NDET * 4 * grid.n_points : 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* rec = red_smem + (size_t)warp * (BC_NCOEF + cal_len);
+    double* cal = rec + BC_NCOEF;
+    const int nl = rq.lin.n;
+    for (long s = (long)blockIdx.x * BB_RED_WARPS + warp; s < n; s += (long)gridDim.x * BB_RED_WARPS) {
+        bb_red_load<CAL>(rec, cal, coef, calrec, s_begin + s, cal_len, lane);
+        double hq[NDET];
+        bb_roq_quadratic<NDET, APPROX, CAL>(rec, cal, grid, rq, lane, hq);
+        if (lane == 0) {
+            double t = 0.0;
+#pragma unroll
+            for (int d = 0; d < NDET; ++d) t += hq[d];
+            hh[s] = (rec[BC_STATUS] != 0.0) ? nan("") : t;
+        }
+        for (int j = lane; j < nl; j += 32) {
+            const double f = rq.lin.f[j];
+            double A, ph;
+            bb_wave<APPROX>(rec, f, rq.lin.u[j], rq.lin.lf[j], rq.lin.q34[j], &A, &ph);
+            double sn, cs;
+            sincospi(ph, &sn, &cs);
+            const double zr0 = A * cs, zi0 = A * sn;
+#pragma unroll
+            for (int d = 0; d < NDET; ++d) {
+                double zr = zr0, zi = zi0;
+                if (CAL) {
+                    double amp1, cr, ci;
+                    bb_cal_factor(cal + d * 4 * grid.n_points, grid.n_points, grid.l0[d], grid.inv_delta[d],
+                                  rq.lin.lf[j], &amp1, &cr, &ci);
+                    const double tr = amp1 * (zr * cr + zi * ci), ti = amp1 * (zi * cr - zr * ci);
+                    zr = tr;
+                    zi = ti;
+                }
+                const double kr = rec[BC_DET + BC_DSTRIDE * d], ki = rec[BC_DET + BC_DSTRIDE * d + 1];
+                V[((size_t)d * n + s) * nl + j] = make_double2(kr * zr + ki * zi, kr * zi - ki * zr);   // conj(K) conj(h)
+            }
+        }
+    }
+}
+
+template <int NDET>
+__global__ void __launch_bounds__(BB_RED_THREADS)
+bb_roq_time_marg_kernel(const double* __restrict__ coef, long s_begin, long n, BBRoqDev rq,
+                        const double2* __restrict__ Y /* [NDET][n][n_time] */, const double* __restrict__ hh,
+                        BBMarg marg, double start_time, double* __restrict__ out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double ts0 = (double)rq.time_start_index * rq.time_step;
+    const double ts1 = (double)(rq.time_start_index + 1) * rq.time_step;
+    const double space = ts1 - ts0;
+    for (long s = (long)blockIdx.x * BB_RED_WARPS + warp; s < n; s += (long)gridDim.x * BB_RED_WARPS) {
+        const double* rec = coef + (s_begin + s) * BC_NCOEF;
+        if (rec[BC_STATUS] != 0.0) {
+            if (lane == 0) out[s_begin + s] = -DBL_MAX;
+            continue;
+        }
+        const double h2 = hh[s], dist = rec[BC_DISTANCE];
+        const double jit = marg.jitter ? rec[BC_JITTER] : 0.0;
+        double delay[NDET];
+#pragma unroll
+        for (int d = 0; d < NDET; ++d) delay[d] = 0.5 * rec[BC_DET + BC_DSTRIDE * d + 2];
+        const double bw = marg.roq_dtc / (marg.time_max - marg.time_min);     // prior.prob(t) * delta_tc
+        double mx = -INFINITY, sum = 0.0;
+        for (int j = lane; j < rq.n_marg; j += 32) {
+            const double tj = rq.marg_start + rq.marg_dtc / 2.0 + (double)j * rq.marg_dtc;   // roq.py:330
+            const double tt = tj + jit;                                         // base.py:795-797
+            if (tt < marg.time_min || tt > marg.time_max) continue;             // base.py:799-806
+            double dre = 0.0, dim = 0.0;
+#pragma unroll
+            for (int d = 0; d < NDET; ++d) {
+                double ifo_t = (tj - start_time) + delay[d];                     // roq.py:536-539
+                if (marg.jitter) ifo_t += jit;
+                const double per = (ifo_t - ts0) / space;
+                const double fl = floor(per);
+                long c = (long)fl;
+                const double2* y = Y + ((size_t)d * n + s) * rq.n_time;
+                double2 v[5];
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    long i = c + k - 2;
+                    i = i < 0 ? 0 : (i > rq.n_time - 1 ? rq.n_time - 1 : i);
+                    v[k] = y[i];
+                }
+                const double b = per - fl;
+                const double2 r = bb_interp5(v, 1.0 - b);
+                dre += r.x;
+                dim += r.y;
+            }
+            const double l = bb_point_lnl(marg, dre, dim, h2, dist);
+            if (l == -INFINITY) continue;
+            if (l > mx) { sum = sum * exp(mx - l) + bw; mx = l; }
+            else sum += bw * exp(l - mx);
+        }
+        double gmx = mx;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) gmx = fmax(gmx, __shfl_xor_sync(0xffffffffu, gmx, o));
+        double part = (mx == -INFINITY) ? 0.0 : sum * exp(mx - gmx);
+        part = bb_warp_sum(part);
+        if (lane == 0) out[s_begin + s] = (gmx == -INFINITY) ? -INFINITY : log(part) + gmx;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5t: relative binning with time marginalisation (relative.py:380-421): the full-grid waveform is rebuilt
+// as h0_d[k] (r0_b + r1_b (f_k - f_centre,b)), so the series h conj(d)/S is P_d[k] (r0 + r1 (f_k - fc)) with
+// P_d = (4/T) h0_d conj(d_d) / S_d precomputed at set-up.  One CTA per sample; warp 0 evaluates the edges.
+// ------------------------------------------------------------------------------------------------
+template <int NDET, int APPROX, bool CAL>
+__global__ void __launch_bounds__(BB_TM_THREADS, 1)
+bb_relbin_time_marg_kernel(const double* __restrict__ coef, long n, BBRelbinDev rb, int n_freq, double df, int nfft,
+                           int log2n, const double2* __restrict__ twiddle, BBMarg marg, double start_time,
+                           double duration, const double* __restrict__ calrec, BBCalGrid grid,
+                           double* __restrict__ out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double2* X = reinterpret_cast<double2*>(smem_raw);
+    const int nb = rb.edges.n - 1;
+    double2* r01 = X + nfft;                                     // [nb][NDET][2]
+    double* c = reinterpret_cast<double*>(r01 + (size_t)nb * NDET * 2);
+    double* red = c + BC_NCOEF;      // [33]
+    double* cal = red + 33;
+    const int cal_len = CAL ? NDET * 4 * grid.n_points : 0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (long s = blockIdx.x; s < n; s += gridDim.x) {
+        __syncthreads();
+        for (int i = tid; i < BC_NCOEF; i += BB_TM_THREADS) c[i] = coef[s * BC_NCOEF + i];
+        if (CAL) for (int i = tid; i < cal_len; i += BB_TM_THREADS) cal[i] = calrec[s * cal_len + i];
+        __syncthreads();
+        if (c[BC_STATUS] != 0.0) {
+            if (tid == 0) out[s] = -DBL_MAX;
+            continue;
+        }
+        if (warp == 0) {
+            double acc[NDET][3];
+#pragma unroll
+            for (int d = 0; d < NDET; ++d) acc[d][0] = acc[d][1] = acc[d][2] = 0.0;
+            bb_relbin_sample<NDET, APPROX, CAL, true>(c, cal, grid, rb, lane, acc, r01);
+            double hh = 0.0;
+#pragma unroll
+            for (int d = 0; d < NDET; ++d) hh += bb_warp_sum(acc[d][2]);
+            if (lane == 0) red[32] = hh;
+        }
+        __syncthreads();
+        const double hh = red[32];
+        for (int k = tid; k < nfft; k += BB_TM_THREADS) {        // Nyquist bin dropped (relative.py:418-420)
+            const int b = (k < n_freq) ? rb.bin_of_k[k] : -1;
+            double vr = 0.0, vi = 0.0;
+            if (b >= 0) {
+                const double df_c = (double)k * df - rb.centre[b];
+#pragma unroll
+                for (int d = 0; d < NDET; ++d) {
+                    const double2 r0 = r01[((size_t)b * NDET + d) * 2], r1 = r01[((size_t)b * NDET + d) * 2 + 1];
+                    const double qr = r0.x + r1.x * df_c, qi = r0.y + r1.y * df_c;
+                    const double2 p = rb.pgrid[(size_t)d * n_freq + k];
+                    vr += p.x * qr - p.y * qi;
+                    vi += p.x * qi + p.y * qr;
+                }
+            }
+            X[bb_bitrev((unsigned)k, log2n)] = make_double2(vr, vi);
+        }
+        __syncthreads();
+        bb_tm_finish(X, nfft, log2n, twiddle, marg, hh, c[BC_DISTANCE], c[BC_JITTER], start_time, duration, red, out + s);
+    }
+}

@@ -1,0 +1,286 @@
+// Host side of the reduced-order likelihoods: set-up entry points of the C ABI and kernel launchers
+// (included by bb_kernels.cu after bb_reduced.cuh).
+#pragma once
+
+static void bb_reduced_clear(bb_handle* h) {
+    for (void* p : h->red_bufs) cudaFree(p);
+    h->red_bufs.clear();
+    delete h->rb;
+    delete h->rq;
+    h->rb = nullptr;
+    h->rq = nullptr;
+    cudaFree(h->d_roq_V); cudaFree(h->d_roq_Y); cudaFree(h->d_roq_hh);
+    h->d_roq_V = h->d_roq_Y = nullptr;
+    h->d_roq_hh = nullptr;
+    h->roq_chunk = 0;
+    h->kind = 0;
+}
+
+template <typename T>
+static int bb_red_upload(bb_handle* h, const T* host, size_t count, const T** dev) {
+    T* d = nullptr;
+    BB_CUDA(cudaMalloc(&d, count * sizeof(T)));
+    h->red_bufs.push_back(d);
+    BB_CUDA(cudaMemcpy(d, host, count * sizeof(T), cudaMemcpyHostToDevice));
+    *dev = d;
+    return 0;
+}
+
+static int bb_upload_nodes(bb_handle* h, const double* f, int n, BBNodes* out) {
+    std::vector<double> u(n), lf(n), q34(n);
+    for (int i = 0; i < n; ++i) {
+        if (!(f[i] > 0.0)) return bb_fail("frequency nodes must be positive");
+        u[i] = pow(f[i], -1.0 / 6.0);
+        lf[i] = log(f[i]);
+        q34[i] = pow(f[i], 0.75);
+    }
+    out->n = n;
+    if (bb_red_upload(h, f, n, &out->f)) return 1;
+    if (bb_red_upload(h, u.data(), n, &out->u)) return 1;
+    if (bb_red_upload(h, lf.data(), n, &out->lf)) return 1;
+    if (bb_red_upload(h, q34.data(), n, &out->q34)) return 1;
+    return 0;
+}
+
+static double2 bb_cinv(double re, double im) {
+    // 1 / (re + i im); zero fiducial strain gives inf/nan like the reference's division (relative.py:373)
+    const double den = re * re + im * im;
+    return make_double2(re / den, -im / den);
+}
+
+extern "C" int bb_set_relative_binning(bb_handle* h, int n_edges, const double* bin_freqs, const double* fiducial,
+                                       const double* summary, const double* fiducial_grid, const int* bin_inds) {
+    if (!h || !h->have_network) return bb_fail("bb_set_relative_binning: network not set");
+    BB_CUDA(cudaSetDevice(h->device));
+    bb_reduced_clear(h);
+    if (n_edges == 0) return 0;
+    if (n_edges < 2 || !bin_freqs || !fiducial || !summary) return bb_fail("bb_set_relative_binning: bad arguments");
+    const int nd = h->net.n_det, nb = n_edges - 1, nf = h->net.n_freq;
+    BBRelbinDev* rb = new BBRelbinDev();
+    memset(rb, 0, sizeof(*rb));
+    h->rb = rb;
+    if (bb_upload_nodes(h, bin_freqs, n_edges, &rb->edges)) return 1;
+    std::vector<double2> ginv((size_t)nd * n_edges), a0((size_t)nd * nb), a1((size_t)nd * nb);
+    std::vector<double> b0((size_t)nd * nb), b1((size_t)nd * nb), iw(nb), centre(nb);
+    for (int d = 0; d < nd; ++d) {
+        for (int j = 0; j < n_edges; ++j) {
+            const double* g = fiducial + ((size_t)d * n_edges + j) * 2;
+            ginv[(size_t)d * n_edges + j] = bb_cinv(g[0], g[1]);
+        }
+        const double* sd = summary + (size_t)d * 4 * nb * 2;
+        for (int b = 0; b < nb; ++b) {
+            a0[(size_t)d * nb + b] = make_double2(sd[(0 * nb + b) * 2], sd[(0 * nb + b) * 2 + 1]);
+            a1[(size_t)d * nb + b] = make_double2(sd[(1 * nb + b) * 2], sd[(1 * nb + b) * 2 + 1]);
+            b0[(size_t)d * nb + b] = sd[(2 * nb + b) * 2];
+            b1[(size_t)d * nb + b] = sd[(3 * nb + b) * 2];
+        }
+    }
+    for (int b = 0; b < nb; ++b) {
+        iw[b] = 1.0 / (bin_freqs[b + 1] - bin_freqs[b]);
+        centre[b] = (bin_freqs[b + 1] + bin_freqs[b]) / 2;
+    }
+    if (bb_red_upload(h, ginv.data(), ginv.size(), &rb->ginv)) return 1;
+    if (bb_red_upload(h, a0.data(), a0.size(), &rb->a0)) return 1;
+    if (bb_red_upload(h, a1.data(), a1.size(), &rb->a1)) return 1;
+    if (bb_red_upload(h, b0.data(), b0.size(), &rb->b0)) return 1;
+    if (bb_red_upload(h, b1.data(), b1.size(), &rb->b1)) return 1;
+    if (bb_red_upload(h, iw.data(), iw.size(), &rb->inv_width)) return 1;
+    if (bb_red_upload(h, centre.data(), centre.size(), &rb->centre)) return 1;
+    if (fiducial_grid && bin_inds) {
+        // series factor of relative.py:417-420: (4/T) h0 conj(d) / S on the full grid.  d/S comes from the tiles'
+        // source arrays, which the handle no longer has on the host: read d_ds back (it already carries 4/T).
+        std::vector<double2> ds((size_t)nd * h->n_pad);
+        BB_CUDA(cudaMemcpy(ds.data(), h->d_ds, ds.size() * sizeof(double2), cudaMemcpyDeviceToHost));
+        std::vector<double2> pg((size_t)nd * nf);
+        for (int d = 0; d < nd; ++d)
+            for (int k = 0; k < nf; ++k) {
+                const double* g = fiducial_grid + ((size_t)d * nf + k) * 2;
+                const double2 q = ds[(size_t)d * h->n_pad + k];          // (4/T) d / S
+                // h0 conj(d/S): (g0 + i g1)(qx - i qy)
+                pg[(size_t)d * nf + k] = make_double2(g[0] * q.x + g[1] * q.y, g[1] * q.x - g[0] * q.y);
+            }
+        std::vector<int> bok(nf, -1);
+        for (int b = 0; b < nb; ++b) {
+            const int hi = (b == nb - 1) ? bin_inds[b + 1] + 1 : bin_inds[b + 1];     // bin_sizes[-1] += 1
+            for (int k = bin_inds[b]; k < hi && k < nf; ++k) bok[k] = b;
+        }
+        if (bb_red_upload(h, pg.data(), pg.size(), &rb->pgrid)) return 1;
+        if (bb_red_upload(h, bok.data(), bok.size(), &rb->bin_of_k)) return 1;
+    }
+    h->rb_fmin = bin_freqs[0];
+    h->kind = 1;
+    return 0;
+}
+
+extern "C" int bb_set_roq(bb_handle* h, int n_linear, const double* nodes_linear, int n_quadratic,
+                          const double* nodes_quadratic, int n_time, long time_start_index, double time_step,
+                          const double* weights_linear, const double* weights_quadratic, int n_marg_times,
+                          double marg_time_start, double marg_delta_tc, double beam_pattern_reference_time) {
+    if (!h || !h->have_network) return bb_fail("bb_set_roq: network not set");
+    BB_CUDA(cudaSetDevice(h->device));
+    bb_reduced_clear(h);
+    if (n_linear == 0) return 0;
+    if (n_linear < 1 || n_quadratic < 1 || n_time < 5 || !nodes_linear || !nodes_quadratic || !weights_linear
+        || !weights_quadratic || !(time_step > 0.0))
+        return bb_fail("bb_set_roq: bad arguments");
+    const int nd = h->net.n_det;
+    BBRoqDev* rq = new BBRoqDev();
+    memset(rq, 0, sizeof(*rq));
+    h->rq = rq;
+    if (bb_upload_nodes(h, nodes_linear, n_linear, &rq->lin)) return 1;
+    if (bb_upload_nodes(h, nodes_quadratic, n_quadratic, &rq->quad)) return 1;
+    if (bb_red_upload(h, (const double2*)weights_linear, (size_t)nd * n_time * n_linear, &rq->W)) return 1;
+    if (bb_red_upload(h, weights_quadratic, (size_t)nd * n_quadratic, &rq->wq)) return 1;
+    rq->n_time = n_time;
+    rq->time_start_index = time_start_index;
+    rq->time_step = time_step;
+    rq->n_marg = n_marg_times;
+    rq->marg_start = marg_time_start;
+    rq->marg_dtc = marg_delta_tc;
+    h->marg.roq_dtc = marg_delta_tc;
+    h->roq_ref_time = beam_pattern_reference_time;
+    double fmin = nodes_linear[0];
+    for (int i = 0; i < n_linear; ++i) fmin = nodes_linear[i] < fmin ? nodes_linear[i] : fmin;
+    for (int i = 0; i < n_quadratic; ++i) fmin = nodes_quadratic[i] < fmin ? nodes_quadratic[i] : fmin;
+    h->roq_fmin = fmin;           // first of the unique (sorted) nodes: f_min of the sequence call
+    if (!h->cublas) {
+        if (cublasCreate(&h->cublas) != CUBLAS_STATUS_SUCCESS) return bb_fail("bb_set_roq: cublasCreate failed");
+    }
+    h->kind = 2;
+    return 0;
+}
+
+// ---- launchers ------------------------------------------------------------------------------------
+static long bb_red_grid(const bb_handle* h, long n) {
+    long blocks = (n + BB_RED_WARPS - 1) / BB_RED_WARPS;
+    const long cap = (long)h->sm_count * 8;          // 8 CTAs of 256 threads per SM
+    return blocks < cap ? blocks : cap;
+}
+
+template <int NDET, int APPROX, bool CAL>
+static int bb_launch_reduced_t(bb_handle* h, long n, double* out, cudaStream_t st) {
+    const size_t smem = (size_t)BB_RED_WARPS * (BC_NCOEF + (CAL ? NDET * 4 * h->cal.n_points : 0)) * sizeof(double);
+    const long grid = bb_red_grid(h, n);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (h->profile) {
+        BB_CUDA(cudaEventCreate(&e0));
+        BB_CUDA(cudaEventCreate(&e1));
+        BB_CUDA(cudaEventRecord(e0, st));
+    }
+    if (h->kind == 1) {
+        BB_CUDA(cudaFuncSetAttribute(bb_relbin_kernel<NDET, APPROX, CAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        bb_relbin_kernel<NDET, APPROX, CAL><<<(unsigned)grid, BB_RED_THREADS, smem, st>>>(
+            h->d_coef, n, *h->rb, h->d_calrec, h->cal, out);
+    } else {
+        BB_CUDA(cudaFuncSetAttribute(bb_roq_kernel<NDET, APPROX, CAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        bb_roq_kernel<NDET, APPROX, CAL><<<(unsigned)grid, BB_RED_THREADS, smem, st>>>(
+            h->d_coef, n, *h->rq, h->d_calrec, h->cal, out);
+    }
+    if (h->profile) {
+        BB_CUDA(cudaEventRecord(e1, st));
+        h->k1_events.emplace_back(e0, e1);
+    }
+    h->launches++;
+    BB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int NDET, int APPROX, bool CAL>
+static int bb_launch_roq_time_marg_t(bb_handle* h, long n, double* out, cudaStream_t st) {
+    const BBRoqDev& rq = *h->rq;
+    if (rq.n_marg < 1) return bb_fail("ROQ time marginalisation: bb_set_roq was called without a time grid");
+    const int nl = rq.lin.n, nt = rq.n_time;
+    // chunk the batch so that Y [NDET][chunk][n_time] stays below ~2 GB
+    size_t chunk = (size_t)(2.0e9 / ((double)NDET * nt * sizeof(double2)));
+    if (chunk > (size_t)n) chunk = (size_t)n;
+    if (chunk < 1) chunk = 1;
+    if (chunk > h->roq_chunk) {
+        cudaFree(h->d_roq_V); cudaFree(h->d_roq_Y); cudaFree(h->d_roq_hh);
+        h->d_roq_V = h->d_roq_Y = nullptr;
+        h->d_roq_hh = nullptr;
+        BB_CUDA(cudaMalloc(&h->d_roq_V, (size_t)NDET * chunk * nl * sizeof(double2)));
+        BB_CUDA(cudaMalloc(&h->d_roq_Y, (size_t)NDET * chunk * nt * sizeof(double2)));
+        BB_CUDA(cudaMalloc(&h->d_roq_hh, chunk * sizeof(double)));
+        h->roq_chunk = chunk;
+    }
+    const size_t smem = (size_t)BB_RED_WARPS * (BC_NCOEF + (CAL ? NDET * 4 * h->cal.n_points : 0)) * sizeof(double);
+    BB_CUDA(cudaFuncSetAttribute(bb_roq_hlinear_kernel<NDET, APPROX, CAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (cublasSetStream(h->cublas, st) != CUBLAS_STATUS_SUCCESS) return bb_fail("cublasSetStream failed");
+    const cuDoubleComplex one = make_cuDoubleComplex(1.0, 0.0), zero = make_cuDoubleComplex(0.0, 0.0);
+    for (long s0 = 0; s0 < n; s0 += (long)chunk) {
+        const long m = (n - s0) < (long)chunk ? (n - s0) : (long)chunk;
+        const long grid = bb_red_grid(h, m);
+        bb_roq_hlinear_kernel<NDET, APPROX, CAL><<<(unsigned)grid, BB_RED_THREADS, smem, st>>>(
+            h->d_coef, s0, m, rq, h->d_calrec, h->cal, h->d_roq_V, h->d_roq_hh);
+        h->launches++;
+        BB_CUDA(cudaGetLastError());
+        for (int d = 0; d < NDET; ++d) {
+            // row-major Y_d[m][nt] = V_d[m][nl] W_d[nt][nl]^T  ==  column-major Y^T (nt x m) = Wcm^T (nt x nl) Vcm (nl x m)
+            const cublasStatus_t cs = cublasZgemm(
+                h->cublas, CUBLAS_OP_T, CUBLAS_OP_N, nt, (int)m, nl, &one,
+                (const cuDoubleComplex*)(rq.W + (size_t)d * nt * nl), nl,
+                (const cuDoubleComplex*)(h->d_roq_V + (size_t)d * m * nl), nl, &zero,
+                (cuDoubleComplex*)(h->d_roq_Y + (size_t)d * m * nt), nt);
+            if (cs != CUBLAS_STATUS_SUCCESS) return bb_fail("cublasZgemm failed");
+            h->launches++;
+        }
+        bb_roq_time_marg_kernel<NDET><<<(unsigned)grid, BB_RED_THREADS, 0, st>>>(
+            h->d_coef, s0, m, rq, h->d_roq_Y, h->d_roq_hh, h->marg, h->net.start_time, out);
+        h->launches++;
+        BB_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+template <int NDET, int APPROX, bool CAL>
+static int bb_launch_relbin_time_marg_t(bb_handle* h, long n, double* out, cudaStream_t st) {
+    const BBRelbinDev& rb = *h->rb;
+    if (!rb.pgrid) return bb_fail("relative binning time marginalisation: bb_set_relative_binning was called without "
+                                  "the full-grid fiducial waveforms");
+    if (h->nfft == 0) return bb_fail("time marginalisation needs n_freq - 1 to be a power of two");
+    const int nfft = h->nfft, nb = rb.edges.n - 1;
+    int log2n = 0;
+    while ((1 << log2n) < nfft) ++log2n;
+    const size_t smem = ((size_t)nfft + (size_t)nb * NDET * 2) * sizeof(double2)
+                        + (BC_NCOEF + 33 + (CAL ? NDET * 4 * h->cal.n_points : 0)) * sizeof(double);
+    if (smem > 227 * 1024) return bb_fail("relative binning time marginalisation: series + bins do not fit shared memory");
+    BB_CUDA(cudaFuncSetAttribute(bb_relbin_time_marg_kernel<NDET, APPROX, CAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+    long grid = (long)h->sm_count * per_sm;
+    if (grid > n) grid = n;
+    bb_relbin_time_marg_kernel<NDET, APPROX, CAL><<<(unsigned)grid, BB_TM_THREADS, smem, st>>>(
+        h->d_coef, n, rb, h->net.n_freq, h->net.df, nfft, log2n, h->d_twiddle, h->marg, h->net.start_time,
+        h->net.duration, h->d_calrec, h->cal, out);
+    h->launches++;
+    BB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// what: 0 inner products (K5 / K6), 1 time-marginalised likelihood
+template <int NDET>
+static int bb_launch_reduced_n(bb_handle* h, long n, double* out, cudaStream_t st, int what) {
+    const bool pd = h->wf.approximant == BB_IMRPHENOMD;
+    const bool cal = h->cal_params != nullptr;
+#define BB_RED_DISPATCH(FN)                                                                              \
+    do {                                                                                                 \
+        if (cal) return pd ? FN<NDET, BB_IMRPHENOMD, true>(h, n, out, st) : FN<NDET, BB_TAYLORF2, true>(h, n, out, st); \
+        return pd ? FN<NDET, BB_IMRPHENOMD, false>(h, n, out, st) : FN<NDET, BB_TAYLORF2, false>(h, n, out, st);        \
+    } while (0)
+    if (what == 0) BB_RED_DISPATCH(bb_launch_reduced_t);
+    if (h->kind == 1) BB_RED_DISPATCH(bb_launch_relbin_time_marg_t);
+    BB_RED_DISPATCH(bb_launch_roq_time_marg_t);
+#undef BB_RED_DISPATCH
+}
+
+static int bb_launch_reduced(bb_handle* h, long n, double* out, cudaStream_t st, int what) {
+    if (h->shard_lo != 0 || h->shard_hi != h->net.n_freq)
+        return bb_fail("reduced-order likelihoods are sample-sharded only (bb_set_frequency_shard is active)");
+    switch (h->net.n_det) {
+        case 1: return bb_launch_reduced_n<1>(h, n, out, st, what);
+        case 2: return bb_launch_reduced_n<2>(h, n, out, st, what);
+        case 3: return bb_launch_reduced_n<3>(h, n, out, st, what);
+        case 4: return bb_launch_reduced_n<4>(h, n, out, st, what);
+    }
+    return bb_fail("bad n_det");
+}

@@ -33,7 +33,7 @@ BB_HD void bb_taylorf2_prologue(const double* p, const BBNetwork& net, const BBW
     const double dist_mpc = p[BB_P_DISTANCE];
     coef[BC_DISTANCE] = dist_mpc;
     coef[BC_JITTER] = p[BB_P_TIME_JITTER];
-    const double dt0 = bb_detector_prologue(p, net, wf.add_jitter, coef);
+    const double dt0 = bb_detector_prologue(p, net, wf, coef);
     const double M = m1 + m2;
     const double MTSUN = BB_G_SI * BB_MSUN_SI / (BB_C_SI * BB_C_SI * BB_C_SI);
     const double MRSUN = BB_G_SI * BB_MSUN_SI / (BB_C_SI * BB_C_SI);
@@ -42,7 +42,7 @@ BB_HD void bb_taylorf2_prologue(const double* p, const BBNetwork& net, const BBW
     const double piM = pi * Ms;
     const double f_isco = (1.0 / sqrt(6.0)) * (1.0 / 6.0) / piM;      // vISCO^3 / (pi M)
     const double f_end = (wf.f_max == 0.0) ? f_isco : wf.f_max;
-    const bool bad = !(m1 > 0.0) || !(m2 > 0.0) || !(dist_mpc > 0.0) || !(f_end > wf.f_min) || !isfinite(M)
+    const bool bad = !(m1 > 0.0) || !(m2 > 0.0) || !(dist_mpc > 0.0) || (!wf.sequence && !(f_end > wf.f_min)) || !isfinite(M)
                      || !isfinite(dist_mpc);
     if (bad) {
         coef[BC_STATUS] = 1.0;

@@ -18,6 +18,63 @@
 
 __device__ __forceinline__ unsigned bb_bitrev(unsigned v, int bits) { return __brev(v) >> (32 - bits); }
 
+// FFT of the (bit-reversed) series in shared memory followed by the weighted logsumexp over the times inside
+// the geocent_time prior; shared by the full-grid and the relative-binning time-marginalised kernels.
+__device__ __forceinline__ void bb_tm_finish(double2* X, int nfft, int log2n, const double2* __restrict__ twiddle,
+                                             const BBMarg& marg, double hh, double dist, double jitter,
+                                             double start_time, double duration, double* red, double* out_s) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // in-place radix-2 DIT butterflies on the bit-reversed series
+    for (int stage = 0; stage < log2n; ++stage) {
+        const int half = 1 << stage;
+        const int tstep = nfft >> (stage + 1);
+        for (int b = tid; b < (nfft >> 1); b += BB_TM_THREADS) {
+            const int j = b & (half - 1);
+            const int i0 = ((b >> stage) << (stage + 1)) + j;
+            const int i1 = i0 + half;
+            const double2 w = twiddle[j * tstep];
+            const double2 a = X[i0], bb = X[i1];
+            const double tr = bb.x * w.x - bb.y * w.y, ti = bb.x * w.y + bb.y * w.x;
+            X[i0] = make_double2(a.x + tr, a.y + ti);
+            X[i1] = make_double2(a.x - tr, a.y - ti);
+        }
+        __syncthreads();
+    }
+
+    // weighted logsumexp over the times inside the prior
+    const double dtc = duration / (double)nfft;     // = 2 / sampling_frequency
+    const double jit = marg.jitter ? jitter : 0.0;
+    const double bw = dtc / (marg.time_max - marg.time_min);
+    double mx = -INFINITY, sum = 0.0;
+    for (int j = tid; j < nfft; j += BB_TM_THREADS) {
+        // times = start_time + linspace(0, T, nfft + 1)[1:]  (+ jitter)
+        const double tj = (start_time + (double)(j + 1) * dtc) + jit;
+        if (tj < marg.time_min || tj > marg.time_max) continue;
+        const double2 v = X[j];
+        const double l = bb_point_lnl(marg, v.x, v.y, hh, dist);
+        if (l == -INFINITY) continue;
+        if (l > mx) { sum = sum * exp(mx - l) + bw; mx = l; }
+        else sum += bw * exp(l - mx);
+    }
+    double gmx = mx;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) gmx = fmax(gmx, __shfl_xor_sync(0xffffffffu, gmx, o));
+    if (lane == 0) red[warp] = gmx;
+    __syncthreads();
+    gmx = red[0];
+    for (int w = 1; w < BB_TM_THREADS / 32; ++w) gmx = fmax(gmx, red[w]);
+    __syncthreads();
+    double part = (mx == -INFINITY) ? 0.0 : sum * exp(mx - gmx);
+    part = bb_warp_sum(part);
+    if (lane == 0) red[warp] = part;
+    __syncthreads();
+    if (tid == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < BB_TM_THREADS / 32; ++w) tot += red[w];
+        *out_s = (gmx == -INFINITY) ? -INFINITY : log(tot) + gmx;
+    }
+}
+
 template <int NDET, int APPROX, bool CAL>
 __global__ void __launch_bounds__(BB_TM_THREADS, 1)
 bb_time_marg_kernel(const double* __restrict__ coef, long n, BBTiles tiles, int n_freq, double df, int nfft,
@@ -86,56 +143,7 @@ bb_time_marg_kernel(const double* __restrict__ coef, long n, BBTiles tiles, int 
         for (int w = 0; w < BB_TM_THREADS / 32; ++w) hh += red[w];
         __syncthreads();
 
-        // in-place radix-2 DIT butterflies on the bit-reversed series
-        for (int stage = 0; stage < log2n; ++stage) {
-            const int half = 1 << stage;
-            const int tstep = nfft >> (stage + 1);
-            for (int b = tid; b < (nfft >> 1); b += BB_TM_THREADS) {
-                const int j = b & (half - 1);
-                const int i0 = ((b >> stage) << (stage + 1)) + j;
-                const int i1 = i0 + half;
-                const double2 w = twiddle[j * tstep];
-                const double2 a = X[i0], bb = X[i1];
-                const double tr = bb.x * w.x - bb.y * w.y, ti = bb.x * w.y + bb.y * w.x;
-                X[i0] = make_double2(a.x + tr, a.y + ti);
-                X[i1] = make_double2(a.x - tr, a.y - ti);
-            }
-            __syncthreads();
-        }
-
-        // weighted logsumexp over the times inside the prior
-        const double dtc = duration / (double)nfft;     // = 2 / sampling_frequency
-        const double jit = marg.jitter ? c[BC_JITTER] : 0.0;
-        const double bw = dtc / (marg.time_max - marg.time_min);
-        const double dist = c[BC_DISTANCE];
-        double mx = -INFINITY, sum = 0.0;
-        for (int j = tid; j < nfft; j += BB_TM_THREADS) {
-            // times = start_time + linspace(0, T, nfft + 1)[1:]  (+ jitter)
-            const double tj = (start_time + (double)(j + 1) * dtc) + jit;
-            if (tj < marg.time_min || tj > marg.time_max) continue;
-            const double2 v = X[j];
-            const double l = bb_point_lnl(marg, v.x, v.y, hh, dist);
-            if (l == -INFINITY) continue;
-            if (l > mx) { sum = sum * exp(mx - l) + bw; mx = l; }
-            else sum += bw * exp(l - mx);
-        }
-        double gmx = mx;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) gmx = fmax(gmx, __shfl_xor_sync(0xffffffffu, gmx, o));
-        if (lane == 0) red[warp] = gmx;
-        __syncthreads();
-        gmx = red[0];
-        for (int w = 1; w < BB_TM_THREADS / 32; ++w) gmx = fmax(gmx, red[w]);
-        __syncthreads();
-        double part = (mx == -INFINITY) ? 0.0 : sum * exp(mx - gmx);
-        part = bb_warp_sum(part);
-        if (lane == 0) red[warp] = part;
-        __syncthreads();
-        if (tid == 0) {
-            double tot = 0.0;
-            for (int w = 0; w < BB_TM_THREADS / 32; ++w) tot += red[w];
-            out[s] = (gmx == -INFINITY) ? -INFINITY : log(tot) + gmx;
-        }
+        bb_tm_finish(X, nfft, log2n, twiddle, marg, hh, c[BC_DISTANCE], c[BC_JITTER], start_time, duration, red, out + s);
     }
 }
 

@@ -50,6 +50,25 @@ class CubicSpline(Recalibrate):
             tmp2[i, i - 1], tmp2[i, i], tmp2[i, i + 1] = 1, -2, 1
         return np.linalg.solve(tmp1, tmp2)
 
+    def get_calibration_factor(self, frequency_array, prefix="recalib_", **params):
+        """calibration.py:349-384 on the host (set-up only: fiducial waveforms of the relative-binning likelihood;
+        the per-sample factor is evaluated inside the CUDA kernels)."""
+        f = np.asarray(frequency_array, dtype=float)
+        with np.errstate(divide="ignore"):
+            x = np.nan_to_num(np.log10(f) - self.log_spline_points[0], neginf=0.0) / self.delta_log_spline_points
+        prev = np.clip(x.astype(int), 0, self.n_points - 2)
+        b = x - prev
+        a = 1 - b
+        c = (a ** 3 - a) / 6
+        d = (b ** 3 - b) / 6
+        out = []
+        for kind in ("amplitude", "phase"):
+            p = np.array([params[f"{prefix}{kind}_{ii}"] for ii in range(self.n_points)], dtype=float)
+            sc = self.nodes_to_spline_coefficients.dot(p)
+            out.append(a * p[prev] + b * p[prev + 1] + c * sc[prev] + d * sc[prev + 1])
+        da, dp = out
+        return np.nan_to_num((1 + da) * (2 + 1j * dp) / (2 - 1j * dp))
+
     def __repr__(self):
         return (f"{self.__class__.__name__}(prefix='{self.prefix}', minimum_frequency={self.minimum_frequency}, "
                 f"maximum_frequency={self.maximum_frequency}, n_points={self.n_points})")

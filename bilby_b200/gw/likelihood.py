@@ -554,3 +554,7 @@ class GravitationalWaveTransient(Likelihood):
     @meta_data.setter
     def meta_data(self, value):
         pass
+
+
+from .relative import RelativeBinningGravitationalWaveTransient  # noqa: E402,F401
+from .roq import ROQGravitationalWaveTransient, BilbyROQParamsRangeError  # noqa: E402,F401

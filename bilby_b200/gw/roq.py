@@ -1,0 +1,285 @@
+"""ROQGravitationalWaveTransient on B200 (bilby/gw/likelihood/roq.py:27-1229).
+
+Set-up (once per data set, host numpy like the reference): ROQ time grid (roq.py:747-767), linear weights by one
+inverse FFT per basis element and detector (roq.py:849-916), quadratic weights (roq.py:976-1004), or weights
+loaded from an .npz file written by ``save_weights``.  Evaluation on the device:
+  K6 ``bb_roq_kernel``          waveform at the nodes, <h|h> from the quadratic weights, <d|h> at the five ROQ
+                                times around the detector arrival time + cubic interpolation (roq.py:467-602)
+  K7 hlinear + ZGEMM + epilogue time marginalisation: the dense all-times contraction W conj(h) (roq.py:604-651)
+Single linear / quadratic basis given as ndarray, .npy file or precomputed weights; multi-basis selection and
+multibanded bases ship only as .hdf5 (h5py is not a dependency here) and raise NotImplementedError.
+"""
+import numpy as np
+
+from .. import _lib
+from ..core.utils import logger, create_frequency_series
+from .likelihood import GravitationalWaveTransient
+
+RADIUS_OF_EARTH = 6378136.6      # bilby/core/utils/constants.py:6
+SPEED_OF_LIGHT = 299792458.0
+
+
+class BilbyROQParamsRangeError(Exception):
+    pass
+
+
+class ROQGravitationalWaveTransient(GravitationalWaveTransient):
+    def __init__(self, interferometers, waveform_generator, priors, weights=None, linear_matrix=None,
+                 quadratic_matrix=None, roq_params=None, roq_params_check=True, roq_scale_factor=1,
+                 distance_marginalization=False, phase_marginalization=False, time_marginalization=False,
+                 jitter_time=True, delta_tc=None, distance_marginalization_lookup_table=None,
+                 reference_frame="sky", time_reference="geocenter", parameter_conversion=None, device=None):
+        if getattr(waveform_generator.frequency_domain_source_model, "_bb_kind", None) != "roq":
+            raise TypeError("ROQGravitationalWaveTransient needs one of the source models binary_black_hole_roq / "
+                            "binary_neutron_star_roq")
+        self._delta_tc = delta_tc
+        self._roq_host = None
+        self._full_time_prior = priors["geocent_time"] if priors is not None and "geocent_time" in priors else None
+        super().__init__(interferometers=interferometers, waveform_generator=waveform_generator, priors=priors,
+                         distance_marginalization=distance_marginalization,
+                         phase_marginalization=phase_marginalization, time_marginalization=time_marginalization,
+                         distance_marginalization_lookup_table=distance_marginalization_lookup_table,
+                         jitter_time=jitter_time, reference_frame=reference_frame, time_reference=time_reference,
+                         device=device)
+        self.roq_params_check = roq_params_check
+        self.roq_scale_factor = roq_scale_factor
+        if isinstance(roq_params, str):
+            self.roq_params_file = roq_params
+            roq_params = np.genfromtxt(roq_params, names=True)
+        elif not (roq_params is None or isinstance(roq_params, np.ndarray)):
+            raise TypeError("roq_params should be array or str")
+        self.roq_params = roq_params
+        if isinstance(weights, dict):
+            self.weights = weights
+        elif isinstance(weights, str):
+            self.weights = self.load_weights(weights)
+        else:
+            linear_matrix = self._parse_basis(linear_matrix, "linear")
+            quadratic_matrix = self._parse_basis(quadratic_matrix, "quadratic")
+            if self.roq_params is not None:
+                for ifo in self.interferometers:
+                    self.perform_roq_params_check(ifo)
+            self.weights = dict()
+            self._set_weights(linear_matrix, quadratic_matrix)
+        self.number_of_bases_linear = len(self.weights[f"{self.interferometers[0].name}_linear"])
+        self.number_of_bases_quadratic = len(self.weights[f"{self.interferometers[0].name}_quadratic"])
+        if self.number_of_bases_linear != 1 or self.number_of_bases_quadratic != 1:
+            raise NotImplementedError("multiple ROQ bases (prior-range selection, roq.py:402-439) are not supported")
+        self.parameter_conversion = parameter_conversion
+        for basis_type in ("linear", "quadratic"):
+            self._check_frequency_nodes_exist_for_single_basis(basis_type)
+        nodes_l = np.asarray(self.weights["frequency_nodes_linear"][0], dtype=float)
+        nodes_q = np.asarray(self.weights["frequency_nodes_quadratic"][0], dtype=float)
+        unique, inverse = np.unique(np.hstack((nodes_l, nodes_q)), return_inverse=True)
+        wa = self.waveform_generator.waveform_arguments
+        wa["frequency_nodes"] = unique                      # roq.py:206-213
+        wa["linear_indices"] = inverse[:len(nodes_l)]
+        wa["quadratic_indices"] = inverse[len(nodes_l):]
+        self._roq_host = self._pack_host_arrays(nodes_l, nodes_q)
+        self._upload_roq()
+
+    # ---- set-up --------------------------------------------------------------------------------
+    @property
+    def roq_params(self):
+        return self._roq_params
+
+    @roq_params.setter
+    def roq_params(self, roq_params):
+        if roq_params is not None:
+            if roq_params.shape != ():
+                raise ValueError(f"roq_params must be a scalar structured array; received shape {roq_params.shape}")
+            missing = {"flow", "fhigh", "seglen"}.difference(roq_params.dtype.names)
+            if missing:
+                raise ValueError("roq_params is missing required fields: " + ", ".join(sorted(missing)))
+        self._roq_params = roq_params
+
+    def _setup_time_marginalization(self):
+        """roq.py:320-331 (overrides base.py:1027-1035)."""
+        if self._delta_tc is None:
+            self._delta_tc = self._get_time_resolution()
+        tcmin = self.priors["geocent_time"].minimum
+        tcmax = self.priors["geocent_time"].maximum
+        number_of_time_samples = int(np.ceil((tcmax - tcmin) / self._delta_tc))
+        self._delta_tc = (tcmax - tcmin) / number_of_time_samples
+        self._times = tcmin + self._delta_tc / 2. + np.arange(number_of_time_samples) * self._delta_tc
+        self._beam_pattern_reference_time = (tcmin + tcmax) / 2.
+        self.time_prior_array = self.priors["geocent_time"].prob(self._times) * self._delta_tc
+
+    @staticmethod
+    def _parse_basis(basis, basis_type):
+        """roq.py:333-366 -> ndarray [n_basis, n_freq]."""
+        if isinstance(basis, str):
+            fmt = basis.split(".")[-1]
+            if fmt == "npy":
+                return np.load(basis)
+            if fmt == "hdf5":
+                raise NotImplementedError("hdf5 ROQ bases need h5py, which is not a dependency of bilby_b200")
+            raise IOError(f"Format {fmt} not recognized.")
+        if isinstance(basis, np.ndarray):
+            return basis.T
+        raise TypeError("basis needs to be str or np.ndarray")
+
+    def _check_frequency_nodes_exist_for_single_basis(self, basis_type):
+        """roq.py:278-295."""
+        key = f"frequency_nodes_{basis_type}"
+        wa = self.waveform_generator.waveform_arguments
+        if not (key in self.weights or key in wa):
+            raise AttributeError(f"{key} should be contained in weights or waveform arguments.")
+        elif key not in wa:
+            wa[key] = self.weights[key][0]
+        elif key not in self.weights:
+            self.weights[key] = [wa[key]]
+
+    def perform_roq_params_check(self, ifo=None):
+        """roq.py:653-734 (frequency / duration checks; the CBCPriorDict mass checks need astropy priors)."""
+        if self.roq_params_check is False:
+            logger.warning("No ROQ params checking performed")
+            return
+        p = self.roq_params
+        if float(ifo.maximum_frequency) > p["fhigh"] * self.roq_scale_factor:
+            raise BilbyROQParamsRangeError("Requested maximum frequency {} larger than ROQ basis fhigh {}".format(
+                ifo.maximum_frequency, p["fhigh"] * self.roq_scale_factor))
+        if float(ifo.minimum_frequency) < p["flow"] * self.roq_scale_factor:
+            raise BilbyROQParamsRangeError("Requested minimum frequency {} lower than ROQ basis flow {}".format(
+                ifo.minimum_frequency, p["flow"] * self.roq_scale_factor))
+        if float(ifo.strain_data.duration) != p["seglen"] / self.roq_scale_factor:
+            raise BilbyROQParamsRangeError("Requested duration differs from ROQ basis seglen")
+
+    def _get_time_resolution(self):
+        """roq.py:1165-1229: time step from the bandwidth the injected SNR can resolve, rounded so that
+        duration / delta_t is a power of two.  (PSD and frequencies of the LAST interferometer, like the
+        reference.)"""
+        from scipy.integrate import simpson
+        inj_snr_sq = 0
+        for ifo in self.interferometers:
+            inj_snr_sq += max(10, ifo.meta_data.get("optimal_SNR", 30)) ** 2
+        psd = ifo.power_spectral_density_array[ifo.frequency_mask]
+        freq = ifo.frequency_array[ifo.frequency_mask]
+        integral1 = simpson(y=np.power(freq, -7. / 3) / psd, x=freq)
+        f_3_bar = simpson(y=np.power(freq, 2. / 3.) / (psd * integral1), x=freq)
+        scaling = (np.pi ** 2 * inj_snr_sq / 6) ** (1 / 3)
+        delta_t = (scaling * f_3_bar ** (1 / 3)) ** -1 / 5
+        duration = self.interferometers.duration
+        n = max(duration / delta_t, self.interferometers.frequency_array[-1] * duration + 1)
+        n = int(2 ** np.ceil(np.log2(n)))
+        return duration / n
+
+    def _set_weights(self, linear_basis, quadratic_basis):
+        """roq.py:736-767 (time grid), 802-837 (basis / data frequency overlap), 849-916 (linear), 976-1004
+        (quadratic).  Bases: [n_basis, n_basis_freq]."""
+        time_space = self._get_time_resolution()
+        duration = self.interferometers.duration
+        start_time = self.interferometers.start_time
+        prior = self._full_time_prior
+        number_of_time_samples = int(duration / time_space)
+        crossing = 2 * RADIUS_OF_EARTH / SPEED_OF_LIGHT + 5 * time_space
+        start_idx = max(0, int(np.floor((prior.minimum - crossing - start_time) / time_space)))
+        end_idx = min(number_of_time_samples - 1, int(np.ceil((prior.maximum + crossing - start_time) / time_space)))
+        self.weights["time_samples"] = np.arange(start_idx, end_idx + 1) * float(time_space)
+        logger.info("Using {} ROQ time samples".format(len(self.weights["time_samples"])))
+        ts = self.weights["time_samples"]
+        space = ts[1] - ts[0]
+        n_time = int(duration / space)
+        lo, hi = int(ts[0] / space), int(ts[-1] / space)
+        for ifo in self.interferometers:
+            mask = ifo.frequency_mask
+            if self.roq_params is not None:
+                fhigh = self.roq_params["fhigh"] * self.roq_scale_factor
+                seglen = self.roq_params["seglen"] / self.roq_scale_factor
+                roq_f = create_frequency_series(sampling_frequency=fhigh * 2, duration=seglen)
+                roq_f = roq_f[roq_f >= self.roq_params["flow"] * self.roq_scale_factor]
+                _, ifo_idxs, roq_idxs = np.intersect1d(ifo.frequency_array[mask], roq_f, return_indices=True)
+            else:
+                roq_idxs = np.arange(linear_basis.shape[1], dtype=int)
+                ifo_idxs = np.arange(int(mask.sum()))
+                if len(ifo_idxs) != len(roq_idxs):
+                    raise ValueError("Mismatch between ROQ basis and frequency array for {}".format(ifo.name))
+            nonzero = ifo_idxs + int(ifo.minimum_frequency * duration)
+            d_over_s = ifo.frequency_domain_strain[mask][ifo_idxs] / ifo.power_spectral_density_array[mask][ifo_idxs]
+            # one inverse FFT per basis element, all elements at once: rows of `spec`
+            spec = np.zeros((linear_basis.shape[0], n_time), dtype=complex)
+            spec[:, nonzero] = d_over_s[None, :] * linear_basis[:, roq_idxs].conj()
+            lw = np.fft.ifft(spec, axis=1)[:, lo:hi + 1].T * (4. * n_time / duration)
+            self.weights[ifo.name + "_linear"] = [np.ascontiguousarray(lw)]
+            inv_psd = 1 / ifo.power_spectral_density_array[mask][ifo_idxs]
+            self.weights[ifo.name + "_quadratic"] = [4. / duration * quadratic_basis.real[:, roq_idxs] @ inv_psd]
+
+    def save_weights(self, filename, format="npz"):
+        """roq.py:1055-1100 (npz flavour)."""
+        if format != "npz":
+            raise IOError(f"Format {format} not supported here (hdf5 needs h5py).")
+        if format not in filename:
+            filename += "." + format
+        out = dict(time_samples=self.weights["time_samples"])
+        for basis_type in ("linear", "quadratic"):
+            for ifo in self.interferometers:
+                key = f"{ifo.name}_{basis_type}"
+                out[key] = self.weights[key][0]
+            key = f"frequency_nodes_{basis_type}"
+            out[key] = self.weights[key][0]
+        np.savez(filename, **out)
+
+    def load_weights(self, filename, format=None):
+        """roq.py:1102-1163 (npz flavour)."""
+        if format is None:
+            format = filename.split(".")[-1]
+        if format != "npz":
+            raise IOError(f"Format {format} not supported here (hdf5 needs h5py).")
+        f = np.load(filename)
+        weights = dict(time_samples=f["time_samples"])
+        for basis_type in ("linear", "quadratic"):
+            for ifo in self.interferometers:
+                key = f"{ifo.name}_{basis_type}"
+                weights[key] = [f[key]]
+            key = f"frequency_nodes_{basis_type}"
+            if key in f:
+                weights[key] = [f[key]]
+        return weights
+
+    def _pack_host_arrays(self, nodes_l, nodes_q):
+        ts = np.asarray(self.weights["time_samples"], dtype=float)
+        names = [ifo.name for ifo in self.interferometers]
+        wl = np.stack([np.asarray(self.weights[n + "_linear"][0], dtype=complex) for n in names])      # [d, t, i]
+        wq = np.stack([np.asarray(self.weights[n + "_quadratic"][0], dtype=float) for n in names])
+        if wl.shape[1] != len(ts) or wl.shape[2] != len(nodes_l) or wq.shape[1] != len(nodes_q):
+            raise ValueError("ROQ weights do not match the time samples / frequency nodes")
+        # time_samples = arange(start_idx, end_idx + 1) * time_space (roq.py:766): recover both exactly
+        if len(ts) > 1 and ts[0] != 0:
+            idx0 = int(round(ts[0] / (ts[1] - ts[0])))
+            step = ts[0] / idx0 if idx0 != 0 else ts[1] - ts[0]
+        else:
+            idx0, step = 0, ts[1] - ts[0]
+        if not np.allclose((idx0 + np.arange(len(ts))) * step, ts, rtol=0, atol=1e-12):
+            raise ValueError("ROQ time samples must be an integer-index multiple of the time step")
+        wlv = np.empty(wl.shape + (2,))
+        wlv[..., 0], wlv[..., 1] = wl.real, wl.imag
+        return dict(nodes_l=np.ascontiguousarray(nodes_l), nodes_q=np.ascontiguousarray(nodes_q),
+                    wl=np.ascontiguousarray(wlv), wq=np.ascontiguousarray(wq), n_time=len(ts), idx0=idx0,
+                    step=float(step))
+
+    def _upload_roq(self):
+        net = self.device_network
+        hst = self._roq_host
+        n_marg, t0, dtc, tref = 0, 0.0, 0.0, 0.0
+        if self.time_marginalization:
+            n_marg = len(self._times)
+            t0 = float(self._full_time_prior.minimum)
+            dtc = float(self._delta_tc)
+            tref = float(self._beam_pattern_reference_time)
+        _lib.check(net.lib.bb_set_roq(
+            net.ptr, len(hst["nodes_l"]), hst["nodes_l"].ctypes.data, len(hst["nodes_q"]), hst["nodes_q"].ctypes.data,
+            hst["n_time"], hst["idx0"], hst["step"], hst["wl"].ctypes.data, hst["wq"].ctypes.data, n_marg, t0, dtc,
+            tref))
+
+    def _configure(self):
+        super()._configure()
+        if self._roq_host is not None:
+            self._upload_roq()
+
+    @property
+    def basis_number_linear(self):
+        return 0
+
+    @property
+    def basis_number_quadratic(self):
+        return 0

@@ -47,5 +47,100 @@ def lal_binary_neutron_star(frequency_array, mass_1, mass_2, luminosity_distance
     return _evaluate(lal_binary_neutron_star, np.asarray(frequency_array), params, kwargs, _DEFAULTS_BNS)
 
 
+def _sequence(model, frequencies, params, kwargs, defaults):
+    """Polarisations at arbitrary frequencies (source.py:1068-1140) through bb_frequency_sequence_strain_device."""
+    from .waveform_generator import WaveformGenerator
+    wa = dict(defaults)
+    wa.update(kwargs)
+    for key in ("minimum_frequency", "maximum_frequency"):
+        wa.pop(key, None)
+    wfg = WaveformGenerator(duration=4.0, sampling_frequency=2048.0, frequency_domain_source_model=model,
+                            waveform_arguments=wa, parameter_conversion=lambda p: (p, []))
+    return wfg.frequency_sequence_strain(params, np.asarray(frequencies, dtype=float))
+
+
+def _bbh_params(mass_1, mass_2, luminosity_distance, a_1, tilt_1, phi_12, a_2, tilt_2, phi_jl, theta_jn, phase):
+    return dict(mass_1=mass_1, mass_2=mass_2, luminosity_distance=luminosity_distance, a_1=a_1, tilt_1=tilt_1,
+                phi_12=phi_12, a_2=a_2, tilt_2=tilt_2, phi_jl=phi_jl, theta_jn=theta_jn, phase=phase)
+
+
+def _relative_binning(model, grid_model, frequency_array, params, kwargs, defaults):
+    """source.py:724-799: fiducial = 1 -> waveform on the full grid, fiducial = 0 -> at frequency_bin_edges."""
+    kwargs = dict(kwargs)
+    fiducial = kwargs.pop("fiducial", 0)
+    if fiducial == 1:
+        kwargs.pop("frequency_bin_edges", None)
+        return _evaluate(grid_model, np.asarray(frequency_array), params, kwargs, defaults)
+    edges = kwargs.pop("frequency_bin_edges")
+    return _sequence(model, edges, params, kwargs, defaults)
+
+
+def lal_binary_black_hole_relative_binning(frequency_array, mass_1, mass_2, luminosity_distance, a_1, tilt_1, phi_12,
+                                           a_2, tilt_2, phi_jl, theta_jn, phase, **kwargs):
+    """source.py:724-761."""
+    params = _bbh_params(mass_1, mass_2, luminosity_distance, a_1, tilt_1, phi_12, a_2, tilt_2, phi_jl, theta_jn, phase)
+    return _relative_binning(lal_binary_black_hole_relative_binning, lal_binary_black_hole, frequency_array, params,
+                             kwargs, _DEFAULTS_BBH)
+
+
+def lal_binary_neutron_star_relative_binning(frequency_array, mass_1, mass_2, luminosity_distance, a_1, tilt_1,
+                                             phi_12, a_2, tilt_2, phi_jl, lambda_1, lambda_2, theta_jn, phase,
+                                             **kwargs):
+    """source.py:764-799."""
+    params = _bbh_params(mass_1, mass_2, luminosity_distance, a_1, tilt_1, phi_12, a_2, tilt_2, phi_jl, theta_jn, phase)
+    params.update(lambda_1=lambda_1, lambda_2=lambda_2)
+    return _relative_binning(lal_binary_neutron_star_relative_binning, lal_binary_neutron_star, frequency_array,
+                             params, kwargs, _DEFAULTS_BNS)
+
+
+def _roq(model, params, kwargs, defaults):
+    """source.py:802-898 _base_roq_waveform: waveform at the unique nodes, gathered into linear / quadratic order."""
+    wa = dict(kwargs)
+    if "frequency_nodes" not in wa:
+        size_linear = len(wa["frequency_nodes_linear"])
+        combined = np.hstack((wa.pop("frequency_nodes_linear"), wa.pop("frequency_nodes_quadratic")))
+        nodes, inverse = np.unique(combined, return_inverse=True)
+        linear_indices, quadratic_indices = inverse[:size_linear], inverse[size_linear:]
+    else:
+        linear_indices = wa.pop("linear_indices")
+        quadratic_indices = wa.pop("quadratic_indices")
+        for key in ("frequency_nodes_linear", "frequency_nodes_quadratic"):
+            wa.pop(key, None)
+        nodes = wa.pop("frequency_nodes")
+    pols = _sequence(model, nodes, params, wa, defaults)
+    if pols is None:
+        return None
+    return dict(linear=dict(plus=pols["plus"][linear_indices], cross=pols["cross"][linear_indices]),
+                quadratic=dict(plus=pols["plus"][quadratic_indices], cross=pols["cross"][quadratic_indices]))
+
+
+def binary_black_hole_roq(frequency_array, mass_1, mass_2, luminosity_distance, a_1, tilt_1, phi_12, a_2, tilt_2,
+                          phi_jl, theta_jn, phase, **waveform_arguments):
+    """source.py:693-706 (reference_frequency defaults to 20 Hz)."""
+    params = _bbh_params(mass_1, mass_2, luminosity_distance, a_1, tilt_1, phi_12, a_2, tilt_2, phi_jl, theta_jn, phase)
+    return _roq(binary_black_hole_roq, params, waveform_arguments, _DEFAULTS_BBH_ROQ)
+
+
+def binary_neutron_star_roq(frequency_array, mass_1, mass_2, luminosity_distance, a_1, tilt_1, phi_12, a_2, tilt_2,
+                            phi_jl, lambda_1, lambda_2, theta_jn, phase, **waveform_arguments):
+    """source.py:709-721."""
+    params = _bbh_params(mass_1, mass_2, luminosity_distance, a_1, tilt_1, phi_12, a_2, tilt_2, phi_jl, theta_jn, phase)
+    params.update(lambda_1=lambda_1, lambda_2=lambda_2)
+    return _roq(binary_neutron_star_roq, params, waveform_arguments, _DEFAULTS_BNS_ROQ)
+
+
+_DEFAULTS_BBH_ROQ = dict(waveform_approximant="IMRPhenomPv2", reference_frequency=20.0, catch_waveform_errors=False,
+                         pn_spin_order=-1, pn_tidal_order=-1, pn_phase_order=-1, pn_amplitude_order=0)
+_DEFAULTS_BNS_ROQ = dict(_DEFAULTS_BBH_ROQ, waveform_approximant="IMRPhenomD_NRTidal")
+
 lal_binary_black_hole._bb_defaults = _DEFAULTS_BBH
 lal_binary_neutron_star._bb_defaults = _DEFAULTS_BNS
+lal_binary_black_hole_relative_binning._bb_defaults = _DEFAULTS_BBH
+lal_binary_neutron_star_relative_binning._bb_defaults = _DEFAULTS_BNS
+binary_black_hole_roq._bb_defaults = _DEFAULTS_BBH_ROQ
+binary_neutron_star_roq._bb_defaults = _DEFAULTS_BNS_ROQ
+for _f, _k in ((lal_binary_black_hole, "grid"), (lal_binary_neutron_star, "grid"),
+               (lal_binary_black_hole_relative_binning, "relative_binning"),
+               (lal_binary_neutron_star_relative_binning, "relative_binning"),
+               (binary_black_hole_roq, "roq"), (binary_neutron_star_roq, "roq")):
+    _f._bb_kind = _k

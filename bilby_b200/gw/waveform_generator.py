@@ -88,6 +88,12 @@ class WaveformGenerator:
         known = {"waveform_approximant", "reference_frequency", "minimum_frequency", "maximum_frequency",
                  "catch_waveform_errors", "pn_spin_order", "pn_tidal_order", "pn_phase_order",
                  "pn_amplitude_order", "mode_array"}
+        kind = getattr(self.frequency_domain_source_model, "_bb_kind", "grid")
+        if kind == "relative_binning":       # source.py:724-799
+            known |= {"fiducial", "frequency_bin_edges"}
+        elif kind == "roq":                  # source.py:802-898
+            known |= {"frequency_nodes", "linear_indices", "quadratic_indices", "frequency_nodes_linear",
+                      "frequency_nodes_quadratic"}
         unused = set(wa) - known
         if unused:
             raise ValueError(f"There are unused waveform kwargs: {sorted(unused)}")   # source.py:687-688
@@ -96,7 +102,7 @@ class WaveformGenerator:
                 raise NotImplementedError(f"{key} != -1 is not supported by the device kernels")
         if wa.get("pn_amplitude_order", 0) != 0:
             raise NotImplementedError("pn_amplitude_order != 0 is not supported by the device kernels")
-        return (_params.APPROXIMANTS[name], float(wa["reference_frequency"]), float(wa["minimum_frequency"]),
+        return (_params.APPROXIMANTS[name], float(wa["reference_frequency"]), float(wa.get("minimum_frequency", 20.0)),
                 float(wa.get("maximum_frequency", 0.0) or 0.0))
 
     @property
@@ -177,6 +183,31 @@ class WaveformGenerator:
         result = dict(plus=arr[0, 0, :, 0] + 1j * arr[0, 0, :, 1], cross=arr[0, 1, :, 0] + 1j * arr[0, 1, :, 1])
         self._cache["waveform"] = result
         return result
+
+    def frequency_sequence_strain(self, parameters, frequencies):
+        """{"plus","cross"} at arbitrary frequencies (source.py:1068-1140 _base_waveform_frequency_sequence)."""
+        import torch
+        from .. import _lib
+        src = self._format_parameters(parameters)
+        h = self._get_handle()
+        approx, f_ref, f_min, f_max = self.approximant_config()
+        _lib.check(h.lib.bb_set_waveform(h.ptr, approx, f_ref, f_min, f_max))
+        rows = _params.pack_rows(src, 1, np)
+        dev = torch.device("cuda", h.device)
+        rows_d = torch.from_numpy(rows).to(dev)
+        fr = torch.from_numpy(np.ascontiguousarray(frequencies, dtype=np.float64)).to(dev)
+        nn = fr.shape[0]
+        out = torch.empty((1, 2, nn, 2), dtype=torch.float64, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(h.lib.bb_frequency_sequence_strain_device(h.ptr, rows_d.data_ptr(), 1, fr.data_ptr(), nn,
+                                                             float(frequencies[0]), out.data_ptr(),
+                                                             ctypes.c_void_p(stream)))
+        arr = out.cpu().numpy()
+        if self._domain_error(src, f_min):
+            if self.catch_waveform_errors:
+                return None
+            raise RuntimeError("Internal function call failed: Input domain error")
+        return dict(plus=arr[0, 0, :, 0] + 1j * arr[0, 0, :, 1], cross=arr[0, 1, :, 0] + 1j * arr[0, 1, :, 1])
 
     @staticmethod
     def _domain_error(src, f_min):

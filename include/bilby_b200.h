@@ -138,6 +138,13 @@ int bb_set_frequency_shard(bb_handle* h, int k_begin, int k_end);
 int bb_frequency_domain_strain_device(bb_handle* h, const double* params_dev, long n, double* out_dev,
                                       void* stream);
 
+/* Polarisations on a frequency SEQUENCE: replaces _base_waveform_frequency_sequence (bilby/gw/source.py:
+ * 1068-1140, lalsim SimInspiralChooseFDWaveformSequence) as used by the ROQ and relative-binning source models.
+ * Every frequency is evaluated (no f_min / f_max masking); first_frequency is the sequence's first element (the
+ * f_min of the upstream domain check).  frequencies_dev device double[n_nodes]; out double[n][2][n_nodes][2]. */
+int bb_frequency_sequence_strain_device(bb_handle* h, const double* params_dev, long n, const double* frequencies_dev,
+                                        int n_nodes, double first_frequency, double* out_dev, void* stream);
+
 /* Detector-frame strain: replaces Interferometer.get_detector_response (interferometer.py:303-368).
  * out double[n][n_det][n_freq][2]. */
 int bb_detector_response_device(bb_handle* h, const double* params_dev, long n, double* out_dev, void* stream);
@@ -168,6 +175,39 @@ int bb_project_polarizations_device(bb_handle* h, int det, const double* plus_de
  * b == NULL means the detector's own data (Interferometer.inner_product).  out: device double[2]. */
 int bb_noise_weighted_inner_product_device(bb_handle* h, int det, const double* a_dev, const double* b_dev,
                                            double* out_dev, void* stream);
+
+/* ---- Reduced-order likelihoods ------------------------------------
+ * Once one of the two set-up calls below has succeeded, bb_inner_products[_cal]_device and
+ * bb_log_likelihood_ratio[_cal]_{device,host} evaluate that likelihood instead of the full-grid one
+ * (same parameter rows, same outputs); n_edges = 0 / n_linear = 0 switches back.
+ *
+ * Relative binning: replaces RelativeBinningGravitationalWaveTransient.calculate_snrs and
+ * compute_waveform_ratio_per_interferometer (bilby/gw/likelihood/relative.py:365-430) with the source model
+ * lal_binary_*_relative_binning evaluated at the bin edges (bilby/gw/source.py:724-799, fiducial = 0).
+ *   bin_freqs host double[n_edges]                  (relative.py:179-240 setup_bins)
+ *   fiducial  host double[n_det][n_edges][2]        per_detector_fiducial_waveform_points (relative.py:236-240)
+ *   summary   host double[n_det][4][n_edges-1][2]   a0, a1, b0, b1 (relative.py:319-363 compute_summary_data)
+ * With BB_MARG_TIME the full-grid reconstruction of relative.py:380-421 is used: pass also
+ *   fiducial_grid host double[n_det][n_freq][2] (per_detector_fiducial_waveforms) and bin_inds host int[n_edges];
+ *   both may be NULL when time marginalisation is off. */
+int bb_set_relative_binning(bb_handle* h, int n_edges, const double* bin_freqs, const double* fiducial,
+                            const double* summary, const double* fiducial_grid, const int* bin_inds);
+
+/* ROQ: replaces ROQGravitationalWaveTransient.calculate_snrs, _closest_time_indices, _interp_five_samples and
+ * _calculate_d_inner_h_array (bilby/gw/likelihood/roq.py:467-651) with the source model binary_*_roq
+ * (bilby/gw/source.py:693-721, 802-898) evaluated at the ROQ frequency nodes.
+ *   nodes_linear host double[n_linear], nodes_quadratic host double[n_quadratic]   (weights['frequency_nodes_*'])
+ *   weights_linear    host double[n_det][n_time][n_linear][2]   weights['{IFO}_linear'][0]   (roq.py:849-916)
+ *   weights_quadratic host double[n_det][n_quadratic]           weights['{IFO}_quadratic'][0] (roq.py:976-1004)
+ *   time_samples = (time_start_index + i) * time_step, i < n_time   weights['time_samples']   (roq.py:747-766)
+ * Time marginalisation (BB_MARG_TIME): the likelihood's own time grid (roq.py:320-331)
+ *   marg_times = marg_time_start + j * marg_delta_tc, j < n_marg_times, antenna response and delays at
+ *   beam_pattern_reference_time; the all-times contraction W conj(h_linear) of roq.py:638 runs as one
+ *   double-complex GEMM per detector. */
+int bb_set_roq(bb_handle* h, int n_linear, const double* nodes_linear, int n_quadratic, const double* nodes_quadratic,
+               int n_time, long time_start_index, double time_step, const double* weights_linear,
+               const double* weights_quadratic, int n_marg_times, double marg_time_start, double marg_delta_tc,
+               double beam_pattern_reference_time);
 
 /* Measurement hooks (bench.py).  With profiling enabled the handle brackets every launch of the
  * dominant kernel (K1, the fused inner-product kernel) with CUDA events on the launching stream;

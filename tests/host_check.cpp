@@ -51,6 +51,7 @@ int main(int argc, char** argv) {
         net.sampling_frequency = in[o++];
         net.start_time = in[o++];
         BBWaveformConfig wf;
+        memset(&wf, 0, sizeof(wf));
         wf.approximant = (int)in[o++];
         wf.add_jitter = 0;
         wf.f_ref = in[o++];
