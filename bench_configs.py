@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""Measurement of the BASELINE.json configurations that are NOT the headline bench line (bench.py measures
+configs[1]).  One JSON line per configuration: device-resident throughput, end-to-end throughput through the
+host entry point, and the roofline of the dominant kernel (CUDA events around its launches, algorithmic work per
+SURVEY.md section 8d / DESIGN.md section 4).  Used for the ncu captures under profiles/ as well.
+
+    python bench_configs.py --config cfg0|cfg2|cfg3|cfg4_relbin|cfg4_roq|cfg4_roq_time [--batch N] [--steps K]
+
+  cfg0          configs[0]: BBH 4 s H1+L1, no marginalisation                      (K0 + K1 + K3)
+  cfg2          configs[2]: BBH 8 s H1L1V1, time marginalisation + CubicSpline     (K0 + K4)
+  cfg3          configs[3]: BNS TaylorF2+tides 128 s @ 4096 Hz H1L1V1             (K0 + K1<TaylorF2>)
+  cfg4_relbin   configs[4]: relative binning for the 128 s BNS                     (K0 + K5)
+  cfg4_roq      configs[4]: ROQ for the 128 s BNS, synthetic basis                 (K0 + K6)
+  cfg4_roq_time configs[4]: ROQ with time marginalisation (dense contraction)      (K0 + K7: hlinear + ZGEMM + epilogue)
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import bench as hb  # noqa: E402  (helpers: ClockSampler, MTSUN)
+
+T_INJ = 1126259642.413
+BNS_INJ = dict(mass_1=1.5, mass_2=1.3, chi_1=0.02, chi_2=0.01, luminosity_distance=100.0, theta_jn=0.4, psi=2.659,
+               phase=1.3, geocent_time=T_INJ, ra=1.375, dec=-1.2108, lambda_1=400.0, lambda_2=600.0)
+NOISE_SEED = 88170235
+
+
+def bns_draws(n, rng, narrow=False):
+    if narrow:     # the box a relative-binning / ROQ analysis of this event would use
+        mc0 = (1.5 * 1.3) ** 0.6 / 2.8 ** 0.2
+        mc = mc0 * (1 + rng.uniform(-1e-4, 1e-4, n))
+        q = rng.uniform(0.8, 0.95, n)
+        t = rng.uniform(T_INJ - 2e-3, T_INJ + 2e-3, n)
+    else:
+        mc, q, t = rng.uniform(1.15, 1.25, n), rng.uniform(0.5, 1.0, n), rng.uniform(T_INJ - 0.1, T_INJ + 0.1, n)
+    return dict(chirp_mass=mc, mass_ratio=q, chi_1=rng.uniform(-0.05, 0.05, n), chi_2=rng.uniform(-0.05, 0.05, n),
+                luminosity_distance=(10.0 ** 3 + rng.uniform(0, 1, n) * (500.0 ** 3 - 10.0 ** 3)) ** (1 / 3),
+                theta_jn=np.arccos(rng.uniform(-1, 1, n)), psi=rng.uniform(0, np.pi, n),
+                phase=rng.uniform(0, 2 * np.pi, n), ra=rng.uniform(0, 2 * np.pi, n),
+                dec=np.arcsin(rng.uniform(-1, 1, n)), geocent_time=t,
+                lambda_1=rng.uniform(0, 5000, n), lambda_2=rng.uniform(0, 5000, n))
+
+
+def make_ifos(names, fs, duration, start, wfg, inj):
+    from bilby_b200.gw.detector import InterferometerList
+    ifos = InterferometerList(names)
+    ifos.set_strain_data_from_power_spectral_densities(fs, duration, start, rng=np.random.default_rng(NOISE_SEED))
+    ifos.inject_signal(parameters=dict(inj), waveform_generator=wfg)
+    return ifos
+
+
+def build(config, n):
+    """-> (likelihood, rows [n,16], cal or None, flop_per_eval(rows) callable, description dict)."""
+    import bilby_b200 as bb
+    from bilby_b200.core.prior import PriorDict, Uniform, PowerLaw
+    from bilby_b200.gw import conversion, source
+    from bilby_b200.workloads import INJECTION, draw_bbh_prior
+    rng = np.random.default_rng(hb.DRAW_SEED)
+    if config in ("cfg0", "cfg2"):
+        duration = 4.0 if config == "cfg0" else 8.0
+        names = ["H1", "L1"] if config == "cfg0" else ["H1", "L1", "V1"]
+        fs = 2048.0
+        inj = dict(INJECTION)
+        start = inj["geocent_time"] - duration + 2
+        wfg = bb.gw.WaveformGenerator(duration=duration, sampling_frequency=fs, start_time=start,
+                                      frequency_domain_source_model=source.lal_binary_black_hole,
+                                      waveform_arguments=dict(waveform_approximant="IMRPhenomD",
+                                                              reference_frequency=50.0, minimum_frequency=20.0))
+        ifos = make_ifos(names, fs, duration, start, wfg, inj)
+        draws = draw_bbh_prior(n, rng)
+        df = 1.0 / duration
+        msec = None
+        if config == "cfg0":
+            like = bb.gw.GravitationalWaveTransient(ifos, wfg)
+            rows = like.pack(draws)
+            cal = None
+            per_bin, extra = 240 + 30 * 2, 10
+            work = "configs[0]: BBH 4s@2048Hz H1+L1 IMRPhenomD, no marginalisation"
+            kernel = "bb_inner_product_kernel<2,IMRPhenomD>"
+        else:
+            from bilby_b200.gw.detector.calibration import CubicSpline
+            for ifo in ifos:
+                ifo.calibration_model = CubicSpline(f"recalib_{ifo.name}_", ifo.minimum_frequency,
+                                                    ifo.maximum_frequency, 10)
+            pri = PriorDict(dict(geocent_time=Uniform(T_INJ - 0.1, T_INJ + 0.1, "geocent_time")))
+            like = bb.gw.GravitationalWaveTransient(ifos, wfg, time_marginalization=True, jitter_time=True, priors=pri)
+            draws["geocent_time"] = np.full(n, float(start))
+            draws["time_jitter"] = rng.uniform(-1 / fs, 1 / fs, n)
+            crng = np.random.default_rng(99)
+            for name in names:
+                for i in range(10):
+                    draws[f"recalib_{name}_amplitude_{i}"] = crng.normal(0, 0.05, n)
+                    draws[f"recalib_{name}_phase_{i}"] = crng.normal(0, 0.05, n)
+            rows = like.pack(draws)
+            cal = like._cal_from_parameters(draws, n, np)
+            per_bin = 240 + 70 * 3
+            n_prior = int(0.2 * fs / 2)
+            extra = 5 * 8192 * 13 + 120 * n_prior
+            work = "configs[2]: BBH 8s@2048Hz H1L1V1 IMRPhenomD, time marginalisation (8192-pt FFT) + CubicSpline(10)"
+            kernel = "bb_time_marg_kernel<3,IMRPhenomD,CAL>"
+
+        def flop(rows_):
+            msec = (rows_[:, 0] + rows_[:, 1]) * hb.MTSUN
+            fmp = np.minimum(fs / 2, 0.2 / msec)
+            k1 = np.minimum(np.floor(fmp / df), np.floor(fs / 2 / df) + 1)
+            bins = np.maximum(k1 - np.ceil(20.0 / df), 0)
+            return float(np.sum(bins) * per_bin + len(rows_) * extra), float(np.mean(bins))
+        return like, rows, cal, flop, dict(workload=work, kernel=kernel)
+
+    # ---- 128 s BNS family
+    duration, fs = 128.0, 4096.0
+    names = ["H1", "L1", "V1"]
+    inj = dict(BNS_INJ)
+    start = T_INJ - duration + 2
+    conv = conversion.convert_to_lal_binary_neutron_star_parameters
+    wa = dict(waveform_approximant="TaylorF2", reference_frequency=50.0, minimum_frequency=20.0)
+    wfg_full = bb.gw.WaveformGenerator(duration=duration, sampling_frequency=fs, start_time=start,
+                                       frequency_domain_source_model=source.lal_binary_neutron_star,
+                                       parameter_conversion=conv, waveform_arguments=dict(wa))
+    ifos = make_ifos(names, fs, duration, start, wfg_full, inj)
+    n_masked = int(ifos[0].frequency_mask.sum())
+    if config == "cfg3":
+        like = bb.gw.GravitationalWaveTransient(ifos, wfg_full)
+        rows = like.pack(bns_draws(n, rng))
+        per = (170 + 30 * 3) * n_masked
+        return like, rows, None, (lambda r: (float(len(r)) * per, float(n_masked))), dict(
+            workload="configs[3]: BNS TaylorF2+tides 128s@4096Hz H1L1V1 (259585 masked bins/detector), no "
+                     "marginalisation, one GPU holds the whole frequency axis", kernel="bb_inner_product_kernel<3,TaylorF2>")
+    mc0 = (1.5 * 1.3) ** 0.6 / 2.8 ** 0.2
+    fid = dict(inj)
+    fid.pop("mass_1"), fid.pop("mass_2")
+    fid.update(chirp_mass=mc0, mass_ratio=1.3 / 1.5)
+    if config == "cfg4_relbin":
+        wfg = bb.gw.WaveformGenerator(duration=duration, sampling_frequency=fs, start_time=start,
+                                      frequency_domain_source_model=source.lal_binary_neutron_star_relative_binning,
+                                      parameter_conversion=conv, waveform_arguments=dict(wa))
+        like = bb.gw.likelihood.RelativeBinningGravitationalWaveTransient(ifos, wfg, fiducial_parameters=fid,
+                                                                          epsilon=0.5, chi=1)
+        rows = like.pack(bns_draws(n, rng, narrow=True))
+        ne = len(like.bin_freqs)
+        per = (170 + 105 * 3) * ne
+        return like, rows, None, (lambda r: (float(len(r)) * per, float(ne))), dict(
+            workload=f"configs[4]: relative binning (epsilon=0.5, chi=1, {ne - 1} bins) for the 128s BNS, H1L1V1",
+            kernel="bb_relbin_kernel<3,TaylorF2>", n_edges=ne)
+    # ---- ROQ with a synthetic empirical-interpolation basis built from device waveforms (set-up, untimed)
+    import torch
+    tm = config == "cfg4_roq_time"
+    n_lin, n_quad, n_train = (256, 96, 384)
+    freqs = ifos[0].frequency_array[ifos[0].frequency_mask]
+    train = bns_draws(n_train, np.random.default_rng(5), narrow=True)
+    h = wfg_full._get_handle()
+    from bilby_b200 import _lib
+    from bilby_b200.gw import _params
+    approx, f_ref, f_min, f_max = wfg_full.approximant_config()
+    _lib.check(h.lib.bb_set_waveform(h.ptr, approx, 20.0, f_min, f_max))
+    conv_tr, _ = conv(dict(train))
+    conv_tr["luminosity_distance"] = np.ones(n_train)
+    conv_tr["theta_jn"] = np.zeros(n_train)
+    conv_tr["phase"] = np.zeros(n_train)
+    rows_tr = torch.from_numpy(_params.pack_rows(conv_tr, n_train, np)).cuda()
+    fr = torch.from_numpy(np.ascontiguousarray(freqs)).cuda()
+    out = torch.empty((n_train, 2, len(freqs), 2), dtype=torch.float64, device="cuda")
+    _lib.check(h.lib.bb_frequency_sequence_strain_device(h.ptr, rows_tr.data_ptr(), n_train, fr.data_ptr(), len(freqs),
+                                                         float(freqs[0]), out.data_ptr(), None))
+    hp = torch.view_as_complex(out[:, 0].contiguous())           # [n_train, n_freq]
+    del out
+
+    def interpolant(tr, nb):
+        tr = tr / torch.linalg.norm(tr, dim=1, keepdim=True)
+        _, _, vh = torch.linalg.svd(tr, full_matrices=False)
+        v = vh[:nb].T.contiguous()                                 # [n_freq, nb]
+        nodes = [int(torch.argmax(v[:, 0].abs()))]
+        for j in range(1, nb):
+            idx = torch.tensor(nodes, device=v.device)
+            c = torch.linalg.solve(v[idx, :j], v[idx, j])
+            r = v[:, j] - v[:, :j] @ c
+            r[idx] = 0
+            nodes.append(int(torch.argmax(r.abs())))
+        nodes = np.array(sorted(nodes))
+        idx = torch.tensor(nodes, device=v.device)
+        b = v @ torch.linalg.inv(v[idx, :])
+        return b.cpu().numpy(), nodes
+    bl, nl = interpolant(hp, n_lin)
+    bq, nq = interpolant((hp.abs() ** 2).to(torch.complex128), n_quad)
+    del hp
+    torch.cuda.empty_cache()
+    wfg = bb.gw.WaveformGenerator(duration=duration, sampling_frequency=fs, start_time=start,
+                                  frequency_domain_source_model=source.binary_neutron_star_roq,
+                                  parameter_conversion=conv,
+                                  waveform_arguments=dict(waveform_approximant="TaylorF2", reference_frequency=20.0,
+                                                          frequency_nodes_linear=freqs[nl],
+                                                          frequency_nodes_quadratic=freqs[nq]))
+    pri = dict(geocent_time=Uniform(T_INJ - 0.05, T_INJ + 0.05, "geocent_time"))
+    kw = {}
+    if tm:
+        pri["phase"] = Uniform(0, 2 * np.pi, "phase")
+        kw = dict(time_marginalization=True, phase_marginalization=True, jitter_time=True)
+    t0 = time.time()
+    like = bb.gw.likelihood.ROQGravitationalWaveTransient(ifos, wfg, PriorDict(pri), linear_matrix=bl,
+                                                          quadratic_matrix=bq, **kw)
+    n_time = len(like.weights["time_samples"])
+    sys.stderr.write(f"ROQ weights: {n_time} time samples x {n_lin} linear, {n_quad} quadratic, built in "
+                     f"{time.time() - t0:.1f} s\n")
+    draws = bns_draws(n, rng, narrow=True)
+    if tm:
+        draws["geocent_time"] = np.full(n, float(start))
+        draws["time_jitter"] = rng.uniform(-like._delta_tc / 2, like._delta_tc / 2, n)
+        per = (170 + 20) * n_lin + 100 * n_quad + 8 * n_time * n_lin * 3 + len(like._times) * (3 * 40 + 100)
+        work = (f"configs[4]: ROQ (synthetic basis N_l={n_lin}, N_q={n_quad}, {n_time} ROQ times) + time&phase "
+                f"marginalisation ({len(like._times)} times) for the 128s BNS: dense W conj(h) contraction")
+        kernel = "bb_roq_hlinear_kernel + cublas ZGEMM + bb_roq_time_marg_kernel"
+    else:
+        per = (170 + 60 + 120) * n_lin + (100 + 6) * n_quad
+        work = (f"configs[4]: ROQ (synthetic basis N_l={n_lin}, N_q={n_quad}, {n_time} ROQ times) for the 128s BNS, "
+                "H1L1V1")
+        kernel = "bb_roq_kernel<3,TaylorF2>"
+    rows = like.pack(draws)
+    return like, rows, None, (lambda r: (float(len(r)) * per, float(n_lin))), dict(
+        workload=work, kernel=kernel, n_linear=n_lin, n_quadratic=n_quad, n_time=n_time)
+
+
+DEFAULT_BATCH = dict(cfg0=1_000_000, cfg2=100_000, cfg3=8192, cfg4_relbin=1_000_000, cfg4_roq=1_000_000,
+                     cfg4_roq_time=65536)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", required=True, choices=sorted(DEFAULT_BATCH))
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    args = ap.parse_args()
+    import torch
+    from bilby_b200 import _lib
+    if not torch.cuda.is_available():
+        raise SystemExit("bench_configs.py needs a CUDA device (bilby_b200 has no CPU path)")
+    n = args.batch or DEFAULT_BATCH[args.config]
+    like, rows_np, cal_np, flop, desc = build(args.config, n)
+    net = like.device_network
+    lib = net.lib
+    rows_np = np.ascontiguousarray(rows_np)
+    rows_dev = torch.from_numpy(rows_np).cuda()
+    cal_dev = torch.from_numpy(np.ascontiguousarray(cal_np)).cuda() if cal_np is not None else None
+    stream = torch.cuda.current_stream()
+    peak = ctypes.c_double(0.0)
+    _lib.check(lib.bb_fp64_peak(net.ptr, ctypes.byref(peak)))
+
+    def step_device():
+        return like._evaluate_device(rows_dev, cal_dev)
+
+    for _ in range(max(3, args.warmup)):
+        out = step_device()
+    torch.cuda.synchronize()
+    _lib.check(lib.bb_profile_enable(net.ptr, 1))
+    launches0 = lib.bb_launch_count(net.ptr)
+    clocks = hb.ClockSampler(0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        out = step_device()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms_total = e0.elapsed_time(e1)
+    launches = lib.bb_launch_count(net.ptr) - launches0
+    k_ms, k_n = ctypes.c_double(0.0), ctypes.c_long(0)
+    _lib.check(lib.bb_profile_read(net.ptr, ctypes.byref(k_ms), ctypes.byref(k_n)))
+    _lib.check(lib.bb_profile_enable(net.ptr, 0))
+    # end to end through the host entry point
+    like.log_likelihood_ratio_rows_host(rows_np, cal_np)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = like.log_likelihood_ratio_rows_host(rows_np, cal_np)
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    clock_info = clocks.stop()
+    total_flop, units = flop(rows_np)
+    k_avg = k_ms.value / max(1, k_n.value) * (k_n.value / args.steps)       # dominant-kernel time per step
+    achieved = total_flop / (k_avg * 1e-3) / 1e12 if k_avg > 0 else 0.0
+    fin = np.isfinite(res)
+    line = dict(metric="log-likelihood evals/sec", config=dict(desc, batch=n), value=n * args.steps / (ms_total * 1e-3),
+                unit="evals/s", n_gpus=1, steps=args.steps, warmup=max(3, args.warmup), ms_per_step=ms_total / args.steps,
+                dtype="f64", data="synthetic", clocks=clock_info,
+                e2e=dict(value=n * args.steps / (e2e_ms * 1e-3), unit="evals/s", ms_per_step=e2e_ms / args.steps,
+                         h2d_bytes_per_step=int(rows_np.nbytes + (cal_np.nbytes if cal_np is not None else 0)),
+                         d2h_bytes_per_step=n * 8),
+                gpu_launches=int(launches),
+                roofline=dict(bound="fp64", achieved=achieved, peak=peak.value, unit="TFLOP/s",
+                              frac=achieved / peak.value if peak.value else None, kernel=desc["kernel"],
+                              kernel_ms_per_step=k_avg, kernel_share_of_step=k_avg / (ms_total / args.steps),
+                              algorithmic_flop_per_step=total_flop, units_per_eval=units,
+                              peak_source="in-run DFMA stream kernel (bb_fp64_peak)"),
+                checksum_lnl=float(np.sum(res[fin])), finite_fraction=float(fin.mean()))
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -457,6 +457,23 @@ static int bb_ensure_scratch(bb_handle* h, size_t n) {
     return 0;
 }
 
+// measurement hook: bracket the dominant kernel(s) of an evaluation with events on the launching stream
+struct BBProfScope {
+    bb_handle* h;
+    cudaStream_t st;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    BBProfScope(bb_handle* h_, cudaStream_t st_) : h(h_), st(st_) {
+        if (h->profile && cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess)
+            cudaEventRecord(e0, st);
+    }
+    ~BBProfScope() {
+        if (e0 && e1) {
+            cudaEventRecord(e1, st);
+            h->k1_events.emplace_back(e0, e1);
+        }
+    }
+};
+
 static BBTiles bb_tiles(const bb_handle* h) {
     BBTiles t;
     t.u = h->d_u;
@@ -719,18 +736,11 @@ static int bb_launch_inner_t(bb_handle* h, long n, double* out, cudaStream_t st)
     const long n_blocks = (n + BB_K1_SB - 1) / BB_K1_SB;
     long grid = (long)h->sm_count;
     if (grid > n_blocks) grid = n_blocks;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (h->profile) {
-        BB_CUDA(cudaEventCreate(&e0));
-        BB_CUDA(cudaEventCreate(&e1));
-        BB_CUDA(cudaEventRecord(e0, st));
-    }
-    bb_inner_product_kernel<NDET, APPROX, CAL><<<(unsigned)grid, BB_K1_THREADS, smem, st>>>(
-        h->d_coef, h->perm_valid ? h->d_perm : nullptr, n, bb_tiles(h), h->net.df, h->shard_lo, h->shard_hi,
-        h->d_calrec, h->cal, out);
-    if (h->profile) {
-        BB_CUDA(cudaEventRecord(e1, st));
-        h->k1_events.emplace_back(e0, e1);
+    {
+        BBProfScope prof(h, st);
+        bb_inner_product_kernel<NDET, APPROX, CAL><<<(unsigned)grid, BB_K1_THREADS, smem, st>>>(
+            h->d_coef, h->perm_valid ? h->d_perm : nullptr, n, bb_tiles(h), h->net.df, h->shard_lo, h->shard_hi,
+            h->d_calrec, h->cal, out);
     }
     h->launches++;
     BB_CUDA(cudaGetLastError());

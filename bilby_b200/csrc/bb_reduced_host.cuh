@@ -161,12 +161,7 @@ template <int NDET, int APPROX, bool CAL>
 static int bb_launch_reduced_t(bb_handle* h, long n, double* out, cudaStream_t st) {
     const size_t smem = (size_t)BB_RED_WARPS * (BC_NCOEF + (CAL ? NDET * 4 * h->cal.n_points : 0)) * sizeof(double);
     const long grid = bb_red_grid(h, n);
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (h->profile) {
-        BB_CUDA(cudaEventCreate(&e0));
-        BB_CUDA(cudaEventCreate(&e1));
-        BB_CUDA(cudaEventRecord(e0, st));
-    }
+    BBProfScope prof(h, st);
     if (h->kind == 1) {
         BB_CUDA(cudaFuncSetAttribute(bb_relbin_kernel<NDET, APPROX, CAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         bb_relbin_kernel<NDET, APPROX, CAL><<<(unsigned)grid, BB_RED_THREADS, smem, st>>>(
@@ -175,10 +170,6 @@ static int bb_launch_reduced_t(bb_handle* h, long n, double* out, cudaStream_t s
         BB_CUDA(cudaFuncSetAttribute(bb_roq_kernel<NDET, APPROX, CAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         bb_roq_kernel<NDET, APPROX, CAL><<<(unsigned)grid, BB_RED_THREADS, smem, st>>>(
             h->d_coef, n, *h->rq, h->d_calrec, h->cal, out);
-    }
-    if (h->profile) {
-        BB_CUDA(cudaEventRecord(e1, st));
-        h->k1_events.emplace_back(e0, e1);
     }
     h->launches++;
     BB_CUDA(cudaGetLastError());
@@ -207,6 +198,7 @@ static int bb_launch_roq_time_marg_t(bb_handle* h, long n, double* out, cudaStre
     BB_CUDA(cudaFuncSetAttribute(bb_roq_hlinear_kernel<NDET, APPROX, CAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (cublasSetStream(h->cublas, st) != CUBLAS_STATUS_SUCCESS) return bb_fail("cublasSetStream failed");
     const cuDoubleComplex one = make_cuDoubleComplex(1.0, 0.0), zero = make_cuDoubleComplex(0.0, 0.0);
+    BBProfScope prof(h, st);
     for (long s0 = 0; s0 < n; s0 += (long)chunk) {
         const long m = (n - s0) < (long)chunk ? (n - s0) : (long)chunk;
         const long grid = bb_red_grid(h, m);
@@ -241,7 +233,7 @@ static int bb_launch_relbin_time_marg_t(bb_handle* h, long n, double* out, cudaS
     const int nfft = h->nfft, nb = rb.edges.n - 1;
     int log2n = 0;
     while ((1 << log2n) < nfft) ++log2n;
-    const size_t smem = ((size_t)nfft + (size_t)nb * NDET * 2) * sizeof(double2)
+    const size_t smem = (bb_tm_series_elems(nfft) + (size_t)nb * NDET * 2) * sizeof(double2)
                         + (BC_NCOEF + 33 + (CAL ? NDET * 4 * h->cal.n_points : 0)) * sizeof(double);
     if (smem > 227 * 1024) return bb_fail("relative binning time marginalisation: series + bins do not fit shared memory");
     BB_CUDA(cudaFuncSetAttribute(bb_relbin_time_marg_kernel<NDET, APPROX, CAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -249,9 +241,12 @@ static int bb_launch_relbin_time_marg_t(bb_handle* h, long n, double* out, cudaS
     per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
     long grid = (long)h->sm_count * per_sm;
     if (grid > n) grid = n;
-    bb_relbin_time_marg_kernel<NDET, APPROX, CAL><<<(unsigned)grid, BB_TM_THREADS, smem, st>>>(
-        h->d_coef, n, rb, h->net.n_freq, h->net.df, nfft, log2n, h->d_twiddle, h->marg, h->net.start_time,
-        h->net.duration, h->d_calrec, h->cal, out);
+    {
+        BBProfScope prof(h, st);
+        bb_relbin_time_marg_kernel<NDET, APPROX, CAL><<<(unsigned)grid, BB_TM_THREADS, smem, st>>>(
+            h->d_coef, n, rb, h->net.n_freq, h->net.df, nfft, log2n, h->d_twiddle, h->marg, h->net.start_time,
+            h->net.duration, h->d_calrec, h->cal, out);
+    }
     h->launches++;
     BB_CUDA(cudaGetLastError());
     return 0;
