@@ -93,23 +93,45 @@ struct BBCalGrid {
     int n_points;                    // 0 = no calibration model
     double l0[BB_MAX_DET];           // log10 of the first node
     double inv_delta[BB_MAX_DET];    // 1 / node spacing in log10 f
+    int shared;                      // every detector has the same node grid: bin weights computed once per bin
 };
 
 // calibration factor C = (1 + dA) (2 + i dphi) / (2 - i dphi) = amp1 * (cr + i ci), |cr + i ci| = 1.
 // rec: [4][n] = node amplitudes, their spline coefficients, node phases, their spline coefficients
-BB_HD void bb_cal_factor(const double* rec, int n, double l0, double inv_delta, double lf, double* amp1,
-                         double* cr, double* ci) {
+// spline bin weights: depend only on the frequency and the node grid (calibration.py:368-376)
+struct BBCalW {
+    int j;
+    double a, b, c, d;
+};
+BB_HD BBCalW bb_cal_weights(int n, double l0, double inv_delta, double lf) {
+    BBCalW w;
     const double x = (lf * 0.43429448190325182765 - l0) * inv_delta;       // log10 f = ln f / ln 10
     int j = (int)x;                                                         // astype(int): truncation
     j = j < 0 ? 0 : (j > n - 2 ? n - 2 : j);
-    const double b = x - (double)j, a = 1.0 - b;
-    const double c = (a * a * a - a) / 6.0, d = (b * b * b - b) / 6.0;
-    const double dA = a * rec[j] + b * rec[j + 1] + c * rec[n + j] + d * rec[n + j + 1];
-    const double dP = a * rec[2 * n + j] + b * rec[2 * n + j + 1] + c * rec[3 * n + j] + d * rec[3 * n + j + 1];
+    w.j = j;
+    w.b = x - (double)j;
+    w.a = 1.0 - w.b;
+    w.c = (w.a * w.a * w.a - w.a) / 6.0;
+    w.d = (w.b * w.b * w.b - w.b) / 6.0;
+    return w;
+}
+BB_HD void bb_cal_apply(const double* rec, int n, const BBCalW& w, double* amp1, double* cr, double* ci) {
+    const int j = w.j;
+    const double dA = w.a * rec[j] + w.b * rec[j + 1] + w.c * rec[n + j] + w.d * rec[n + j + 1];
+    const double dP = w.a * rec[2 * n + j] + w.b * rec[2 * n + j + 1] + w.c * rec[3 * n + j] + w.d * rec[3 * n + j + 1];
+#ifdef __CUDA_ARCH__
+    const double den = __drcp_rn(4.0 + dP * dP);
+#else
     const double den = 1.0 / (4.0 + dP * dP);
+#endif
     *amp1 = 1.0 + dA;
     *cr = (4.0 - dP * dP) * den;
     *ci = 4.0 * dP * den;
+}
+BB_HD void bb_cal_factor(const double* rec, int n, double l0, double inv_delta, double lf, double* amp1,
+                         double* cr, double* ci) {
+    const BBCalW w = bb_cal_weights(n, l0, inv_delta, lf);
+    bb_cal_apply(rec, n, w, amp1, cr, ci);
 }
 
 struct BBQnmTable {

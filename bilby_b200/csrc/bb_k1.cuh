@@ -192,6 +192,8 @@ __device__ __forceinline__ void bb_k1_accumulate(K1State<NDET>& st, const K1Tile
     A = act ? A : 0.0;
     const double zr = A * cs, zi = A * sn;      // A e^{+i Phi} = conj(h22 incl. geocentric shift)
     const double A2 = A * A;
+    BBCalW cw;
+    if (CAL) cw = bb_cal_weights(st.grid.n_points, st.grid.l0[0], st.grid.inv_delta[0], tile.lf[i]);
 #pragma unroll
     for (int d = 0; d < NDET; ++d) {
         const double rc = st.ramp[d][0], rs = st.ramp[d][1];
@@ -200,8 +202,9 @@ __device__ __forceinline__ void bb_k1_accumulate(K1State<NDET>& st, const K1Tile
         if (CAL) {
             // h_det *= C(f)  =>  conj(h) picks up amp1 (cr - i ci), |h|^2 picks up amp1^2
             double amp1, cr, ci;
-            bb_cal_factor(st.cal + d * 4 * st.grid.n_points, st.grid.n_points, st.grid.l0[d], st.grid.inv_delta[d],
-                          tile.lf[i], &amp1, &cr, &ci);
+            if (d > 0 && !st.grid.shared)
+                cw = bb_cal_weights(st.grid.n_points, st.grid.l0[d], st.grid.inv_delta[d], tile.lf[i]);
+            bb_cal_apply(st.cal + d * 4 * st.grid.n_points, st.grid.n_points, cw, &amp1, &cr, &ci);
             const double tr = amp1 * (wr * cr + wi * ci), ti = amp1 * (wi * cr - wr * ci);
             wr = tr;
             wi = ti;

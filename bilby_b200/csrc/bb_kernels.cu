@@ -94,7 +94,10 @@ struct bb_handle {
     bool perm_valid = false;
     double *d_params = nullptr, *d_out = nullptr;   // staging for the host entry point
     size_t stage_cap = 0;
-    double *h_params = nullptr, *h_out = nullptr;   // pinned
+    double *h_params = nullptr, *h_out = nullptr, *h_calpar = nullptr;   // pinned
+    size_t pinned_cap = 0;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    std::vector<cudaEvent_t> chunk_events;
     // reduced-order likelihoods (bb_reduced.cuh): 0 full grid, 1 relative binning, 2 ROQ
     int kind = 0;
     std::vector<void*> red_bufs;           // device allocations owned by the current reduced-order set-up
@@ -531,6 +534,10 @@ extern "C" void bb_destroy(bb_handle* h) {
     cudaFree(h->d_keys); cudaFree(h->d_keys_out); cudaFree(h->d_index); cudaFree(h->d_perm); cudaFree(h->d_sort_tmp);
     if (h->h_params) cudaFreeHost(h->h_params);
     if (h->h_out) cudaFreeHost(h->h_out);
+    if (h->h_calpar) cudaFreeHost(h->h_calpar);
+    for (cudaEvent_t e : h->chunk_events) cudaEventDestroy(e);
+    if (h->copy_in) cudaStreamDestroy(h->copy_in);
+    if (h->copy_out) cudaStreamDestroy(h->copy_out);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -815,10 +822,18 @@ extern "C" int bb_log_likelihood_ratio_device(bb_handle* h, const double* params
     return 0;
 }
 
-extern "C" int bb_log_likelihood_ratio_host(bb_handle* h, const double* params_host, long n, double* out_host) {
-    if (!h || !h->have_network) return bb_fail("bb_log_likelihood_ratio_host: network not set");
-    if (n <= 0) return 0;
+// Host entry point: the batch is cut into chunks that flow through three streams (H2D copy, compute, D2H copy)
+// so that the PCIe transfers - and, for pageable caller memory, the staging memcpy - overlap the kernels.
+#define BB_HOST_CHUNK 131072L
+
+static int bb_host_pipeline(bb_handle* h, const double* params_host, const double* cal_host, long n, double* out_host) {
     BB_CUDA(cudaSetDevice(h->device));
+    const size_t per_cal = cal_host ? (size_t)h->net.n_det * 2 * h->cal.n_points : 0;
+    cudaPointerAttributes pa, oa, ca;
+    const bool in_pinned = cudaPointerGetAttributes(&pa, params_host) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    const bool out_pinned = cudaPointerGetAttributes(&oa, out_host) == cudaSuccess && oa.type == cudaMemoryTypeHost;
+    const bool cal_pinned = cal_host && cudaPointerGetAttributes(&ca, cal_host) == cudaSuccess && ca.type == cudaMemoryTypeHost;
+    cudaGetLastError();
     if ((size_t)n > h->stage_cap) {
         cudaFree(h->d_params); cudaFree(h->d_out);
         if (h->h_params) cudaFreeHost(h->h_params);
@@ -827,28 +842,80 @@ extern "C" int bb_log_likelihood_ratio_host(bb_handle* h, const double* params_h
         const size_t cap = n < 4096 ? 4096 : (size_t)n;
         BB_CUDA(cudaMalloc(&h->d_params, cap * BB_NPARAM * sizeof(double)));
         BB_CUDA(cudaMalloc(&h->d_out, cap * sizeof(double)));
-        BB_CUDA(cudaMallocHost(&h->h_params, cap * BB_NPARAM * sizeof(double)));
-        BB_CUDA(cudaMallocHost(&h->h_out, cap * sizeof(double)));
         h->stage_cap = cap;
+        h->pinned_cap = 0;
     }
-    // caller buffers that are already page-locked are copied directly; pageable ones hop through the
-    // handle's pinned staging so the H2D / D2H copies run at full PCIe rate
-    cudaPointerAttributes pa, oa;
-    const bool in_pinned = cudaPointerGetAttributes(&pa, params_host) == cudaSuccess && pa.type == cudaMemoryTypeHost;
-    const bool out_pinned = cudaPointerGetAttributes(&oa, out_host) == cudaSuccess && oa.type == cudaMemoryTypeHost;
-    cudaGetLastError();
-    const double* src = params_host;
-    if (!in_pinned) {
-        memcpy(h->h_params, params_host, (size_t)n * BB_NPARAM * sizeof(double));
-        src = h->h_params;
+    if ((!in_pinned || !out_pinned) && (size_t)n > h->pinned_cap) {
+        if (h->h_params) cudaFreeHost(h->h_params);
+        if (h->h_out) cudaFreeHost(h->h_out);
+        h->h_params = h->h_out = nullptr;
+        BB_CUDA(cudaMallocHost(&h->h_params, h->stage_cap * BB_NPARAM * sizeof(double)));
+        BB_CUDA(cudaMallocHost(&h->h_out, h->stage_cap * sizeof(double)));
+        h->pinned_cap = h->stage_cap;
     }
-    BB_CUDA(cudaMemcpyAsync(h->d_params, src, (size_t)n * BB_NPARAM * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    if (bb_log_likelihood_ratio_device(h, h->d_params, n, h->d_out, h->stream)) return 1;
-    double* dst = out_pinned ? out_host : h->h_out;
-    BB_CUDA(cudaMemcpyAsync(dst, h->d_out, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    BB_CUDA(cudaStreamSynchronize(h->stream));
+    if (cal_host && (size_t)n > h->calpar_cap) {
+        cudaFree(h->d_calpar);
+        if (h->h_calpar) cudaFreeHost(h->h_calpar);
+        h->d_calpar = h->h_calpar = nullptr;
+        const size_t cap = n < 4096 ? 4096 : (size_t)n;
+        BB_CUDA(cudaMalloc(&h->d_calpar, cap * per_cal * sizeof(double)));
+        if (!cal_pinned) BB_CUDA(cudaMallocHost(&h->h_calpar, cap * per_cal * sizeof(double)));
+        h->calpar_cap = cap;
+    } else if (cal_host && !cal_pinned && !h->h_calpar) {
+        BB_CUDA(cudaMallocHost(&h->h_calpar, h->calpar_cap * per_cal * sizeof(double)));
+    }
+    if (!h->copy_in) BB_CUDA(cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking));
+    if (!h->copy_out) BB_CUDA(cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking));
+    const long n_chunks = (n + BB_HOST_CHUNK - 1) / BB_HOST_CHUNK;
+    while ((long)h->chunk_events.size() < 2 * n_chunks) {
+        cudaEvent_t e;
+        BB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->chunk_events.push_back(e);
+    }
+    int rc = 0;
+    for (long c = 0; c < n_chunks && rc == 0; ++c) {
+        const long off = c * BB_HOST_CHUNK;
+        const long m = (n - off) < BB_HOST_CHUNK ? (n - off) : BB_HOST_CHUNK;
+        const double* src = params_host + off * BB_NPARAM;
+        if (!in_pinned) {
+            memcpy(h->h_params + off * BB_NPARAM, src, (size_t)m * BB_NPARAM * sizeof(double));
+            src = h->h_params + off * BB_NPARAM;
+        }
+        BB_CUDA(cudaMemcpyAsync(h->d_params + off * BB_NPARAM, src, (size_t)m * BB_NPARAM * sizeof(double),
+                                cudaMemcpyHostToDevice, h->copy_in));
+        if (cal_host) {
+            const double* csrc = cal_host + (size_t)off * per_cal;
+            if (!cal_pinned) {
+                memcpy(h->h_calpar + (size_t)off * per_cal, csrc, (size_t)m * per_cal * sizeof(double));
+                csrc = h->h_calpar + (size_t)off * per_cal;
+            }
+            BB_CUDA(cudaMemcpyAsync(h->d_calpar + (size_t)off * per_cal, csrc, (size_t)m * per_cal * sizeof(double),
+                                    cudaMemcpyHostToDevice, h->copy_in));
+        }
+        BB_CUDA(cudaEventRecord(h->chunk_events[2 * c], h->copy_in));
+        BB_CUDA(cudaStreamWaitEvent(h->stream, h->chunk_events[2 * c], 0));
+        h->cal_params = cal_host ? h->d_calpar + (size_t)off * per_cal : nullptr;
+        rc = bb_log_likelihood_ratio_device(h, h->d_params + off * BB_NPARAM, m, h->d_out + off, h->stream);
+        h->cal_params = nullptr;
+        if (rc) break;
+        BB_CUDA(cudaEventRecord(h->chunk_events[2 * c + 1], h->stream));
+        BB_CUDA(cudaStreamWaitEvent(h->copy_out, h->chunk_events[2 * c + 1], 0));
+        double* dst = out_pinned ? out_host + off : h->h_out + off;
+        BB_CUDA(cudaMemcpyAsync(dst, h->d_out + off, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, h->copy_out));
+    }
+    cudaStreamSynchronize(h->copy_in);
+    cudaStreamSynchronize(h->stream);
+    BB_CUDA(cudaStreamSynchronize(h->copy_out));
+    if (rc) return rc;
     if (!out_pinned) memcpy(out_host, h->h_out, (size_t)n * sizeof(double));
     return 0;
+}
+
+extern "C" int bb_log_likelihood_ratio_host(bb_handle* h, const double* params_host, long n, double* out_host) {
+    if (!h || !h->have_network) return bb_fail("bb_log_likelihood_ratio_host: network not set");
+    if (n <= 0) return 0;
+    if (!params_host || !out_host) return bb_fail("bb_log_likelihood_ratio_host: null buffer");
+    return bb_host_pipeline(h, params_host, nullptr, n, out_host);
 }
 
 static int bb_strain_common(bb_handle* h, const double* params_dev, long n, double* out_dev, void* stream, int mode) {
@@ -980,9 +1047,11 @@ extern "C" int bb_set_calibration(bb_handle* h, int n_points, const double* log1
     if (n_points < 4 || n_points > BB_NCAL_MAX) return bb_fail("bb_set_calibration: n_points must be in [4, 32]");
     BB_CUDA(cudaSetDevice(h->device));
     h->cal.n_points = n_points;
+    h->cal.shared = 1;
     for (int d = 0; d < h->net.n_det; ++d) {
         h->cal.l0[d] = log10_fmin[d];
         h->cal.inv_delta[d] = (double)(n_points - 1) / (log10_fmax[d] - log10_fmin[d]);
+        if (h->cal.l0[d] != h->cal.l0[0] || h->cal.inv_delta[d] != h->cal.inv_delta[0]) h->cal.shared = 0;
     }
     cudaFree(h->d_calM);
     h->d_calM = nullptr;
@@ -1014,20 +1083,9 @@ extern "C" int bb_log_likelihood_ratio_cal_host(bb_handle* h, const double* para
                                                 long n, double* out_host) {
     if (!h || !h->have_network) return bb_fail("bb_log_likelihood_ratio_cal_host: network not set");
     if (n <= 0) return 0;
-    BB_CUDA(cudaSetDevice(h->device));
-    const size_t per = (size_t)h->net.n_det * 2 * h->cal.n_points;
-    if ((size_t)n > h->calpar_cap) {
-        cudaFree(h->d_calpar);
-        h->d_calpar = nullptr;
-        const size_t cap = n < 4096 ? 4096 : (size_t)n;
-        BB_CUDA(cudaMalloc(&h->d_calpar, cap * per * sizeof(double)));
-        h->calpar_cap = cap;
-    }
-    BB_CUDA(cudaMemcpyAsync(h->d_calpar, cal_params_host, (size_t)n * per * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    h->cal_params = h->d_calpar;
-    const int rc = bb_log_likelihood_ratio_host(h, params_host, n, out_host);
-    h->cal_params = nullptr;
-    return rc;
+    if (!params_host || !out_host || !cal_params_host) return bb_fail("bb_log_likelihood_ratio_cal_host: null buffer");
+    if (h->cal.n_points < 4) return bb_fail("bb_log_likelihood_ratio_cal_host: bb_set_calibration was not called");
+    return bb_host_pipeline(h, params_host, cal_params_host, n, out_host);
 }
 
 extern "C" int bb_profile_enable(bb_handle* h, int on) {

@@ -418,7 +418,9 @@ bb_relbin_time_marg_kernel(const double* __restrict__ coef, long n, BBRelbinDev 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double2* X = reinterpret_cast<double2*>(smem_raw);
     const int nb = rb.edges.n - 1;
-    double2* r01 = X + bb_tm_series_elems(nfft);                 // [nb][NDET][2]
+    int plan_a, plan_b, ps;
+    bb_tm_plan(log2n, &plan_a, &plan_b, &ps);
+    double2* r01 = X + bb_tm_series_elems(nfft, ps);             // [nb][NDET][2]
     double* c = reinterpret_cast<double*>(r01 + (size_t)nb * NDET * 2);
     double* red = c + BC_NCOEF;      // [33]
     double* cal = red + 33;
@@ -459,7 +461,7 @@ bb_relbin_time_marg_kernel(const double* __restrict__ coef, long n, BBRelbinDev 
                     vi += p.x * qi + p.y * qr;
                 }
             }
-            X[bb_tm_pos(k)] = make_double2(vr, vi);
+            X[bb_tm_pos(k, ps)] = make_double2(vr, vi);
         }
         __syncthreads();
         bb_tm_finish(X, nfft, log2n, twiddle, marg, hh, c[BC_DISTANCE], c[BC_JITTER], start_time, duration, red, out + s);

@@ -233,7 +233,9 @@ static int bb_launch_relbin_time_marg_t(bb_handle* h, long n, double* out, cudaS
     const int nfft = h->nfft, nb = rb.edges.n - 1;
     int log2n = 0;
     while ((1 << log2n) < nfft) ++log2n;
-    const size_t smem = (bb_tm_series_elems(nfft) + (size_t)nb * NDET * 2) * sizeof(double2)
+    int plan_a, plan_b, ps;
+    bb_tm_plan(log2n, &plan_a, &plan_b, &ps);
+    const size_t smem = (bb_tm_series_elems(nfft, ps) + (size_t)nb * NDET * 2) * sizeof(double2)
                         + (BC_NCOEF + 33 + (CAL ? NDET * 4 * h->cal.n_points : 0)) * sizeof(double);
     if (smem > 227 * 1024) return bb_fail("relative binning time marginalisation: series + bins do not fit shared memory");
     BB_CUDA(cudaFuncSetAttribute(bb_relbin_time_marg_kernel<NDET, APPROX, CAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -20,77 +20,93 @@
 
 __device__ __forceinline__ unsigned bb_bitrev(unsigned v, int bits) { return __brev(v) >> (32 - bits); }
 
-// The series lives in shared memory with one 16-byte pad after every 8 elements: with it every access pattern of
-// the radix-8 passes below (element stride q = nfft/8, nfft/64, ... 1) and the natural-order fill is free of bank
-// conflicts.
-__device__ __forceinline__ int bb_tm_pos(int i) { return i + (i >> 3); }
-__host__ __device__ inline size_t bb_tm_series_elems(int nfft) { return (size_t)nfft + ((size_t)nfft >> 3) + 1; }
+// The series lives in shared memory with one 16-byte pad after every 2^PS elements (PS = 3, or 4 when every pass
+// is radix-16): with it every access pattern of the passes below (element stride q = nfft/16, ... 1) and the
+// natural-order fill are free of bank conflicts.
+__device__ __forceinline__ int bb_tm_pos(int i, int ps) { return i + (i >> ps); }
+__host__ __device__ inline size_t bb_tm_series_elems(int nfft, int ps) { return (size_t)nfft + ((size_t)nfft >> ps) + 1; }
+// pass plan: a radix-16 passes followed by b radix-8 passes with 4a + 3b = log2n (a as large as possible); any
+// remainder runs as radix-2 stages
+__host__ __device__ inline void bb_tm_plan(int log2n, int* a, int* b, int* ps) {
+    *a = 0;
+    *b = 0;
+    for (int aa = log2n / 4; aa >= 0; --aa)
+        if ((log2n - 4 * aa) % 3 == 0) { *a = aa; *b = (log2n - 4 * aa) / 3; break; }
+    *ps = (*b == 0 && *a > 0) ? 4 : 3;
+}
 
 __device__ __forceinline__ double2 bb_cmul(double2 a, double2 b) {
     return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
-// In-place decimation-in-frequency FFT (natural order in, bit-reversed order out: output j is at index
-// bitrev(j)).  Three radix-2 stages at a time are fused into one radix-8 pass held in registers (8 elements of
-// stride q per thread, one twiddle load per thread and pass: the other six follow from w^2, w^4 and the eighth
-// roots of unity); the remaining one or two stages run as plain radix-2 passes.
-__device__ __forceinline__ void bb_tm_fft_dif(double2* X, int nfft, int log2n, const double2* __restrict__ twiddle) {
-    const int tid = threadIdx.x;
-    const double r = 0.70710678118654752440;
-    int s = 0;
-    for (; s + 3 <= log2n; s += 3) {
-        const int q = nfft >> (s + 3);
-        for (int t = tid; t < (nfft >> 3); t += BB_TM_THREADS) {
-            const int blk = t / q, jp = t - blk * q;
-            const int base = blk * 8 * q + jp;
-            double2 v[8];
+// x * exp(-2 pi i k / 16); k is a compile-time constant after unrolling
+__device__ __forceinline__ double2 bb_mul_omega16(double2 x, int k) {
+    const double r = 0.70710678118654752440, c1 = 0.92387953251128675613, s1 = 0.38268343236508977173;
+    switch (k & 15) {
+        case 0: return x;
+        case 1: return make_double2(x.x * c1 + x.y * s1, x.y * c1 - x.x * s1);
+        case 2: return make_double2(r * (x.x + x.y), r * (x.y - x.x));
+        case 3: return make_double2(x.x * s1 + x.y * c1, x.y * s1 - x.x * c1);
+        case 4: return make_double2(x.y, -x.x);
+        case 5: return make_double2(x.y * c1 - x.x * s1, -x.x * c1 - x.y * s1);
+        case 6: return make_double2(r * (x.y - x.x), -r * (x.x + x.y));
+        case 7: return make_double2(x.y * s1 - x.x * c1, -x.x * s1 - x.y * c1);
+        default: return make_double2(-x.x, -x.y);
+    }
+}
+
+// one radix-2^R decimation-in-frequency pass (R fused radix-2 stages s .. s+R-1) held in registers: 2^R elements of
+// stride q per thread, one twiddle load per thread (the others follow by squaring and by the 16th roots of unity)
+template <int R>
+__device__ __forceinline__ void bb_tm_pass(double2* X, int nfft, int s, int ps, const double2* __restrict__ twiddle) {
+    constexpr int M = 1 << R;
+    const int q = nfft >> (s + R);
+    for (int t = threadIdx.x; t < (nfft >> R); t += BB_TM_THREADS) {
+        const int blk = t / q, jp = t - blk * q;
+        const int base = blk * M * q + jp;
+        double2 v[M];
 #pragma unroll
-            for (int m = 0; m < 8; ++m) v[m] = X[bb_tm_pos(base + m * q)];
-            const double2 w1 = twiddle[jp << s];
-            const double2 w2 = bb_cmul(w1, w1), w4 = bb_cmul(w2, w2);
-            // stage s: (m, m+4), twiddle w1 * w8^m
-            const double2 t1 = make_double2(r * (w1.x + w1.y), r * (w1.y - w1.x));      // w1 * (1 - i)/sqrt2
-            const double2 t2 = make_double2(w1.y, -w1.x);                                // w1 * (-i)
-            const double2 t3 = make_double2(r * (w1.y - w1.x), -r * (w1.x + w1.y));     // w1 * (-1 - i)/sqrt2
-            const double2 ws[4] = {w1, t1, t2, t3};
+        for (int m = 0; m < M; ++m) v[m] = X[bb_tm_pos(base + m * q, ps)];
+        double2 wt = twiddle[jp << s];
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                const double2 a = v[m], b = v[m + 4];
-                v[m] = make_double2(a.x + b.x, a.y + b.y);
-                v[m + 4] = bb_cmul(make_double2(a.x - b.x, a.y - b.y), ws[m]);
-            }
-            // stage s+1: (m, m+2) inside each half, twiddle w2 * (-i)^(m&1)
-            const double2 w2i = make_double2(w2.y, -w2.x);
+        for (int st = 0; st < R; ++st) {
+            const int half = M >> (st + 1);
+            double2 wk[M / 2];
 #pragma unroll
-            for (int hb = 0; hb < 8; hb += 4) {
+            for (int m = 0; m < half; ++m) wk[m] = bb_mul_omega16(wt, (m << st) * (16 / M));
 #pragma unroll
-                for (int m = 0; m < 2; ++m) {
-                    const double2 a = v[hb + m], b = v[hb + m + 2];
-                    v[hb + m] = make_double2(a.x + b.x, a.y + b.y);
-                    v[hb + m + 2] = bb_cmul(make_double2(a.x - b.x, a.y - b.y), m ? w2i : w2);
+            for (int g = 0; g < M; g += 2 * half) {
+#pragma unroll
+                for (int m = 0; m < half; ++m) {
+                    const double2 a = v[g + m], b = v[g + m + half];
+                    v[g + m] = make_double2(a.x + b.x, a.y + b.y);
+                    v[g + m + half] = bb_cmul(make_double2(a.x - b.x, a.y - b.y), wk[m]);
                 }
             }
-            // stage s+2: (m, m+1), twiddle w4
-#pragma unroll
-            for (int m = 0; m < 8; m += 2) {
-                const double2 a = v[m], b = v[m + 1];
-                v[m] = make_double2(a.x + b.x, a.y + b.y);
-                v[m + 1] = bb_cmul(make_double2(a.x - b.x, a.y - b.y), w4);
-            }
-#pragma unroll
-            for (int m = 0; m < 8; ++m) X[bb_tm_pos(base + m * q)] = v[m];
+            wt = bb_cmul(wt, wt);
         }
-        __syncthreads();
+#pragma unroll
+        for (int m = 0; m < M; ++m) X[bb_tm_pos(base + m * q, ps)] = v[m];
     }
+    __syncthreads();
+}
+
+// In-place decimation-in-frequency FFT (natural order in, bit-reversed order out: output j is at index bitrev(j)).
+__device__ __forceinline__ void bb_tm_fft_dif(double2* X, int nfft, int log2n, const double2* __restrict__ twiddle) {
+    int a, b, ps;
+    bb_tm_plan(log2n, &a, &b, &ps);
+    int s = 0;
+    for (int i = 0; i < a; ++i, s += 4) bb_tm_pass<4>(X, nfft, s, ps, twiddle);
+    for (int i = 0; i < b; ++i, s += 3) bb_tm_pass<3>(X, nfft, s, ps, twiddle);
     for (; s < log2n; ++s) {
         const int h = nfft >> (s + 1);
-        for (int b = tid; b < (nfft >> 1); b += BB_TM_THREADS) {
-            const int blk = b / h, j = b - blk * h;
+        for (int bb = threadIdx.x; bb < (nfft >> 1); bb += BB_TM_THREADS) {
+            const int blk = bb / h, j = bb - blk * h;
             const int i0 = blk * 2 * h + j;
             const double2 w = twiddle[j << s];
-            const double2 a = X[bb_tm_pos(i0)], c = X[bb_tm_pos(i0 + h)];
-            X[bb_tm_pos(i0)] = make_double2(a.x + c.x, a.y + c.y);
-            X[bb_tm_pos(i0 + h)] = bb_cmul(make_double2(a.x - c.x, a.y - c.y), w);
+            const double2 x0 = X[bb_tm_pos(i0, ps)], x1 = X[bb_tm_pos(i0 + h, ps)];
+            X[bb_tm_pos(i0, ps)] = make_double2(x0.x + x1.x, x0.y + x1.y);
+            X[bb_tm_pos(i0 + h, ps)] = bb_cmul(make_double2(x0.x - x1.x, x0.y - x1.y), w);
         }
         __syncthreads();
     }
@@ -104,6 +120,8 @@ __device__ __forceinline__ void bb_tm_finish(double2* X, int nfft, int log2n, co
                                              double start_time, double duration, double* red, double* out_s) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     bb_tm_fft_dif(X, nfft, log2n, twiddle);
+    int pa, pb, ps;
+    bb_tm_plan(log2n, &pa, &pb, &ps);
 
     // weighted logsumexp over the times inside the prior
     const double dtc = duration / (double)nfft;     // = 2 / sampling_frequency
@@ -116,7 +134,7 @@ __device__ __forceinline__ void bb_tm_finish(double2* X, int nfft, int log2n, co
     for (int j = j_lo + tid; j < j_hi; j += BB_TM_THREADS) {
         const double tj = (start_time + (double)(j + 1) * dtc) + jit;
         if (tj < marg.time_min || tj > marg.time_max) continue;
-        const double2 v = X[bb_tm_pos((int)bb_bitrev((unsigned)j, log2n))];
+        const double2 v = X[bb_tm_pos((int)bb_bitrev((unsigned)j, log2n), ps)];
         const double l = bb_point_lnl(marg, v.x, v.y, hh, dist);
         if (l == -INFINITY) continue;
         if (l > mx) { sum = sum * exp(mx - l) + bw; mx = l; }
@@ -149,6 +167,7 @@ struct TMState {
     double hh;
     const double* cal;
     BBCalGrid grid;
+    int ps;
 };
 
 template <int NDET, bool CAL>
@@ -160,6 +179,8 @@ __device__ __forceinline__ void bb_tm_bin(TMState<NDET>& st, const BBTiles& g, c
     const double zr = A * cs, zi = A * sn;      // conj(h22 incl. geocentric shift)
     const double A2 = A * A;
     double vr = 0.0, vi = 0.0;
+    BBCalW cw;
+    if (CAL) cw = bb_cal_weights(st.grid.n_points, st.grid.l0[0], st.grid.inv_delta[0], lfk);
 #pragma unroll
     for (int d = 0; d < NDET; ++d) {
         const double rc = st.ramp[d][0], rs = st.ramp[d][1];
@@ -167,8 +188,8 @@ __device__ __forceinline__ void bb_tm_bin(TMState<NDET>& st, const BBTiles& g, c
         double hw = A2;
         if (CAL) {
             double amp1, cr, ci;
-            bb_cal_factor(st.cal + d * 4 * st.grid.n_points, st.grid.n_points, st.grid.l0[d], st.grid.inv_delta[d],
-                          lfk, &amp1, &cr, &ci);
+            if (d > 0 && !st.grid.shared) cw = bb_cal_weights(st.grid.n_points, st.grid.l0[d], st.grid.inv_delta[d], lfk);
+            bb_cal_apply(st.cal + d * 4 * st.grid.n_points, st.grid.n_points, cw, &amp1, &cr, &ci);
             const double tr = amp1 * (wr * cr + wi * ci), ti = amp1 * (wi * cr - wr * ci);
             wr = tr;
             wi = ti;
@@ -183,7 +204,7 @@ __device__ __forceinline__ void bb_tm_bin(TMState<NDET>& st, const BBTiles& g, c
         st.ramp[d][0] = rc * st.step[d][0] - rs * st.step[d][1];
         st.ramp[d][1] = rc * st.step[d][1] + rs * st.step[d][0];
     }
-    if (act && k < nfft) X[bb_tm_pos(k)] = make_double2(vr, -vi);     // h conj(d)/S = conj(conj(h) d/S)
+    if (act && k < nfft) X[bb_tm_pos(k, st.ps)] = make_double2(vr, -vi);     // h conj(d)/S = conj(conj(h) d/S)
 }
 
 // this warp's rows r, r + BB_TM_WARPS, ... < rstop, all inside amplitude region AR and phase region PR
@@ -227,22 +248,34 @@ bb_time_marg_kernel(const double* __restrict__ coef, long n, BBTiles tiles, int 
                     double duration, const double* __restrict__ calrec, BBCalGrid grid, double* __restrict__ out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double2* X = reinterpret_cast<double2*>(smem_raw);
-    const int n_series = (int)bb_tm_series_elems(nfft);
+    int plan_a, plan_b, ps;
+    bb_tm_plan(log2n, &plan_a, &plan_b, &ps);
+    const int n_series = (int)bb_tm_series_elems(nfft, ps);
     double* c = reinterpret_cast<double*>(X + n_series);
     double* red = c + BC_NCOEF;      // [32]
-    double* cal = red + 32;          // CAL: [NDET][4][n_points]
+    double* stepbuf = red + 32;      // [2 * BB_MAX_DET] ramp advance over BB_TM_WARPS rows
+    double* cal = stepbuf + 2 * BB_MAX_DET;          // CAL: [NDET][4][n_points]
     const int cal_len = CAL ? NDET * 4 * grid.n_points : 0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     for (long s = blockIdx.x; s < n; s += gridDim.x) {
         __syncthreads();
         for (int i = tid; i < BC_NCOEF; i += BB_TM_THREADS) c[i] = coef[s * BC_NCOEF + i];
-        for (int i = tid; i < n_series; i += BB_TM_THREADS) X[i] = make_double2(0.0, 0.0);
         if (CAL) for (int i = tid; i < cal_len; i += BB_TM_THREADS) cal[i] = calrec[s * cal_len + i];
         __syncthreads();
         if (c[BC_STATUS] != 0.0) {
             if (tid == 0) out[s] = -DBL_MAX;
             continue;
+        }
+        {
+            // zero the series outside the active range (the fill below writes every active bin)
+            const int z0 = min((int)c[BC_KMIN], nfft), z1 = min((int)c[BC_KMAX], nfft);
+            for (int i = tid; i < z0; i += BB_TM_THREADS) X[bb_tm_pos(i, ps)] = make_double2(0.0, 0.0);
+            for (int i = z1 + tid; i < nfft; i += BB_TM_THREADS) X[bb_tm_pos(i, ps)] = make_double2(0.0, 0.0);
+            if (tid < NDET)
+                sincospi(c[BC_DET + BC_DSTRIDE * tid + 2] * ((double)(BB_TM_WARPS * BB_ROW) * df),
+                         &stepbuf[2 * tid + 1], &stepbuf[2 * tid]);
+            __syncthreads();
         }
         // rows of 32 bins; warp w owns rows r = w (mod BB_TM_WARPS).  Nyquist bin: in <h|h>, not in the series.
         const int kmin = (int)c[BC_KMIN], kmax = (int)c[BC_KMAX];
@@ -252,11 +285,13 @@ bb_time_marg_kernel(const double* __restrict__ coef, long n, BBTiles tiles, int 
         st.hh = 0.0;
         st.cal = cal;
         st.grid = grid;
+        st.ps = ps;
 #pragma unroll
         for (int d = 0; d < NDET; ++d) {
             const double two_dt = c[BC_DET + BC_DSTRIDE * d + 2];
             sincospi(two_dt * ((double)(r * BB_ROW + lane) * df), &st.ramp[d][1], &st.ramp[d][0]);
-            sincospi(two_dt * ((double)(BB_TM_WARPS * BB_ROW) * df), &st.step[d][1], &st.step[d][0]);
+            st.step[d][0] = stepbuf[2 * d];
+            st.step[d][1] = stepbuf[2 * d + 1];
         }
         if (APPROX == BB_IMRPHENOMD) {
             const int ka1 = (int)c[BC_KA1], ka2 = (int)c[BC_KA2], kp1 = (int)c[BC_KP1], kp2 = (int)c[BC_KP2];
@@ -307,7 +342,10 @@ static int bb_launch_time_marg_t(bb_handle* h, long n, double* out, cudaStream_t
     const int nfft = h->nfft;
     int log2n = 0;
     while ((1 << log2n) < nfft) ++log2n;
-    const size_t smem = bb_tm_series_elems(nfft) * sizeof(double2) + (BC_NCOEF + 32 + (CAL ? NDET * 4 * h->cal.n_points : 0)) * sizeof(double);
+    int plan_a, plan_b, ps;
+    bb_tm_plan(log2n, &plan_a, &plan_b, &ps);
+    const size_t smem = bb_tm_series_elems(nfft, ps) * sizeof(double2)
+                        + (BC_NCOEF + 32 + 2 * BB_MAX_DET + (CAL ? NDET * 4 * h->cal.n_points : 0)) * sizeof(double);
     if (smem > 227 * 1024) return bb_fail("time marginalisation: series does not fit shared memory (nfft > 8192)");
     BB_CUDA(cudaFuncSetAttribute(bb_time_marg_kernel<NDET, APPROX, CAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = (int)((227 * 1024) / (smem + 1024));
