@@ -41,6 +41,8 @@ def load():
         "bb_inner_products_cal_device": (i, [vp, vp, vp, lng, vp, vp]),
         "bb_likelihood_from_inner_products_device": (i, [vp, vp, vp, lng, vp, vp]),
         "bb_set_frequency_shard": (i, [vp, i, i]),
+        "bb_set_reference_frame": (i, [vp, vp, vp]),
+        "bb_sky_frame_parameters_device": (i, [vp, vp, lng, vp, vp]),
         "bb_frequency_domain_strain_device": (i, [vp, vp, lng, vp, vp]),
         "bb_frequency_sequence_strain_device": (i, [vp, vp, lng, vp, i, d, vp, vp]),
         "bb_set_relative_binning": (i, [vp, i, vp, vp, vp, vp, vp]),
@@ -68,7 +70,7 @@ EXPORTED_SYMBOLS = (
     "bb_last_error", "bb_abi_version", "bb_create", "bb_destroy", "bb_set_network", "bb_set_waveform",
     "bb_set_marginalization", "bb_log_likelihood_ratio_device", "bb_log_likelihood_ratio_host",
     "bb_inner_products_device", "bb_set_calibration", "bb_log_likelihood_ratio_cal_device",
-    "bb_log_likelihood_ratio_cal_host", "bb_inner_products_cal_device", "bb_likelihood_from_inner_products_device", "bb_set_frequency_shard",
+    "bb_log_likelihood_ratio_cal_host", "bb_inner_products_cal_device", "bb_likelihood_from_inner_products_device", "bb_set_frequency_shard", "bb_set_reference_frame", "bb_sky_frame_parameters_device",
     "bb_frequency_domain_strain_device", "bb_frequency_sequence_strain_device", "bb_set_relative_binning",
     "bb_set_roq", "bb_detector_response_device", "bb_build_distance_table",
     "bb_antenna_response_device", "bb_ln_i0_device", "bb_project_polarizations_device",

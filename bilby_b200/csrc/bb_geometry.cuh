@@ -90,3 +90,33 @@ BB_HD double bb_time_delay(const double* vertex, double ra, double dec, double g
     // omega . (0 - vertex) / c
     return (ox * (0.0 - vertex[0]) + oy * (0.0 - vertex[1]) + oz * (0.0 - vertex[2])) / BB_C_SI;
 }
+
+// Detector-based sky frame and detector time reference (bilby/gw/likelihood/base.py:1091-1137
+// get_sky_frame_parameters; gw/utils.py:232-256 zenith_azimuth_to_ra_dec; gw/geometry.py:215-258, 346-377).
+struct BBFrame {
+    int sky_frame;          // 1: columns (RA, DEC) hold (azimuth, zenith) in the frame of a detector pair
+    int detector_time;      // 1: column GEOCENT_TIME holds the arrival time at the reference detector
+    double rotation[9];     // rotation_matrix_from_delta(vertex_1 - vertex_2), row-major
+    double ref_vertex[3];   // vertex of the time-reference detector [m]
+};
+
+// in: (azimuth|ra, zenith|dec, reference time)  ->  out: (ra, dec, geocent_time)
+BB_HD void bb_sky_frame(const BBFrame& fr, double a, double b, double time, double* ra, double* dec, double* tgeo) {
+    double r = a, d = b;
+    if (fr.sky_frame) {
+        const double sz = sin(b);
+        const double o[3] = {sz * cos(a), sz * sin(a), cos(b)};
+        const double* R = fr.rotation;
+        const double x = R[0] * o[0] + R[1] * o[1] + R[2] * o[2];
+        const double y = R[3] * o[0] + R[4] * o[1] + R[5] * o[2];
+        const double z = R[6] * o[0] + R[7] * o[1] + R[8] * o[2];
+        const double theta = acos(z);
+        const double phi = bb_wrap_2pi(atan2(y, x));
+        // theta_phi_to_ra_dec with the UNWRAPPED gmst of the reference time, then ra % 2 pi
+        r = bb_wrap_2pi(phi + bb_gmst(time));
+        d = BB_PI / 2 - theta;
+    }
+    *ra = r;
+    *dec = d;
+    *tgeo = fr.detector_time ? time - bb_time_delay(fr.ref_vertex, r, d, bb_wrap_2pi(bb_gmst(time))) : time;
+}

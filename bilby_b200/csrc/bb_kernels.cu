@@ -98,6 +98,9 @@ struct bb_handle {
     size_t pinned_cap = 0;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     std::vector<cudaEvent_t> chunk_events;
+    BBFrame frame{};                       // detector-based sky frame / time reference (base.py:1091-1137)
+    double* d_params_sky = nullptr;        // parameter rows converted to (ra, dec, geocent_time)
+    size_t params_sky_cap = 0;
     // reduced-order likelihoods (bb_reduced.cuh): 0 full grid, 1 relative binning, 2 ROQ
     int kind = 0;
     std::vector<void*> red_bufs;           // device allocations owned by the current reduced-order set-up
@@ -152,6 +155,28 @@ __global__ void bb_prologue_kernel(const double* __restrict__ params, long n, BB
         const unsigned count = (unsigned)(c[BC_KMAX] - c[BC_KMIN]);
         keys[i] = (1u << 24) - min(count, (1u << 24) - 1u);
         index[i] = (unsigned)i;
+    }
+}
+
+// sky-frame conversion of the parameter rows (base.py:1091-1137): (azimuth, zenith, detector time) -> (ra, dec, t_c)
+__global__ void bb_sky_frame_kernel(const double* __restrict__ params, long n, BBFrame fr, double* __restrict__ out,
+                                    double* __restrict__ sky /* optional [n][3] */) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* p = params + i * BB_NPARAM;
+    double ra, dec, tg;
+    bb_sky_frame(fr, p[BB_P_RA], p[BB_P_DEC], p[BB_P_GEOCENT_TIME], &ra, &dec, &tg);
+    if (out) {
+        double* o = out + i * BB_NPARAM;
+        for (int k = 0; k < BB_NPARAM; ++k) o[k] = p[k];
+        o[BB_P_RA] = ra;
+        o[BB_P_DEC] = dec;
+        o[BB_P_GEOCENT_TIME] = tg;
+    }
+    if (sky) {
+        sky[3 * i] = ra;
+        sky[3 * i + 1] = dec;
+        sky[3 * i + 2] = tg;
     }
 }
 
@@ -528,7 +553,7 @@ extern "C" void bb_destroy(bb_handle* h) {
     cudaFree(h->d_tx); cudaFree(h->d_ty); cudaFree(h->d_c);
     cudaFree(h->d_coef); cudaFree(h->d_snr); cudaFree(h->d_params); cudaFree(h->d_out);
     cudaFree(h->d_mask); cudaFree(h->d_twiddle);
-    cudaFree(h->d_calM); cudaFree(h->d_calrec); cudaFree(h->d_calpar);
+    cudaFree(h->d_calM); cudaFree(h->d_calrec); cudaFree(h->d_calpar); cudaFree(h->d_params_sky);
     bb_reduced_clear(h);
     if (h->cublas) cublasDestroy(h->cublas);
     cudaFree(h->d_keys); cudaFree(h->d_keys_out); cudaFree(h->d_index); cudaFree(h->d_perm); cudaFree(h->d_sort_tmp);
@@ -642,6 +667,30 @@ extern "C" int bb_set_waveform(bb_handle* h, int approximant, double reference_f
     return 0;
 }
 
+extern "C" int bb_set_reference_frame(bb_handle* h, const double* rotation, const double* time_reference_vertex) {
+    if (!h) return bb_fail("bb_set_reference_frame: null handle");
+    memset(&h->frame, 0, sizeof(h->frame));
+    if (rotation) {
+        h->frame.sky_frame = 1;
+        memcpy(h->frame.rotation, rotation, 9 * sizeof(double));
+    }
+    if (time_reference_vertex) {
+        h->frame.detector_time = 1;
+        memcpy(h->frame.ref_vertex, time_reference_vertex, 3 * sizeof(double));
+    }
+    return 0;
+}
+
+extern "C" int bb_sky_frame_parameters_device(bb_handle* h, const double* params_dev, long n, double* out_dev, void* stream) {
+    if (!h) return bb_fail("bb_sky_frame_parameters_device: null handle");
+    if (n <= 0) return 0;
+    BB_CUDA(cudaSetDevice(h->device));
+    bb_sky_frame_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(params_dev, n, h->frame, nullptr, out_dev);
+    h->launches++;
+    BB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int bb_set_frequency_shard(bb_handle* h, int k_begin, int k_end) {
     if (!h || !h->have_network) return bb_fail("bb_set_frequency_shard: network not set");
     if (k_begin < 0 || k_end > h->net.n_freq || k_end < k_begin) return bb_fail("bb_set_frequency_shard: bad range");
@@ -685,6 +734,19 @@ extern "C" int bb_set_marginalization(bb_handle* h, int flags, double ref_dist, 
 }
 
 static int bb_launch_prologue(bb_handle* h, const double* params_dev, long n, cudaStream_t st) {
+    if (h->frame.sky_frame || h->frame.detector_time) {
+        if ((size_t)n > h->params_sky_cap) {
+            cudaFree(h->d_params_sky);
+            h->d_params_sky = nullptr;
+            const size_t cap = n < 4096 ? 4096 : (size_t)n;
+            BB_CUDA(cudaMalloc(&h->d_params_sky, cap * BB_NPARAM * sizeof(double)));
+            h->params_sky_cap = cap;
+        }
+        bb_sky_frame_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(params_dev, n, h->frame, h->d_params_sky, nullptr);
+        h->launches++;
+        BB_CUDA(cudaGetLastError());
+        params_dev = h->d_params_sky;
+    }
     BBWaveformConfig wf = h->wf;
     if (!(wf.f_max > 0.0)) wf.f_max = h->net.df * (h->net.n_freq - 1);
     wf.add_jitter = ((h->marg.flags & BB_MARG_TIME) && h->marg.jitter) ? 1 : 0;

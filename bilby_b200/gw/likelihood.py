@@ -131,8 +131,6 @@ class GravitationalWaveTransient(Likelihood):
         super().__init__()
         if calibration_marginalization:
             raise NotImplementedError("calibration marginalisation is a 'next' row (SURVEY.md section 8f)")
-        if reference_frame != "sky" or "geocent" not in time_reference:
-            raise NotImplementedError("only reference_frame='sky', time_reference='geocenter' are implemented")
         self.waveform_generator = waveform_generator
         self.interferometers = InterferometerList(interferometers)
         self.time_marginalization = time_marginalization
@@ -144,7 +142,17 @@ class GravitationalWaveTransient(Likelihood):
         self._noise_log_likelihood_value = None
         self.jitter_time = jitter_time
         self.reference_frame = reference_frame
-        self.time_reference = "geocent"
+        if "geocent" not in time_reference:            # base.py:171-181
+            from .detector.networks import get_empty_interferometer
+            self.time_reference = time_reference
+            self.reference_ifo = get_empty_interferometer(self.time_reference)
+            if self.time_marginalization:
+                logger.info("Cannot marginalise over non-geocenter time.")
+                self.time_marginalization = False
+                self.jitter_time = False
+        else:
+            self.time_reference = "geocent"
+            self.reference_ifo = None
         self._device_index = device
         self._net = None
         self._net_versions = None
@@ -368,13 +376,93 @@ class GravitationalWaveTransient(Likelihood):
             _lib.check(net.lib.bb_set_marginalization(net.ptr, flags, 1.0, None, 0, None, 0, None, 0.0, 0.0, 0.0,
                                                       0.0, tmin, tmax, int(bool(self.jitter_time))))
 
+    # ---- reference frame (base.py:1063-1137) ------------------------------------------------------
+    @property
+    def reference_frame(self):
+        return self._reference_frame
+
+    @reference_frame.setter
+    def reference_frame(self, frame):
+        if isinstance(frame, str) and frame == "sky":
+            self._reference_frame = frame
+        elif isinstance(frame, InterferometerList):
+            self._reference_frame = InterferometerList(list(frame)[:2])
+        elif isinstance(frame, list):
+            self._reference_frame = InterferometerList(frame[:2])
+        elif isinstance(frame, str):
+            self._reference_frame = InterferometerList([frame[:2], frame[2:4]])
+        else:
+            raise ValueError("Unable to parse reference frame {}".format(frame))
+
+    @property
+    def _reference_frame_str(self):
+        if isinstance(self.reference_frame, str):
+            return self.reference_frame
+        return "".join([ifo.name for ifo in self.reference_frame])
+
+    @staticmethod
+    def _rotation_matrix_from_delta(delta_x):
+        """bilby/gw/geometry.py:215-258 (set-up: one 3x3 matrix per likelihood)."""
+        d = np.asarray(delta_x, dtype=float)
+        d = d / np.sqrt((d ** 2).sum())
+        alpha, beta, gamma = np.arctan2(-d[1] * d[2], d[0]), np.arccos(d[2]), np.arctan2(d[1], d[0])
+
+        def rz(a):
+            return np.array([[np.cos(a), -np.sin(a), 0.0], [np.sin(a), np.cos(a), 0.0], [0.0, 0.0, 1.0]])
+        ry = np.array([[np.cos(beta), 0.0, np.sin(beta)], [0.0, 1.0, 0.0], [-np.sin(beta), 0.0, np.cos(beta)]])
+        return rz(gamma) @ ry @ rz(alpha)
+
+    def _set_device_frame(self, use_sky_frame):
+        """Tell the handle how to read the (RA, DEC, GEOCENT_TIME) columns (bb_set_reference_frame)."""
+        net = self.device_network
+        rot = vert = None
+        if use_sky_frame:
+            f = self.reference_frame
+            rot = np.ascontiguousarray(self._rotation_matrix_from_delta(f[0].vertex - f[1].vertex), dtype=np.float64)
+        if self.reference_ifo is not None:
+            vert = np.ascontiguousarray(self.reference_ifo.vertex, dtype=np.float64)
+        state = (None if rot is None else rot.tobytes(), None if vert is None else vert.tobytes())
+        if getattr(net, "_frame_state", (None, None)) != state:
+            _lib.check(net.lib.bb_set_reference_frame(net.ptr, None if rot is None else rot.ctypes.data,
+                                                      None if vert is None else vert.ctypes.data))
+            net._frame_state = state
+
+    def _frame_columns(self, parameters):
+        """Parameters as the device reads them: (ra|azimuth, dec|zenith, geocent_time|{IFO}_time).  Mirrors the
+        fall-backs of base.py:1107-1136."""
+        time_key = f"{self.time_reference}_time"
+        out = dict(parameters)
+        use_frame = False
+        if self.reference_frame != "sky":
+            if "zenith" in parameters and "azimuth" in parameters:
+                out["ra"], out["dec"] = parameters["azimuth"], parameters["zenith"]
+                use_frame = True
+            elif "ra" in parameters and "dec" in parameters:
+                logger.warning("Cannot convert from zenith/azimuth to ra/dec falling back to provided ra/dec")
+            else:
+                raise KeyError("zenith")
+        if self.reference_ifo is not None:
+            if time_key not in parameters:
+                raise KeyError(time_key)
+            out["geocent_time"] = parameters[time_key]
+        self._set_device_frame(use_frame)
+        return out
+
     # ---- evaluation ----------------------------------------------------------------------------
     def get_sky_frame_parameters(self, parameters):
-        """base.py:1091-1137 for reference_frame='sky', time_reference='geocent'."""
-        return dict(ra=parameters["ra"], dec=parameters["dec"], geocent_time=parameters["geocent_time"])
+        """base.py:1091-1137: {ra, dec, geocent_time} of one parameter dict (converted on the device)."""
+        if self.reference_frame == "sky" and self.reference_ifo is None:
+            return dict(ra=parameters["ra"], dec=parameters["dec"], geocent_time=parameters["geocent_time"])
+        cols = self._frame_columns(parameters)
+        net = self.device_network
+        rows = net._rows(ra=float(cols["ra"]), dec=float(cols["dec"]), geocent_time=float(cols["geocent_time"]))
+        out = net.torch.empty((1, 3), dtype=net.torch.float64, device=net.device)
+        _lib.check(net.lib.bb_sky_frame_parameters_device(net.ptr, rows.data_ptr(), 1, out.data_ptr(), net._stream()))
+        ra, dec, tg = out[0].cpu().numpy()
+        return dict(ra=float(ra), dec=float(dec), geocent_time=float(tg))
 
     def _rows_from_parameters(self, parameters, n, xp, device=None):
-        converted = self.waveform_generator.convert(parameters)
+        converted = self.waveform_generator.convert(self._frame_columns(parameters))
         return _params.pack_rows(converted, n, xp, device=device)
 
     def _cal_from_parameters(self, parameters, n, xp, device=None):
@@ -399,7 +487,6 @@ class GravitationalWaveTransient(Likelihood):
     def log_likelihood_ratio(self, parameters):
         """base.py:419-446: one parameter dict in, one float out (a batch of one through the same kernels)."""
         parameters = copy.deepcopy(parameters)
-        parameters.update(self.get_sky_frame_parameters(parameters))
         rows = np.ascontiguousarray(self._rows_from_parameters(parameters, 1, np))
         return float(self.log_likelihood_ratio_rows_host(rows, self._cal_from_parameters(parameters, 1, np))[0])
 

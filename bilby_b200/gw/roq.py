@@ -9,7 +9,10 @@ loaded from an .npz file written by ``save_weights``.  Evaluation on the device:
 Single linear / quadratic basis given as ndarray, .npy file or precomputed weights; multi-basis selection and
 multibanded bases ship only as .hdf5 (h5py is not a dependency here) and raise NotImplementedError.
 """
+import os
+
 import numpy as np
+from scipy import fft as _fft
 
 from .. import _lib
 from ..core.utils import logger, create_frequency_series
@@ -197,10 +200,15 @@ class ROQGravitationalWaveTransient(GravitationalWaveTransient):
             nonzero = ifo_idxs + int(ifo.minimum_frequency * duration)
             d_over_s = ifo.frequency_domain_strain[mask][ifo_idxs] / ifo.power_spectral_density_array[mask][ifo_idxs]
             # one inverse FFT per basis element, all elements at once: rows of `spec`
-            spec = np.zeros((linear_basis.shape[0], n_time), dtype=complex)
-            spec[:, nonzero] = d_over_s[None, :] * linear_basis[:, roq_idxs].conj()
-            lw = np.fft.ifft(spec, axis=1)[:, lo:hi + 1].T * (4. * n_time / duration)
-            self.weights[ifo.name + "_linear"] = [np.ascontiguousarray(lw)]
+            # (scipy's pocketfft with all host cores, in slabs of 32 elements to bound memory)
+            lw = np.empty((hi - lo + 1, linear_basis.shape[0]), dtype=complex)
+            for b0 in range(0, linear_basis.shape[0], 32):
+                sl = slice(b0, min(b0 + 32, linear_basis.shape[0]))
+                spec = np.zeros((sl.stop - sl.start, n_time), dtype=complex)
+                spec[:, nonzero] = d_over_s[None, :] * linear_basis[sl][:, roq_idxs].conj()
+                lw[:, sl] = _fft.ifft(spec, axis=1, workers=os.cpu_count() or 1)[:, lo:hi + 1].T
+            lw *= 4. * n_time / duration
+            self.weights[ifo.name + "_linear"] = [lw]
             inv_psd = 1 / ifo.power_spectral_density_array[mask][ifo_idxs]
             self.weights[ifo.name + "_quadratic"] = [4. / duration * quadratic_basis.real[:, roq_idxs] @ inv_psd]
 

@@ -128,6 +128,18 @@ int bb_inner_products_device(bb_handle* h, const double* params_dev, long n, dou
 int bb_likelihood_from_inner_products_device(bb_handle* h, const double* params_dev, const double* snrs_dev,
                                              long n, double* out_dev, void* stream);
 
+/* Detector-based sky frame and detector time reference: replaces GravitationalWaveTransient.get_sky_frame_parameters
+ * (base.py:1091-1137) -> zenith_azimuth_to_ra_dec (gw/utils.py:232-256, gw/geometry.py:215-258, 346-377).
+ *   rotation: host double[9] = rotation_matrix_from_delta(vertex_1 - vertex_2) of the two reference detectors
+ *             (reference_frame="H1L1"), or NULL for reference_frame="sky".  When set, columns BB_RA / BB_DEC of the
+ *             parameter rows hold (azimuth, zenith).
+ *   time_reference_vertex: host double[3], vertex [m] of the time-reference detector (time_reference="H1"), or NULL
+ *             for "geocent".  When set, column BB_GEOCENT_TIME holds the arrival time at that detector.
+ * The conversion runs on the device in front of the prologue kernel for every evaluation entry point. */
+int bb_set_reference_frame(bb_handle* h, const double* rotation, const double* time_reference_vertex);
+/* (ra, dec, geocent_time) for each parameter row under the current reference frame; out double[n][3]. */
+int bb_sky_frame_parameters_device(bb_handle* h, const double* params_dev, long n, double* out_dev, void* stream);
+
 /* Restrict this handle to the contiguous bin range [k_begin, k_end) (frequency sharding of long
  * signals across GPUs).  Pass (0, n_freq) to undo. */
 int bb_set_frequency_shard(bb_handle* h, int k_begin, int k_end);

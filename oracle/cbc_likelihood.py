@@ -605,3 +605,47 @@ def draw_bbh_prior(n, rng, t_inj=INJECTION["geocent_time"]):
     out["dec"] = np.arcsin(rng.uniform(-1, 1, n))
     out["geocent_time"] = rng.uniform(t_inj - 0.1, t_inj + 0.1, n)
     return out
+
+
+# --------------------------------------------------------------------------------------
+# detector-based sky frame / detector time reference (base.py:1091-1137)
+# --------------------------------------------------------------------------------------
+def rotation_matrix_from_delta(delta_x):
+    """bilby/gw/geometry.py:215-258."""
+    delta_x = np.asarray(delta_x, dtype=float)
+    delta_x = delta_x / (delta_x ** 2).sum() ** 0.5
+    alpha = np.arctan2(-delta_x[1] * delta_x[2], delta_x[0])
+    beta = np.arccos(delta_x[2])
+    gamma = np.arctan2(delta_x[1], delta_x[0])
+    r1 = np.array([[np.cos(alpha), -np.sin(alpha), 0], [np.sin(alpha), np.cos(alpha), 0], [0, 0, 1]])
+    r2 = np.array([[np.cos(beta), 0, np.sin(beta)], [0, 1, 0], [-np.sin(beta), 0, np.cos(beta)]])
+    r3 = np.array([[np.cos(gamma), -np.sin(gamma), 0], [np.sin(gamma), np.cos(gamma), 0], [0, 0, 1]])
+    return r3 @ r2 @ r1
+
+
+def zenith_azimuth_to_ra_dec(zenith, azimuth, time, vertex_1, vertex_2):
+    """bilby/gw/utils.py:232-256 with geometry.py:346-377 (zenith_azimuth_to_theta_phi for a detector pair,
+    delta_x = vertex_1 - vertex_2, detector/networks.py:487-490) and theta_phi_to_ra_dec."""
+    omega_prime = np.array([np.sin(zenith) * np.cos(azimuth), np.sin(zenith) * np.sin(azimuth), np.cos(zenith)])
+    omega = rotation_matrix_from_delta(np.asarray(vertex_1) - np.asarray(vertex_2)) @ omega_prime
+    theta = np.arccos(omega[2])
+    phi = np.arctan2(omega[1], omega[0]) % (2 * np.pi)
+    gmst = greenwich_mean_sidereal_time(time)
+    ra = (phi + gmst) % (2 * np.pi)
+    dec = np.pi / 2 - theta
+    return ra, dec
+
+
+def get_sky_frame_parameters(parameters, frame_vertices=None, time_reference_vertex=None, time_key="geocent_time"):
+    """base.py:1091-1137.  frame_vertices = (vertex_1, vertex_2) of the reference detector pair or None for the
+    sky frame; time_reference_vertex = vertex of the time-reference detector or None for the geocentre."""
+    time = parameters[time_key]
+    if frame_vertices is not None:
+        ra, dec = zenith_azimuth_to_ra_dec(parameters["zenith"], parameters["azimuth"], time, *frame_vertices)
+    else:
+        ra, dec = parameters["ra"], parameters["dec"]
+    if time_reference_vertex is not None:
+        geocent_time = time - time_delay_from_geocenter(time_reference_vertex, ra, dec, time)
+    else:
+        geocent_time = parameters["geocent_time"]
+    return dict(ra=ra, dec=dec, geocent_time=geocent_time)

@@ -329,3 +329,66 @@ def test_calibration_spline_time_marginalised_vs_reference(mode):
     ref = g["lnl_" + mode]
     err = np.abs(lnl - ref) / _scale(g, ref)
     assert err.max() < RTOL, err.max()
+
+
+def test_detector_sky_frame_and_time_reference_vs_reference():
+    """reference_frame="H1L1", time_reference="H1" (base.py:1091-1137) converted on the
+    device in front of the prologue; golden from the unmodified reference (oracle/tools/make_golden_frame.py)."""
+    import bilby_b200 as bb
+    from bilby_b200.gw.detector import InterferometerList
+    from bilby_b200.gw.source import lal_binary_black_hole
+    g = np.load(os.path.join(GOLDEN, "sky_frame_4s_H1L1V1.npz"))
+    ifos = InterferometerList([str(x) for x in g["detectors"]])
+    for ifo in ifos:
+        ifo.minimum_frequency, ifo.maximum_frequency = 20.0, 1024.0
+        ifo.set_strain_data_from_frequency_domain_strain(g[f"strain_{ifo.name}"], sampling_frequency=2048.0,
+                                                         duration=4.0, start_time=float(g["start_time"]))
+    wfg = bb.gw.WaveformGenerator(
+        duration=4.0, sampling_frequency=2048.0, frequency_domain_source_model=lal_binary_black_hole,
+        waveform_arguments=dict(waveform_approximant="IMRPhenomD", reference_frequency=50.0, minimum_frequency=20.0))
+    like = bb.gw.GravitationalWaveTransient(ifos, wfg, reference_frame="H1L1", time_reference="H1")
+    draws = {k[6:]: g[k] for k in g.files if k.startswith("param_")}
+    n = len(draws["zenith"])
+    for i in (0, 7, 19):
+        sky = like.get_sky_frame_parameters({k: float(v[i]) for k, v in draws.items()})
+        assert abs(sky["ra"] - g["sky"][i, 0]) < 1e-11
+        assert abs(sky["dec"] - g["sky"][i, 1]) < 1e-12
+        assert abs(sky["geocent_time"] - g["sky"][i, 2]) < 5e-7     # float64 resolution of a GPS time is 2.4e-7 s
+    lnl = like.log_likelihood_ratio_batch(draws)
+    # |d lnL| <= 1e-8 max(|lnL|, SNR^2/2); SNR^2/2 of this data set ~ 200
+    assert np.max(np.abs(lnl - g["lnl_none"]) / np.maximum(np.abs(g["lnl_none"]), 200.0)) < RTOL
+    one = like.log_likelihood_ratio({k: float(v[5]) for k, v in draws.items()})
+    assert abs(one - lnl[5]) < 1e-10 * max(1.0, abs(lnl[5]))
+    # detector time reference in the sky frame
+    from bilby_b200.workloads import draw_bbh_prior
+    d2 = draw_bbh_prior(n, np.random.default_rng(20261017))
+    d2["L1_time"] = d2.pop("geocent_time")
+    like2 = bb.gw.GravitationalWaveTransient(ifos, wfg, time_reference="L1")
+    lnl2 = like2.log_likelihood_ratio_batch(d2)
+    assert np.max(np.abs(lnl2 - g["lnl_L1_time"]) / np.maximum(np.abs(g["lnl_L1_time"]), 200.0)) < RTOL
+
+
+def test_batched_sampler_adaptor_matches_one_point_calls():
+    """arrays of theta through one launch == the reference's one-point-per-call path."""
+    from bilby_b200.core.prior import PriorDict, Uniform, PowerLaw, Sine, Cosine
+    from bilby_b200.core.sampler import BatchedLikelihood, DeviceBatchPool
+    g, like, draws = _build("noise_H1L1V1", phase_marginalization=True, priors=_priors(phase=True))
+    t = 1126259642.413
+    priors = PriorDict(dict(
+        chirp_mass=Uniform(25, 35, "chirp_mass"), mass_ratio=Uniform(0.125, 1, "mass_ratio"),
+        chi_1=Uniform(-0.99, 0.99, "chi_1"), chi_2=Uniform(-0.99, 0.99, "chi_2"),
+        luminosity_distance=PowerLaw(2, 100.0, 5000.0, "luminosity_distance"), theta_jn=Sine(name="theta_jn"),
+        psi=Uniform(0, np.pi, "psi"), ra=Uniform(0, 2 * np.pi, "ra"), dec=Cosine(name="dec"),
+        geocent_time=Uniform(t - 0.1, t + 0.1, "geocent_time"), phase=0.0))
+    bl = BatchedLikelihood(like, priors)
+    assert "phase" not in bl.search_parameter_keys and bl.ndim == 10
+    u = np.random.default_rng(4).uniform(0, 1, (256, bl.ndim))
+    theta = bl.prior_transform_batch(u)
+    lnl = bl.log_likelihood_batch(theta)
+    for i in (0, 17, 255):
+        assert abs(bl.log_likelihood(theta[i]) - lnl[i]) < 1e-10 * max(1.0, abs(lnl[i]))
+    pool = DeviceBatchPool(bl)
+    assert np.array_equal(np.array(pool.map(None, [theta[i] for i in range(32)])), lnl[:32])
+    import torch
+    dev = bl.log_likelihood_batch(torch.from_numpy(theta).cuda())
+    assert dev.is_cuda and np.max(np.abs(dev.cpu().numpy() - lnl)) < 1e-9 * np.max(np.abs(lnl))

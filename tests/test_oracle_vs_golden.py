@@ -177,3 +177,18 @@ def test_calibration_spline_path_vs_reference():
         like = ocl.OracleLikelihood(ifos, waveform_arguments=WA, time_marginalization=True, time_prior=tp, **kw)
         got = _eval(like, draws, n, skip=(), geocent_time=float(g["start_time"]))
         assert np.allclose(got, g["lnl_" + mode][:n], rtol=1e-11, atol=1e-11)
+
+
+def test_sky_frame_parameters_vs_reference():
+    """base.py:1091-1137 restated in oracle/cbc_likelihood.py vs the unmodified reference."""
+    g = np.load(os.path.join(GOLDEN, "sky_frame_4s_H1L1V1.npz"))
+    h1 = ocl.OracleInterferometer("H1", 2048.0, 4.0, float(g["start_time"]))
+    l1 = ocl.OracleInterferometer("L1", 2048.0, 4.0, float(g["start_time"]))
+    for i in range(len(g["param_zenith"])):
+        p = dict(zenith=float(g["param_zenith"][i]), azimuth=float(g["param_azimuth"][i]),
+                 H1_time=float(g["param_H1_time"][i]))
+        s = ocl.get_sky_frame_parameters(p, frame_vertices=(h1.vertex, l1.vertex), time_reference_vertex=h1.vertex,
+                                         time_key="H1_time")
+        assert abs(s["ra"] - g["sky"][i, 0]) < 1e-13
+        assert abs(s["dec"] - g["sky"][i, 1]) < 1e-14
+        assert s["geocent_time"] == g["sky"][i, 2]
