@@ -13,6 +13,8 @@
 #define BB_HD inline
 #endif
 
+#include "bb_math.cuh"
+
 #define BB_MAX_DET 4
 #define BB_NPARAM 16
 
@@ -111,19 +113,15 @@ BB_HD BBCalW bb_cal_weights(int n, double l0, double inv_delta, double lf) {
     w.j = j;
     w.b = x - (double)j;
     w.a = 1.0 - w.b;
-    w.c = (w.a * w.a * w.a - w.a) / 6.0;
-    w.d = (w.b * w.b * w.b - w.b) / 6.0;
+    w.c = (w.a * w.a * w.a - w.a) * (1.0 / 6.0);
+    w.d = (w.b * w.b * w.b - w.b) * (1.0 / 6.0);
     return w;
 }
 BB_HD void bb_cal_apply(const double* rec, int n, const BBCalW& w, double* amp1, double* cr, double* ci) {
     const int j = w.j;
     const double dA = w.a * rec[j] + w.b * rec[j + 1] + w.c * rec[n + j] + w.d * rec[n + j + 1];
     const double dP = w.a * rec[2 * n + j] + w.b * rec[2 * n + j + 1] + w.c * rec[3 * n + j] + w.d * rec[3 * n + j + 1];
-#ifdef __CUDA_ARCH__
-    const double den = __drcp_rn(4.0 + dP * dP);
-#else
-    const double den = 1.0 / (4.0 + dP * dP);
-#endif
+    const double den = bb_rcp_pos(4.0 + dP * dP);
     *amp1 = 1.0 + dA;
     *cr = (4.0 - dP * dP) * den;
     *ci = 4.0 * dP * den;

@@ -93,6 +93,8 @@ struct K1Amp<0> {
 #pragma unroll
         for (int i = 0; i < 10; ++i) c.k[i] = r[BC_AINS + i];
     }
+    __device__ __forceinline__ void begin(double f0, double dfrow) {}
+    __device__ __forceinline__ void next() {}
     __device__ __forceinline__ double eval(double f, double x) const {
         double a = c.k[9];
 #pragma unroll
@@ -109,6 +111,8 @@ struct K1Amp<1> {
         c.f1 = r[BC_AINT_F1];
         c.invw = r[BC_AINT_INVW];
     }
+    __device__ __forceinline__ void begin(double f0, double dfrow) {}
+    __device__ __forceinline__ void next() {}
     __device__ __forceinline__ double eval(double f, double x) const {
         const double xs = (f - c.f1) * c.invw;
         double a = c.k[4];
@@ -126,9 +130,16 @@ struct K1Amp<2> {
         c.g = r[BC_MR_G];
         c.lam = r[BC_MR_LAM];
     }
+    // exp(-lam (f - f_RD)) advances from row to row by one multiplication (rows are equally spaced in f)
+    double e, ratio;
+    __device__ __forceinline__ void begin(double f0, double dfrow) {
+        e = c.g * exp(-c.lam * (f0 - c.frd));
+        ratio = exp(-c.lam * dfrow);
+    }
+    __device__ __forceinline__ void next() { e *= ratio; }
     __device__ __forceinline__ double eval(double f, double x) const {
         const double d = f - c.frd;
-        return c.g * exp(-c.lam * d) / (d * d + c.wl2);
+        return e * bb_rcp_pos(fma(d, d, c.wl2));
     }
 };
 
@@ -170,7 +181,7 @@ struct K1Ph<2> {
         for (int i = 0; i < 7; ++i) c.q[i] = r[BC_PMR + i];
     }
     __device__ __forceinline__ double eval(double f, double t, double x, double lf, double q34) const {
-        return c.q[0] + c.q[1] * f + c.q[2] * (t * t * t) + c.q[3] * q34 + c.q[4] * atan((f - c.q[5]) * c.q[6]);
+        return c.q[0] + c.q[1] * f + c.q[2] * (t * t * t) + c.q[3] * q34 + c.q[4] * bb_atan((f - c.q[5]) * c.q[6]);
     }
 };
 
@@ -188,7 +199,7 @@ template <int NDET, bool CAL>
 __device__ __forceinline__ void bb_k1_accumulate(K1State<NDET>& st, const K1Tile<NDET>& tile, int i, bool act,
                                                  double A, double ph) {
     double sn, cs;
-    sincospi(act ? ph : 0.0, &sn, &cs);
+    bb_sincospi(act ? ph : 0.0, &sn, &cs);
     A = act ? A : 0.0;
     const double zr = A * cs, zi = A * sn;      // A e^{+i Phi} = conj(h22 incl. geocentric shift)
     const double A2 = A * A;
@@ -211,9 +222,9 @@ __device__ __forceinline__ void bb_k1_accumulate(K1State<NDET>& st, const K1Tile
             hw = A2 * amp1 * amp1;
         }
         const double2 dd = tile.ds[d][i];
-        st.acc[d][0] += wr * dd.x - wi * dd.y;
-        st.acc[d][1] += wr * dd.y + wi * dd.x;
-        st.acc[d][2] += hw * tile.is[d][i];
+        st.acc[d][0] = fma(wr, dd.x, fma(-wi, dd.y, st.acc[d][0]));
+        st.acc[d][1] = fma(wr, dd.y, fma(wi, dd.x, st.acc[d][1]));
+        st.acc[d][2] = fma(hw, tile.is[d][i], st.acc[d][2]);
         // advance the ramp to the next row
         st.ramp[d][0] = rc * st.step[d][0] - rs * st.step[d][1];
         st.ramp[d][1] = rc * st.step[d][1] + rs * st.step[d][0];
@@ -229,6 +240,7 @@ __device__ __forceinline__ void bb_k1_rows_pd(K1State<NDET>& st, const K1Tile<ND
     amp.load(rec);
     phs.load(rec);
     const double a0 = rec[BC_A0];
+    amp.begin((double)(r0 * BB_ROW + lane) * df, (double)BB_ROW * df);
     for (int r = r0; r < r1; ++r) {
         const int k = r * BB_ROW + lane, i = k - c0;
         const bool act = (k >= kmin) && (k < kmax);
@@ -237,6 +249,7 @@ __device__ __forceinline__ void bb_k1_rows_pd(K1State<NDET>& st, const K1Tile<ND
         const double A = amp.eval(f, x) * a0 * (u * (t * t * t));
         const double ph = phs.eval(f, t, x, tile.lf[i], tile.q34[i]);
         bb_k1_accumulate<NDET, CAL>(st, tile, i, act, A, ph);
+        amp.next();
     }
 }
 
@@ -336,7 +349,7 @@ bb_inner_product_kernel(const double* __restrict__ coef, const unsigned* __restr
         for (int d = 0; d < NDET; ++d) {
             st.acc[d][0] = st.acc[d][1] = st.acc[d][2] = 0.0;
             const double f0 = (double)(row_first * BB_ROW + lane) * df;
-            sincospi(rec[BC_DET + BC_DSTRIDE * d + 2] * f0, &st.ramp[d][1], &st.ramp[d][0]);
+            bb_sincospi(rec[BC_DET + BC_DSTRIDE * d + 2] * f0, &st.ramp[d][1], &st.ramp[d][0]);
             st.step[d][0] = rec[BC_DET + BC_DSTRIDE * d + 4];
             st.step[d][1] = rec[BC_DET + BC_DSTRIDE * d + 5];
         }

@@ -97,6 +97,11 @@ struct bb_handle {
     double *h_params = nullptr, *h_out = nullptr, *h_calpar = nullptr;   // pinned
     size_t pinned_cap = 0;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    double2* d_series = nullptr;           // K4a -> K4b scratch: two chunks of series (time marginalisation)
+    size_t series_cap = 0;                 // elements
+    double* d_slotrec = nullptr;           // per-slot records handed from K4a to K4b
+    cudaStream_t aux = nullptr;            // K4b runs here, beside K4a on the caller's stream
+    std::vector<cudaEvent_t> tm_events;
     std::vector<cudaEvent_t> chunk_events;
     BBFrame frame{};                       // detector-based sky frame / time reference (base.py:1091-1137)
     double* d_params_sky = nullptr;        // parameter rows converted to (ra, dec, geocent_time)
@@ -514,6 +519,7 @@ static BBTiles bb_tiles(const bb_handle* h) {
 }
 
 #include "bb_timemarg.cuh"
+#include "bb_timemarg_split.cuh"
 #include "bb_reduced.cuh"
 #include "bb_reduced_host.cuh"
 
@@ -561,6 +567,10 @@ extern "C" void bb_destroy(bb_handle* h) {
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->h_calpar) cudaFreeHost(h->h_calpar);
     for (cudaEvent_t e : h->chunk_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->tm_events) cudaEventDestroy(e);
+    cudaFree(h->d_series);
+    cudaFree(h->d_slotrec);
+    if (h->aux) cudaStreamDestroy(h->aux);
     if (h->copy_in) cudaStreamDestroy(h->copy_in);
     if (h->copy_out) cudaStreamDestroy(h->copy_out);
     if (h->stream) cudaStreamDestroy(h->stream);

@@ -87,7 +87,7 @@ __device__ __forceinline__ void bb_relbin_sample(const double* rec, const double
         for (int d = 0; d < NDET; ++d) {
             const double* cd = rec + BC_DET + BC_DSTRIDE * d;
             double sn, cs;
-            sincospi(ph + cd[2] * f, &sn, &cs);            // h22 e^{-2 pi i f (dt0 + delay)} = A (cs - i sn)
+            bb_sincospi(ph + cd[2] * f, &sn, &cs);            // h22 e^{-2 pi i f (dt0 + delay)} = A (cs - i sn)
             double hr = A * (cd[0] * cs + cd[1] * sn), hi = A * (cd[1] * cs - cd[0] * sn);   // K h
             if (CAL) {
                 double amp1, cr, ci;
@@ -242,7 +242,7 @@ bb_roq_kernel(const double* __restrict__ coef, long n, BBRoqDev rq, const double
             double A, ph;
             bb_wave<APPROX>(rec, f, rq.lin.u[j], rq.lin.lf[j], rq.lin.q34[j], &A, &ph);
             double sn, cs;
-            sincospi(ph, &sn, &cs);
+            bb_sincospi(ph, &sn, &cs);
             const double zr0 = A * cs, zi0 = A * sn;        // conj(h22) = A e^{+i Phi}
 #pragma unroll
             for (int d = 0; d < NDET; ++d) {
@@ -323,7 +323,7 @@ bb_roq_hlinear_kernel(const double* __restrict__ coef, long s_begin, long n, BBR
             double A, ph;
             bb_wave<APPROX>(rec, f, rq.lin.u[j], rq.lin.lf[j], rq.lin.q34[j], &A, &ph);
             double sn, cs;
-            sincospi(ph, &sn, &cs);
+            bb_sincospi(ph, &sn, &cs);
             const double zr0 = A * cs, zi0 = A * sn;
 #pragma unroll
             for (int d = 0; d < NDET; ++d) {
@@ -464,6 +464,7 @@ bb_relbin_time_marg_kernel(const double* __restrict__ coef, long n, BBRelbinDev 
             X[bb_tm_pos(k, ps)] = make_double2(vr, vi);
         }
         __syncthreads();
-        bb_tm_finish(X, nfft, log2n, twiddle, marg, hh, c[BC_DISTANCE], c[BC_JITTER], start_time, duration, red, out + s);
+        bb_tm_fft_dif(X, nfft, log2n, twiddle);
+        bb_tm_finish(X, nfft, log2n, marg, hh, c[BC_DISTANCE], c[BC_JITTER], start_time, duration, red, out + s);
     }
 }

@@ -57,11 +57,11 @@ __device__ __forceinline__ double2 bb_mul_omega16(double2 x, int k) {
 
 // one radix-2^R decimation-in-frequency pass (R fused radix-2 stages s .. s+R-1) held in registers: 2^R elements of
 // stride q per thread, one twiddle load per thread (the others follow by squaring and by the 16th roots of unity)
-template <int R>
+template <int R, int NT = BB_TM_THREADS>
 __device__ __forceinline__ void bb_tm_pass(double2* X, int nfft, int s, int ps, const double2* __restrict__ twiddle) {
     constexpr int M = 1 << R;
     const int q = nfft >> (s + R);
-    for (int t = threadIdx.x; t < (nfft >> R); t += BB_TM_THREADS) {
+    for (int t = threadIdx.x; t < (nfft >> R); t += NT) {
         const int blk = t / q, jp = t - blk * q;
         const int base = blk * M * q + jp;
         double2 v[M];
@@ -91,16 +91,13 @@ __device__ __forceinline__ void bb_tm_pass(double2* X, int nfft, int s, int ps, 
     __syncthreads();
 }
 
-// In-place decimation-in-frequency FFT (natural order in, bit-reversed order out: output j is at index bitrev(j)).
-__device__ __forceinline__ void bb_tm_fft_dif(double2* X, int nfft, int log2n, const double2* __restrict__ twiddle) {
-    int a, b, ps;
-    bb_tm_plan(log2n, &a, &b, &ps);
-    int s = 0;
-    for (int i = 0; i < a; ++i, s += 4) bb_tm_pass<4>(X, nfft, s, ps, twiddle);
-    for (int i = 0; i < b; ++i, s += 3) bb_tm_pass<3>(X, nfft, s, ps, twiddle);
+// radix-2 stages s .. log2n-1 (whatever the radix-16 / radix-8 plan leaves over)
+template <int NT = BB_TM_THREADS>
+__device__ __forceinline__ void bb_tm_radix2_tail(double2* X, int nfft, int log2n, int s, int ps,
+                                                  const double2* __restrict__ twiddle) {
     for (; s < log2n; ++s) {
         const int h = nfft >> (s + 1);
-        for (int bb = threadIdx.x; bb < (nfft >> 1); bb += BB_TM_THREADS) {
+        for (int bb = threadIdx.x; bb < (nfft >> 1); bb += NT) {
             const int blk = bb / h, j = bb - blk * h;
             const int i0 = blk * 2 * h + j;
             const double2 w = twiddle[j << s];
@@ -112,29 +109,70 @@ __device__ __forceinline__ void bb_tm_fft_dif(double2* X, int nfft, int log2n, c
     }
 }
 
-// FFT of the series in shared memory followed by the weighted logsumexp over the times inside the geocent_time
+// In-place decimation-in-frequency FFT (natural order in, bit-reversed order out: output j is at index bitrev(j)).
+__device__ __forceinline__ void bb_tm_fft_dif(double2* X, int nfft, int log2n, const double2* __restrict__ twiddle) {
+    int a, b, ps;
+    bb_tm_plan(log2n, &a, &b, &ps);
+    int s = 0;
+    for (int i = 0; i < a; ++i, s += 4) bb_tm_pass<4>(X, nfft, s, ps, twiddle);
+    for (int i = 0; i < b; ++i, s += 3) bb_tm_pass<3>(X, nfft, s, ps, twiddle);
+    bb_tm_radix2_tail(X, nfft, log2n, s, ps, twiddle);
+}
+
+// After the FFT of the series in shared memory: the weighted logsumexp over the times inside the geocent_time
 // prior; shared by the full-grid and the relative-binning time-marginalised kernels.  Must be entered with the
 // series complete (after a __syncthreads()).
-__device__ __forceinline__ void bb_tm_finish(double2* X, int nfft, int log2n, const double2* __restrict__ twiddle,
-                                             const BBMarg& marg, double hh, double dist, double jitter,
-                                             double start_time, double duration, double* red, double* out_s) {
+// times = start_time + linspace(0, T, nfft + 1)[1:] (+ jitter): the range [j_lo, j_hi) that can lie inside the prior
+__device__ __forceinline__ void bb_tm_window(const BBMarg& marg, double jitter, double start_time, double duration,
+                                             int nfft, int* j_lo, int* j_hi) {
+    const double dtc = duration / (double)nfft;     // = 2 / sampling_frequency
+    const double jit = marg.jitter ? jitter : 0.0;
+    *j_lo = (int)fmin(fmax(floor((marg.time_min - jit - start_time) / dtc) - 2.0, 0.0), (double)nfft);
+    *j_hi = (int)fmin(fmax(ceil((marg.time_max - jit - start_time) / dtc) + 1.0, 0.0), (double)nfft);
+}
+
+// PRUNED = false: the FFT is complete (output j at index bitrev(j)).
+// PRUNED = true: only the first 8 radix-2 stages ran; block c = bitrev8(j & 255) of L = nfft / 256 consecutive
+// elements holds the sequence whose L-point DFT gives the outputs j = (j & 255) + 256 n2, and the few outputs inside
+// the prior are summed directly (wl[e] = exp(-2 pi i e / L) in shared memory).
+template <int NT = BB_TM_THREADS, bool PRUNED = false>
+__device__ __forceinline__ void bb_tm_finish(double2* X, int nfft, int log2n, const BBMarg& marg, double hh, double dist, double jitter,
+                                             double start_time, double duration, double* red, double* out_s,
+                                             const double2* wl = nullptr, int ps_in = -1) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    bb_tm_fft_dif(X, nfft, log2n, twiddle);
     int pa, pb, ps;
     bb_tm_plan(log2n, &pa, &pb, &ps);
+    if (ps_in >= 0) ps = ps_in;
 
     // weighted logsumexp over the times inside the prior
     const double dtc = duration / (double)nfft;     // = 2 / sampling_frequency
     const double jit = marg.jitter ? jitter : 0.0;
     const double bw = dtc / (marg.time_max - marg.time_min);
-    // times = start_time + linspace(0, T, nfft + 1)[1:] (+ jitter): only j with times inside the prior
-    const int j_lo = (int)fmin(fmax(floor((marg.time_min - jit - start_time) / dtc) - 2.0, 0.0), (double)nfft);
-    const int j_hi = (int)fmin(fmax(ceil((marg.time_max - jit - start_time) / dtc) + 1.0, 0.0), (double)nfft);
+    int j_lo, j_hi;
+    bb_tm_window(marg, jitter, start_time, duration, nfft, &j_lo, &j_hi);
     double mx = -INFINITY, sum = 0.0;
-    for (int j = j_lo + tid; j < j_hi; j += BB_TM_THREADS) {
+    for (int j = j_lo + tid; j < j_hi; j += NT) {
         const double tj = (start_time + (double)(j + 1) * dtc) + jit;
         if (tj < marg.time_min || tj > marg.time_max) continue;
-        const double2 v = X[bb_tm_pos((int)bb_bitrev((unsigned)j, log2n), ps)];
+        double2 v;
+        if (PRUNED) {
+            const int logl = log2n - 8, L = 1 << logl;
+            const int base = (int)(__brev((unsigned)(j & 255)) >> 24) << logl;
+            const int n2 = j >> 8;
+            double vr = 0.0, vi = 0.0;
+            // start at a lane-dependent element so that neighbouring outputs do not hit the same banks
+            const int rot = (j * 5) & (L - 1);
+            for (int i = 0; i < L; ++i) {
+                const int jp = (i + rot) & (L - 1);
+                const double2 z = X[bb_tm_pos(base + jp, ps)];
+                const double2 w = wl[(jp * n2) & (L - 1)];
+                vr += z.x * w.x - z.y * w.y;
+                vi += z.x * w.y + z.y * w.x;
+            }
+            v = make_double2(vr, vi);
+        } else {
+            v = X[bb_tm_pos((int)bb_bitrev((unsigned)j, log2n), ps)];
+        }
         const double l = bb_point_lnl(marg, v.x, v.y, hh, dist);
         if (l == -INFINITY) continue;
         if (l > mx) { sum = sum * exp(mx - l) + bw; mx = l; }
@@ -146,7 +184,7 @@ __device__ __forceinline__ void bb_tm_finish(double2* X, int nfft, int log2n, co
     if (lane == 0) red[warp] = gmx;
     __syncthreads();
     gmx = red[0];
-    for (int w = 1; w < BB_TM_WARPS; ++w) gmx = fmax(gmx, red[w]);
+    for (int w = 1; w < NT / 32; ++w) gmx = fmax(gmx, red[w]);
     __syncthreads();
     double part = (mx == -INFINITY) ? 0.0 : sum * exp(mx - gmx);
     part = bb_warp_sum(part);
@@ -154,7 +192,7 @@ __device__ __forceinline__ void bb_tm_finish(double2* X, int nfft, int log2n, co
     __syncthreads();
     if (tid == 0) {
         double tot = 0.0;
-        for (int w = 0; w < BB_TM_WARPS; ++w) tot += red[w];
+        for (int w = 0; w < NT / 32; ++w) tot += red[w];
         *out_s = (gmx == -INFINITY) ? -INFINITY : log(tot) + gmx;
     }
 }
@@ -174,7 +212,7 @@ template <int NDET, bool CAL>
 __device__ __forceinline__ void bb_tm_bin(TMState<NDET>& st, const BBTiles& g, const double* rec, double2* X, int k,
                                           bool act, int nfft, double A, double ph, double lfk) {
     double sn, cs;
-    sincospi(act ? ph : 0.0, &sn, &cs);
+    bb_sincospi(act ? ph : 0.0, &sn, &cs);
     A = act ? A : 0.0;
     const double zr = A * cs, zi = A * sn;      // conj(h22 incl. geocentric shift)
     const double A2 = A * A;
@@ -216,6 +254,7 @@ __device__ __forceinline__ int bb_tm_rows_pd(TMState<NDET>& st, const BBTiles& g
     amp.load(rec);
     phs.load(rec);
     const double a0 = rec[BC_A0];
+    amp.begin((double)(r * BB_ROW + lane) * df, (double)(BB_TM_WARPS * BB_ROW) * df);
     for (; r < rstop; r += BB_TM_WARPS) {
         const int k = r * BB_ROW + lane;
         const bool act = (k >= kmin) && (k < kmax);
@@ -225,6 +264,7 @@ __device__ __forceinline__ int bb_tm_rows_pd(TMState<NDET>& st, const BBTiles& g
         const double A = amp.eval(f, x) * a0 * (u * (t * t * t));
         const double ph = phs.eval(f, t, x, lfk, g.q34[k]);
         bb_tm_bin<NDET, CAL>(st, g, rec, X, k, act, nfft, A, ph, lfk);
+        amp.next();
     }
     return r;
 }
@@ -245,7 +285,8 @@ template <int NDET, int APPROX, bool CAL>
 __global__ void __launch_bounds__(BB_TM_THREADS, 1)
 bb_time_marg_kernel(const double* __restrict__ coef, long n, BBTiles tiles, int n_freq, double df, int nfft,
                     int log2n, const double2* __restrict__ twiddle, BBMarg marg, double start_time,
-                    double duration, const double* __restrict__ calrec, BBCalGrid grid, double* __restrict__ out) {
+                    double duration, const double* __restrict__ calrec, BBCalGrid grid, double* __restrict__ out,
+                    long long* __restrict__ phase_clk) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double2* X = reinterpret_cast<double2*>(smem_raw);
     int plan_a, plan_b, ps;
@@ -258,8 +299,17 @@ bb_time_marg_kernel(const double* __restrict__ coef, long n, BBTiles tiles, int 
     const int cal_len = CAL ? NDET * 4 * grid.n_points : 0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
+    // BB_TM_PHASES=1 (debug): cycles per phase, summed over samples by thread 0 of every CTA
+    long long pclk[4] = {0, 0, 0, 0}, pt = 0;
+#define BB_TM_MARK(i)                                                                  \
+    if (phase_clk != nullptr && tid == 0) {                                            \
+        const long long now = clock64();                                               \
+        pclk[i] += now - pt;                                                           \
+        pt = now;                                                                      \
+    }
     for (long s = blockIdx.x; s < n; s += gridDim.x) {
         __syncthreads();
+        if (phase_clk != nullptr && tid == 0) pt = clock64();
         for (int i = tid; i < BC_NCOEF; i += BB_TM_THREADS) c[i] = coef[s * BC_NCOEF + i];
         if (CAL) for (int i = tid; i < cal_len; i += BB_TM_THREADS) cal[i] = calrec[s * cal_len + i];
         __syncthreads();
@@ -277,6 +327,7 @@ bb_time_marg_kernel(const double* __restrict__ coef, long n, BBTiles tiles, int 
                          &stepbuf[2 * tid + 1], &stepbuf[2 * tid]);
             __syncthreads();
         }
+        BB_TM_MARK(0)
         // rows of 32 bins; warp w owns rows r = w (mod BB_TM_WARPS).  Nyquist bin: in <h|h>, not in the series.
         const int kmin = (int)c[BC_KMIN], kmax = (int)c[BC_KMAX];
         const int row_first = kmin / BB_ROW, row_last = (kmax + BB_ROW - 1) / BB_ROW;
@@ -333,9 +384,18 @@ bb_time_marg_kernel(const double* __restrict__ coef, long n, BBTiles tiles, int 
         hh = 0.0;
         for (int w = 0; w < BB_TM_WARPS; ++w) hh += red[w];
         __syncthreads();
-        bb_tm_finish(X, nfft, log2n, twiddle, marg, hh, c[BC_DISTANCE], c[BC_JITTER], start_time, duration, red, out + s);
+        BB_TM_MARK(1)
+        bb_tm_fft_dif(X, nfft, log2n, twiddle);
+        BB_TM_MARK(2)
+        bb_tm_finish(X, nfft, log2n, marg, hh, c[BC_DISTANCE], c[BC_JITTER], start_time, duration, red, out + s);
+        BB_TM_MARK(3)
     }
+    if (phase_clk != nullptr && tid == 0)
+        for (int i = 0; i < 4; ++i) atomicAdd((unsigned long long*)phase_clk + i, (unsigned long long)pclk[i]);
+#undef BB_TM_MARK
 }
+
+static int bb_launch_time_marg_split(bb_handle* h, long n, double* out, cudaStream_t st);
 
 template <int NDET, int APPROX, bool CAL>
 static int bb_launch_time_marg_t(bb_handle* h, long n, double* out, cudaStream_t st) {
@@ -353,14 +413,27 @@ static int bb_launch_time_marg_t(bb_handle* h, long n, double* out, cudaStream_t
     if (per_sm > 4) per_sm = 4;
     long grid = (long)h->sm_count * per_sm;
     if (grid > n) grid = n;
+    long long* d_phase = nullptr;
+    if (getenv("BB_TM_PHASES")) {
+        BB_CUDA(cudaMalloc(&d_phase, 4 * sizeof(long long)));
+        BB_CUDA(cudaMemsetAsync(d_phase, 0, 4 * sizeof(long long), st));
+    }
     {
         BBProfScope prof(h, st);
         bb_time_marg_kernel<NDET, APPROX, CAL><<<(unsigned)grid, BB_TM_THREADS, smem, st>>>(
             h->d_coef, n, bb_tiles(h), h->net.n_freq, h->net.df, nfft, log2n, h->d_twiddle, h->marg,
-            h->net.start_time, h->net.duration, h->d_calrec, h->cal, out);
+            h->net.start_time, h->net.duration, h->d_calrec, h->cal, out, d_phase);
     }
     h->launches++;
     BB_CUDA(cudaGetLastError());
+    if (d_phase) {
+        long long pc[4];
+        BB_CUDA(cudaStreamSynchronize(st));
+        BB_CUDA(cudaMemcpy(pc, d_phase, sizeof(pc), cudaMemcpyDeviceToHost));
+        BB_CUDA(cudaFree(d_phase));
+        fprintf(stderr, "bb_time_marg phases (cycles/sample): load+zero %.0f  fill %.0f  fft %.0f  logsumexp %.0f  (n=%ld)\n",
+                (double)pc[0] / n, (double)pc[1] / n, (double)pc[2] / n, (double)pc[3] / n, n);
+    }
     return 0;
 }
 
@@ -368,6 +441,12 @@ static int bb_launch_time_marg(bb_handle* h, long n, double* out, cudaStream_t s
     if (h->nfft == 0) return bb_fail("time marginalisation needs n_freq - 1 to be a power of two");
     if (h->shard_lo != 0 || h->shard_hi != h->net.n_freq)
         return bb_fail("time marginalisation cannot be frequency-sharded (SURVEY.md section 8e)");
+    {
+        // large batches: the two-kernel pipeline (bb_timemarg_split.cuh); BB_TM_SPLIT=0/1 forces the choice
+        const char* force = getenv("BB_TM_SPLIT");
+        const bool split = (h->nfft >= 512) && (force ? (force[0] == '1') : (n >= 2048));
+        if (split) return bb_launch_time_marg_split(h, n, out, st);
+    }
     const bool pd = h->wf.approximant == BB_IMRPHENOMD;
     const bool cal = h->cal_params != nullptr;
 #define BB_TM_CASE(N)                                                                                          \
