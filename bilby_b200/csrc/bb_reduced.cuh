@@ -199,7 +199,7 @@ __device__ __forceinline__ double2 bb_interp5(const double2* v, double a) {
 }
 
 template <int NDET, int APPROX, bool CAL>
-__global__ void __launch_bounds__(BB_RED_THREADS)
+__global__ void __launch_bounds__(BB_RED_THREADS, 2)
 bb_roq_kernel(const double* __restrict__ coef, long n, BBRoqDev rq, const double* __restrict__ calrec,
               BBCalGrid grid, double* __restrict__ out) {
     extern __shared__ __align__(16) double red_smem[];
