@@ -354,6 +354,22 @@ def ln_i0(value):
     return np.log(i0e(value)) + np.abs(value)
 
 
+def interped_sample(xx, yy, u):
+    """Interped(xx, yy).rescale(u): core/prior/interpolated.py:12-60, 88-94, 161-176 (grid replaced by a linspace of
+    the same length, density re-interpolated linearly, trapezoid normalisation, cumulative trapezoid with the last
+    element forced to one, linear inverse interpolation)."""
+    from scipy.integrate import cumulative_trapezoid
+    xx = np.asarray(xx, dtype=float)
+    yy = np.asarray(yy, dtype=float)
+    all_interpolated = interp1d(x=xx, y=yy, bounds_error=False, fill_value=0)
+    grid = np.linspace(float(min(xx)), float(max(xx)), len(xx))
+    dens = all_interpolated(grid)
+    dens = dens / np.trapezoid(dens, grid)
+    cdf = cumulative_trapezoid(dens, grid, initial=0)
+    cdf[-1] = 1
+    return float(interp1d(x=cdf, y=grid, bounds_error=True)(u))
+
+
 class OracleUniform:
     def __init__(self, minimum, maximum):
         self.minimum, self.maximum = minimum, maximum
@@ -556,6 +572,96 @@ class OracleLikelihood:
         else:
             log_l = arr.real - hh / 2
         return logsumexp(log_l, b=time_prior_array, axis=-1)
+
+    # ---- marginalised-parameter reconstruction (base.py:502-773); `uniforms` = the unit-interval draws that
+    #      Interped.sample() (core/prior/base.py:143-164) would make, in the order time, distance, phase
+    def generate_posterior_sample_from_marginalized_likelihood(self, parameters, uniforms):
+        """base.py:502-541."""
+        parameters = dict(parameters)
+        if not (self.time_marginalization or self.distance_marginalization or self.phase_marginalization):
+            return parameters
+        pols = {k: v.copy() for k, v in self.polarizations(parameters).items()}
+        uniforms = list(uniforms)
+        if self.time_marginalization:
+            parameters["geocent_time"] = self.generate_time_sample(pols, parameters, uniforms[0])
+        if self.distance_marginalization:
+            parameters["luminosity_distance"] = self.generate_distance_sample(pols, parameters, uniforms[1])
+        if self.phase_marginalization:
+            parameters["phase"] = self.generate_phase_sample(pols, parameters, uniforms[2])
+        return parameters
+
+    def _inner_products(self, pols, parameters):
+        """base.py:715-725."""
+        d_inner_h, hh = 0j, 0.0
+        for ifo in self.ifos:
+            signal = ifo.get_detector_response(pols, parameters)
+            d_inner_h += ifo.inner_product(signal)
+            hh += ifo.optimal_snr_squared(signal)
+        return d_inner_h, hh
+
+    def generate_time_sample(self, pols, parameters, u):
+        """base.py:578-658: the 16384 Hz zero-padded FFT of h conj(d) / S (NO 4/T factor in the reference), point
+        likelihood per time, prior, > max/1000 cut, Interped sample."""
+        if self.jitter_time:
+            parameters["geocent_time"] = parameters["geocent_time"] + parameters["time_jitter"]
+        n_time_steps = int(self.duration * 16384)
+        times = np.linspace(parameters["geocent_time"] - self.start_time,
+                            self.duration + (parameters["geocent_time"] - self.start_time) - 1 / 16384,
+                            num=n_time_steps)                         # core/utils/series.py:91-112
+        times = times % self.duration
+        times += self.start_time
+        prior = self.time_prior
+        in_prior = (times >= prior.minimum) & (times < prior.maximum)
+        times = times[in_prior]
+        d_inner_h = np.zeros(len(times), dtype=complex)
+        psd = np.ones(n_time_steps)
+        signal_long = np.zeros(n_time_steps, dtype=complex)
+        data = np.zeros(n_time_steps, dtype=complex)
+        hh = np.zeros(1)
+        for ifo in self.ifos:
+            n_ifo = len(ifo.frequency_domain_strain)
+            mask = ifo.frequency_mask
+            signal = ifo.get_detector_response(pols, parameters)
+            signal_long[:n_ifo] = signal
+            data[:n_ifo] = np.conj(ifo.frequency_domain_strain)
+            psd[:n_ifo][mask] = ifo.power_spectral_density_array[mask]
+            d_inner_h += np.fft.fft(signal_long * data / psd)[in_prior]
+            hh += ifo.optimal_snr_squared(signal).real
+        if self.distance_marginalization:
+            time_log_like = self.distance_marginalized_likelihood(d_inner_h, hh, parameters)
+        elif self.phase_marginalization:
+            time_log_like = ln_i0(abs(d_inner_h)) - hh.real / 2
+        else:
+            time_log_like = d_inner_h.real - hh.real / 2
+        time_post = np.exp(time_log_like - max(time_log_like)) * prior.prob(times)
+        keep = time_post > max(time_post) / 1000
+        if sum(keep) < 3:
+            keep[1:-1] = keep[1:-1] | keep[2:] | keep[:-2]
+        return interped_sample(times[keep], time_post[keep], u)
+
+    def generate_distance_sample(self, pols, parameters, u):
+        """base.py:660-713 (incl. the in-place rescaling of the polarisations, :711 -> _rescale_signal :1020-1025)."""
+        d_inner_h, hh = self._inner_products(pols, parameters)
+        d_dist = d_inner_h * parameters["luminosity_distance"] / self._distance_array
+        hh_dist = hh * parameters["luminosity_distance"] ** 2 / self._distance_array ** 2
+        if self.phase_marginalization:
+            log_like = ln_i0(abs(d_dist)) - hh_dist.real / 2
+        else:
+            log_like = d_dist.real - hh_dist.real / 2
+        post = np.exp(log_like - max(log_like)) * self.distance_prior_array
+        new_distance = interped_sample(self._distance_array, post, u)
+        for mode in pols:
+            pols[mode] *= self._ref_dist / new_distance
+        return new_distance
+
+    def generate_phase_sample(self, pols, parameters, u):
+        """base.py:746-773."""
+        d_inner_h, hh = self._inner_products(pols, parameters)
+        phases = np.linspace(0, 2 * np.pi, 101)
+        phasor = np.exp(-2j * phases)
+        log_post = d_inner_h * phasor - hh / 2
+        post = np.exp(log_post.real - max(log_post.real))
+        return interped_sample(phases, post, u)
 
     def noise_log_likelihood(self):
         """base.py:402-417."""
