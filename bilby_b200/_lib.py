@@ -57,6 +57,8 @@ def load():
         "bb_profile_read": (i, [vp, ctypes.POINTER(d), ctypes.POINTER(lng)]),
         "bb_fp64_peak": (i, [vp, ctypes.POINTER(d)]),
         "bb_launch_count": (lng, [vp]),
+        "bb_set_reconstruction_grid": (i, [vp, vp, vp, i]),
+        "bb_reconstruct_marginalized_device": (i, [vp, vp, vp, lng, vp, vp, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is missing
@@ -75,7 +77,7 @@ EXPORTED_SYMBOLS = (
     "bb_set_roq", "bb_detector_response_device", "bb_build_distance_table",
     "bb_antenna_response_device", "bb_ln_i0_device", "bb_project_polarizations_device",
     "bb_noise_weighted_inner_product_device", "bb_profile_enable", "bb_profile_read", "bb_fp64_peak",
-    "bb_launch_count")
+    "bb_launch_count", "bb_set_reconstruction_grid", "bb_reconstruct_marginalized_device")
 
 
 def check(rc):

@@ -100,6 +100,12 @@ struct bb_handle {
     double2* d_series = nullptr;           // K4a -> K4b scratch: two chunks of series (time marginalisation)
     size_t series_cap = 0;                 // elements
     double* d_slotrec = nullptr;           // per-slot records handed from K4a to K4b
+    // marginalised-parameter reconstruction (bb_recon.cuh)
+    double *d_rc_dist = nullptr, *d_rc_prior = nullptr;   // distance grid and prior on it
+    int rc_nd = 0;
+    double *d_rc_rows = nullptr, *d_rc_rows2 = nullptr, *d_rc_y = nullptr, *d_slotrec_rc = nullptr;
+    size_t rc_rows_cap = 0, rc_rows2_cap = 0, rc_y_cap = 0;
+    double2* d_fine = nullptr;
     cudaStream_t aux = nullptr;            // K4b runs here, beside K4a on the caller's stream
     std::vector<cudaEvent_t> tm_events;
     std::vector<cudaEvent_t> chunk_events;
@@ -570,6 +576,8 @@ extern "C" void bb_destroy(bb_handle* h) {
     for (cudaEvent_t e : h->tm_events) cudaEventDestroy(e);
     cudaFree(h->d_series);
     cudaFree(h->d_slotrec);
+    cudaFree(h->d_rc_dist); cudaFree(h->d_rc_prior); cudaFree(h->d_rc_rows); cudaFree(h->d_rc_rows2);
+    cudaFree(h->d_rc_y); cudaFree(h->d_slotrec_rc); cudaFree(h->d_fine);
     if (h->aux) cudaStreamDestroy(h->aux);
     if (h->copy_in) cudaStreamDestroy(h->copy_in);
     if (h->copy_out) cudaStreamDestroy(h->copy_out);
@@ -844,6 +852,33 @@ static int bb_launch_inner(bb_handle* h, long n, double* out, cudaStream_t st) {
         case 4: return bb_launch_inner_n<4>(h, n, out, st);
     }
     return bb_fail("bad n_det");
+}
+
+#include "bb_recon.cuh"
+
+extern "C" int bb_set_reconstruction_grid(bb_handle* h, const double* distance_array, const double* distance_prior_array,
+                                          int n_distance) {
+    if (!h) return bb_fail("bb_set_reconstruction_grid: null handle");
+    if (n_distance < 2 || !distance_array || !distance_prior_array) return bb_fail("bb_set_reconstruction_grid: bad grid");
+    BB_CUDA(cudaSetDevice(h->device));
+    cudaFree(h->d_rc_dist);
+    cudaFree(h->d_rc_prior);
+    h->d_rc_dist = h->d_rc_prior = nullptr;
+    BB_CUDA(cudaMalloc(&h->d_rc_dist, (size_t)n_distance * sizeof(double)));
+    BB_CUDA(cudaMalloc(&h->d_rc_prior, (size_t)n_distance * sizeof(double)));
+    BB_CUDA(cudaMemcpy(h->d_rc_dist, distance_array, (size_t)n_distance * sizeof(double), cudaMemcpyHostToDevice));
+    BB_CUDA(cudaMemcpy(h->d_rc_prior, distance_prior_array, (size_t)n_distance * sizeof(double), cudaMemcpyHostToDevice));
+    h->rc_nd = n_distance;
+    return 0;
+}
+
+extern "C" int bb_reconstruct_marginalized_device(bb_handle* h, const double* params_dev, const double* cal_params_dev,
+                                                  long n, const double* uniforms_dev, double* out_dev, void* stream) {
+    if (!h || !h->have_network) return bb_fail("bb_reconstruct_marginalized_device: network not set");
+    if (n <= 0) return 0;
+    if (!params_dev || !uniforms_dev || !out_dev) return bb_fail("bb_reconstruct_marginalized_device: null buffer");
+    BB_CUDA(cudaSetDevice(h->device));
+    return bb_reconstruct(h, params_dev, cal_params_dev, n, uniforms_dev, out_dev, (cudaStream_t)stream);
 }
 
 extern "C" int bb_inner_products_device(bb_handle* h, const double* params_dev, long n, double* out_dev, void* stream) {

@@ -122,6 +122,26 @@ __device__ __forceinline__ void bb_tm_fft_dif(double2* X, int nfft, int log2n, c
 // After the FFT of the series in shared memory: the weighted logsumexp over the times inside the geocent_time
 // prior; shared by the full-grid and the relative-binning time-marginalised kernels.  Must be entered with the
 // series complete (after a __syncthreads()).
+// Output j of the transform after only the first 8 radix-2 stages: block c = bitrev8(j & 255) of L = nfft / 256
+// consecutive elements holds the sequence whose L-point DFT gives the outputs (j & 255) + 256 n2;
+// wl[e] = exp(-2 pi i e / L) in shared memory.
+__device__ __forceinline__ double2 bb_tm_pruned_value(const double2* X, int j, int log2n, int ps, const double2* wl) {
+    const int logl = log2n - 8, L = 1 << logl;
+    const int base = (int)(__brev((unsigned)(j & 255)) >> 24) << logl;
+    const int n2 = j >> 8;
+    double vr = 0.0, vi = 0.0;
+    // start at a lane-dependent element so that neighbouring outputs do not hit the same banks
+    const int rot = (j * 5) & (L - 1);
+    for (int i = 0; i < L; ++i) {
+        const int jp = (i + rot) & (L - 1);
+        const double2 z = X[bb_tm_pos(base + jp, ps)];
+        const double2 w = wl[(jp * n2) & (L - 1)];
+        vr += z.x * w.x - z.y * w.y;
+        vi += z.x * w.y + z.y * w.x;
+    }
+    return make_double2(vr, vi);
+}
+
 // times = start_time + linspace(0, T, nfft + 1)[1:] (+ jitter): the range [j_lo, j_hi) that can lie inside the prior
 __device__ __forceinline__ void bb_tm_window(const BBMarg& marg, double jitter, double start_time, double duration,
                                              int nfft, int* j_lo, int* j_hi) {
@@ -156,20 +176,7 @@ __device__ __forceinline__ void bb_tm_finish(double2* X, int nfft, int log2n, co
         if (tj < marg.time_min || tj > marg.time_max) continue;
         double2 v;
         if (PRUNED) {
-            const int logl = log2n - 8, L = 1 << logl;
-            const int base = (int)(__brev((unsigned)(j & 255)) >> 24) << logl;
-            const int n2 = j >> 8;
-            double vr = 0.0, vi = 0.0;
-            // start at a lane-dependent element so that neighbouring outputs do not hit the same banks
-            const int rot = (j * 5) & (L - 1);
-            for (int i = 0; i < L; ++i) {
-                const int jp = (i + rot) & (L - 1);
-                const double2 z = X[bb_tm_pos(base + jp, ps)];
-                const double2 w = wl[(jp * n2) & (L - 1)];
-                vr += z.x * w.x - z.y * w.y;
-                vi += z.x * w.y + z.y * w.x;
-            }
-            v = make_double2(vr, vi);
+            v = bb_tm_pruned_value(X, j, log2n, ps, wl);
         } else {
             v = X[bb_tm_pos((int)bb_bitrev((unsigned)j, log2n), ps)];
         }

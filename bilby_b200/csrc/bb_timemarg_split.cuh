@@ -68,10 +68,11 @@ struct SFState {
     const double* cal;
     BBCalGrid grid;
     double2* series;         // this sample's row of the scratch buffer
+    int nstore;              // bins k < nstore go to the series (nfft; nfft + 1 when the Nyquist bin is wanted)
 };
 
 template <int NDET, bool CAL>
-__device__ __forceinline__ void bb_sf_bin(SFState<NDET>& st, const SFTile<NDET>& tile, int i, int k, bool act, int nfft,
+__device__ __forceinline__ void bb_sf_bin(SFState<NDET>& st, const SFTile<NDET>& tile, int i, int k, bool act,
                                           double A, double ph) {
     double sn, cs;
     bb_sincospi(act ? ph : 0.0, &sn, &cs);
@@ -104,12 +105,12 @@ __device__ __forceinline__ void bb_sf_bin(SFState<NDET>& st, const SFTile<NDET>&
     }
     st.hh = fma(A * A, hs, st.hh);
     // h conj(d)/S = conj(conj(h) d/S); the Nyquist bin k = nfft is in <h|h> but not in the series
-    if (act && k < nfft) st.series[k] = make_double2(zr * sr - zi * si, -(zr * si + zi * sr));
+    if (act && k < st.nstore) st.series[k] = make_double2(zr * sr - zi * si, -(zr * si + zi * sr));
 }
 
 template <int NDET, int AR, int PR, bool CAL>
 __device__ __forceinline__ void bb_sf_rows_pd(SFState<NDET>& st, const SFTile<NDET>& tile, const double* rec, int r0,
-                                              int r1, int c0, int lane, int kmin, int kmax, int nfft, double df) {
+                                              int r1, int c0, int lane, int kmin, int kmax, double df) {
     K1Amp<AR> amp;
     K1Ph<PR> phs;
     amp.load(rec);
@@ -123,29 +124,28 @@ __device__ __forceinline__ void bb_sf_rows_pd(SFState<NDET>& st, const SFTile<ND
         const double u = tile.u[i], t = u * u, x = f * t * t;
         const double A = amp.eval(f, x) * a0 * (u * (t * t * t));
         const double ph = phs.eval(f, t, x, tile.lf[i], tile.q34[i]);
-        bb_sf_bin<NDET, CAL>(st, tile, i, k, act, nfft, A, ph);
+        bb_sf_bin<NDET, CAL>(st, tile, i, k, act, A, ph);
         amp.next();
     }
 }
 
 template <int NDET, int APPROX, bool CAL>
 __device__ __forceinline__ void bb_sf_rows_generic(SFState<NDET>& st, const SFTile<NDET>& tile, const double* rec,
-                                                   int r0, int r1, int c0, int lane, int kmin, int kmax, int nfft,
-                                                   double df) {
+                                                   int r0, int r1, int c0, int lane, int kmin, int kmax, double df) {
     for (int r = r0; r < r1; ++r) {
         const int k = r * BB_ROW + lane, i = k - c0;
         const bool act = (k >= kmin) && (k < kmax);
         const double f = (double)k * df;
         double A, ph;
         bb_wave<APPROX>(rec, f, tile.u[i], tile.lf[i], tile.q34[i], &A, &ph);
-        bb_sf_bin<NDET, CAL>(st, tile, i, k, act, nfft, A, ph);
+        bb_sf_bin<NDET, CAL>(st, tile, i, k, act, A, ph);
     }
 }
 
 template <int NDET, int APPROX, bool CAL>
 __global__ void __maxnreg__(128)
 bb_series_fill_kernel(const double* __restrict__ coef, const unsigned* __restrict__ perm, long n, int chunk,
-                      int n_chunks, int n_slots, BBTiles tiles, double df, int nfft,
+                      int n_chunks, int n_slots, BBTiles tiles, double df, int nstore, int ld,
                       const double* __restrict__ calrec, BBCalGrid grid, double2* __restrict__ series,
                       double* __restrict__ slotrec) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -206,7 +206,8 @@ bb_series_fill_kernel(const double* __restrict__ coef, const unsigned* __restric
         st.cal = sm_cal + (warp < ns ? warp : 0) * cal_len;
         st.grid = grid;
         st.hh = 0.0;
-        st.series = series + (size_t)(slot0 + warp) * nfft;
+        st.series = series + (size_t)(slot0 + warp) * ld;
+        st.nstore = nstore;
 #pragma unroll
         for (int d = 0; d < NDET; ++d) {
             const double f0 = (double)(row_first * BB_ROW + lane) * df;
@@ -249,33 +250,33 @@ bb_series_fill_kernel(const double* __restrict__ coef, const unsigned* __restric
                         if (kp1 > kf) nb = min(nb, kp1);
                         if (kp2 > kf) nb = min(nb, kp2);
                         if (nb < kf + BB_ROW) {
-                            bb_sf_rows_generic<NDET, BB_IMRPHENOMD, CAL>(st, tile, rec, r, r + 1, c0, lane, kmin, kmax, nfft, df);
+                            bb_sf_rows_generic<NDET, BB_IMRPHENOMD, CAL>(st, tile, rec, r, r + 1, c0, lane, kmin, kmax, df);
                             r += 1;
                         } else {
                             const int rstop = (nb == INT_MAX) ? rend : min(rend, nb / BB_ROW);
                             switch (ar * 3 + pr) {
-                                case 0: bb_sf_rows_pd<NDET, 0, 0, CAL>(st, tile, rec, r, rstop, c0, lane, kmin, kmax, nfft, df); break;
-                                case 3: bb_sf_rows_pd<NDET, 1, 0, CAL>(st, tile, rec, r, rstop, c0, lane, kmin, kmax, nfft, df); break;
-                                case 4: bb_sf_rows_pd<NDET, 1, 1, CAL>(st, tile, rec, r, rstop, c0, lane, kmin, kmax, nfft, df); break;
-                                case 5: bb_sf_rows_pd<NDET, 1, 2, CAL>(st, tile, rec, r, rstop, c0, lane, kmin, kmax, nfft, df); break;
-                                case 8: bb_sf_rows_pd<NDET, 2, 2, CAL>(st, tile, rec, r, rstop, c0, lane, kmin, kmax, nfft, df); break;
-                                default: bb_sf_rows_generic<NDET, BB_IMRPHENOMD, CAL>(st, tile, rec, r, rstop, c0, lane, kmin, kmax, nfft, df); break;
+                                case 0: bb_sf_rows_pd<NDET, 0, 0, CAL>(st, tile, rec, r, rstop, c0, lane, kmin, kmax, df); break;
+                                case 3: bb_sf_rows_pd<NDET, 1, 0, CAL>(st, tile, rec, r, rstop, c0, lane, kmin, kmax, df); break;
+                                case 4: bb_sf_rows_pd<NDET, 1, 1, CAL>(st, tile, rec, r, rstop, c0, lane, kmin, kmax, df); break;
+                                case 5: bb_sf_rows_pd<NDET, 1, 2, CAL>(st, tile, rec, r, rstop, c0, lane, kmin, kmax, df); break;
+                                case 8: bb_sf_rows_pd<NDET, 2, 2, CAL>(st, tile, rec, r, rstop, c0, lane, kmin, kmax, df); break;
+                                default: bb_sf_rows_generic<NDET, BB_IMRPHENOMD, CAL>(st, tile, rec, r, rstop, c0, lane, kmin, kmax, df); break;
                             }
                             r = rstop;
                         }
                     }
                 } else {
-                    bb_sf_rows_generic<NDET, APPROX, CAL>(st, tile, rec, r, rend, c0, lane, kmin, kmax, nfft, df);
+                    bb_sf_rows_generic<NDET, APPROX, CAL>(st, tile, rec, r, rend, c0, lane, kmin, kmax, df);
                 }
             }
             __syncthreads();
         }
         if (warp < ns) {
-            // slot record for K4b: status, kmin, kmax, distance, jitter, <h|h>, sample index
+            // slot record for K4b: status, kmin, kmax, distance, jitter, <h|h>, sample index, t_c - t_start
             const double hh = bb_warp_sum(st.hh);
             const long s = perm ? (long)perm[p0 + warp] : p0 + warp;
             const double v = lane == 0 ? rec[BC_STATUS] : lane == 1 ? rec[BC_KMIN] : lane == 2 ? rec[BC_KMAX]
-                           : lane == 3 ? rec[BC_DISTANCE] : lane == 4 ? rec[BC_JITTER] : lane == 5 ? hh : (double)s;
+                           : lane == 3 ? rec[BC_DISTANCE] : lane == 4 ? rec[BC_JITTER] : lane == 5 ? hh : lane == 6 ? (double)s : rec[BC_DT0];
             if (lane < BB_SF_SLOTREC) slotrec[(size_t)(slot0 + warp) * BB_SF_SLOTREC + lane] = v;
         }
         __syncthreads();
@@ -438,7 +439,7 @@ static int bb_launch_time_marg_split_t(bb_handle* h, long n, double* out, cudaSt
             if (c >= 2) BB_CUDA(cudaStreamWaitEvent(st, h->tm_events[2 * (c - 2) + 1], 0));
             const unsigned grid_a = (unsigned)(nb < h->sm_count ? nb : h->sm_count);
             bb_series_fill_kernel<NDET, APPROX, CAL><<<grid_a, BB_SF_THREADS, smem_a, st>>>(
-                h->d_coef, perm, n, c, n_chunks, n_slots, bb_tiles(h), h->net.df, nfft, h->d_calrec, h->cal, buf, srec);
+                h->d_coef, perm, n, c, n_chunks, n_slots, bb_tiles(h), h->net.df, nfft, nfft, h->d_calrec, h->cal, buf, srec);
             BB_CUDA(cudaGetLastError());
             BB_CUDA(cudaEventRecord(h->tm_events[2 * c], st));
             BB_CUDA(cudaStreamWaitEvent(h->aux, h->tm_events[2 * c], 0));

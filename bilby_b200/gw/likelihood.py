@@ -602,6 +602,85 @@ class GravitationalWaveTransient(Likelihood):
                             complex_matched_filter_snr=dih / s[d, 2] ** 0.5))
         return out
 
+    def compute_snrs_batch(self, parameters):
+        """Per-detector matched-filter and optimal SNRs for a batch of samples: the batched form of
+        bilby.gw.conversion.compute_snrs (conversion.py:2215-2288 -> base.py:260-300).  Returns
+        ``{"<IFO>_matched_filter_snr": complex[n], "<IFO>_optimal_snr": float[n]}``."""
+        net = self.device_network
+        torch = net.torch
+        n = max(np.size(v) for v in parameters.values())
+        rows = torch.from_numpy(np.ascontiguousarray(self._rows_from_parameters(parameters, n, np))).to(net.device)
+        cal = self._cal_from_parameters(parameters, n, np)
+        cal = None if cal is None else torch.from_numpy(np.ascontiguousarray(cal)).to(net.device)
+        s = self.inner_products_batch(rows, cal).cpu().numpy()
+        out = {}
+        for d, ifo in enumerate(self.interferometers):
+            dih = s[:, d, 0] + 1j * s[:, d, 1]
+            out[f"{ifo.name}_matched_filter_snr"] = dih / s[:, d, 2] ** 0.5
+            out[f"{ifo.name}_optimal_snr"] = s[:, d, 2] ** 0.5
+        return out
+
+    # ---- marginalised-parameter reconstruction (base.py:502-773) ----------------------------------------------
+    def generate_posterior_samples_from_marginalized_likelihood_batch(self, parameters, uniforms=None, rng=None):
+        """Batched generate_posterior_sample_from_marginalized_likelihood (base.py:502-541): dict of arrays in, the
+        same dict with new ``geocent_time`` / ``luminosity_distance`` / ``phase`` columns out (only for the
+        marginalisations that are on; the steps run in the reference's order and each sees the values drawn
+        before it).
+
+        uniforms: [n, 3] unit-interval draws standing for the ``Interped.sample()`` calls of the time, distance
+        and phase steps; drawn from ``rng`` (default: a fresh numpy Generator) when omitted."""
+        if not self._marginalized_parameters:
+            return dict(parameters)
+        if getattr(self, "calibration_marginalization", False):
+            raise NotImplementedError("calibration marginalisation is not built (SURVEY.md section 8f rank 4)")
+        net = self.device_network
+        torch = net.torch
+        n = max(np.size(v) for v in parameters.values())
+        if uniforms is None:
+            rng = np.random.default_rng() if rng is None else rng
+            uniforms = rng.uniform(0, 1, size=(n, 3))
+        uniforms = np.array(np.broadcast_to(np.asarray(uniforms, dtype=np.float64), (n, 3)), order="C")
+        pars = dict(parameters)
+        if self.time_marginalization and "time_jitter" not in pars:
+            pars["time_jitter"] = np.zeros(n)
+        rows = torch.from_numpy(np.ascontiguousarray(self._rows_from_parameters(pars, n, np))).to(net.device)
+        cal = self._cal_from_parameters(pars, n, np)
+        cal_ptr = None
+        if cal is not None:
+            cal = torch.from_numpy(np.ascontiguousarray(cal)).to(net.device)
+            cal_ptr = cal.data_ptr()
+        if self.distance_marginalization and not getattr(self, "_recon_grid_set", False):
+            dist = np.ascontiguousarray(self._distance_array, dtype=np.float64)
+            prior = np.ascontiguousarray(self.distance_prior_array, dtype=np.float64)
+            _lib.check(net.lib.bb_set_reconstruction_grid(net.ptr, dist.ctypes.data, prior.ctypes.data, len(dist)))
+            self._recon_grid_set = True
+        u_dev = torch.from_numpy(uniforms).to(net.device)
+        out = torch.full((n, 3), float("nan"), dtype=torch.float64, device=net.device)
+        _lib.check(net.lib.bb_reconstruct_marginalized_device(net.ptr, rows.data_ptr(), cal_ptr, n, u_dev.data_ptr(),
+                                                              out.data_ptr(), net._stream()))
+        res = out.cpu().numpy()
+        new = {k: (np.array(v, copy=True) if np.ndim(v) else v) for k, v in parameters.items()}
+        if self.time_marginalization:
+            new["geocent_time"] = res[:, 0]
+        if self.distance_marginalization:
+            new["luminosity_distance"] = res[:, 1]
+        if self.phase_marginalization:
+            new["phase"] = res[:, 2]
+        return new
+
+    def generate_posterior_sample_from_marginalized_likelihood(self, parameters, rng=None):
+        """base.py:502-541 for one parameter dict (a batch of one through the same kernels)."""
+        if not self._marginalized_parameters:
+            return parameters
+        one = {k: np.atleast_1d(np.asarray(v, dtype=np.float64)) for k, v in parameters.items()
+               if np.isscalar(v) or np.ndim(v) == 0}
+        new = self.generate_posterior_samples_from_marginalized_likelihood_batch(one, rng=rng)
+        out = dict(parameters)
+        for k in ("geocent_time", "luminosity_distance", "phase"):
+            if k in new:
+                out[k] = float(np.asarray(new[k])[0])
+        return out
+
     def _calculate_noise_log_likelihood(self):
         """base.py:402-411 through the device inner-product kernel."""
         log_l = 0.0

@@ -221,6 +221,26 @@ int bb_set_roq(bb_handle* h, int n_linear, const double* nodes_linear, int n_qua
                const double* weights_quadratic, int n_marg_times, double marg_time_start, double marg_delta_tc,
                double beam_pattern_reference_time);
 
+/* Marginalised-parameter reconstruction, batched: replaces
+ * GravitationalWaveTransient.generate_posterior_sample_from_marginalized_likelihood and
+ * generate_{time,distance,phase}_sample_from_marginalized_likelihood (bilby/gw/likelihood/base.py:502-773), which
+ * bilby.gw.conversion.generate_posterior_samples_from_marginalized_likelihood (conversion.py:2366-2449) maps over the
+ * posterior rows with a process pool.  The marginalisation flags of bb_set_marginalization select the steps (time ->
+ * distance -> phase, each seeing the values drawn before it).
+ *   bb_set_reconstruction_grid: likelihood._distance_array and likelihood.distance_prior_array (base.py:916-919),
+ *     needed when distance marginalisation is on.
+ *   uniforms_dev [n][3]: the unit-interval draws Interped.sample() (core/prior/base.py:143-164,
+ *     core/prior/interpolated.py:88-94) would make for (time, distance, phase); columns of steps that are off are
+ *     not read.
+ *   out_dev [n][3]: new geocent_time, luminosity_distance, phase (for steps that are off: the time column is not
+ *     written, distance / phase are copied from the row).  NaN for waveform-domain errors.
+ * Restrictions: full-grid likelihood (not ROQ / relative binning), uniform geocent_time prior not wider than 0.249 s,
+ * 32768 / sampling_frequency a power of two, no calibration marginalisation. */
+int bb_set_reconstruction_grid(bb_handle* h, const double* distance_array, const double* distance_prior_array,
+                               int n_distance);
+int bb_reconstruct_marginalized_device(bb_handle* h, const double* params_dev, const double* cal_params_dev, long n,
+                                       const double* uniforms_dev, double* out_dev, void* stream);
+
 /* Measurement hooks (bench.py).  With profiling enabled the handle brackets every launch of the
  * dominant kernel (K1, the fused inner-product kernel) with CUDA events on the launching stream;
  * bb_profile_read synchronises and returns the summed duration and the number of launches since the

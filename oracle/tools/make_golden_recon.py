@@ -114,6 +114,36 @@ def main():
     res["optimal_snr"] = opt
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "recon_4s_H1L1V1.npz"), **res)
     print("written", n, "samples")
+    main_8s(draws, n0)
+
+
+def main_8s(draws, n0):
+    """8 s, zero-noise H1+L1, time + phase: duration != 4 s exposes the normalisation of the reference's 16384 Hz
+    transform (base.py:626 has no 4/T factor, unlike calculate_snrs :325-330)."""
+    names = ["H1", "L1"]
+    inj, start_time, wfg, ifos = build(8.0, 2048.0, names, noise_seed=None)
+    idx = [0, 3, n0, n0 + 1, n0 + 4, n0 + 6]
+    t_inj = inj["geocent_time"]
+    pri = dict(geocent_time=Uniform(t_inj - 0.1, t_inj + 0.1, "geocent_time"), phase=Uniform(0, 2 * np.pi, "phase"))
+    like = bilby.gw.likelihood.GravitationalWaveTransient(ifos, wfg, priors=PriorDict(pri), time_marginalization=True,
+                                                          phase_marginalization=True, jitter_time=True)
+    res = dict(start_time=start_time, duration=8.0, sampling_frequency=2048.0, detectors=np.array(names))
+    for k in draws:
+        res["param_" + k] = draws[k][idx]
+    out = np.zeros((len(idx), 3))
+    uni = np.full((len(idx), 3), np.nan)
+    for m, i in enumerate(idx):
+        p = {k: float(draws[k][i]) for k in draws}
+        brandom.seed(2000 + i)
+        new = like.generate_posterior_sample_from_marginalized_likelihood(p)
+        out[m] = [new["geocent_time"], new["luminosity_distance"], new["phase"]]
+        replay = np.random.default_rng(2000 + i)
+        uni[m, 0] = replay.uniform(0, 1)
+        uni[m, 2] = replay.uniform(0, 1)
+    res["recon_time_phase"] = out
+    res["uniforms_time_phase"] = uni
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "recon_8s_zero_H1L1.npz"), **res)
+    print("8 s:", out)
 
 
 if __name__ == "__main__":

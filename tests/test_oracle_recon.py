@@ -90,3 +90,21 @@ def test_per_detector_snrs():
         for d, (dh, hh) in enumerate(per_det):
             assert abs(dh / hh ** 0.5 - g["matched_filter_snr"][i, d]) < 1e-10 * abs(g["matched_filter_snr"][i, d])
             assert abs(hh ** 0.5 - g["optimal_snr"][i, d]) < 1e-10 * g["optimal_snr"][i, d]
+
+
+def test_reconstruction_8s_normalisation_matches_reference():
+    """duration != 4 s: pins that the reference's 16384 Hz transform carries no 4/T factor (base.py:626)."""
+    g = np.load(os.path.join(GOLDEN, "recon_8s_zero_H1L1.npz"))
+    ifos = [ocl.OracleInterferometer(str(n), 2048.0, 8.0, float(g["start_time"])) for n in g["detectors"]]
+    conv = ocl.convert_to_lal_binary_black_hole_parameters(dict(ocl.INJECTION))
+    pols = ocl.lal_binary_black_hole(ifos[0].frequency_array, *[conv[k] for k in ocl.SOURCE_ARGS], **WA)
+    for ifo in ifos:
+        ifo.frequency_domain_strain = ifo.get_detector_response(pols, conv)
+    t_inj = ocl.INJECTION["geocent_time"]
+    like = ocl.OracleLikelihood(ifos, waveform_arguments=WA, time_marginalization=True, phase_marginalization=True,
+                                time_prior=ocl.OracleUniform(t_inj - 0.1, t_inj + 0.1))
+    draws = {k[6:]: g[k] for k in g.files if k.startswith("param_")}
+    got = recon(like, draws, g["uniforms_time_phase"], range(len(g["recon_time_phase"])), True)
+    ref = g["recon_time_phase"]
+    assert np.allclose(got[:, 0], ref[:, 0], rtol=0, atol=1e-9)
+    assert np.allclose(got[:, 2], ref[:, 2], rtol=1e-9, atol=1e-9)
