@@ -12,6 +12,7 @@ SURVEY.md section 8d / DESIGN.md section 4).  Used for the ncu captures under pr
   cfg4_relbin   configs[4]: relative binning for the 128 s BNS                     (K0 + K5)
   cfg4_roq      configs[4]: ROQ for the 128 s BNS, synthetic basis                 (K0 + K6)
   cfg4_roq_time configs[4]: ROQ with time marginalisation (dense contraction)      (K0 + K7: hlinear + ZGEMM + epilogue)
+  recon         SURVEY 8f rank 2: marginalised-parameter reconstruction, 4 s H1L1V1, time + distance + phase
 """
 import argparse
 import ctypes
@@ -105,7 +106,7 @@ def build(config, n):
             n_prior = int(0.2 * fs / 2)
             extra = 5 * 8192 * 13 + 120 * n_prior
             work = "configs[2]: BBH 8s@2048Hz H1L1V1 IMRPhenomD, time marginalisation (8192-pt FFT) + CubicSpline(10)"
-            kernel = "bb_time_marg_kernel<3,IMRPhenomD,CAL>"
+            kernel = "bb_series_fill_kernel<3,IMRPhenomD,CAL> || bb_series_fft_kernel (two streams)"
 
         def flop(rows_):
             msec = (rows_[:, 0] + rows_[:, 1]) * hb.MTSUN
@@ -231,9 +232,72 @@ DEFAULT_BATCH = dict(cfg0=1_000_000, cfg2=100_000, cfg3=8192, cfg4_relbin=1_000_
                      cfg4_roq_time=65536)
 
 
+def recon_bench(n, steps):
+    """Rows per second of generate_posterior_samples_from_marginalized_likelihood_batch (host arrays in, host arrays
+    out) next to the oracle's restatement of the reference's per-row loop on one host core."""
+    import torch
+    import bilby_b200 as bb
+    from bilby_b200.core.prior import PriorDict, Uniform, PowerLaw
+    from bilby_b200.gw import source
+    from bilby_b200.workloads import INJECTION
+    duration, fs, names = 4.0, 2048.0, ["H1", "L1", "V1"]
+    inj = dict(INJECTION)
+    start = inj["geocent_time"] - duration + 2
+    wa = dict(waveform_approximant="IMRPhenomD", reference_frequency=50.0, minimum_frequency=20.0)
+    wfg = bb.gw.WaveformGenerator(duration=duration, sampling_frequency=fs, start_time=start,
+                                  frequency_domain_source_model=source.lal_binary_black_hole, waveform_arguments=wa)
+    ifos = make_ifos(names, fs, duration, start, wfg, inj)
+    pri = PriorDict(dict(geocent_time=Uniform(T_INJ - 0.1, T_INJ + 0.1, "geocent_time"),
+                         phase=Uniform(0, 2 * np.pi, "phase"),
+                         luminosity_distance=PowerLaw(2, 100.0, 5000.0, "luminosity_distance")))
+    like = bb.gw.GravitationalWaveTransient(ifos, wfg, time_marginalization=True, distance_marginalization=True,
+                                            phase_marginalization=True, jitter_time=True, priors=pri)
+    rng = np.random.default_rng(hb.DRAW_SEED)
+    rows = dict(chirp_mass=28.0956 + rng.normal(0, 0.05, n), mass_ratio=np.clip(29 / 36 + rng.normal(0, 0.02, n), 0.2, 1),
+                chi_1=0.4 + rng.normal(0, 0.02, n), chi_2=0.3 + rng.normal(0, 0.02, n),
+                luminosity_distance=np.full(n, float(like._ref_dist)), theta_jn=0.4 + rng.normal(0, 0.1, n),
+                psi=np.full(n, 2.659), phase=np.zeros(n), ra=1.375 + rng.normal(0, 0.02, n),
+                dec=-1.2108 + rng.normal(0, 0.02, n), geocent_time=T_INJ + rng.normal(0, 1e-3, n),
+                time_jitter=rng.uniform(-1 / fs, 1 / fs, n))
+    uni = rng.uniform(0, 1, (n, 3))
+    for _ in range(2):
+        new = like.generate_posterior_samples_from_marginalized_likelihood_batch(rows, uniforms=uni)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        new = like.generate_posterior_samples_from_marginalized_likelihood_batch(rows, uniforms=uni)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    # CPU: the oracle's restatement of base.py:502-773, one row at a time (what the reference's pool workers run)
+    from oracle import cbc_likelihood as ocl
+    oifos = [ocl.OracleInterferometer(nm, fs, duration, start) for nm in names]
+    for o, ifo in zip(oifos, ifos):
+        o.frequency_domain_strain = np.asarray(ifo.frequency_domain_strain)
+    table = np.asarray(like._dist_margd_loglikelihood_array)
+    olike = ocl.OracleLikelihood(oifos, waveform_arguments=wa, time_marginalization=True, distance_marginalization=True,
+                                 phase_marginalization=True, distance_prior=ocl.OraclePowerLaw(2, 100.0, 5000.0),
+                                 time_prior=ocl.OracleUniform(T_INJ - 0.1, T_INJ + 0.1), lookup_table=table)
+    m = 8
+    t0 = time.perf_counter()
+    ref = np.array([[v for v in (lambda q: (q["geocent_time"], q["luminosity_distance"], q["phase"]))(
+        olike.generate_posterior_sample_from_marginalized_likelihood({k: float(v[i]) for k, v in rows.items()}, uni[i]))]
+        for i in range(m)])
+    cpu_dt = (time.perf_counter() - t0) / m
+    got = np.stack([new["geocent_time"][:m], new["luminosity_distance"][:m], new["phase"][:m]], axis=1)
+    err = float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1.0)))
+    print(json.dumps(dict(metric="reconstructed posterior rows/sec", value=n / dt, unit="rows/s", n_gpus=1, steps=steps,
+                          config=dict(workload="SURVEY 8f rank 2: time + distance + phase reconstruction, BBH 4s H1L1V1, "
+                                               "16384 Hz time posterior (16 modulated 4096-pt transforms per row)",
+                                      batch=n),
+                          ms_per_step=dt * 1e3, dtype="f64", data="synthetic",
+                          cpu_baseline=dict(value=1.0 / cpu_dt, unit="rows/s", cores=1, kind="port",
+                                            sample=f"{m} rows, oracle restatement of base.py:502-773"),
+                          max_rel_diff_vs_oracle=err)))
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", required=True, choices=sorted(DEFAULT_BATCH))
+    ap.add_argument("--config", required=True, choices=sorted(DEFAULT_BATCH) + ["recon"])
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
@@ -242,6 +306,8 @@ def main():
     from bilby_b200 import _lib
     if not torch.cuda.is_available():
         raise SystemExit("bench_configs.py needs a CUDA device (bilby_b200 has no CPU path)")
+    if args.config == "recon":
+        return recon_bench(args.batch or 20000, args.steps)
     n = args.batch or DEFAULT_BATCH[args.config]
     like, rows_np, cal_np, flop, desc = build(args.config, n)
     net = like.device_network

@@ -119,3 +119,20 @@ def test_reconstruction_8s_vs_reference():
     ref = g["recon_time_phase"]
     assert np.abs(new["geocent_time"] - ref[:, 0]).max() < 1e-9
     assert np.abs(new["phase"] - ref[:, 2]).max() < 1e-8
+
+
+def test_conversion_module_mirrors_on_a_dataframe():
+    """bilby.gw.conversion.compute_snrs / generate_posterior_samples_from_marginalized_likelihood on a DataFrame
+    (conversion.py:2215-2271, 2400-2492)."""
+    import pandas as pd
+    from bilby_b200.gw import conversion
+    g, like, draws = _likelihood("distance_phase")
+    frame = pd.DataFrame({k: v for k, v in draws.items() if k != "time_jitter"})
+    before = frame["luminosity_distance"].to_numpy().copy()
+    out = conversion.generate_posterior_samples_from_marginalized_likelihood(frame, like, rng=np.random.default_rng(0))
+    assert out is frame and not np.array_equal(frame["luminosity_distance"].to_numpy(), before)
+    assert ((frame["luminosity_distance"] >= 100.0) & (frame["luminosity_distance"] <= 5000.0)).all()
+    conversion.compute_snrs(frame, like)
+    assert np.iscomplexobj(frame["H1_matched_filter_snr"].to_numpy()) and (frame["L1_optimal_snr"] > 0).all()
+    d = dict(luminosity_distance=1.0)
+    assert conversion.generate_posterior_samples_from_marginalized_likelihood(d, like) is d
