@@ -4,7 +4,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libbilby_b200.so")
+LIB_PATH = os.environ.get("BILBY_B200_LIB") or os.path.join(_HERE, "_lib", "libbilby_b200.so")
 
 c_double_p = ctypes.c_void_p
 _lib = None

@@ -57,6 +57,26 @@ __device__ __forceinline__ void bb_red_load(double* rec, double* cal, const doub
     __syncwarp();
 }
 
+// The same, asynchronously (cp.async, 16-byte pieces: a record is 84 doubles, a calibration record a multiple of
+// 24): the warp fetches the NEXT sample's records into its second slot while it works on the current one.
+template <bool CAL>
+__device__ __forceinline__ void bb_red_prefetch(double* rec, double* cal, const double* coef, const double* calrec,
+                                                long s, int cal_len, int lane) {
+    const char* src = reinterpret_cast<const char*>(coef + s * BC_NCOEF);
+    for (int i = lane; i < BC_NCOEF / 2; i += 32)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(bb_smem_u32(rec) + 16u * i), "l"(src + 16 * i) : "memory");
+    if (CAL) {
+        const char* csrc = reinterpret_cast<const char*>(calrec + s * cal_len);
+        for (int i = lane; i < cal_len / 2; i += 32)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(bb_smem_u32(cal) + 16u * i), "l"(csrc + 16 * i) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bb_red_wait() {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------------
 // K5: relative binning
 //   r(f_j) = h_det(f_j) / h0_det(f_j) at the bin edges; r0 = mean, r1 = slope over each bin;
@@ -128,10 +148,20 @@ bb_relbin_kernel(const double* __restrict__ coef, long n, BBRelbinDev rb, const 
     extern __shared__ __align__(16) double red_smem[];
     const int cal_len = CAL ? NDET * 4 * grid.n_points : 0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* rec = red_smem + (size_t)warp * (BC_NCOEF + cal_len);
-    double* cal = rec + BC_NCOEF;
-    for (long s = (long)blockIdx.x * BB_RED_WARPS + warp; s < n; s += (long)gridDim.x * BB_RED_WARPS) {
-        bb_red_load<CAL>(rec, cal, coef, calrec, s, cal_len, lane);
+    // two record slots per warp: the next sample's records arrive while this one is evaluated
+    const int slot_len = BC_NCOEF + cal_len;
+    double* slots = red_smem + (size_t)warp * 2 * slot_len;
+    const long stride = (long)gridDim.x * BB_RED_WARPS;
+    long s = (long)blockIdx.x * BB_RED_WARPS + warp;
+    if (s < n) bb_red_prefetch<CAL>(slots, slots + BC_NCOEF, coef, calrec, s, cal_len, lane);
+    for (int ping = 0; s < n; s += stride, ping ^= 1) {
+        double* rec = slots + ping * slot_len;
+        double* cal = rec + BC_NCOEF;
+        bb_red_wait();
+        if (s + stride < n) {
+            double* nxt = slots + (ping ^ 1) * slot_len;
+            bb_red_prefetch<CAL>(nxt, nxt + BC_NCOEF, coef, calrec, s + stride, cal_len, lane);
+        }
         double acc[NDET][3];
 #pragma unroll
         for (int d = 0; d < NDET; ++d) acc[d][0] = acc[d][1] = acc[d][2] = 0.0;
@@ -146,6 +176,7 @@ bb_relbin_kernel(const double* __restrict__ coef, long n, BBRelbinDev rb, const 
                 o[2] = (rec[BC_STATUS] != 0.0) ? nan("") : sh;
             }
         }
+        __syncwarp();       // every lane is done with this slot before it is refilled two samples later
     }
 }
 
@@ -205,14 +236,23 @@ bb_roq_kernel(const double* __restrict__ coef, long n, BBRoqDev rq, const double
     extern __shared__ __align__(16) double red_smem[];
     const int cal_len = CAL ? NDET * 4 * grid.n_points : 0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* rec = red_smem + (size_t)warp * (BC_NCOEF + cal_len);
-    double* cal = rec + BC_NCOEF;
+    const int slot_len = BC_NCOEF + cal_len;
+    double* slots = red_smem + (size_t)warp * 2 * slot_len;
     const int nl = rq.lin.n;
     const double ts0 = (double)rq.time_start_index * rq.time_step;
     const double ts1 = (double)(rq.time_start_index + 1) * rq.time_step;
     const double space = ts1 - ts0;                          // samples[1] - samples[0] (roq.py:571)
-    for (long s = (long)blockIdx.x * BB_RED_WARPS + warp; s < n; s += (long)gridDim.x * BB_RED_WARPS) {
-        bb_red_load<CAL>(rec, cal, coef, calrec, s, cal_len, lane);
+    const long stride = (long)gridDim.x * BB_RED_WARPS;
+    long s = (long)blockIdx.x * BB_RED_WARPS + warp;
+    if (s < n) bb_red_prefetch<CAL>(slots, slots + BC_NCOEF, coef, calrec, s, cal_len, lane);
+    for (int ping = 0; s < n; s += stride, ping ^= 1) {
+        double* rec = slots + ping * slot_len;
+        double* cal = rec + BC_NCOEF;
+        bb_red_wait();
+        if (s + stride < n) {
+            double* nxt = slots + (ping ^ 1) * slot_len;
+            bb_red_prefetch<CAL>(nxt, nxt + BC_NCOEF, coef, calrec, s + stride, cal_len, lane);
+        }
         double hq[NDET];
         bb_roq_quadratic<NDET, APPROX, CAL>(rec, cal, grid, rq, lane, hq);
         // five neighbouring ROQ times per detector (roq.py:509-516, 551-574)
@@ -287,6 +327,7 @@ bb_roq_kernel(const double* __restrict__ coef, long n, BBRoqDev rq, const double
                 o[2] = (rec[BC_STATUS] != 0.0) ? nan("") : hq[d];
             }
         }
+        __syncwarp();
     }
 }
 

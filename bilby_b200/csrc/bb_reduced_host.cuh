@@ -159,7 +159,7 @@ static long bb_red_grid(const bb_handle* h, long n) {
 
 template <int NDET, int APPROX, bool CAL>
 static int bb_launch_reduced_t(bb_handle* h, long n, double* out, cudaStream_t st) {
-    const size_t smem = (size_t)BB_RED_WARPS * (BC_NCOEF + (CAL ? NDET * 4 * h->cal.n_points : 0)) * sizeof(double);
+    const size_t smem = (size_t)2 * BB_RED_WARPS * (BC_NCOEF + (CAL ? NDET * 4 * h->cal.n_points : 0)) * sizeof(double);
     const long grid = bb_red_grid(h, n);
     BBProfScope prof(h, st);
     if (h->kind == 1) {
