@@ -20,6 +20,11 @@ KERNELS = {   # label -> (mangled-name regex, keep full listing)
     "k1_inner_product_3det_taylorf2": (r"_Z23bb_inner_product_kernelILi3ELi1ELb0E", False),
     "k3_epilogue": (r"_Z23bb_epilogue_coef_kernel", False),
     "k4_time_marg_3det_imrphenomd_cal": (r"_Z19bb_time_marg_kernelILi3ELi0ELb1E", True),
+    "k4a_series_fill_3det_imrphenomd_cal": (r"_Z21bb_series_fill_kernelILi3ELi0ELb1E", True),
+    "k4b_series_fft": (r"_Z20bb_series_fft_kernel", False),
+    "k4r_series_fine": (r"_Z21bb_series_fine_kernel", False),
+    "kr_recon_time": (r"_Z20bb_recon_time_kernel", False),
+    "kr_recon_distance_phase": (r"_Z30bb_recon_distance_phase_kernel", False),
     "k5_relbin_3det_taylorf2": (r"_Z16bb_relbin_kernelILi3ELi1ELb0E", False),
     "k5t_relbin_time_marg_3det_imrphenomd": (r"_Z26bb_relbin_time_marg_kernelILi3ELi0ELb0E", False),
     "k6_roq_3det_taylorf2": (r"_Z13bb_roq_kernelILi3ELi1ELb0E", False),
