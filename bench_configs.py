@@ -12,6 +12,7 @@ SURVEY.md section 8d / DESIGN.md section 4).  Used for the ncu captures under pr
   cfg4_relbin   configs[4]: relative binning for the 128 s BNS                     (K0 + K5)
   cfg4_roq      configs[4]: ROQ for the 128 s BNS, synthetic basis                 (K0 + K6)
   cfg4_roq_time configs[4]: ROQ with time marginalisation (dense contraction)      (K0 + K7: hlinear + ZGEMM + epilogue)
+  calmarg       SURVEY 8f rank 4: calibration (1000 curves) + phase marginalisation, 4 s H1L1V1  (K0 + series + ZGEMM/DGEMM)
   recon         SURVEY 8f rank 2: marginalised-parameter reconstruction, 4 s H1L1V1, time + distance + phase
 """
 import argparse
@@ -65,8 +66,8 @@ def build(config, n):
     from bilby_b200.gw import conversion, source
     from bilby_b200.workloads import INJECTION, draw_bbh_prior
     rng = np.random.default_rng(hb.DRAW_SEED)
-    if config in ("cfg0", "cfg2"):
-        duration = 4.0 if config == "cfg0" else 8.0
+    if config in ("cfg0", "cfg2", "calmarg"):
+        duration = 8.0 if config == "cfg2" else 4.0
         names = ["H1", "L1"] if config == "cfg0" else ["H1", "L1", "V1"]
         fs = 2048.0
         inj = dict(INJECTION)
@@ -79,6 +80,31 @@ def build(config, n):
         draws = draw_bbh_prior(n, rng)
         df = 1.0 / duration
         msec = None
+        if config == "calmarg":
+            from bilby_b200.core.prior import Gaussian
+            from bilby_b200.gw.detector.calibration import CubicSpline
+            n_curves = 1000
+            pri = dict(phase=Uniform(0, 2 * np.pi, "phase"))
+            for ifo in ifos:
+                ifo.calibration_model = CubicSpline(f"recalib_{ifo.name}_", ifo.minimum_frequency,
+                                                    ifo.maximum_frequency, 10)
+                for i in range(10):
+                    for kind in ("amplitude", "phase"):
+                        key = f"recalib_{ifo.name}_{kind}_{i}"
+                        pri[key] = Gaussian(0.0, 0.05, key)
+            like = bb.gw.GravitationalWaveTransient(ifos, wfg, phase_marginalization=True, calibration_marginalization=True,
+                                                    number_of_response_curves=n_curves, priors=PriorDict(pri))
+            rows = like.pack(draws)
+            ldk = (len(ifos[0].frequency_array) + 7) // 8 * 8
+            per = (8 + 2) * 3 * ldk * n_curves
+
+            def flop_cm(rows_):
+                return float(len(rows_)) * per, float(3 * ldk)
+            return like, rows, None, flop_cm, dict(
+                workload=f"SURVEY 8f rank 4: calibration marginalisation over {n_curves} CubicSpline(10) response curves + "
+                         "phase marginalisation, BBH 4s@2048Hz H1L1V1 IMRPhenomD: [batch x 3*4104] x [3*4104 x 1000] "
+                         "ZGEMM + DGEMM per chunk", kernel="bb_calmarg_series_kernel + cublas ZGEMM/DGEMM + epilogue",
+                bound="FP64 tensor path (DMMA) through cuBLAS", n_curves=n_curves)
         if config == "cfg0":
             like = bb.gw.GravitationalWaveTransient(ifos, wfg)
             rows = like.pack(draws)
@@ -228,7 +254,7 @@ def build(config, n):
         workload=work, kernel=kernel, n_linear=n_lin, n_quadratic=n_quad, n_time=n_time)
 
 
-DEFAULT_BATCH = dict(cfg0=1_000_000, cfg2=100_000, cfg3=8192, cfg4_relbin=1_000_000, cfg4_roq=1_000_000,
+DEFAULT_BATCH = dict(calmarg=16384, cfg0=1_000_000, cfg2=100_000, cfg3=8192, cfg4_relbin=1_000_000, cfg4_roq=1_000_000,
                      cfg4_roq_time=65536)
 
 

@@ -58,6 +58,7 @@ def load():
         "bb_fp64_peak": (i, [vp, ctypes.POINTER(d)]),
         "bb_launch_count": (lng, [vp]),
         "bb_set_reconstruction_grid": (i, [vp, vp, vp, i]),
+        "bb_set_calibration_marginalization": (i, [vp, i, vp]),
         "bb_reconstruct_marginalized_device": (i, [vp, vp, vp, lng, vp, vp, vp]),
     }
     for name, (res, args) in sigs.items():
@@ -77,7 +78,8 @@ EXPORTED_SYMBOLS = (
     "bb_set_roq", "bb_detector_response_device", "bb_build_distance_table",
     "bb_antenna_response_device", "bb_ln_i0_device", "bb_project_polarizations_device",
     "bb_noise_weighted_inner_product_device", "bb_profile_enable", "bb_profile_read", "bb_fp64_peak",
-    "bb_launch_count", "bb_set_reconstruction_grid", "bb_reconstruct_marginalized_device")
+    "bb_launch_count", "bb_set_reconstruction_grid", "bb_reconstruct_marginalized_device",
+    "bb_set_calibration_marginalization")
 
 
 def check(rc):

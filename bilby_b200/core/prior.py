@@ -77,6 +77,22 @@ class PowerLaw(Prior):
                                  / (self.maximum ** (1 + self.alpha) - self.minimum ** (1 + self.alpha))) * inside
 
 
+class Gaussian(Prior):
+    """bilby/core/prior/analytical.py Gaussian: rescale = mu + erfinv(2 u - 1) sqrt(2) sigma."""
+
+    def __init__(self, mu, sigma, name=None, latex_label=None, unit=None, boundary=None):
+        super().__init__(name=name, latex_label=latex_label, unit=unit, boundary=boundary)
+        self.mu = mu
+        self.sigma = sigma
+
+    def rescale(self, val):
+        from scipy.special import erfinv
+        return self.mu + erfinv(2 * np.asarray(val) - 1) * 2 ** 0.5 * self.sigma
+
+    def prob(self, val):
+        return np.exp(-(self.mu - np.asarray(val)) ** 2 / (2 * self.sigma ** 2)) / (2 * np.pi) ** 0.5 / self.sigma
+
+
 class Cosine(Prior):
     def __init__(self, minimum=-np.pi / 2, maximum=np.pi / 2, name=None, latex_label=None, unit=None, boundary=None):
         super().__init__(name=name, latex_label=latex_label, minimum=minimum, maximum=maximum,

@@ -1,0 +1,163 @@
+// Calibration marginalisation (included by bb_kernels.cu after the launch helpers).
+//
+// Replaces, per sample, GravitationalWaveTransient.calculate_snrs' calibration arrays (bilby/gw/likelihood/
+// base.py:333-346) and calibration_marginalized_likelihood (:860-877):
+//
+//   D[c] = sum_det sum_k (4/T) conj(d_k) h_det,k / S_k * C_det,c(f_k)        (complex; note conj(d) h, base.py:334-339)
+//   H[c] = sum_det sum_k (4/T) |h_det,k|^2 / S_k * |C_det,c(f_k)|^2          (real; base.py:341-346)
+//   lnL  = logsumexp_c( point likelihood(D[c], H[c]) ) - ln n_curves          (plain | phase | distance(+phase))
+//
+// over the n_curves response curves drawn once at set-up (base.py:1037-1051, calibration.py:503-591).  This is the one
+// place on the path where the arithmetic is a dense contraction over the frequency axis: per chunk of samples
+//   X [chunk][n_det * ldk] (complex) , Y [chunk][n_det * ldk] (real)      <- bb_calmarg_series_kernel
+//   D = X C^T (ZGEMM) , H = Y A^T (DGEMM)  with C, A = [n_curves][n_det * ldk]   <- cuBLAS (FP64 tensor path, DMMA)
+//   lnL                                                                           <- bb_calmarg_epilogue_kernel
+// The detectors are concatenated along the contraction axis, so the sum over detectors comes out of the GEMM.
+#pragma once
+
+#define BB_CM_CHUNK 2048
+
+template <int NDET, int APPROX>
+__global__ void bb_calmarg_series_kernel(const double* __restrict__ coef, long s0, int m, BBTiles tiles, int n_freq,
+                                         double df, int ldk, double2* __restrict__ X, double* __restrict__ Y) {
+    const int s = blockIdx.y;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= m || k >= ldk) return;
+    const double* c = coef + (s0 + s) * BC_NCOEF;
+    const bool active = k < n_freq && c[BC_STATUS] == 0.0 && k >= (int)c[BC_KMIN] && k < (int)c[BC_KMAX];
+    double A = 0.0, ph = 0.0;
+    const double f = (double)k * df;
+    if (active) bb_wave<APPROX>(c, f, tiles.u[k], tiles.lf[k], tiles.q34[k], &A, &ph);
+#pragma unroll
+    for (int d = 0; d < NDET; ++d) {
+        double2 x = make_double2(0.0, 0.0);
+        double y = 0.0;
+        if (active) {
+            const double* cd = c + BC_DET + BC_DSTRIDE * d;
+            double sn, cs;
+            bb_sincospi(ph + cd[2] * f, &sn, &cs);       // h22 e^{-2 pi i f (dt0 + delay)} = A (cs - i sn)
+            const double hr = A * (cd[0] * cs + cd[1] * sn), hi = A * (cd[1] * cs - cd[0] * sn);      // K h
+            const double2 dd = tiles.ds[(size_t)d * tiles.n_pad + k];                                 // (4/T) d / S
+            x = make_double2(hr * dd.x + hi * dd.y, hi * dd.x - hr * dd.y);                           // h conj(d) / S
+            y = (hr * hr + hi * hi) * tiles.is[(size_t)d * tiles.n_pad + k];
+        }
+        X[((size_t)s * NDET + d) * ldk + k] = x;
+        Y[((size_t)s * NDET + d) * ldk + k] = y;
+    }
+}
+
+// one warp per sample: logsumexp over the curves
+__global__ void bb_calmarg_epilogue_kernel(const double* __restrict__ coef, long s0, int m, const double2* __restrict__ D,
+                                           const double* __restrict__ H, int n_curves, BBMarg marg,
+                                           double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (s >= m) return;
+    const double* c = coef + (s0 + s) * BC_NCOEF;
+    if (c[BC_STATUS] != 0.0) {
+        if (lane == 0) out[s0 + s] = -DBL_MAX;
+        return;
+    }
+    const double dist = c[BC_DISTANCE];
+    double mx = -INFINITY, sum = 0.0;
+    for (int i = lane; i < n_curves; i += 32) {
+        const double2 d = D[(size_t)s * n_curves + i];
+        const double l = bb_point_lnl(marg, d.x, d.y, H[(size_t)s * n_curves + i], dist);
+        if (l == -INFINITY) continue;
+        if (l > mx) { sum = sum * exp(mx - l) + 1.0; mx = l; }
+        else sum += exp(l - mx);
+    }
+    double gmx = mx;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) gmx = fmax(gmx, __shfl_xor_sync(0xffffffffu, gmx, o));
+    double part = (mx == -INFINITY) ? 0.0 : sum * exp(mx - gmx);
+    part = bb_warp_sum(part);
+    if (lane == 0) out[s0 + s] = (gmx == -INFINITY) ? -INFINITY : (log(part) + gmx) - log((double)n_curves);
+}
+
+template <int NDET, int APPROX>
+static int bb_launch_calmarg_t(bb_handle* h, long n, double* out, cudaStream_t st) {
+    const int nc = h->cm_n_curves, ldk = h->cm_ldk;
+    const size_t kk = (size_t)NDET * ldk;
+    if (!h->d_cm_X) {
+        BB_CUDA(cudaMalloc(&h->d_cm_X, (size_t)BB_CM_CHUNK * kk * sizeof(double2)));
+        BB_CUDA(cudaMalloc(&h->d_cm_Y, (size_t)BB_CM_CHUNK * kk * sizeof(double)));
+        BB_CUDA(cudaMalloc(&h->d_cm_D, (size_t)BB_CM_CHUNK * nc * sizeof(double2)));
+        BB_CUDA(cudaMalloc(&h->d_cm_H, (size_t)BB_CM_CHUNK * nc * sizeof(double)));
+    }
+    if (cublasSetStream(h->cublas, st) != CUBLAS_STATUS_SUCCESS) return bb_fail("cublasSetStream failed");
+    const cuDoubleComplex one = make_cuDoubleComplex(1.0, 0.0), zero = make_cuDoubleComplex(0.0, 0.0);
+    const double done = 1.0, dzero = 0.0;
+    BBMarg point = h->marg;
+    point.flags &= ~BB_MARG_TIME;
+    BBProfScope prof(h, st);
+    for (long s0 = 0; s0 < n; s0 += BB_CM_CHUNK) {
+        const int m = (int)((n - s0) < BB_CM_CHUNK ? (n - s0) : BB_CM_CHUNK);
+        dim3 grid((ldk + 127) / 128, (unsigned)m);
+        bb_calmarg_series_kernel<NDET, APPROX><<<grid, 128, 0, st>>>(h->d_coef, s0, m, bb_tiles(h), h->net.n_freq, h->net.df,
+                                                                   ldk, h->d_cm_X, h->d_cm_Y);
+        BB_CUDA(cudaGetLastError());
+        // D^T [nc x m] = C [K x nc]^T  X [K x m]   (column-major views of the row-major buffers)
+        if (cublasZgemm(h->cublas, CUBLAS_OP_T, CUBLAS_OP_N, nc, m, (int)kk, &one,
+                        reinterpret_cast<const cuDoubleComplex*>(h->d_cm_C), (int)kk,
+                        reinterpret_cast<const cuDoubleComplex*>(h->d_cm_X), (int)kk, &zero,
+                        reinterpret_cast<cuDoubleComplex*>(h->d_cm_D), nc) != CUBLAS_STATUS_SUCCESS)
+            return bb_fail("calibration marginalisation: cublasZgemm failed");
+        if (cublasDgemm(h->cublas, CUBLAS_OP_T, CUBLAS_OP_N, nc, m, (int)kk, &done, h->d_cm_A, (int)kk, h->d_cm_Y, (int)kk,
+                        &dzero, h->d_cm_H, nc) != CUBLAS_STATUS_SUCCESS)
+            return bb_fail("calibration marginalisation: cublasDgemm failed");
+        bb_calmarg_epilogue_kernel<<<(unsigned)((m * 32L + 127) / 128), 128, 0, st>>>(h->d_coef, s0, m, h->d_cm_D, h->d_cm_H,
+                                                                                     nc, point, out);
+        BB_CUDA(cudaGetLastError());
+        h->launches += 4;
+    }
+    return 0;
+}
+
+static int bb_launch_calmarg(bb_handle* h, long n, double* out, cudaStream_t st) {
+    if (h->marg.flags & BB_MARG_TIME) return bb_fail("time + calibration marginalisation is not supported on the device");
+    if (h->kind != 0) return bb_fail("calibration marginalisation: full-grid likelihood only");
+    if (h->cal_params) return bb_fail("calibration marginalisation excludes per-sample calibration parameters");
+    if (h->shard_lo != 0 || h->shard_hi != h->net.n_freq) return bb_fail("calibration marginalisation cannot be frequency-sharded");
+    const bool pd = h->wf.approximant == BB_IMRPHENOMD;
+    switch (h->net.n_det) {
+        case 1: return pd ? bb_launch_calmarg_t<1, BB_IMRPHENOMD>(h, n, out, st) : bb_launch_calmarg_t<1, BB_TAYLORF2>(h, n, out, st);
+        case 2: return pd ? bb_launch_calmarg_t<2, BB_IMRPHENOMD>(h, n, out, st) : bb_launch_calmarg_t<2, BB_TAYLORF2>(h, n, out, st);
+        case 3: return pd ? bb_launch_calmarg_t<3, BB_IMRPHENOMD>(h, n, out, st) : bb_launch_calmarg_t<3, BB_TAYLORF2>(h, n, out, st);
+        case 4: return pd ? bb_launch_calmarg_t<4, BB_IMRPHENOMD>(h, n, out, st) : bb_launch_calmarg_t<4, BB_TAYLORF2>(h, n, out, st);
+    }
+    return bb_fail("bad n_det");
+}
+
+// curves: [n_det][n_curves][n_freq] complex (re, im) on the full frequency grid (anything outside the mask is
+// multiplied by a zero of the data tiles); n_curves = 0 switches the marginalisation off
+static int bb_calmarg_upload(bb_handle* h, int n_curves, const double* curves) {
+    cudaFree(h->d_cm_C); cudaFree(h->d_cm_A); cudaFree(h->d_cm_X); cudaFree(h->d_cm_Y); cudaFree(h->d_cm_D); cudaFree(h->d_cm_H);
+    h->d_cm_C = nullptr; h->d_cm_A = nullptr; h->d_cm_X = nullptr; h->d_cm_Y = nullptr; h->d_cm_D = nullptr; h->d_cm_H = nullptr;
+    h->cm_n_curves = 0;
+    if (n_curves <= 0) return 0;
+    if (!curves) return bb_fail("bb_set_calibration_marginalization: null curves");
+    if (!h->cublas && cublasCreate(&h->cublas) != CUBLAS_STATUS_SUCCESS) return bb_fail("cublasCreate failed");
+    const int n_det = h->net.n_det, nf = h->net.n_freq;
+    const int ldk = (nf + 7) & ~7;
+    const size_t kk = (size_t)n_det * ldk;
+    std::vector<double2> C((size_t)n_curves * kk, make_double2(0.0, 0.0));
+    std::vector<double> A((size_t)n_curves * kk, 0.0);
+    for (int d = 0; d < n_det; ++d)
+        for (int c = 0; c < n_curves; ++c) {
+            const double* src = curves + ((size_t)d * n_curves + c) * nf * 2;
+            double2* dc = C.data() + (size_t)c * kk + (size_t)d * ldk;
+            double* da = A.data() + (size_t)c * kk + (size_t)d * ldk;
+            for (int k = 0; k < nf; ++k) {
+                dc[k] = make_double2(src[2 * k], src[2 * k + 1]);
+                da[k] = src[2 * k] * src[2 * k] + src[2 * k + 1] * src[2 * k + 1];
+            }
+        }
+    BB_CUDA(cudaMalloc(&h->d_cm_C, C.size() * sizeof(double2)));
+    BB_CUDA(cudaMalloc(&h->d_cm_A, A.size() * sizeof(double)));
+    BB_CUDA(cudaMemcpy(h->d_cm_C, C.data(), C.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    BB_CUDA(cudaMemcpy(h->d_cm_A, A.data(), A.size() * sizeof(double), cudaMemcpyHostToDevice));
+    h->cm_n_curves = n_curves;
+    h->cm_ldk = ldk;
+    return 0;
+}

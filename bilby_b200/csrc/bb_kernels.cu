@@ -106,6 +106,10 @@ struct bb_handle {
     double *d_rc_rows = nullptr, *d_rc_rows2 = nullptr, *d_rc_y = nullptr, *d_slotrec_rc = nullptr;
     size_t rc_rows_cap = 0, rc_rows2_cap = 0, rc_y_cap = 0;
     double2* d_fine = nullptr;
+    // calibration marginalisation (bb_calmarg.cuh)
+    int cm_n_curves = 0, cm_ldk = 0;
+    double2 *d_cm_C = nullptr, *d_cm_X = nullptr, *d_cm_D = nullptr;
+    double *d_cm_A = nullptr, *d_cm_Y = nullptr, *d_cm_H = nullptr;
     cudaStream_t aux = nullptr;            // K4b runs here, beside K4a on the caller's stream
     std::vector<cudaEvent_t> tm_events;
     std::vector<cudaEvent_t> chunk_events;
@@ -578,6 +582,7 @@ extern "C" void bb_destroy(bb_handle* h) {
     cudaFree(h->d_slotrec);
     cudaFree(h->d_rc_dist); cudaFree(h->d_rc_prior); cudaFree(h->d_rc_rows); cudaFree(h->d_rc_rows2);
     cudaFree(h->d_rc_y); cudaFree(h->d_slotrec_rc); cudaFree(h->d_fine);
+    cudaFree(h->d_cm_C); cudaFree(h->d_cm_A); cudaFree(h->d_cm_X); cudaFree(h->d_cm_Y); cudaFree(h->d_cm_D); cudaFree(h->d_cm_H);
     if (h->aux) cudaStreamDestroy(h->aux);
     if (h->copy_in) cudaStreamDestroy(h->copy_in);
     if (h->copy_out) cudaStreamDestroy(h->copy_out);
@@ -855,6 +860,13 @@ static int bb_launch_inner(bb_handle* h, long n, double* out, cudaStream_t st) {
 }
 
 #include "bb_recon.cuh"
+#include "bb_calmarg.cuh"
+
+extern "C" int bb_set_calibration_marginalization(bb_handle* h, int n_curves, const double* curves) {
+    if (!h || !h->have_network) return bb_fail("bb_set_calibration_marginalization: network not set");
+    BB_CUDA(cudaSetDevice(h->device));
+    return bb_calmarg_upload(h, n_curves, curves);
+}
 
 extern "C" int bb_set_reconstruction_grid(bb_handle* h, const double* distance_array, const double* distance_prior_array,
                                           int n_distance) {
@@ -918,6 +930,7 @@ extern "C" int bb_log_likelihood_ratio_device(bb_handle* h, const double* params
         if (h->marg.flags & BB_MARG_TIME) return bb_launch_reduced(h, n, out_dev, st, 1);
         if (bb_launch_reduced(h, n, h->d_snr, st, 0)) return 1;
     } else {
+        if (h->cm_n_curves > 0) return bb_launch_calmarg(h, n, out_dev, st);
         if (h->marg.flags & BB_MARG_TIME) return bb_launch_time_marg(h, n, out_dev, st);
         if (bb_launch_inner(h, n, h->d_snr, st)) return 1;
     }

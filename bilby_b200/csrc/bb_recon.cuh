@@ -518,6 +518,7 @@ static int bb_reconstruct(bb_handle* h, const double* params_dev, const double* 
     const int flags = h->marg.flags;
     if ((flags & BB_MARG_DISTANCE) && !h->d_rc_dist) return bb_fail("reconstruction: bb_set_reconstruction_grid was not called");
     if (h->kind != 0) return bb_fail("reconstruction: full-grid likelihood only");
+    if (h->cm_n_curves > 0) return bb_fail("reconstruction with calibration marginalisation is not built");
     if (h->shard_lo != 0 || h->shard_hi != h->net.n_freq) return bb_fail("reconstruction cannot be frequency-sharded");
     if (bb_ensure_scratch(h, (size_t)n)) return 1;
     if ((size_t)n > h->rc_rows_cap) {

@@ -72,3 +72,56 @@ class CubicSpline(Recalibrate):
     def __repr__(self):
         return (f"{self.__class__.__name__}(prefix='{self.prefix}', minimum_frequency={self.minimum_frequency}, "
                 f"maximum_frequency={self.maximum_frequency}, n_points={self.n_points})")
+
+
+def curves_from_spline_and_prior(parameters, label, n_points, frequency_array, n_curves):
+    """bilby/gw/detector/calibration.py:578-591: ``parameters`` is a dict of arrays (or DataFrame) holding
+    ``recalib_<label>_{amplitude,phase}_<i>`` draws; returns complex curves [n_curves, len(frequency_array)]."""
+    spline = CubicSpline(prefix=f"recalib_{label}_", minimum_frequency=frequency_array[0],
+                         maximum_frequency=frequency_array[-1], n_points=n_points)
+    curves = []
+    for ii in range(n_curves):
+        row = {k: np.asarray(parameters[k])[ii] for k in parameters.keys()}
+        curves.append(spline.get_calibration_factor(frequency_array, prefix=spline.prefix, **row))
+    return curves
+
+
+def build_calibration_lookup(interferometers, lookup_files=None, priors=None, number_of_response_curves=1000,
+                             starting_index=0, rng=None):
+    """bilby/gw/detector/calibration.py:503-575.  HDF5 look-up files need h5py (absent here): ``lookup_files`` may
+    instead map a detector name to an array of response curves [n_curves, n_masked_bins] or to a dict / DataFrame
+    of spline-node draws.  Without an entry the curves are drawn from the ``recalib_<IFO>_*`` priors of a
+    CubicSpline model, as the reference does; like the reference the detector's model is then reset to the
+    identity (:552)."""
+    if lookup_files is None and priors is None:
+        raise ValueError("One of calibration_lookup_table or priors must be specified for "
+                         "building calibration marginalization lookup table.")
+    lookup_files = dict() if lookup_files is None else lookup_files
+    draws, parameters = dict(), dict()
+    for interferometer in interferometers:
+        name = interferometer.name
+        frequencies = interferometer.frequency_array[interferometer.frequency_mask]
+        entry = lookup_files.get(name)
+        if isinstance(entry, str):
+            raise NotImplementedError("HDF5 calibration files need h5py, which is not available in this image")
+        idxs = np.arange(number_of_response_curves, dtype=int) + starting_index
+        if isinstance(entry, np.ndarray):
+            draws[name] = np.asarray(entry)[idxs]
+            parameters[name] = None
+        else:
+            if entry is not None:
+                pars = {k: np.asarray(entry[k])[idxs] for k in entry.keys()}
+            else:
+                if priors is None:
+                    raise ValueError("Priors must be passed to generate calibration response curves for cubic spline.")
+                rng = np.random.default_rng() if rng is None else rng
+                pars = {k: np.asarray(priors[k].sample(number_of_response_curves, rng=rng))
+                        for k in priors.keys() if "recalib" in k and name in k and hasattr(priors[k], "sample")}
+            n_points = getattr(interferometer.calibration_model, "n_points", None)
+            if n_points is None:
+                n_points = len([k for k in pars if "amplitude" in k])
+            draws[name] = np.array(curves_from_spline_and_prior(pars, name, n_points, frequencies,
+                                                                number_of_response_curves))
+            parameters[name] = pars
+        interferometer.calibration_model = Recalibrate()
+    return draws, parameters

@@ -129,14 +129,12 @@ class GravitationalWaveTransient(Likelihood):
                  number_of_response_curves=1000, starting_index=0, jitter_time=True, reference_frame="sky",
                  time_reference="geocenter", device=None):
         super().__init__()
-        if calibration_marginalization:
-            raise NotImplementedError("calibration marginalisation is a 'next' row (SURVEY.md section 8f)")
         self.waveform_generator = waveform_generator
         self.interferometers = InterferometerList(interferometers)
         self.time_marginalization = time_marginalization
         self.distance_marginalization = distance_marginalization
         self.phase_marginalization = phase_marginalization
-        self.calibration_marginalization = False
+        self.calibration_marginalization = calibration_marginalization
         self.priors = priors
         self._check_set_duration_and_sampling_frequency_of_waveform_generator()
         self._noise_log_likelihood_value = None
@@ -191,11 +189,34 @@ class GravitationalWaveTransient(Likelihood):
             priors["luminosity_distance"] = float(self._ref_dist)
             self._marginalized_parameters.append("luminosity_distance")
 
+        if self.calibration_marginalization:           # base.py:225-229
+            if self.time_marginalization:
+                raise NotImplementedError("time + calibration marginalisation (one FFT per response curve, "
+                                          "base.py:305-323) is not built")
+            self.number_of_response_curves = number_of_response_curves
+            self.starting_index = starting_index
+            self._setup_calibration_marginalization(calibration_lookup_table, priors)
+            self._marginalized_parameters.append("recalib_index")
+
+    def _setup_calibration_marginalization(self, calibration_lookup_table, priors=None):
+        """base.py:1037-1051."""
+        from .detector import calibration
+        from ..core.prior import DeltaFunction
+        self.calibration_draws, self.calibration_parameter_draws = calibration.build_calibration_lookup(
+            interferometers=self.interferometers, lookup_files=calibration_lookup_table, priors=priors,
+            number_of_response_curves=self.number_of_response_curves, starting_index=self.starting_index)
+        for name, parameters in self.calibration_parameter_draws.items():
+            if parameters is not None and priors is not None:
+                for key in set(parameters.keys()).intersection(priors.keys()):
+                    priors[key] = DeltaFunction(0.0)
+        self.calibration_abs_draws = {name: np.abs(c) ** 2 for name, c in self.calibration_draws.items()}
+
     def __repr__(self):
         return (f"{self.__class__.__name__}(interferometers={self.interferometers},\n\twaveform_generator="
                 f"{self.waveform_generator},\n\ttime_marginalization={self.time_marginalization}, "
                 f"distance_marginalization={self.distance_marginalization}, phase_marginalization="
-                f"{self.phase_marginalization}, calibration_marginalization=False, priors={self.priors})")
+                f"{self.phase_marginalization}, calibration_marginalization={self.calibration_marginalization}, "
+                f"priors={self.priors})")
 
     # ---- set-up --------------------------------------------------------------------------------
     @property
@@ -375,6 +396,19 @@ class GravitationalWaveTransient(Likelihood):
         else:
             _lib.check(net.lib.bb_set_marginalization(net.ptr, flags, 1.0, None, 0, None, 0, None, 0.0, 0.0, 0.0,
                                                       0.0, tmin, tmax, int(bool(self.jitter_time))))
+
+        if self.calibration_marginalization:
+            # response curves on the full frequency grid, [n_det, n_curves, n_freq] complex
+            ifos = self.interferometers
+            n_freq = len(ifos[0].frequency_array)
+            full = np.zeros((len(ifos), self.number_of_response_curves, n_freq), dtype=np.complex128)
+            for d, ifo in enumerate(ifos):
+                full[d][:, ifo.frequency_mask] = self.calibration_draws[ifo.name]
+            buf = np.ascontiguousarray(np.stack([full.real, full.imag], axis=-1))
+            _lib.check(net.lib.bb_set_calibration_marginalization(net.ptr, self.number_of_response_curves,
+                                                                  buf.ctypes.data))
+        else:
+            _lib.check(net.lib.bb_set_calibration_marginalization(net.ptr, 0, None))
 
     # ---- reference frame (base.py:1063-1137) ------------------------------------------------------
     @property

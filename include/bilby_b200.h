@@ -241,6 +241,15 @@ int bb_set_reconstruction_grid(bb_handle* h, const double* distance_array, const
 int bb_reconstruct_marginalized_device(bb_handle* h, const double* params_dev, const double* cal_params_dev, long n,
                                        const double* uniforms_dev, double* out_dev, void* stream);
 
+/* Calibration marginalisation: GravitationalWaveTransient(calibration_marginalization=True)
+ * (bilby/gw/likelihood/base.py:333-346 the per-curve arrays of calculate_snrs, :860-877
+ * calibration_marginalized_likelihood, :1037-1051 set-up).  curves: likelihood.calibration_draws, as
+ * [n_det][n_curves][n_freq] complex (re, im) on the FULL frequency grid (entries outside the frequency mask are
+ * ignored).  After this call bb_log_likelihood_ratio_{device,host} return the calibration-marginalised likelihood,
+ * combined with phase / distance marginalisation as bb_set_marginalization says; time marginalisation and
+ * per-sample calibration parameters are refused.  n_curves = 0 switches it off. */
+int bb_set_calibration_marginalization(bb_handle* h, int n_curves, const double* curves);
+
 /* Measurement hooks (bench.py).  With profiling enabled the handle brackets every launch of the
  * dominant kernel (K1, the fused inner-product kernel) with CUDA events on the launching stream;
  * bb_profile_read synchronises and returns the summed duration and the number of launches since the

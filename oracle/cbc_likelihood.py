@@ -253,6 +253,20 @@ class OracleCubicSpline:
         return np.nan_to_num((1 + da) * (2 + 1j * dp) / (2 - 1j * dp))
 
 
+def curves_from_spline_nodes(name, nodes, frequency_array, n_points):
+    """calibration.py:578-591 curves_from_spline_and_prior: nodes [n_curves, 2 (amplitude, phase), n_points] ->
+    complex response curves [n_curves, len(frequency_array)]; the spline spans frequency_array[0] .. [-1]."""
+    spline = OracleCubicSpline(f"recalib_{name}_", frequency_array[0], frequency_array[-1], n_points)
+    curves = []
+    for c in range(len(nodes)):
+        params = {}
+        for i in range(n_points):
+            params[f"recalib_{name}_amplitude_{i}"] = nodes[c, 0, i]
+            params[f"recalib_{name}_phase_{i}"] = nodes[c, 1, i]
+        curves.append(spline.get_calibration_factor(frequency_array, **params))
+    return np.array(curves)
+
+
 # --------------------------------------------------------------------------------------
 # source model (bilby/gw/source.py:269-348, 552-690; conversion.py:146-153)
 # --------------------------------------------------------------------------------------
@@ -424,7 +438,8 @@ class OracleLikelihood:
     def __init__(self, interferometers, source_model=lal_binary_black_hole, waveform_arguments=None,
                  parameter_conversion=convert_to_lal_binary_black_hole_parameters,
                  time_marginalization=False, distance_marginalization=False, phase_marginalization=False,
-                 distance_prior=None, time_prior=None, jitter_time=True, lookup_table=None, table_processes=1):
+                 distance_prior=None, time_prior=None, jitter_time=True, lookup_table=None, table_processes=1,
+                 calibration_draws=None):
         self.ifos = list(interferometers)
         self.duration = self.ifos[0].duration
         self.sampling_frequency = self.ifos[0].sampling_frequency
@@ -438,6 +453,14 @@ class OracleLikelihood:
         self.phase_marginalization = phase_marginalization
         self.jitter_time = jitter_time and time_marginalization
         self.time_prior = time_prior
+        # calibration marginalisation (base.py:1037-1051): {detector name: complex [n_curves, n_masked_bins]}
+        self.calibration_marginalization = calibration_draws is not None
+        if self.calibration_marginalization:
+            if time_marginalization:
+                raise NotImplementedError("time + calibration marginalisation is not restated")
+            self.calibration_draws = {k: np.asarray(v) for k, v in calibration_draws.items()}
+            self.calibration_abs_draws = {k: np.abs(v) ** 2 for k, v in self.calibration_draws.items()}
+            self.number_of_response_curves = len(next(iter(self.calibration_draws.values())))
         if time_marginalization:
             self._delta_tc = 2 / self.sampling_frequency
             self._times = self.start_time + np.linspace(
@@ -538,6 +561,8 @@ class OracleLikelihood:
                 arr = a if arr is None else arr + a
         if return_snrs:
             return per_det
+        if self.calibration_marginalization:
+            return float(np.real(self.calibration_marginalized_likelihood(pols, parameters)))
         if self.time_marginalization:
             log_l = self.time_marginalized_likelihood(arr, hh, parameters)
         elif self.distance_marginalization:
@@ -547,6 +572,26 @@ class OracleLikelihood:
         else:
             log_l = np.real(d_inner_h) - hh / 2
         return float(np.real(log_l))
+
+    def calibration_marginalized_likelihood(self, pols, parameters):
+        """base.py:333-346 (per-detector arrays over the response curves; note conj(d) * h, the conjugate of
+        inner_product's convention), :109-148 (arrays add over detectors), :860-877."""
+        d_arr, hh_arr = 0, 0
+        for ifo in self.ifos:
+            signal = ifo.get_detector_response(pols, parameters)
+            m = ifo.frequency_mask
+            norm = 4 / self.duration
+            integrand = norm * ifo.frequency_domain_strain.conj() * signal / ifo.power_spectral_density_array
+            d_arr = d_arr + np.dot(integrand[m], self.calibration_draws[ifo.name].T)
+            hh_integrand = norm * np.abs(signal) ** 2 / ifo.power_spectral_density_array
+            hh_arr = hh_arr + np.dot(hh_integrand[m], self.calibration_abs_draws[ifo.name].T)
+        if self.distance_marginalization:
+            log_l = self.distance_marginalized_likelihood(d_arr, hh_arr, parameters)
+        elif self.phase_marginalization:
+            log_l = ln_i0(abs(d_arr)) - hh_arr / 2
+        else:
+            log_l = np.real(d_arr - hh_arr / 2)
+        return logsumexp(log_l) - np.log(self.number_of_response_curves)
 
     def distance_marginalized_likelihood(self, d_inner_h, hh, parameters):
         """base.py:775-784, 879-885."""
