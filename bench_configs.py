@@ -82,6 +82,8 @@ def build(config, n):
         msec = None
         if config == "calmarg":
             from bilby_b200.core.prior import Gaussian
+            from bilby_b200.core.utils import random as bb_random
+            bb_random.seed(hb.NOISE_SEED)
             from bilby_b200.gw.detector.calibration import CubicSpline
             n_curves = 1000
             pri = dict(phase=Uniform(0, 2 * np.pi, "phase"))

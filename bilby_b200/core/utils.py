@@ -38,3 +38,13 @@ def create_white_noise(sampling_frequency, duration, rng):
     if np.mod(number_of_samples, 2) == 0:
         white_noise[-1] = 0
     return white_noise, frequencies
+
+
+class random:
+    """Mirror of ``bilby.core.utils.random`` (core/utils/random.py:25-70): one process-wide numpy Generator,
+    re-seeded with ``random.seed(n)``; read it as ``random.rng`` at the point of use."""
+    rng = np.random.default_rng()
+
+    @classmethod
+    def seed(cls, seed):
+        cls.rng = np.random.default_rng(seed)

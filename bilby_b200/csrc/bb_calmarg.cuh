@@ -18,12 +18,14 @@
 #define BB_CM_CHUNK 2048
 
 template <int NDET, int APPROX>
-__global__ void bb_calmarg_series_kernel(const double* __restrict__ coef, long s0, int m, BBTiles tiles, int n_freq,
-                                         double df, int ldk, double2* __restrict__ X, double* __restrict__ Y) {
+__global__ void bb_calmarg_series_kernel(const double* __restrict__ coef, const unsigned* __restrict__ perm, long s0,
+                                         int m, BBTiles tiles, int n_freq, double df, int ldk, int k_lo, int k_hi,
+                                         double2* __restrict__ X, double* __restrict__ Y) {
     const int s = blockIdx.y;
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= m || k >= ldk) return;
-    const double* c = coef + (s0 + s) * BC_NCOEF;
+    const int k = k_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= m || k >= k_hi) return;
+    const long sample = perm ? (long)perm[s0 + s] : s0 + s;
+    const double* c = coef + sample * BC_NCOEF;
     const bool active = k < n_freq && c[BC_STATUS] == 0.0 && k >= (int)c[BC_KMIN] && k < (int)c[BC_KMAX];
     double A = 0.0, ph = 0.0;
     const double f = (double)k * df;
@@ -47,15 +49,16 @@ __global__ void bb_calmarg_series_kernel(const double* __restrict__ coef, long s
 }
 
 // one warp per sample: logsumexp over the curves
-__global__ void bb_calmarg_epilogue_kernel(const double* __restrict__ coef, long s0, int m, const double2* __restrict__ D,
-                                           const double* __restrict__ H, int n_curves, BBMarg marg,
-                                           double* __restrict__ out) {
+__global__ void bb_calmarg_epilogue_kernel(const double* __restrict__ coef, const unsigned* __restrict__ perm, long s0,
+                                           int m, const double2* __restrict__ D, const double* __restrict__ H,
+                                           int n_curves, BBMarg marg, double* __restrict__ out) {
     const int lane = threadIdx.x & 31;
     const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (s >= m) return;
-    const double* c = coef + (s0 + s) * BC_NCOEF;
+    const long sample = perm ? (long)perm[s0 + s] : s0 + s;
+    const double* c = coef + sample * BC_NCOEF;
     if (c[BC_STATUS] != 0.0) {
-        if (lane == 0) out[s0 + s] = -DBL_MAX;
+        if (lane == 0) out[sample] = -DBL_MAX;
         return;
     }
     const double dist = c[BC_DISTANCE];
@@ -72,7 +75,18 @@ __global__ void bb_calmarg_epilogue_kernel(const double* __restrict__ coef, long
     for (int o = 16; o > 0; o >>= 1) gmx = fmax(gmx, __shfl_xor_sync(0xffffffffu, gmx, o));
     double part = (mx == -INFINITY) ? 0.0 : sum * exp(mx - gmx);
     part = bb_warp_sum(part);
-    if (lane == 0) out[s0 + s] = (gmx == -INFINITY) ? -INFINITY : (log(part) + gmx) - log((double)n_curves);
+    if (lane == 0) out[sample] = (gmx == -INFINITY) ? -INFINITY : (log(part) + gmx) - log((double)n_curves);
+}
+
+// active bin range of every chunk: the samples arrive sorted by active-bin count (longest first), so the first sample
+// of a chunk bounds the others from above; kmin is the same for all
+__global__ void bb_calmarg_window_kernel(const double* __restrict__ coef, const unsigned* __restrict__ perm, long n,
+                                         int n_chunks, int* __restrict__ win /* [n_chunks][2] */) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chunks) return;
+    const long s = perm[(long)c * BB_CM_CHUNK];
+    win[2 * c] = (int)coef[s * BC_NCOEF + BC_KMIN];
+    win[2 * c + 1] = (int)coef[s * BC_NCOEF + BC_KMAX];
 }
 
 template <int NDET, int APPROX>
@@ -90,26 +104,52 @@ static int bb_launch_calmarg_t(bb_handle* h, long n, double* out, cudaStream_t s
     const double done = 1.0, dzero = 0.0;
     BBMarg point = h->marg;
     point.flags &= ~BB_MARG_TIME;
+    // contraction window per chunk (needs the sorted order; one small read-back per call)
+    const int n_chunks = (int)((n + BB_CM_CHUNK - 1) / BB_CM_CHUNK);
+    const unsigned* perm = (h->perm_valid && !getenv("BB_CM_NOTRIM")) ? h->d_perm : nullptr;
+    std::vector<int> win(2 * (size_t)n_chunks);
+    if (perm) {
+        int* d_win = nullptr;
+        BB_CUDA(cudaMalloc(&d_win, win.size() * sizeof(int)));
+        bb_calmarg_window_kernel<<<(n_chunks + 127) / 128, 128, 0, st>>>(h->d_coef, perm, n, n_chunks, d_win);
+        BB_CUDA(cudaMemcpyAsync(win.data(), d_win, win.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+        BB_CUDA(cudaStreamSynchronize(st));
+        BB_CUDA(cudaFree(d_win));
+        h->launches++;
+    }
     BBProfScope prof(h, st);
-    for (long s0 = 0; s0 < n; s0 += BB_CM_CHUNK) {
+    for (int c = 0; c < n_chunks; ++c) {
+        const long s0 = (long)c * BB_CM_CHUNK;
         const int m = (int)((n - s0) < BB_CM_CHUNK ? (n - s0) : BB_CM_CHUNK);
-        dim3 grid((ldk + 127) / 128, (unsigned)m);
-        bb_calmarg_series_kernel<NDET, APPROX><<<grid, 128, 0, st>>>(h->d_coef, s0, m, bb_tiles(h), h->net.n_freq, h->net.df,
-                                                                   ldk, h->d_cm_X, h->d_cm_Y);
+        int k_lo = 0, k_hi = ldk;
+        if (perm) {
+            k_lo = win[2 * c] & ~7;
+            k_hi = (win[2 * c + 1] + 7) & ~7;
+            if (k_lo < 0) k_lo = 0;
+            if (k_hi > ldk) k_hi = ldk;
+            if (k_hi <= k_lo) k_hi = k_lo + 8 <= ldk ? k_lo + 8 : ldk;
+        }
+        const int kw = k_hi - k_lo;
+        dim3 grid((kw + 127) / 128, (unsigned)m);
+        bb_calmarg_series_kernel<NDET, APPROX><<<grid, 128, 0, st>>>(h->d_coef, perm, s0, m, bb_tiles(h), h->net.n_freq,
+                                                                   h->net.df, ldk, k_lo, k_hi, h->d_cm_X, h->d_cm_Y);
         BB_CUDA(cudaGetLastError());
-        // D^T [nc x m] = C [K x nc]^T  X [K x m]   (column-major views of the row-major buffers)
-        if (cublasZgemm(h->cublas, CUBLAS_OP_T, CUBLAS_OP_N, nc, m, (int)kk, &one,
-                        reinterpret_cast<const cuDoubleComplex*>(h->d_cm_C), (int)kk,
-                        reinterpret_cast<const cuDoubleComplex*>(h->d_cm_X), (int)kk, &zero,
-                        reinterpret_cast<cuDoubleComplex*>(h->d_cm_D), nc) != CUBLAS_STATUS_SUCCESS)
-            return bb_fail("calibration marginalisation: cublasZgemm failed");
-        if (cublasDgemm(h->cublas, CUBLAS_OP_T, CUBLAS_OP_N, nc, m, (int)kk, &done, h->d_cm_A, (int)kk, h->d_cm_Y, (int)kk,
-                        &dzero, h->d_cm_H, nc) != CUBLAS_STATUS_SUCCESS)
-            return bb_fail("calibration marginalisation: cublasDgemm failed");
-        bb_calmarg_epilogue_kernel<<<(unsigned)((m * 32L + 127) / 128), 128, 0, st>>>(h->d_coef, s0, m, h->d_cm_D, h->d_cm_H,
-                                                                                     nc, point, out);
+        // per detector: D^T [nc x m] (+)= C_d [kw x nc]^T  X_d [kw x m]   (column-major views of the row-major buffers)
+        for (int d = 0; d < NDET; ++d) {
+            const size_t off = (size_t)d * ldk + k_lo;
+            if (cublasZgemm(h->cublas, CUBLAS_OP_T, CUBLAS_OP_N, nc, m, kw, &one,
+                            reinterpret_cast<const cuDoubleComplex*>(h->d_cm_C + off), (int)kk,
+                            reinterpret_cast<const cuDoubleComplex*>(h->d_cm_X + off), (int)kk, d ? &one : &zero,
+                            reinterpret_cast<cuDoubleComplex*>(h->d_cm_D), nc) != CUBLAS_STATUS_SUCCESS)
+                return bb_fail("calibration marginalisation: cublasZgemm failed");
+            if (cublasDgemm(h->cublas, CUBLAS_OP_T, CUBLAS_OP_N, nc, m, kw, &done, h->d_cm_A + off, (int)kk,
+                            h->d_cm_Y + off, (int)kk, d ? &done : &dzero, h->d_cm_H, nc) != CUBLAS_STATUS_SUCCESS)
+                return bb_fail("calibration marginalisation: cublasDgemm failed");
+        }
+        bb_calmarg_epilogue_kernel<<<(unsigned)((m * 32L + 127) / 128), 128, 0, st>>>(h->d_coef, perm, s0, m, h->d_cm_D,
+                                                                                     h->d_cm_H, nc, point, out);
         BB_CUDA(cudaGetLastError());
-        h->launches += 4;
+        h->launches += 2 + 2 * NDET;
     }
     return 0;
 }

@@ -114,7 +114,9 @@ def build_calibration_lookup(interferometers, lookup_files=None, priors=None, nu
             else:
                 if priors is None:
                     raise ValueError("Priors must be passed to generate calibration response curves for cubic spline.")
-                rng = np.random.default_rng() if rng is None else rng
+                if rng is None:
+                    from ...core.utils import random
+                    rng = random.rng
                 pars = {k: np.asarray(priors[k].sample(number_of_response_curves, rng=rng))
                         for k in priors.keys() if "recalib" in k and name in k and hasattr(priors[k], "sample")}
             n_points = getattr(interferometer.calibration_model, "n_points", None)

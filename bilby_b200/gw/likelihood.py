@@ -671,7 +671,9 @@ class GravitationalWaveTransient(Likelihood):
         torch = net.torch
         n = max(np.size(v) for v in parameters.values())
         if uniforms is None:
-            rng = np.random.default_rng() if rng is None else rng
+            if rng is None:
+                from ..core.utils import random
+                rng = random.rng
             uniforms = rng.uniform(0, 1, size=(n, 3))
         uniforms = np.array(np.broadcast_to(np.asarray(uniforms, dtype=np.float64), (n, 3)), order="C")
         pars = dict(parameters)
