@@ -392,3 +392,42 @@ def test_batched_sampler_adaptor_matches_one_point_calls():
     import torch
     dev = bl.log_likelihood_batch(torch.from_numpy(theta).cuda())
     assert dev.is_cuda and np.max(np.abs(dev.cpu().numpy() - lnl)) < 1e-9 * np.max(np.abs(lnl))
+
+
+@pytest.mark.parametrize("half_width", [0.1, 0.45])
+def test_time_marginalisation_two_kernel_path_equals_fused_and_oracle(half_width, monkeypatch):
+    """The two-kernel pipeline (bb_timemarg_split.cuh: series fill || FFT, used for batches >= 2048) against the fused
+    one-CTA-per-sample kernel and the oracle: a +-0.1 s prior takes the pruned final DFT, a +-0.45 s prior (1843 grid
+    times > BB_SFT_PRUNE_MAX) the full transform; 5000 draws so that several pipeline chunks are in flight."""
+    from bilby_b200.core.prior import PriorDict, Uniform
+    from bilby_b200.workloads import draw_bbh_prior
+    from oracle import cbc_likelihood as ocl
+    t = 1126259642.413
+    pri = PriorDict(dict(geocent_time=Uniform(t - half_width, t + half_width, "geocent_time"),
+                         phase=Uniform(0, 2 * np.pi, "phase")))
+    g, like, _ = _build("noise_H1L1V1", time_marginalization=True, jitter_time=True, phase_marginalization=True, priors=pri)
+    n = 5000
+    draws = draw_bbh_prior(n, np.random.default_rng(11))
+    draws["geocent_time"] = np.full(n, float(g["start_time"]))
+    draws["time_jitter"] = np.random.default_rng(12).uniform(-1 / 2048.0, 1 / 2048.0, n)
+    monkeypatch.setenv("BB_TM_SPLIT", "0")
+    fused = like.log_likelihood_ratio_batch(draws)
+    monkeypatch.setenv("BB_TM_SPLIT", "1")
+    split = like.log_likelihood_ratio_batch(draws)
+    monkeypatch.delenv("BB_TM_SPLIT")
+    default = like.log_likelihood_ratio_batch(draws)
+    assert np.array_equal(default, split)                  # n >= 2048 takes the two-kernel path by itself
+    fin = np.isfinite(fused)
+    assert fin.all() and np.isfinite(split).all()
+    assert np.abs(split - fused).max() < 1e-9 * np.abs(fused).max()
+    # a few rows against the oracle
+    names = [str(x) for x in g["detectors"]]
+    oifos = [ocl.OracleInterferometer(nm, 2048.0, 4.0, float(g["start_time"])) for nm in names]
+    for o in oifos:
+        o.frequency_domain_strain = g[f"strain_{o.name}"]
+    wa = dict(waveform_approximant="IMRPhenomD", reference_frequency=50.0, minimum_frequency=20.0)
+    olike = ocl.OracleLikelihood(oifos, waveform_arguments=wa, time_marginalization=True, phase_marginalization=True,
+                                 time_prior=ocl.OracleUniform(t - half_width, t + half_width))
+    for i in (0, 1234, 4999):
+        ref = olike.log_likelihood_ratio({k: float(v[i]) for k, v in draws.items()})
+        assert abs(split[i] - ref) < 1e-8 * max(abs(ref), 1.0), (i, split[i], ref)
