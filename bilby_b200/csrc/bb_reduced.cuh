@@ -13,6 +13,8 @@
 
 #define BB_RED_THREADS 256
 #define BB_RED_WARPS (BB_RED_THREADS / 32)
+#define BB_ROQ_THREADS 128     // K6: 4 warps per CTA, 3 CTAs per SM (shared-memory stages of W)
+#define BB_ROQ_WARPS (BB_ROQ_THREADS / 32)
 
 struct BBNodes {
     const double* f;
@@ -230,7 +232,7 @@ __device__ __forceinline__ double2 bb_interp5(const double2* v, double a) {
 }
 
 template <int NDET, int APPROX, bool CAL>
-__global__ void __launch_bounds__(BB_RED_THREADS, 2)
+__global__ void __launch_bounds__(BB_ROQ_THREADS, 3)
 bb_roq_kernel(const double* __restrict__ coef, long n, BBRoqDev rq, const double* __restrict__ calrec,
               BBCalGrid grid, double* __restrict__ out) {
     extern __shared__ __align__(16) double red_smem[];
@@ -238,12 +240,15 @@ bb_roq_kernel(const double* __restrict__ coef, long n, BBRoqDev rq, const double
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot_len = BC_NCOEF + cal_len;
     double* slots = red_smem + (size_t)warp * 2 * slot_len;
+    // per warp: two stages of the 5 x NDET rows of W for the 32 nodes of one pass, filled with cp.async one pass ahead
+    // (the waveform arithmetic of the current pass hides the L2 latency; no registers are held by loads in flight)
+    double2* wst = reinterpret_cast<double2*>(red_smem + (size_t)BB_ROQ_WARPS * 2 * slot_len) + (size_t)warp * 2 * NDET * 5 * 32;
     const int nl = rq.lin.n;
     const double ts0 = (double)rq.time_start_index * rq.time_step;
     const double ts1 = (double)(rq.time_start_index + 1) * rq.time_step;
     const double space = ts1 - ts0;                          // samples[1] - samples[0] (roq.py:571)
-    const long stride = (long)gridDim.x * BB_RED_WARPS;
-    long s = (long)blockIdx.x * BB_RED_WARPS + warp;
+    const long stride = (long)gridDim.x * BB_ROQ_WARPS;
+    long s = (long)blockIdx.x * BB_ROQ_WARPS + warp;
     if (s < n) bb_red_prefetch<CAL>(slots, slots + BC_NCOEF, coef, calrec, s, cal_len, lane);
     for (int ping = 0; s < n; s += stride, ping ^= 1) {
         double* rec = slots + ping * slot_len;
@@ -277,32 +282,85 @@ bb_roq_kernel(const double* __restrict__ coef, long n, BBRoqDev rq, const double
         for (int d = 0; d < NDET; ++d)
 #pragma unroll
             for (int k = 0; k < 5; ++k) acc[d][k] = make_double2(0.0, 0.0);
-        for (int j = lane; j < nl; j += 32) {
-            const double f = rq.lin.f[j];
-            double A, ph;
-            bb_wave<APPROX>(rec, f, rq.lin.u[j], rq.lin.lf[j], rq.lin.q34[j], &A, &ph);
-            double sn, cs;
-            bb_sincospi(ph, &sn, &cs);
-            const double zr0 = A * cs, zi0 = A * sn;        // conj(h22) = A e^{+i Phi}
+        const int n_pass = (nl + 31) / 32;
+        // element offsets of the 5 x NDET rows of W (fit 32 bits: bb_set_roq refuses larger weight arrays)
+        unsigned rowoff[NDET][5];
 #pragma unroll
-            for (int d = 0; d < NDET; ++d) {
-                double zr = zr0, zi = zi0;
-                if (CAL) {
-                    double amp1, cr, ci;                    // conj(h C) = conj(h) amp1 (cr - i ci)
-                    bb_cal_factor(cal + d * 4 * grid.n_points, grid.n_points, grid.l0[d], grid.inv_delta[d],
-                                  rq.lin.lf[j], &amp1, &cr, &ci);
-                    const double tr = amp1 * (zr * cr + zi * ci), ti = amp1 * (zi * cr - zr * ci);
-                    zr = tr;
-                    zi = ti;
-                }
-                const double2* Wd = rq.W + (size_t)d * rq.n_time * nl;
+        for (int d = 0; d < NDET; ++d)
 #pragma unroll
-                for (int k = 0; k < 5; ++k) {
-                    const double2 w = Wd[(size_t)idx[d][k] * nl + j];
-                    acc[d][k].x += zr * w.x - zi * w.y;
-                    acc[d][k].y += zr * w.y + zi * w.x;
+            for (int k = 0; k < 5; ++k) rowoff[d][k] = (unsigned)(((size_t)d * rq.n_time + idx[d][k]) * nl);
+        auto stage_fill = [&](int pass) {
+            const int j = pass * 32 + lane;
+            if (j < nl) {
+                const unsigned dst0 = bb_smem_u32(wst + (size_t)(pass & 1) * NDET * 5 * 32 + lane);
+#pragma unroll
+                for (int d = 0; d < NDET; ++d)
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) {
+                        const double2* src = rq.W + (rowoff[d][k] + (unsigned)j);
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst0 + 16u * 32u * (d * 5 + k)), "l"(src) : "memory");
+                    }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        stage_fill(0);
+        for (int pass = 0; pass < n_pass; ++pass) {
+            const int j = pass * 32 + lane;
+            if (pass + 1 < n_pass) stage_fill(pass + 1);
+            double zr0 = 0.0, zi0 = 0.0, lfj = 0.0;
+            if (j < nl) {
+                const double f = rq.lin.f[j];
+                double A, ph, sn, cs;
+                lfj = rq.lin.lf[j];
+                bb_wave<APPROX>(rec, f, rq.lin.u[j], lfj, rq.lin.q34[j], &A, &ph);
+                bb_sincospi(ph, &sn, &cs);
+                zr0 = A * cs;                                   // conj(h22) = A e^{+i Phi}
+                zi0 = A * sn;
+            }
+            if (pass + 1 < n_pass) asm volatile("cp.async.wait_group 1;" ::: "memory");
+            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            if (j < nl) {
+                const double2* wrow = wst + (size_t)(pass & 1) * NDET * 5 * 32 + lane;
+#pragma unroll
+                for (int d = 0; d < NDET; ++d) {
+                    double zr = zr0, zi = zi0;
+                    if (CAL) {
+                        double amp1, cr, ci;                    // conj(h C) = conj(h) amp1 (cr - i ci)
+                        bb_cal_factor(cal + d * 4 * grid.n_points, grid.n_points, grid.l0[d], grid.inv_delta[d],
+                                      lfj, &amp1, &cr, &ci);
+                        const double tr = amp1 * (zr * cr + zi * ci), ti = amp1 * (zi * cr - zr * ci);
+                        zr = tr;
+                        zi = ti;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) {
+                        const double2 w = wrow[32 * (d * 5 + k)];
+                        acc[d][k].x = fma(zr, w.x, fma(-zi, w.y, acc[d][k].x));
+                        acc[d][k].y = fma(zr, w.y, fma(zi, w.x, acc[d][k].y));
+                    }
                 }
             }
+        }
+        // reduce the 10 * NDET partial sums over the lanes through the (now idle) W stage: lane q sums quantity q
+        {
+            double* tr = reinterpret_cast<double*>(wst);            // [10 * NDET][33]
+            __syncwarp();
+#pragma unroll
+            for (int d = 0; d < NDET; ++d)
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    tr[(d * 10 + 2 * k) * 33 + lane] = acc[d][k].x;
+                    tr[(d * 10 + 2 * k + 1) * 33 + lane] = acc[d][k].y;
+                }
+            __syncwarp();
+            double tsum = 0.0;
+            if (lane < 10 * NDET) {
+#pragma unroll 8
+                for (int i = 0; i < 32; ++i) tsum += tr[lane * 33 + i];
+            }
+            __syncwarp();
+            if (lane < 10 * NDET) tr[lane] = tsum;
+            __syncwarp();
         }
 #pragma unroll
         for (int d = 0; d < NDET; ++d) {
@@ -310,7 +368,8 @@ bb_roq_kernel(const double* __restrict__ coef, long n, BBRoqDev rq, const double
             const double kr = rec[BC_DET + BC_DSTRIDE * d], ki = rec[BC_DET + BC_DSTRIDE * d + 1];
 #pragma unroll
             for (int k = 0; k < 5; ++k) {
-                const double sr = bb_warp_sum(acc[d][k].x), si = bb_warp_sum(acc[d][k].y);
+                const double* tr = reinterpret_cast<const double*>(wst);
+                const double sr = tr[d * 10 + 2 * k], si = tr[d * 10 + 2 * k + 1];
                 v[k] = make_double2(kr * sr + ki * si, kr * si - ki * sr);      // conj(K) * sum
             }
             if (lane == 0) {

@@ -167,8 +167,14 @@ static int bb_launch_reduced_t(bb_handle* h, long n, double* out, cudaStream_t s
         bb_relbin_kernel<NDET, APPROX, CAL><<<(unsigned)grid, BB_RED_THREADS, smem, st>>>(
             h->d_coef, n, *h->rb, h->d_calrec, h->cal, out);
     } else {
-        BB_CUDA(cudaFuncSetAttribute(bb_roq_kernel<NDET, APPROX, CAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        bb_roq_kernel<NDET, APPROX, CAL><<<(unsigned)grid, BB_RED_THREADS, smem, st>>>(
+        const size_t smem_k6 = (size_t)2 * BB_ROQ_WARPS * (BC_NCOEF + (CAL ? NDET * 4 * h->cal.n_points : 0)) * sizeof(double)
+                               + (size_t)BB_ROQ_WARPS * 2 * NDET * 5 * 32 * sizeof(double2);
+        if ((size_t)NDET * h->rq->n_time * h->rq->lin.n >= ((size_t)1 << 32))
+            return bb_fail("K6: linear ROQ weights with 2^32 or more elements are not supported");
+        long grid_k6 = (n + BB_ROQ_WARPS - 1) / BB_ROQ_WARPS;
+        if (grid_k6 > 3L * h->sm_count) grid_k6 = 3L * h->sm_count;
+        BB_CUDA(cudaFuncSetAttribute(bb_roq_kernel<NDET, APPROX, CAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k6));
+        bb_roq_kernel<NDET, APPROX, CAL><<<(unsigned)grid_k6, BB_ROQ_THREADS, smem_k6, st>>>(
             h->d_coef, n, *h->rq, h->d_calrec, h->cal, out);
     }
     h->launches++;
