@@ -59,6 +59,7 @@ def load():
         "bb_launch_count": (lng, [vp]),
         "bb_set_reconstruction_grid": (i, [vp, vp, vp, i]),
         "bb_set_calibration_marginalization": (i, [vp, i, vp]),
+        "bb_build_roq_linear_weights": (i, [i, i, i, vp, i, vp, vp, lng, lng, i, d, vp]),
         "bb_reconstruct_marginalized_device": (i, [vp, vp, vp, lng, vp, vp, vp]),
     }
     for name, (res, args) in sigs.items():
@@ -79,7 +80,7 @@ EXPORTED_SYMBOLS = (
     "bb_antenna_response_device", "bb_ln_i0_device", "bb_project_polarizations_device",
     "bb_noise_weighted_inner_product_device", "bb_profile_enable", "bb_profile_read", "bb_fp64_peak",
     "bb_launch_count", "bb_set_reconstruction_grid", "bb_reconstruct_marginalized_device",
-    "bb_set_calibration_marginalization")
+    "bb_set_calibration_marginalization", "bb_build_roq_linear_weights")
 
 
 def check(rc):

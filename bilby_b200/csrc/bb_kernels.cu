@@ -862,6 +862,7 @@ static int bb_launch_inner(bb_handle* h, long n, double* out, cudaStream_t st) {
 
 #include "bb_recon.cuh"
 #include "bb_calmarg.cuh"
+#include "bb_roq_weights.cuh"
 
 extern "C" int bb_set_calibration_marginalization(bb_handle* h, int n_curves, const double* curves) {
     if (!h || !h->have_network) return bb_fail("bb_set_calibration_marginalization: network not set");

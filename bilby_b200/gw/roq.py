@@ -184,6 +184,8 @@ class ROQGravitationalWaveTransient(GravitationalWaveTransient):
         space = ts[1] - ts[0]
         n_time = int(duration / space)
         lo, hi = int(ts[0] / space), int(ts[-1] / space)
+        # per detector: overlap of the basis frequencies with the data (roq.py:802-837), then the two weight sets
+        setups = []
         for ifo in self.interferometers:
             mask = ifo.frequency_mask
             if self.roq_params is not None:
@@ -199,18 +201,54 @@ class ROQGravitationalWaveTransient(GravitationalWaveTransient):
                     raise ValueError("Mismatch between ROQ basis and frequency array for {}".format(ifo.name))
             nonzero = ifo_idxs + int(ifo.minimum_frequency * duration)
             d_over_s = ifo.frequency_domain_strain[mask][ifo_idxs] / ifo.power_spectral_density_array[mask][ifo_idxs]
-            # one inverse FFT per basis element, all elements at once: rows of `spec`
-            # (scipy's pocketfft with all host cores, in slabs of 32 elements to bound memory)
-            lw = np.empty((hi - lo + 1, linear_basis.shape[0]), dtype=complex)
-            for b0 in range(0, linear_basis.shape[0], 32):
-                sl = slice(b0, min(b0 + 32, linear_basis.shape[0]))
-                spec = np.zeros((sl.stop - sl.start, n_time), dtype=complex)
-                spec[:, nonzero] = d_over_s[None, :] * linear_basis[sl][:, roq_idxs].conj()
-                lw[:, sl] = _fft.ifft(spec, axis=1, workers=os.cpu_count() or 1)[:, lo:hi + 1].T
-            lw *= 4. * n_time / duration
-            self.weights[ifo.name + "_linear"] = [lw]
+            setups.append((ifo, roq_idxs, ifo_idxs, nonzero, d_over_s))
             inv_psd = 1 / ifo.power_spectral_density_array[mask][ifo_idxs]
             self.weights[ifo.name + "_quadratic"] = [4. / duration * quadratic_basis.real[:, roq_idxs] @ inv_psd]
+        # linear weights (roq.py:849-918): on the device, all detectors in one call when they share the frequency set
+        same = all(np.array_equal(su[1], setups[0][1]) and np.array_equal(su[3], setups[0][3]) for su in setups)
+        groups = [setups] if same else [[su] for su in setups]
+        for group in groups:
+            roq_idxs, nonzero = group[0][1], group[0][3]
+            identity = len(roq_idxs) == linear_basis.shape[1] and np.array_equal(roq_idxs, np.arange(linear_basis.shape[1]))
+            basis = linear_basis if identity else linear_basis[:, roq_idxs]
+            lws = self._linear_weights_device(np.array([su[4] for su in group]), basis, nonzero, n_time, lo, hi, duration)
+            for i, (ifo, _, _, _, d_over_s) in enumerate(group):
+                if lws is not None:
+                    lw = lws[i]
+                else:
+                    # no CUDA device in this process (set-up only, e.g. building weight files on a login node): one
+                    # inverse FFT per basis element with scipy's pocketfft, in slabs of 32 elements to bound memory
+                    lw = np.empty((hi - lo + 1, linear_basis.shape[0]), dtype=complex)
+                    for b0 in range(0, linear_basis.shape[0], 32):
+                        sl = slice(b0, min(b0 + 32, linear_basis.shape[0]))
+                        spec = np.zeros((sl.stop - sl.start, n_time), dtype=complex)
+                        spec[:, nonzero] = d_over_s[None, :] * basis[sl].conj()
+                        lw[:, sl] = _fft.ifft(spec, axis=1, workers=os.cpu_count() or 1)[:, lo:hi + 1].T
+                    lw *= 4. * n_time / duration
+                self.weights[ifo.name + "_linear"] = [lw]
+
+    def _linear_weights_device(self, d_over_s, basis, bin_index, n_time, lo, hi, duration):
+        """roq.py:849-918 on the device (bb_build_roq_linear_weights: the wanted time samples as one ZGEMM against an
+        exact phase matrix).  Returns None when the process has no CUDA device."""
+        try:
+            import torch
+            if not torch.cuda.is_available():
+                return None
+            dev = torch.cuda.current_device() if self._device_index is None else int(self._device_index)
+        except ImportError:      # pragma: no cover
+            return None
+        from .. import _lib
+        lib = _lib.load()
+        n_win = hi - lo + 1
+        # complex128 arrays are (re, im) pairs in memory: hand them over without copies
+        dos = np.ascontiguousarray(d_over_s, dtype=np.complex128)
+        bas = np.ascontiguousarray(basis, dtype=np.complex128)
+        idx = np.ascontiguousarray(bin_index, dtype=np.int32)
+        out = np.empty((dos.shape[0], n_win, bas.shape[0]), dtype=np.complex128)
+        _lib.check(lib.bb_build_roq_linear_weights(dev, dos.shape[0], len(idx), dos.ctypes.data, bas.shape[0],
+                                                   bas.ctypes.data, idx.ctypes.data, int(n_time), int(lo), int(n_win),
+                                                   float(duration), out.ctypes.data))
+        return out
 
     def save_weights(self, filename, format="npz"):
         """roq.py:1055-1100 (npz flavour)."""

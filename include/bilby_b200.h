@@ -250,6 +250,16 @@ int bb_reconstruct_marginalized_device(bb_handle* h, const double* params_dev, c
  * per-sample calibration parameters are refused.  n_curves = 0 switches it off. */
 int bb_set_calibration_marginalization(bb_handle* h, int n_curves, const double* curves);
 
+/* Set-up artefact builder (no handle needed): the linear ROQ weights of n_det detectors sharing one basis,
+ * ROQGravitationalWaveTransient._set_weights_linear (bilby/gw/likelihood/roq.py:849-918) - one zero-padded inverse FFT
+ * of data * conj(basis_b) / PSD per basis element, of which only the time samples [lo, lo + n_win) are kept.
+ *   d_over_s   [n_det][n_freq_sel] complex (re, im): strain / PSD at the basis frequencies that overlap the data
+ *   basis      [n_basis][n_freq_sel] complex: linear basis at the same frequencies (NOT conjugated)
+ *   bin_index  [n_freq_sel]: index of each frequency in the n_time-point transform (ifo_idxs + f_min * T, roq.py:901)
+ *   out        [n_det][n_win][n_basis] complex = (4 n_time / T) * ifft(...)[lo : lo + n_win].T */
+int bb_build_roq_linear_weights(int device, int n_det, int n_freq_sel, const double* d_over_s, int n_basis, const double* basis,
+                                const int* bin_index, long n_time, long lo, int n_win, double duration, double* out);
+
 /* Measurement hooks (bench.py).  With profiling enabled the handle brackets every launch of the
  * dominant kernel (K1, the fused inner-product kernel) with CUDA events on the launching stream;
  * bb_profile_read synchronises and returns the summed duration and the number of launches since the
