@@ -13,7 +13,8 @@
 
 #define BB_RED_THREADS 256
 #define BB_RED_WARPS (BB_RED_THREADS / 32)
-#define BB_ROQ_THREADS 128     // K6: 4 warps per CTA, 3 CTAs per SM (shared-memory stages of W)
+#define BB_ROQ_THREADS 128     // K6: 4 warps per CTA, BB_ROQ_CTAS CTAs per SM (one shared-memory stage of W per warp)
+#define BB_ROQ_CTAS 4
 #define BB_ROQ_WARPS (BB_ROQ_THREADS / 32)
 
 struct BBNodes {
@@ -36,6 +37,11 @@ struct BBRelbinDev {
     const double2* pgrid;     // [n_det][n_freq]
     const int* bin_of_k;      // [n_freq], -1 outside [bin_inds[0], bin_inds[-1]]
     const double* centre;     // [n_bins] bin_centers
+    // edge form of the two sums (bb_relbin_edge_sample): [n_det][ne_pad], zero beyond the last edge
+    const double2* lin_c;     // <d|h> = sum_j lin_c[j] conj(h_j)
+    const double* quad_e;     // <h|h> = sum_j quad_e[j] |h_j|^2 + Re(cross_g[j] h_j conj(h_{j-1}))
+    const double2* cross_g;
+    int ne_pad;
 };
 
 struct BBRoqDev {
@@ -143,6 +149,60 @@ __device__ __forceinline__ void bb_relbin_sample(const double* rec, const double
     }
 }
 
+
+// K5, edge form (the likelihood-only path).  With r_j = h_j / h0_j at the edges, r0 = (r_{j} + r_{j-1}) / 2 and
+// r1 = (r_j - r_{j-1}) / width, both sums of relative.py:423-430 regroup into sums over EDGES:
+//   <d|h> = sum_j conj(h_j) C_j,          C_j = conj(1/h0_j) [ (a0/2 + a1/w)_{bin j-1} + (a0/2 - a1/w)_{bin j} ]
+//   <h|h> = sum_j |h_j|^2 E_j + Re( G_j h_j conj(h_{j-1}) ),
+//           E_j = |1/h0_j|^2 [ (b0/4 + b1/w)_{bin j-1} + (b0/4 - b1/w)_{bin j} ],  G_j = (b0/2)_{bin j-1} (1/h0_j) conj(1/h0_{j-1})
+// (2 b1 Re(r0 conj r1) = b1 (|r_j|^2 - |r_{j-1}|^2) / w: the cross terms cancel).  The tables are built once in
+// bb_set_relative_binning, zero-padded to a multiple of 32 edges, so the loop has no per-bin branches, no ratio and
+// one neighbour exchange.
+template <int NDET, int APPROX, bool CAL>
+__device__ __forceinline__ void bb_relbin_edge_sample(const double* rec, const double* cal, const BBCalGrid& grid,
+                                                      const BBRelbinDev& rb, int lane, double (*acc)[3]) {
+    const int ne = rb.edges.n, np = rb.ne_pad;
+    double2 carry[NDET];
+#pragma unroll
+    for (int d = 0; d < NDET; ++d) carry[d] = make_double2(0.0, 0.0);
+    for (int base = 0; base < ne; base += 32) {
+        const int j = base + lane;
+        const int jj = j < ne ? j : ne - 1;
+        const double f = rb.edges.f[jj];
+        double A, ph;
+        bb_wave<APPROX>(rec, f, rb.edges.u[jj], rb.edges.lf[jj], rb.edges.q34[jj], &A, &ph);
+        const bool more = base + 32 < ne;
+#pragma unroll
+        for (int d = 0; d < NDET; ++d) {
+            const double* cd = rec + BC_DET + BC_DSTRIDE * d;
+            double sn, cs;
+            bb_sincospi(ph + cd[2] * f, &sn, &cs);            // h22 e^{-2 pi i f (dt0 + delay)} = A (cs - i sn)
+            double hr = A * (cd[0] * cs + cd[1] * sn), hi = A * (cd[1] * cs - cd[0] * sn);   // K h
+            if (CAL) {
+                double amp1, cr, ci;
+                bb_cal_factor(cal + d * 4 * grid.n_points, grid.n_points, grid.l0[d], grid.inv_delta[d],
+                              rb.edges.lf[jj], &amp1, &cr, &ci);
+                const double tr = amp1 * (hr * cr - hi * ci), ti = amp1 * (hr * ci + hi * cr);
+                hr = tr;
+                hi = ti;
+            }
+            const double2 c = rb.lin_c[(size_t)d * np + j];
+            const double e = rb.quad_e[(size_t)d * np + j];
+            const double2 g = rb.cross_g[(size_t)d * np + j];
+            double lr = __shfl_up_sync(0xffffffffu, hr, 1), li = __shfl_up_sync(0xffffffffu, hi, 1);
+            if (lane == 0) { lr = carry[d].x; li = carry[d].y; }
+            if (more) {
+                carry[d].x = __shfl_sync(0xffffffffu, hr, 31);
+                carry[d].y = __shfl_sync(0xffffffffu, hi, 31);
+            }
+            acc[d][0] = fma(c.x, hr, fma(c.y, hi, acc[d][0]));           // C conj(h)
+            acc[d][1] = fma(c.y, hr, fma(-c.x, hi, acc[d][1]));
+            const double pr = fma(hr, lr, hi * li), pi = fma(hi, lr, -hr * li);      // h_j conj(h_{j-1})
+            acc[d][2] = fma(e, fma(hr, hr, hi * hi), fma(g.x, pr, fma(-g.y, pi, acc[d][2])));
+        }
+    }
+}
+
 template <int NDET, int APPROX, bool CAL>
 __global__ void __launch_bounds__(BB_RED_THREADS)
 bb_relbin_kernel(const double* __restrict__ coef, long n, BBRelbinDev rb, const double* __restrict__ calrec,
@@ -167,7 +227,7 @@ bb_relbin_kernel(const double* __restrict__ coef, long n, BBRelbinDev rb, const 
         double acc[NDET][3];
 #pragma unroll
         for (int d = 0; d < NDET; ++d) acc[d][0] = acc[d][1] = acc[d][2] = 0.0;
-        bb_relbin_sample<NDET, APPROX, CAL, false>(rec, cal, grid, rb, lane, acc, nullptr);
+        bb_relbin_edge_sample<NDET, APPROX, CAL>(rec, cal, grid, rb, lane, acc);
 #pragma unroll
         for (int d = 0; d < NDET; ++d) {
             const double sr = bb_warp_sum(acc[d][0]), si = bb_warp_sum(acc[d][1]), sh = bb_warp_sum(acc[d][2]);
@@ -231,8 +291,19 @@ __device__ __forceinline__ double2 bb_interp5(const double2* v, double a) {
     return o;
 }
 
+// bb_interp5 as a linear combination: o = sum_k ck[k] v[k]
+__device__ __forceinline__ void bb_interp5_coeffs(double a, double* ck) {
+    const double b = 1.0 - a;
+    const double c = (a * a * a - a) / 6.0, d = (b * b * b - b) / 6.0;
+    ck[0] = -0.25 * c;
+    ck[1] = 2.0 * c;
+    ck[2] = a - 3.5 * c + d;
+    ck[3] = b + 2.0 * c - 2.0 * d;
+    ck[4] = d - 0.25 * c;
+}
+
 template <int NDET, int APPROX, bool CAL>
-__global__ void __launch_bounds__(BB_ROQ_THREADS, 3)
+__global__ void __launch_bounds__(BB_ROQ_THREADS, BB_ROQ_CTAS)
 bb_roq_kernel(const double* __restrict__ coef, long n, BBRoqDev rq, const double* __restrict__ calrec,
               BBCalGrid grid, double* __restrict__ out) {
     extern __shared__ __align__(16) double red_smem[];
@@ -240,9 +311,10 @@ bb_roq_kernel(const double* __restrict__ coef, long n, BBRoqDev rq, const double
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot_len = BC_NCOEF + cal_len;
     double* slots = red_smem + (size_t)warp * 2 * slot_len;
-    // per warp: two stages of the 5 x NDET rows of W for the 32 nodes of one pass, filled with cp.async one pass ahead
-    // (the waveform arithmetic of the current pass hides the L2 latency; no registers are held by loads in flight)
-    double2* wst = reinterpret_cast<double2*>(red_smem + (size_t)BB_ROQ_WARPS * 2 * slot_len) + (size_t)warp * 2 * NDET * 5 * 32;
+    // per warp: one stage of the 5 x NDET rows of W for the 32 nodes of one pass, refilled with cp.async as soon as the
+    // previous pass has consumed it (the waveform arithmetic of the pass hides the L2 latency; no registers are held
+    // by loads in flight)
+    double2* wst = reinterpret_cast<double2*>(red_smem + (size_t)BB_ROQ_WARPS * 2 * slot_len) + (size_t)warp * NDET * 5 * 32;
     const int nl = rq.lin.n;
     const double ts0 = (double)rq.time_start_index * rq.time_step;
     const double ts1 = (double)(rq.time_start_index + 1) * rq.time_step;
@@ -277,11 +349,22 @@ bb_roq_kernel(const double* __restrict__ coef, long n, BBRoqDev rq, const double
                 idx[d][k] = (int)i;
             }
         }
-        double2 acc[NDET][5];
+        // The five-sample interpolation (bb_interp5) is linear in the five contractions with REAL coefficients that
+        // depend only on the sample's time, so the five rows of W are combined first (10 DFMA) and contracted once
+        // (4 DFMA) instead of five complex multiply-accumulates (20 DFMA) and 30 running sums per lane.
+        double ck[NDET][5];
 #pragma unroll
-        for (int d = 0; d < NDET; ++d)
+        for (int d = 0; d < NDET; ++d) {
+            // a = (time_samples[3] - time) / max(time_samples[1] - time_samples[0], 1e-12) on the CLIPPED indices
+            const double t3 = (double)(rq.time_start_index + idx[d][3]) * rq.time_step;
+            const double t1 = (double)(rq.time_start_index + idx[d][1]) * rq.time_step;
+            const double t0 = (double)(rq.time_start_index + idx[d][0]) * rq.time_step;
+            const double a = (t3 - ifo_time[d]) / fmax(t1 - t0, 1e-12);
+            bb_interp5_coeffs(a, ck[d]);
+        }
+        double2 acc[NDET];
 #pragma unroll
-            for (int k = 0; k < 5; ++k) acc[d][k] = make_double2(0.0, 0.0);
+        for (int d = 0; d < NDET; ++d) acc[d] = make_double2(0.0, 0.0);
         const int n_pass = (nl + 31) / 32;
         // element offsets of the 5 x NDET rows of W (fit 32 bits: bb_set_roq refuses larger weight arrays)
         unsigned rowoff[NDET][5];
@@ -292,7 +375,7 @@ bb_roq_kernel(const double* __restrict__ coef, long n, BBRoqDev rq, const double
         auto stage_fill = [&](int pass) {
             const int j = pass * 32 + lane;
             if (j < nl) {
-                const unsigned dst0 = bb_smem_u32(wst + (size_t)(pass & 1) * NDET * 5 * 32 + lane);
+                const unsigned dst0 = bb_smem_u32(wst + lane);
 #pragma unroll
                 for (int d = 0; d < NDET; ++d)
 #pragma unroll
@@ -306,7 +389,6 @@ bb_roq_kernel(const double* __restrict__ coef, long n, BBRoqDev rq, const double
         stage_fill(0);
         for (int pass = 0; pass < n_pass; ++pass) {
             const int j = pass * 32 + lane;
-            if (pass + 1 < n_pass) stage_fill(pass + 1);
             double zr0 = 0.0, zi0 = 0.0, lfj = 0.0;
             if (j < nl) {
                 const double f = rq.lin.f[j];
@@ -317,10 +399,9 @@ bb_roq_kernel(const double* __restrict__ coef, long n, BBRoqDev rq, const double
                 zr0 = A * cs;                                   // conj(h22) = A e^{+i Phi}
                 zi0 = A * sn;
             }
-            if (pass + 1 < n_pass) asm volatile("cp.async.wait_group 1;" ::: "memory");
-            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
             if (j < nl) {
-                const double2* wrow = wst + (size_t)(pass & 1) * NDET * 5 * 32 + lane;
+                const double2* wrow = wst + lane;
 #pragma unroll
                 for (int d = 0; d < NDET; ++d) {
                     double zr = zr0, zi = zi0;
@@ -332,57 +413,28 @@ bb_roq_kernel(const double* __restrict__ coef, long n, BBRoqDev rq, const double
                         zr = tr;
                         zi = ti;
                     }
+                    double wx = 0.0, wy = 0.0;
 #pragma unroll
                     for (int k = 0; k < 5; ++k) {
                         const double2 w = wrow[32 * (d * 5 + k)];
-                        acc[d][k].x = fma(zr, w.x, fma(-zi, w.y, acc[d][k].x));
-                        acc[d][k].y = fma(zr, w.y, fma(zi, w.x, acc[d][k].y));
+                        wx = fma(ck[d][k], w.x, wx);
+                        wy = fma(ck[d][k], w.y, wy);
                     }
+                    acc[d].x = fma(zr, wx, fma(-zi, wy, acc[d].x));
+                    acc[d].y = fma(zr, wy, fma(zi, wx, acc[d].y));
                 }
             }
-        }
-        // reduce the 10 * NDET partial sums over the lanes through the (now idle) W stage: lane q sums quantity q
-        {
-            double* tr = reinterpret_cast<double*>(wst);            // [10 * NDET][33]
-            __syncwarp();
-#pragma unroll
-            for (int d = 0; d < NDET; ++d)
-#pragma unroll
-                for (int k = 0; k < 5; ++k) {
-                    tr[(d * 10 + 2 * k) * 33 + lane] = acc[d][k].x;
-                    tr[(d * 10 + 2 * k + 1) * 33 + lane] = acc[d][k].y;
-                }
-            __syncwarp();
-            double tsum = 0.0;
-            if (lane < 10 * NDET) {
-#pragma unroll 8
-                for (int i = 0; i < 32; ++i) tsum += tr[lane * 33 + i];
-            }
-            __syncwarp();
-            if (lane < 10 * NDET) tr[lane] = tsum;
-            __syncwarp();
+            if (pass + 1 < n_pass) stage_fill(pass + 1);      // each lane refills only the slots it has just read
         }
 #pragma unroll
         for (int d = 0; d < NDET; ++d) {
-            double2 v[5];
             const double kr = rec[BC_DET + BC_DSTRIDE * d], ki = rec[BC_DET + BC_DSTRIDE * d + 1];
-#pragma unroll
-            for (int k = 0; k < 5; ++k) {
-                const double* tr = reinterpret_cast<const double*>(wst);
-                const double sr = tr[d * 10 + 2 * k], si = tr[d * 10 + 2 * k + 1];
-                v[k] = make_double2(kr * sr + ki * si, kr * si - ki * sr);      // conj(K) * sum
-            }
+            const double sr = bb_warp_sum(acc[d].x), si = bb_warp_sum(acc[d].y);
             if (lane == 0) {
-                // a = (time_samples[3] - time) / max(time_samples[1] - time_samples[0], 1e-12) on the CLIPPED indices
-                const double t3 = (double)(rq.time_start_index + idx[d][3]) * rq.time_step;
-                const double t1 = (double)(rq.time_start_index + idx[d][1]) * rq.time_step;
-                const double t0 = (double)(rq.time_start_index + idx[d][0]) * rq.time_step;
-                const double a = (t3 - ifo_time[d]) / fmax(t1 - t0, 1e-12);
-                const double2 dh = bb_interp5(v, a);
                 double* o = out + (s * NDET + d) * 3;
-                // out of the ROQ time window: d_inner_h += log(False) (roq.py:532-533)
-                o[0] = inb[d] ? dh.x : -INFINITY;
-                o[1] = dh.y;
+                // conj(K) * sum; out of the ROQ time window: d_inner_h += log(False) (roq.py:532-533)
+                o[0] = inb[d] ? kr * sr + ki * si : -INFINITY;
+                o[1] = kr * si - ki * sr;
                 o[2] = (rec[BC_STATUS] != 0.0) ? nan("") : hq[d];
             }
         }

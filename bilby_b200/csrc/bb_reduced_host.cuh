@@ -86,6 +86,40 @@ extern "C" int bb_set_relative_binning(bb_handle* h, int n_edges, const double* 
     if (bb_red_upload(h, b1.data(), b1.size(), &rb->b1)) return 1;
     if (bb_red_upload(h, iw.data(), iw.size(), &rb->inv_width)) return 1;
     if (bb_red_upload(h, centre.data(), centre.size(), &rb->centre)) return 1;
+    {
+        // edge form of the sums (bb_relbin_edge_sample in bb_reduced.cuh), zero-padded to whole rows of 32 edges
+        const int np = (n_edges + 31) / 32 * 32;
+        std::vector<double2> lc((size_t)nd * np, make_double2(0.0, 0.0)), cg((size_t)nd * np, make_double2(0.0, 0.0));
+        std::vector<double> qe((size_t)nd * np, 0.0);
+        for (int d = 0; d < nd; ++d)
+            for (int j = 0; j < n_edges; ++j) {
+                const double2 gi = ginv[(size_t)d * n_edges + j];
+                double cx = 0.0, cy = 0.0, e = 0.0;
+                if (j >= 1) {                 // bin j-1, whose right edge is j
+                    const size_t b = (size_t)d * nb + j - 1;
+                    cx += 0.5 * a0[b].x + a1[b].x * iw[j - 1];
+                    cy += 0.5 * a0[b].y + a1[b].y * iw[j - 1];
+                    e += 0.25 * b0[b] + b1[b] * iw[j - 1];
+                    const double2 gl = ginv[(size_t)d * n_edges + j - 1];
+                    const double hb = 0.5 * b0[b];
+                    // (1/h0_j) conj(1/h0_{j-1})
+                    cg[(size_t)d * np + j] = make_double2(hb * (gi.x * gl.x + gi.y * gl.y), hb * (gi.y * gl.x - gi.x * gl.y));
+                }
+                if (j <= nb - 1) {            // bin j, whose left edge is j
+                    const size_t b = (size_t)d * nb + j;
+                    cx += 0.5 * a0[b].x - a1[b].x * iw[j];
+                    cy += 0.5 * a0[b].y - a1[b].y * iw[j];
+                    e += 0.25 * b0[b] - b1[b] * iw[j];
+                }
+                // C = conj(1/h0_j) (cx + i cy)
+                lc[(size_t)d * np + j] = make_double2(cx * gi.x + cy * gi.y, cy * gi.x - cx * gi.y);
+                qe[(size_t)d * np + j] = e * (gi.x * gi.x + gi.y * gi.y);
+            }
+        if (bb_red_upload(h, lc.data(), lc.size(), &rb->lin_c)) return 1;
+        if (bb_red_upload(h, qe.data(), qe.size(), &rb->quad_e)) return 1;
+        if (bb_red_upload(h, cg.data(), cg.size(), &rb->cross_g)) return 1;
+        rb->ne_pad = np;
+    }
     if (fiducial_grid && bin_inds) {
         // series factor of relative.py:417-420: (4/T) h0 conj(d) / S on the full grid.  d/S comes from the tiles'
         // source arrays, which the handle no longer has on the host: read d_ds back (it already carries 4/T).
@@ -168,11 +202,11 @@ static int bb_launch_reduced_t(bb_handle* h, long n, double* out, cudaStream_t s
             h->d_coef, n, *h->rb, h->d_calrec, h->cal, out);
     } else {
         const size_t smem_k6 = (size_t)2 * BB_ROQ_WARPS * (BC_NCOEF + (CAL ? NDET * 4 * h->cal.n_points : 0)) * sizeof(double)
-                               + (size_t)BB_ROQ_WARPS * 2 * NDET * 5 * 32 * sizeof(double2);
+                               + (size_t)BB_ROQ_WARPS * NDET * 5 * 32 * sizeof(double2);
         if ((size_t)NDET * h->rq->n_time * h->rq->lin.n >= ((size_t)1 << 32))
             return bb_fail("K6: linear ROQ weights with 2^32 or more elements are not supported");
         long grid_k6 = (n + BB_ROQ_WARPS - 1) / BB_ROQ_WARPS;
-        if (grid_k6 > 3L * h->sm_count) grid_k6 = 3L * h->sm_count;
+        if (grid_k6 > (long)BB_ROQ_CTAS * h->sm_count) grid_k6 = (long)BB_ROQ_CTAS * h->sm_count;
         BB_CUDA(cudaFuncSetAttribute(bb_roq_kernel<NDET, APPROX, CAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k6));
         bb_roq_kernel<NDET, APPROX, CAL><<<(unsigned)grid_k6, BB_ROQ_THREADS, smem_k6, st>>>(
             h->d_coef, n, *h->rq, h->d_calrec, h->cal, out);
