@@ -47,6 +47,7 @@ struct BBRelbinDev {
 struct BBRoqDev {
     BBNodes lin, quad;
     const double2* W;         // [n_det][n_time][n_lin]
+    const double2* W2;        // [n_det][ceil(n_lin/32)][n_time][32] node-blocked copy for K6, zero beyond n_lin
     const double* wq;         // [n_det][n_quad]
     int n_time;
     long time_start_index;    // time_samples[i] = (time_start_index + i) * time_step   (roq.py:766)
@@ -302,6 +303,11 @@ __device__ __forceinline__ void bb_interp5_coeffs(double a, double* ck) {
     ck[4] = d - 0.25 * c;
 }
 
+// K6 mapping: one warp per sample, lane = linear node 32 p + l of pass p.  W is stored a second time in node blocks,
+// W2[det][p][time][32] (bb_set_roq), so the five neighbouring ROQ times of one pass are ONE contiguous 2560-byte
+// piece per detector: lane 0 fetches them with cp.async.bulk into the warp's stage (completion on the warp's
+// mbarrier) right after the previous pass has been consumed, and the waveform arithmetic of the pass hides the L2
+// latency.  No LSU instruction, shared-memory write wavefront or register is spent on the transfer.
 template <int NDET, int APPROX, bool CAL>
 __global__ void __launch_bounds__(BB_ROQ_THREADS, BB_ROQ_CTAS)
 bb_roq_kernel(const double* __restrict__ coef, long n, BBRoqDev rq, const double* __restrict__ calrec,
@@ -311,11 +317,17 @@ bb_roq_kernel(const double* __restrict__ coef, long n, BBRoqDev rq, const double
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int slot_len = BC_NCOEF + cal_len;
     double* slots = red_smem + (size_t)warp * 2 * slot_len;
-    // per warp: one stage of the 5 x NDET rows of W for the 32 nodes of one pass, refilled with cp.async as soon as the
-    // previous pass has consumed it (the waveform arithmetic of the pass hides the L2 latency; no registers are held
-    // by loads in flight)
-    double2* wst = reinterpret_cast<double2*>(red_smem + (size_t)BB_ROQ_WARPS * 2 * slot_len) + (size_t)warp * NDET * 5 * 32;
+    double2* wst0 = reinterpret_cast<double2*>(red_smem + (size_t)BB_ROQ_WARPS * 2 * slot_len);
+    double2* wst = wst0 + (size_t)warp * NDET * 5 * 32;
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(wst0 + (size_t)BB_ROQ_WARPS * NDET * 5 * 32) + warp;
+    if (lane == 0) {
+        bb_mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    unsigned parity = 0;                                     // parity of the next completion of this warp's barrier
     const int nl = rq.lin.n;
+    const int n_pass = (nl + 31) / 32;
     const double ts0 = (double)rq.time_start_index * rq.time_step;
     const double ts1 = (double)(rq.time_start_index + 1) * rq.time_step;
     const double space = ts1 - ts0;                          // samples[1] - samples[0] (roq.py:571)
@@ -330,63 +342,53 @@ bb_roq_kernel(const double* __restrict__ coef, long n, BBRoqDev rq, const double
             double* nxt = slots + (ping ^ 1) * slot_len;
             bb_red_prefetch<CAL>(nxt, nxt + BC_NCOEF, coef, calrec, s + stride, cal_len, lane);
         }
-        double hq[NDET];
-        bb_roq_quadratic<NDET, APPROX, CAL>(rec, cal, grid, rq, lane, hq);
-        // five neighbouring ROQ times per detector (roq.py:509-516, 551-574)
-        int idx[NDET][5];
+        // five neighbouring ROQ times per detector (roq.py:509-516, 551-574): first = closest - 2, clipped per index
+        int first[NDET];
         bool inb[NDET];
-        double ifo_time[NDET];
-#pragma unroll
-        for (int d = 0; d < NDET; ++d) {
-            ifo_time[d] = rec[BC_DT0] + 0.5 * rec[BC_DET + BC_DSTRIDE * d + 2];
-            const double q = floor((ifo_time[d] - ts0) / space);
-            const long closest = (long)fmin(fmax(q, -1.0e9), 1.0e9);
-            inb[d] = (closest - 2 >= 0) && (closest + 2 < (long)rq.n_time);
-#pragma unroll
-            for (int k = 0; k < 5; ++k) {
-                long i = closest + k - 2;
-                i = i < 0 ? 0 : (i > rq.n_time - 1 ? rq.n_time - 1 : i);
-                idx[d][k] = (int)i;
-            }
-        }
-        // The five-sample interpolation (bb_interp5) is linear in the five contractions with REAL coefficients that
-        // depend only on the sample's time, so the five rows of W are combined first (10 DFMA) and contracted once
-        // (4 DFMA) instead of five complex multiply-accumulates (20 DFMA) and 30 running sums per lane.
         double ck[NDET][5];
 #pragma unroll
         for (int d = 0; d < NDET; ++d) {
+            const double ifo_time = rec[BC_DT0] + 0.5 * rec[BC_DET + BC_DSTRIDE * d + 2];
+            const double q = floor((ifo_time - ts0) / space);
+            const long closest = (long)fmin(fmax(q, -1.0e9), 1.0e9);
+            inb[d] = (closest - 2 >= 0) && (closest + 2 < (long)rq.n_time);
+            first[d] = (int)(closest - 2);
             // a = (time_samples[3] - time) / max(time_samples[1] - time_samples[0], 1e-12) on the CLIPPED indices
-            const double t3 = (double)(rq.time_start_index + idx[d][3]) * rq.time_step;
-            const double t1 = (double)(rq.time_start_index + idx[d][1]) * rq.time_step;
-            const double t0 = (double)(rq.time_start_index + idx[d][0]) * rq.time_step;
-            const double a = (t3 - ifo_time[d]) / fmax(t1 - t0, 1e-12);
+            const int i3 = min(max(first[d] + 3, 0), rq.n_time - 1), i1 = min(max(first[d] + 1, 0), rq.n_time - 1),
+                      i0 = min(max(first[d], 0), rq.n_time - 1);
+            const double t3 = (double)(rq.time_start_index + i3) * rq.time_step;
+            const double t1 = (double)(rq.time_start_index + i1) * rq.time_step;
+            const double t0 = (double)(rq.time_start_index + i0) * rq.time_step;
+            const double a = (t3 - ifo_time) / fmax(t1 - t0, 1e-12);
+            // The five-sample interpolation (bb_interp5) is linear in the five contractions with REAL coefficients that
+            // depend only on the sample's time: the five rows of W are combined first (10 DFMA) and contracted once
+            // (4 DFMA) instead of five complex multiply-accumulates (20 DFMA) and 30 running sums per lane.
             bb_interp5_coeffs(a, ck[d]);
         }
+        auto stage_fill = [&](int pass) {
+            if (lane == 0) {
+                bb_mbar_expect_tx(bar, (unsigned)(NDET * 5 * 32 * sizeof(double2)));
+#pragma unroll
+                for (int d = 0; d < NDET; ++d) {
+                    const double2* blk = rq.W2 + ((size_t)d * n_pass + pass) * rq.n_time * 32;
+                    if (inb[d]) {
+                        bb_bulk_g2s(wst + d * 5 * 32, blk + (size_t)first[d] * 32, 5 * 32 * sizeof(double2), bar);
+                    } else {
+                        for (int k = 0; k < 5; ++k) {
+                            const int i = min(max(first[d] + k, 0), rq.n_time - 1);
+                            bb_bulk_g2s(wst + (d * 5 + k) * 32, blk + (size_t)i * 32, 32 * sizeof(double2), bar);
+                        }
+                    }
+                }
+            }
+        };
+        __syncwarp();
+        stage_fill(0);
+        double hq[NDET];
+        bb_roq_quadratic<NDET, APPROX, CAL>(rec, cal, grid, rq, lane, hq);
         double2 acc[NDET];
 #pragma unroll
         for (int d = 0; d < NDET; ++d) acc[d] = make_double2(0.0, 0.0);
-        const int n_pass = (nl + 31) / 32;
-        // element offsets of the 5 x NDET rows of W (fit 32 bits: bb_set_roq refuses larger weight arrays)
-        unsigned rowoff[NDET][5];
-#pragma unroll
-        for (int d = 0; d < NDET; ++d)
-#pragma unroll
-            for (int k = 0; k < 5; ++k) rowoff[d][k] = (unsigned)(((size_t)d * rq.n_time + idx[d][k]) * nl);
-        auto stage_fill = [&](int pass) {
-            const int j = pass * 32 + lane;
-            if (j < nl) {
-                const unsigned dst0 = bb_smem_u32(wst + lane);
-#pragma unroll
-                for (int d = 0; d < NDET; ++d)
-#pragma unroll
-                    for (int k = 0; k < 5; ++k) {
-                        const double2* src = rq.W + (rowoff[d][k] + (unsigned)j);
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst0 + 16u * 32u * (d * 5 + k)), "l"(src) : "memory");
-                    }
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-        stage_fill(0);
         for (int pass = 0; pass < n_pass; ++pass) {
             const int j = pass * 32 + lane;
             double zr0 = 0.0, zi0 = 0.0, lfj = 0.0;
@@ -399,32 +401,32 @@ bb_roq_kernel(const double* __restrict__ coef, long n, BBRoqDev rq, const double
                 zr0 = A * cs;                                   // conj(h22) = A e^{+i Phi}
                 zi0 = A * sn;
             }
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            if (j < nl) {
-                const double2* wrow = wst + lane;
+            bb_mbar_wait(bar, parity);
+            parity ^= 1u;
+            const double2* wrow = wst + lane;                   // W2 is zero beyond the last node
 #pragma unroll
-                for (int d = 0; d < NDET; ++d) {
-                    double zr = zr0, zi = zi0;
-                    if (CAL) {
-                        double amp1, cr, ci;                    // conj(h C) = conj(h) amp1 (cr - i ci)
-                        bb_cal_factor(cal + d * 4 * grid.n_points, grid.n_points, grid.l0[d], grid.inv_delta[d],
-                                      lfj, &amp1, &cr, &ci);
-                        const double tr = amp1 * (zr * cr + zi * ci), ti = amp1 * (zi * cr - zr * ci);
-                        zr = tr;
-                        zi = ti;
-                    }
-                    double wx = 0.0, wy = 0.0;
-#pragma unroll
-                    for (int k = 0; k < 5; ++k) {
-                        const double2 w = wrow[32 * (d * 5 + k)];
-                        wx = fma(ck[d][k], w.x, wx);
-                        wy = fma(ck[d][k], w.y, wy);
-                    }
-                    acc[d].x = fma(zr, wx, fma(-zi, wy, acc[d].x));
-                    acc[d].y = fma(zr, wy, fma(zi, wx, acc[d].y));
+            for (int d = 0; d < NDET; ++d) {
+                double zr = zr0, zi = zi0;
+                if (CAL) {
+                    double amp1, cr, ci;                    // conj(h C) = conj(h) amp1 (cr - i ci)
+                    bb_cal_factor(cal + d * 4 * grid.n_points, grid.n_points, grid.l0[d], grid.inv_delta[d],
+                                  lfj, &amp1, &cr, &ci);
+                    const double tr = amp1 * (zr * cr + zi * ci), ti = amp1 * (zi * cr - zr * ci);
+                    zr = tr;
+                    zi = ti;
                 }
+                double wx = 0.0, wy = 0.0;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    const double2 w = wrow[32 * (d * 5 + k)];
+                    wx = fma(ck[d][k], w.x, wx);
+                    wy = fma(ck[d][k], w.y, wy);
+                }
+                acc[d].x = fma(zr, wx, fma(-zi, wy, acc[d].x));
+                acc[d].y = fma(zr, wy, fma(zi, wx, acc[d].y));
             }
-            if (pass + 1 < n_pass) stage_fill(pass + 1);      // each lane refills only the slots it has just read
+            __syncwarp();                                       // every lane has read the stage
+            if (pass + 1 < n_pass) stage_fill(pass + 1);
         }
 #pragma unroll
         for (int d = 0; d < NDET; ++d) {

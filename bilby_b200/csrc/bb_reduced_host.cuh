@@ -164,6 +164,17 @@ extern "C" int bb_set_roq(bb_handle* h, int n_linear, const double* nodes_linear
     if (bb_upload_nodes(h, nodes_linear, n_linear, &rq->lin)) return 1;
     if (bb_upload_nodes(h, nodes_quadratic, n_quadratic, &rq->quad)) return 1;
     if (bb_red_upload(h, (const double2*)weights_linear, (size_t)nd * n_time * n_linear, &rq->W)) return 1;
+    {
+        // node-blocked copy for K6: W2[d][p][t][l] = W[d][t][32 p + l]
+        const int nblk = (n_linear + 31) / 32;
+        std::vector<double2> w2((size_t)nd * nblk * n_time * 32, make_double2(0.0, 0.0));
+        const double2* w = (const double2*)weights_linear;
+        for (int d = 0; d < nd; ++d)
+            for (int t = 0; t < n_time; ++t)
+                for (int j = 0; j < n_linear; ++j)
+                    w2[(((size_t)d * nblk + (j >> 5)) * n_time + t) * 32 + (j & 31)] = w[((size_t)d * n_time + t) * n_linear + j];
+        if (bb_red_upload(h, w2.data(), w2.size(), &rq->W2)) return 1;
+    }
     if (bb_red_upload(h, weights_quadratic, (size_t)nd * n_quadratic, &rq->wq)) return 1;
     rq->n_time = n_time;
     rq->time_start_index = time_start_index;
@@ -202,9 +213,7 @@ static int bb_launch_reduced_t(bb_handle* h, long n, double* out, cudaStream_t s
             h->d_coef, n, *h->rb, h->d_calrec, h->cal, out);
     } else {
         const size_t smem_k6 = (size_t)2 * BB_ROQ_WARPS * (BC_NCOEF + (CAL ? NDET * 4 * h->cal.n_points : 0)) * sizeof(double)
-                               + (size_t)BB_ROQ_WARPS * NDET * 5 * 32 * sizeof(double2);
-        if ((size_t)NDET * h->rq->n_time * h->rq->lin.n >= ((size_t)1 << 32))
-            return bb_fail("K6: linear ROQ weights with 2^32 or more elements are not supported");
+                               + (size_t)BB_ROQ_WARPS * NDET * 5 * 32 * sizeof(double2) + BB_ROQ_WARPS * sizeof(unsigned long long);
         long grid_k6 = (n + BB_ROQ_WARPS - 1) / BB_ROQ_WARPS;
         if (grid_k6 > (long)BB_ROQ_CTAS * h->sm_count) grid_k6 = (long)BB_ROQ_CTAS * h->sm_count;
         BB_CUDA(cudaFuncSetAttribute(bb_roq_kernel<NDET, APPROX, CAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k6));
