@@ -179,6 +179,22 @@ def build(config, n):
         return like, rows, None, (lambda r: (float(len(r)) * per, float(ne))), dict(
             workload=f"configs[4]: relative binning (epsilon=0.5, chi=1, {ne - 1} bins) for the 128s BNS, H1L1V1",
             kernel="bb_relbin_kernel<3,TaylorF2>", n_edges=ne)
+    if config == "mb":
+        wfg = bb.gw.WaveformGenerator(duration=duration, sampling_frequency=fs, start_time=start,
+                                      frequency_domain_source_model=source.binary_neutron_star_frequency_sequence,
+                                      parameter_conversion=conv,
+                                      waveform_arguments=dict(waveform_approximant="TaylorF2", reference_frequency=50.0))
+        pri = PriorDict(dict(geocent_time=Uniform(T_INJ - 0.1, T_INJ + 0.1, "geocent_time")))
+        t0 = time.time()
+        like = bb.gw.likelihood.MBGravitationalWaveTransient(ifos, wfg, reference_chirp_mass=1.15, priors=pri)
+        npts = len(like.banded_frequency_points)
+        sys.stderr.write(f"multi-banding: {like.number_of_bands} bands, {npts} points, set up in {time.time() - t0:.1f} s\n")
+        rows = like.pack(bns_draws(n, rng, narrow=True))
+        per = (170 + 78 * 3) * npts          # per (point, detector): sincospi 60, K h 6, <d|h> 8, <h|h> 4
+        return like, rows, None, (lambda r: (float(len(r)) * per, float(npts))), dict(
+            workload=f"SURVEY 8f rank 4: multi-banded likelihood ({like.number_of_bands} bands, {npts} banded points vs "
+                     f"{n_masked} grid bins) for the 128s BNS, H1L1V1", kernel="bb_relbin_kernel<3,TaylorF2,edge form>",
+            n_points=npts, n_bands=int(like.number_of_bands))
     # ---- ROQ with a synthetic empirical-interpolation basis built from device waveforms (set-up, untimed)
     import torch
     tm = config == "cfg4_roq_time"
@@ -257,7 +273,7 @@ def build(config, n):
 
 
 DEFAULT_BATCH = dict(calmarg=16384, cfg0=1_000_000, cfg2=100_000, cfg3=8192, cfg4_relbin=1_000_000, cfg4_roq=1_000_000,
-                     cfg4_roq_time=65536)
+                     cfg4_roq_time=65536, mb=65536)
 
 
 def recon_bench(n, steps):

@@ -159,7 +159,7 @@ __device__ __forceinline__ void bb_relbin_sample(const double* rec, const double
 // (2 b1 Re(r0 conj r1) = b1 (|r_j|^2 - |r_{j-1}|^2) / w: the cross terms cancel).  The tables are built once in
 // bb_set_relative_binning, zero-padded to a multiple of 32 edges, so the loop has no per-bin branches, no ratio and
 // one neighbour exchange.
-template <int NDET, int APPROX, bool CAL>
+template <int NDET, int APPROX, bool CAL, bool CROSS>
 __device__ __forceinline__ void bb_relbin_edge_sample(const double* rec, const double* cal, const BBCalGrid& grid,
                                                       const BBRelbinDev& rb, int lane, double (*acc)[3]) {
     const int ne = rb.edges.n, np = rb.ne_pad;
@@ -189,22 +189,26 @@ __device__ __forceinline__ void bb_relbin_edge_sample(const double* rec, const d
             }
             const double2 c = rb.lin_c[(size_t)d * np + j];
             const double e = rb.quad_e[(size_t)d * np + j];
-            const double2 g = rb.cross_g[(size_t)d * np + j];
-            double lr = __shfl_up_sync(0xffffffffu, hr, 1), li = __shfl_up_sync(0xffffffffu, hi, 1);
-            if (lane == 0) { lr = carry[d].x; li = carry[d].y; }
-            if (more) {
-                carry[d].x = __shfl_sync(0xffffffffu, hr, 31);
-                carry[d].y = __shfl_sync(0xffffffffu, hi, 31);
-            }
             acc[d][0] = fma(c.x, hr, fma(c.y, hi, acc[d][0]));           // C conj(h)
             acc[d][1] = fma(c.y, hr, fma(-c.x, hi, acc[d][1]));
-            const double pr = fma(hr, lr, hi * li), pi = fma(hi, lr, -hr * li);      // h_j conj(h_{j-1})
-            acc[d][2] = fma(e, fma(hr, hr, hi * hi), fma(g.x, pr, fma(-g.y, pi, acc[d][2])));
+            if (CROSS) {
+                const double2 g = rb.cross_g[(size_t)d * np + j];
+                double lr = __shfl_up_sync(0xffffffffu, hr, 1), li = __shfl_up_sync(0xffffffffu, hi, 1);
+                if (lane == 0) { lr = carry[d].x; li = carry[d].y; }
+                if (more) {
+                    carry[d].x = __shfl_sync(0xffffffffu, hr, 31);
+                    carry[d].y = __shfl_sync(0xffffffffu, hi, 31);
+                }
+                const double pr = fma(hr, lr, hi * li), pi = fma(hi, lr, -hr * li);      // h_j conj(h_{j-1})
+                acc[d][2] = fma(e, fma(hr, hr, hi * hi), fma(g.x, pr, fma(-g.y, pi, acc[d][2])));
+            } else {
+                acc[d][2] = fma(e, fma(hr, hr, hi * hi), acc[d][2]);     // multi-banding: no neighbour term
+            }
         }
     }
 }
 
-template <int NDET, int APPROX, bool CAL>
+template <int NDET, int APPROX, bool CAL, bool CROSS>
 __global__ void __launch_bounds__(BB_RED_THREADS)
 bb_relbin_kernel(const double* __restrict__ coef, long n, BBRelbinDev rb, const double* __restrict__ calrec,
                  BBCalGrid grid, double* __restrict__ out) {
@@ -228,7 +232,7 @@ bb_relbin_kernel(const double* __restrict__ coef, long n, BBRelbinDev rb, const 
         double acc[NDET][3];
 #pragma unroll
         for (int d = 0; d < NDET; ++d) acc[d][0] = acc[d][1] = acc[d][2] = 0.0;
-        bb_relbin_edge_sample<NDET, APPROX, CAL>(rec, cal, grid, rb, lane, acc);
+        bb_relbin_edge_sample<NDET, APPROX, CAL, CROSS>(rec, cal, grid, rb, lane, acc);
 #pragma unroll
         for (int d = 0; d < NDET; ++d) {
             const double sr = bb_warp_sum(acc[d][0]), si = bb_warp_sum(acc[d][1]), sh = bb_warp_sum(acc[d][2]);

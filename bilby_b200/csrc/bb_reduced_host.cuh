@@ -146,6 +146,37 @@ extern "C" int bb_set_relative_binning(bb_handle* h, int n_edges, const double* 
     return 0;
 }
 
+extern "C" int bb_set_multiband(bb_handle* h, int n_points, const double* frequencies, const double* linear_coeffs,
+                                const double* quadratic_coeffs) {
+    if (!h || !h->have_network) return bb_fail("bb_set_multiband: network not set");
+    BB_CUDA(cudaSetDevice(h->device));
+    bb_reduced_clear(h);
+    if (n_points == 0) return 0;
+    if (n_points < 1 || !frequencies || !linear_coeffs || !quadratic_coeffs) return bb_fail("bb_set_multiband: bad arguments");
+    const int nd = h->net.n_det;
+    BBRelbinDev* rb = new BBRelbinDev();
+    memset(rb, 0, sizeof(*rb));
+    h->rb = rb;
+    if (bb_upload_nodes(h, frequencies, n_points, &rb->edges)) return 1;
+    // edge form of K5: C_k = conj(linear_coeffs[k]), E_k = quadratic_coeffs[k], no neighbour term (cross_g stays NULL)
+    const int np = (n_points + 31) / 32 * 32;
+    std::vector<double2> lc((size_t)nd * np, make_double2(0.0, 0.0));
+    std::vector<double> qe((size_t)nd * np, 0.0);
+    for (int d = 0; d < nd; ++d)
+        for (int k = 0; k < n_points; ++k) {
+            const double* c = linear_coeffs + ((size_t)d * n_points + k) * 2;
+            lc[(size_t)d * np + k] = make_double2(c[0], -c[1]);
+            qe[(size_t)d * np + k] = quadratic_coeffs[(size_t)d * n_points + k];
+        }
+    if (bb_red_upload(h, lc.data(), lc.size(), &rb->lin_c)) return 1;
+    if (bb_red_upload(h, qe.data(), qe.size(), &rb->quad_e)) return 1;
+    rb->ne_pad = np;
+    h->rb_fmin = frequencies[0];
+    for (int k = 1; k < n_points; ++k) if (frequencies[k] < h->rb_fmin) h->rb_fmin = frequencies[k];
+    h->kind = 1;
+    return 0;
+}
+
 extern "C" int bb_set_roq(bb_handle* h, int n_linear, const double* nodes_linear, int n_quadratic,
                           const double* nodes_quadratic, int n_time, long time_start_index, double time_step,
                           const double* weights_linear, const double* weights_quadratic, int n_marg_times,
@@ -208,9 +239,15 @@ static int bb_launch_reduced_t(bb_handle* h, long n, double* out, cudaStream_t s
     const long grid = bb_red_grid(h, n);
     BBProfScope prof(h, st);
     if (h->kind == 1) {
-        BB_CUDA(cudaFuncSetAttribute(bb_relbin_kernel<NDET, APPROX, CAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        bb_relbin_kernel<NDET, APPROX, CAL><<<(unsigned)grid, BB_RED_THREADS, smem, st>>>(
-            h->d_coef, n, *h->rb, h->d_calrec, h->cal, out);
+        if (h->rb->cross_g) {
+            BB_CUDA(cudaFuncSetAttribute(bb_relbin_kernel<NDET, APPROX, CAL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            bb_relbin_kernel<NDET, APPROX, CAL, true><<<(unsigned)grid, BB_RED_THREADS, smem, st>>>(
+                h->d_coef, n, *h->rb, h->d_calrec, h->cal, out);
+        } else {            // multi-banding (bb_set_multiband)
+            BB_CUDA(cudaFuncSetAttribute(bb_relbin_kernel<NDET, APPROX, CAL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            bb_relbin_kernel<NDET, APPROX, CAL, false><<<(unsigned)grid, BB_RED_THREADS, smem, st>>>(
+                h->d_coef, n, *h->rb, h->d_calrec, h->cal, out);
+        }
     } else {
         const size_t smem_k6 = (size_t)2 * BB_ROQ_WARPS * (BC_NCOEF + (CAL ? NDET * 4 * h->cal.n_points : 0)) * sizeof(double)
                                + (size_t)BB_ROQ_WARPS * NDET * 5 * 32 * sizeof(double2) + BB_ROQ_WARPS * sizeof(unsigned long long);

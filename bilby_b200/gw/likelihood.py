@@ -760,3 +760,4 @@ class GravitationalWaveTransient(Likelihood):
 
 from .relative import RelativeBinningGravitationalWaveTransient  # noqa: E402,F401
 from .roq import ROQGravitationalWaveTransient, BilbyROQParamsRangeError  # noqa: E402,F401
+from .multiband import MBGravitationalWaveTransient  # noqa: E402,F401

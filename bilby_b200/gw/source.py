@@ -129,6 +129,27 @@ def binary_neutron_star_roq(frequency_array, mass_1, mass_2, luminosity_distance
     return _roq(binary_neutron_star_roq, params, waveform_arguments, _DEFAULTS_BNS_ROQ)
 
 
+def binary_black_hole_frequency_sequence(frequency_array, mass_1, mass_2, luminosity_distance, a_1, tilt_1, phi_12,
+                                         a_2, tilt_2, phi_jl, theta_jn, phase, **waveform_kwargs):
+    """source.py:901-979: the waveform at waveform_kwargs['frequencies'] (the multi-banded likelihood's points)."""
+    params = _bbh_params(mass_1, mass_2, luminosity_distance, a_1, tilt_1, phi_12, a_2, tilt_2, phi_jl, theta_jn, phase)
+    wa = dict(waveform_kwargs)
+    return _sequence(binary_black_hole_frequency_sequence, wa.pop("frequencies"), params, wa, _DEFAULTS_BBH_SEQ)
+
+
+def binary_neutron_star_frequency_sequence(frequency_array, mass_1, mass_2, luminosity_distance, a_1, tilt_1, phi_12,
+                                           a_2, tilt_2, phi_jl, lambda_1, lambda_2, theta_jn, phase,
+                                           **waveform_kwargs):
+    """source.py:982-1065."""
+    params = _bbh_params(mass_1, mass_2, luminosity_distance, a_1, tilt_1, phi_12, a_2, tilt_2, phi_jl, theta_jn, phase)
+    params.update(lambda_1=lambda_1, lambda_2=lambda_2)
+    wa = dict(waveform_kwargs)
+    return _sequence(binary_neutron_star_frequency_sequence, wa.pop("frequencies"), params, wa, _DEFAULTS_BNS_SEQ)
+
+
+_DEFAULTS_BBH_SEQ = dict(waveform_approximant="IMRPhenomPv2", reference_frequency=50.0, catch_waveform_errors=False,
+                         pn_spin_order=-1, pn_tidal_order=-1, pn_phase_order=-1, pn_amplitude_order=0)
+_DEFAULTS_BNS_SEQ = dict(_DEFAULTS_BBH_SEQ, waveform_approximant="IMRPhenomPv2_NRTidal")
 _DEFAULTS_BBH_ROQ = dict(waveform_approximant="IMRPhenomPv2", reference_frequency=20.0, catch_waveform_errors=False,
                          pn_spin_order=-1, pn_tidal_order=-1, pn_phase_order=-1, pn_amplitude_order=0)
 _DEFAULTS_BNS_ROQ = dict(_DEFAULTS_BBH_ROQ, waveform_approximant="IMRPhenomD_NRTidal")
@@ -139,8 +160,12 @@ lal_binary_black_hole_relative_binning._bb_defaults = _DEFAULTS_BBH
 lal_binary_neutron_star_relative_binning._bb_defaults = _DEFAULTS_BNS
 binary_black_hole_roq._bb_defaults = _DEFAULTS_BBH_ROQ
 binary_neutron_star_roq._bb_defaults = _DEFAULTS_BNS_ROQ
+binary_black_hole_frequency_sequence._bb_defaults = _DEFAULTS_BBH_SEQ
+binary_neutron_star_frequency_sequence._bb_defaults = _DEFAULTS_BNS_SEQ
 for _f, _k in ((lal_binary_black_hole, "grid"), (lal_binary_neutron_star, "grid"),
                (lal_binary_black_hole_relative_binning, "relative_binning"),
                (lal_binary_neutron_star_relative_binning, "relative_binning"),
-               (binary_black_hole_roq, "roq"), (binary_neutron_star_roq, "roq")):
+               (binary_black_hole_roq, "roq"), (binary_neutron_star_roq, "roq"),
+               (binary_black_hole_frequency_sequence, "frequency_sequence"),
+               (binary_neutron_star_frequency_sequence, "frequency_sequence")):
     _f._bb_kind = _k

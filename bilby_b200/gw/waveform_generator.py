@@ -94,6 +94,8 @@ class WaveformGenerator:
         elif kind == "roq":                  # source.py:802-898
             known |= {"frequency_nodes", "linear_indices", "quadratic_indices", "frequency_nodes_linear",
                       "frequency_nodes_quadratic"}
+        elif kind == "frequency_sequence":   # source.py:901-1140
+            known |= {"frequencies"}
         unused = set(wa) - known
         if unused:
             raise ValueError(f"There are unused waveform kwargs: {sorted(unused)}")   # source.py:687-688
@@ -162,6 +164,11 @@ class WaveformGenerator:
         self._cache["parameters"] = parameters.copy()
         self._cache["model"] = self.frequency_domain_source_model
         src = self._format_parameters(parameters)
+        if getattr(self.frequency_domain_source_model, "_bb_kind", "grid") == "frequency_sequence":
+            # source.py:901-1140: the polarisations at waveform_arguments['frequencies'], not on the grid
+            result = self.frequency_sequence_strain(parameters, self.waveform_arguments["frequencies"])
+            self._cache["waveform"] = result
+            return result
         h = self._get_handle()
         approx, f_ref, f_min, f_max = self.approximant_config()
         _lib.check(h.lib.bb_set_waveform(h.ptr, approx, f_ref, f_min, f_max))

@@ -205,6 +205,19 @@ int bb_noise_weighted_inner_product_device(bb_handle* h, int det, const double* 
 int bb_set_relative_binning(bb_handle* h, int n_edges, const double* bin_freqs, const double* fiducial,
                             const double* summary, const double* fiducial_grid, const int* bin_inds);
 
+/* Multi-banding (S. Morisaki, arXiv:2104.07813): replaces MBGravitationalWaveTransient.calculate_snrs
+ * (bilby/gw/likelihood/multiband.py:728-765, linear-interpolation form of (h, h)) with the source model
+ * binary_*_frequency_sequence (bilby/gw/source.py:901-1140) evaluated at the banded frequency points:
+ *   <d|h> = conj( sum_k h_det(f_k) linear_coeffs[k] ),  <h|h> = sum_k |h_det(f_k)|^2 quadratic_coeffs[k].
+ *   frequencies      host double[n_points]             banded_frequency_points (multiband.py:449-478; duplicates
+ *                                                      between neighbouring bands are evaluated twice)
+ *   linear_coeffs    host double[n_det][n_points][2]   linear_coeffs[ifo.name]    (multiband.py:529-549)
+ *   quadratic_coeffs host double[n_det][n_points]      quadratic_coeffs[ifo.name] (multiband.py:551-611)
+ * Runs on the relative-binning kernel K5 in its edge form (no neighbour term); n_points = 0 switches back to the
+ * full grid.  Time marginalisation and the IFFT-FFT form of (h, h) are not provided. */
+int bb_set_multiband(bb_handle* h, int n_points, const double* frequencies, const double* linear_coeffs,
+                     const double* quadratic_coeffs);
+
 /* ROQ: replaces ROQGravitationalWaveTransient.calculate_snrs, _closest_time_indices, _interp_five_samples and
  * _calculate_d_inner_h_array (bilby/gw/likelihood/roq.py:467-651) with the source model binary_*_roq
  * (bilby/gw/source.py:693-721, 802-898) evaluated at the ROQ frequency nodes.

@@ -91,3 +91,17 @@ def roq_oracle(g, **kw):
         time_prior=ocl.OracleUniform(t_inj - 0.1, t_inj + 0.1),
         waveform_arguments=dict(waveform_approximant="IMRPhenomD", reference_frequency=20.0),
         optimal_snrs=list(g["optimal_snrs"]), **kw), ifos
+
+
+def multiband_oracle(g, bns, **kw):
+    """Oracle multi-banded likelihood on the data of tests/golden/multiband_*.npz (oracle/tools/make_golden_multiband.py)."""
+    from oracle import cbc_multiband as ocm
+    inj = injection_of(g)
+    approx = str(g["approximant"])
+    wa_full = dict(waveform_approximant=approx, reference_frequency=50.0, minimum_frequency=20.0)
+    grid_source = ocl.lal_binary_neutron_star if bns else ocl.lal_binary_black_hole
+    ifos = oracle_ifos(g, inj, grid_source, wa_full, lambdas=bns)
+    model = ocm.binary_neutron_star_frequency_sequence if bns else ocm.binary_black_hole_frequency_sequence
+    return ocm.OracleMultiband(ifos, float(g["reference_chirp_mass"]), source_model=model,
+                               waveform_arguments=dict(waveform_approximant=approx, reference_frequency=50.0),
+                               geocent_time_prior=tuple(g["geocent_time_prior"]), **kw), ifos
