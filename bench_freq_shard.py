@@ -26,6 +26,9 @@ def main():
     ap.add_argument("--batch", type=int, default=8192)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"],
+                    help="fused: K1 stores partials into peer memory + flag round (csrc/bb_exchange.cuh); "
+                         "nccl: one NCCL all-reduce")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -40,7 +43,7 @@ def main():
     like, rows_np, _, flop, desc = bc.build("cfg3", args.batch)
     rows = torch.from_numpy(np.ascontiguousarray(rows_np)).cuda()
     check = like.log_likelihood_ratio_batch(rows[:256]).cpu().numpy()          # unsharded, before the shard is set
-    sharded = FrequencyShardedLikelihood(like, rank, world)
+    sharded = FrequencyShardedLikelihood(like, rank, world, fused_max_rows=args.batch if args.exchange == "fused" else 0)
 
     def barrier():
         if world > 1:
@@ -71,6 +74,7 @@ def main():
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(ar, op=dist.ReduceOp.MAX)
+    sharded.check_exchange()
     err = float(np.max(np.abs(out[:256].cpu().numpy() - check)) / np.max(np.abs(check)))
     if rank == 0:
         total_flop, _ = flop(rows_np)
@@ -81,7 +85,9 @@ def main():
             scaling="strong", dtype="f64", data="synthetic",
             config=dict(workload=desc["workload"], batch=args.batch,
                         partition=f"frequency axis in {world} contiguous shards, bins [{sharded.k_begin}, {sharded.k_end}) "
-                                  f"on rank 0; all-reduce of {args.batch * 3 * 3 * 8} bytes per step"),
+                                  f"on rank 0; exchange of {args.batch * 3 * 3 * 8} bytes per rank per step",
+                        exchange=("fused into K1 (peer-memory stores over NVLink + flag round)" if sharded.fused
+                                  else "NCCL all-reduce")),
             allreduce_ms_per_step=float(ar.item()) / args.steps,
             algorithmic_tflops=total_flop / t / 1e12, max_rel_diff_vs_unsharded=err)))
     if world > 1:

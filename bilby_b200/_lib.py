@@ -48,6 +48,11 @@ def load():
         "bb_set_relative_binning": (i, [vp, i, vp, vp, vp, vp, vp]),
         "bb_set_roq": (i, [vp, i, vp, i, vp, i, lng, d, vp, vp, i, d, d, d]),
         "bb_set_multiband": (i, [vp, i, vp, vp, vp]),
+        "bb_exchange_create": (i, [vp, i, i, lng, vp]),
+        "bb_exchange_connect": (i, [vp, vp]),
+        "bb_log_likelihood_ratio_sharded_device": (i, [vp, vp, lng, vp, vp]),
+        "bb_exchange_status": (i, [vp, ctypes.POINTER(ctypes.c_int)]),
+        "bb_exchange_destroy": (i, [vp]),
         "bb_detector_response_device": (i, [vp, vp, lng, vp, vp]),
         "bb_build_distance_table": (i, [vp, vp, i, vp, i, vp, vp, i, d, i, vp]),
         "bb_antenna_response_device": (i, [vp, vp, lng, vp, vp]),
@@ -81,7 +86,9 @@ EXPORTED_SYMBOLS = (
     "bb_antenna_response_device", "bb_ln_i0_device", "bb_project_polarizations_device",
     "bb_noise_weighted_inner_product_device", "bb_profile_enable", "bb_profile_read", "bb_fp64_peak",
     "bb_launch_count", "bb_set_reconstruction_grid", "bb_reconstruct_marginalized_device",
-    "bb_set_calibration_marginalization", "bb_build_roq_linear_weights", "bb_set_multiband")
+    "bb_set_calibration_marginalization", "bb_build_roq_linear_weights", "bb_set_multiband",
+    "bb_exchange_create", "bb_exchange_connect", "bb_log_likelihood_ratio_sharded_device", "bb_exchange_status",
+    "bb_exchange_destroy")
 
 
 def check(rc):

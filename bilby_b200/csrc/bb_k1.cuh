@@ -282,11 +282,20 @@ __device__ __forceinline__ void bb_k1_dispatch_pd(K1State<NDET>& st, const K1Til
     }
 }
 
+// Frequency-sharded runs (bb_exchange.cuh): instead of one local result array the partial inner products are
+// stored straight into this rank's slot of EVERY rank's exchange buffer (peer memory over NVLink; dst[r] already
+// points at the slot), sample by sample as the warps finish, so the transfer rides under the arithmetic.
+#define BB_MAX_RANKS 8
+struct BBPush {
+    double* dst[BB_MAX_RANKS];
+    int n_dst;               // 0: store to `out` only
+};
+
 template <int NDET, int APPROX, bool CAL>
 __global__ void __launch_bounds__(BB_K1_THREADS, 1)
 bb_inner_product_kernel(const double* __restrict__ coef, const unsigned* __restrict__ perm, long n, BBTiles tiles,
                         double df, int shard_lo, int shard_hi, const double* __restrict__ calrec, BBCalGrid grid,
-                        double* __restrict__ out) {
+                        double* __restrict__ out, BBPush push) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     K1Smem<NDET>& sm = *reinterpret_cast<K1Smem<NDET>*>(smem_raw);
     double* sm_cal = reinterpret_cast<double*>(smem_raw + sizeof(K1Smem<NDET>));   // [SB][NDET*4*n_points] (CAL)
@@ -415,10 +424,22 @@ bb_inner_product_kernel(const double* __restrict__ coef, const unsigned* __restr
                 const double sh = bb_warp_sum(st.acc[d][2]);
                 if (lane == 0) {
                     const double kr = rec[BC_DET + BC_DSTRIDE * d], ki = rec[BC_DET + BC_DSTRIDE * d + 1];
-                    double* o = out + (s * NDET + d) * 3;
-                    o[0] = kr * sr + ki * si;        // <h|d> = conj(K) * sum
-                    o[1] = kr * si - ki * sr;
-                    o[2] = (rec[BC_STATUS] != 0.0) ? nan("") : rec[BC_DET + BC_DSTRIDE * d + 3] * sh;
+                    const double v0 = kr * sr + ki * si;        // <h|d> = conj(K) * sum
+                    const double v1 = kr * si - ki * sr;
+                    const double v2 = (rec[BC_STATUS] != 0.0) ? nan("") : rec[BC_DET + BC_DSTRIDE * d + 3] * sh;
+                    if (push.n_dst == 0) {
+                        double* o = out + (s * NDET + d) * 3;
+                        o[0] = v0;
+                        o[1] = v1;
+                        o[2] = v2;
+                    } else {
+                        for (int r = 0; r < push.n_dst; ++r) {
+                            double* o = push.dst[r] + (s * NDET + d) * 3;
+                            o[0] = v0;
+                            o[1] = v1;
+                            o[2] = v2;
+                        }
+                    }
                 }
             }
         }

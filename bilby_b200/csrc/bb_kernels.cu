@@ -132,6 +132,14 @@ struct bb_handle {
     int sm_count = 148;
     long launches = 0;
     bool profile = false;
+    // frequency-shard exchange over peer memory (bb_exchange.cuh)
+    int xc_world = 0, xc_rank = 0;
+    long xc_cap = 0;
+    unsigned long long xc_epoch = 0;
+    void* xc_local = nullptr;                 // [flags 4096 B][2 parities][world][cap][n_det][3] doubles
+    void* xc_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int* xc_error = nullptr;                  // device flag set when the wait times out
+    bool xc_push_next = false;                // the next K1 launch pushes into the exchange buffers
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> k1_events;
 };
 
@@ -563,6 +571,8 @@ extern "C" int bb_create(int device, bb_handle** out) {
     return 0;
 }
 
+static void bb_exchange_release(bb_handle* h);
+
 extern "C" void bb_destroy(bb_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
@@ -588,6 +598,7 @@ extern "C" void bb_destroy(bb_handle* h) {
     if (h->copy_in) cudaStreamDestroy(h->copy_in);
     if (h->copy_out) cudaStreamDestroy(h->copy_out);
     if (h->stream) cudaStreamDestroy(h->stream);
+    bb_exchange_release(h);
     delete h;
 }
 
@@ -821,6 +832,21 @@ static int bb_launch_prologue(bb_handle* h, const double* params_dev, long n, cu
     return 0;
 }
 
+#define BB_XC_HEADER 4096          // bytes reserved for the arrival flags at the head of an exchange buffer
+static BBPush bb_exchange_push(bb_handle* h) {
+    BBPush p;
+    p.n_dst = 0;
+    for (int r = 0; r < BB_MAX_RANKS; ++r) p.dst[r] = nullptr;
+    if (!h->xc_push_next) return p;
+    const size_t slot = (size_t)h->xc_cap * h->net.n_det * 3;                 // doubles per (parity, source rank)
+    const size_t parity = (size_t)(h->xc_epoch & 1ull);
+    for (int r = 0; r < h->xc_world; ++r)
+        p.dst[r] = reinterpret_cast<double*>(static_cast<char*>(h->xc_peer[r]) + BB_XC_HEADER)
+                   + (parity * h->xc_world + h->xc_rank) * slot;
+    p.n_dst = h->xc_world;
+    return p;
+}
+
 template <int NDET, int APPROX, bool CAL>
 static int bb_launch_inner_t(bb_handle* h, long n, double* out, cudaStream_t st) {
     const size_t smem = sizeof(K1Smem<NDET>) + (CAL ? (size_t)BB_K1_SB * NDET * 4 * h->cal.n_points * sizeof(double) : 0);
@@ -833,7 +859,7 @@ static int bb_launch_inner_t(bb_handle* h, long n, double* out, cudaStream_t st)
         BBProfScope prof(h, st);
         bb_inner_product_kernel<NDET, APPROX, CAL><<<(unsigned)grid, BB_K1_THREADS, smem, st>>>(
             h->d_coef, h->perm_valid ? h->d_perm : nullptr, n, bb_tiles(h), h->net.df, h->shard_lo, h->shard_hi,
-            h->d_calrec, h->cal, out);
+            h->d_calrec, h->cal, out, bb_exchange_push(h));
     }
     h->launches++;
     BB_CUDA(cudaGetLastError());
@@ -863,6 +889,7 @@ static int bb_launch_inner(bb_handle* h, long n, double* out, cudaStream_t st) {
 #include "bb_recon.cuh"
 #include "bb_calmarg.cuh"
 #include "bb_roq_weights.cuh"
+#include "bb_exchange.cuh"
 
 extern "C" int bb_set_calibration_marginalization(bb_handle* h, int n_curves, const double* curves) {
     if (!h || !h->have_network) return bb_fail("bb_set_calibration_marginalization: network not set");

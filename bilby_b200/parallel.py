@@ -40,9 +40,14 @@ def allreduce_inner_products(snrs):
 
 
 class FrequencyShardedLikelihood:
-    """Wraps a GravitationalWaveTransient so that each rank owns one contiguous bin range."""
+    """Wraps a GravitationalWaveTransient so that each rank owns one contiguous bin range.
 
-    def __init__(self, likelihood, rank, world_size):
+    fused_max_rows > 0 (GPUs of one node, world_size <= 8): the exchange is fused into the kernels - K1 stores its
+    partial sums into every rank's buffer over NVLink peer memory, a flag round replaces the collective, and the
+    epilogue sums the partials (csrc/bb_exchange.cuh).  torch.distributed is used once, to pass the 64-byte CUDA IPC
+    handles around.  Otherwise: one NCCL / gloo all-reduce of the partial inner products."""
+
+    def __init__(self, likelihood, rank, world_size, fused_max_rows=0):
         from . import _lib
         self.likelihood = likelihood
         self.rank, self.world_size = rank, world_size
@@ -52,8 +57,46 @@ class FrequencyShardedLikelihood:
         shards = frequency_shards(int(idx[0]), int(idx[-1]), world_size, net.n_freq)
         self.k_begin, self.k_end = shards[rank]
         _lib.check(net.lib.bb_set_frequency_shard(net.ptr, self.k_begin, self.k_end))
+        self.fused = False
+        if fused_max_rows > 0 and world_size > 1:
+            self._connect(net, int(fused_max_rows))
+
+    def _connect(self, net, max_rows):
+        import ctypes
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        mine = (ctypes.c_ubyte * 64)()
+        _lib.check(net.lib.bb_exchange_create(net.ptr, self.world_size, self.rank, max_rows, mine))
+        local = torch.tensor(list(mine), dtype=torch.uint8, device=net.device)
+        gathered = [torch.empty_like(local) for _ in range(self.world_size)]
+        dist.all_gather(gathered, local)
+        handles = torch.stack(gathered).cpu().numpy().tobytes()
+        _lib.check(net.lib.bb_exchange_connect(net.ptr, handles))
+        dist.barrier()
+        self.fused = True
 
     def log_likelihood_ratio_rows(self, rows):
+        if self.fused:
+            import ctypes
+            from . import _lib
+            net = self.likelihood.device_network
+            torch = net.torch
+            out = torch.empty(rows.shape[0], dtype=torch.float64, device=rows.device)
+            _lib.check(net.lib.bb_log_likelihood_ratio_sharded_device(net.ptr, rows.data_ptr(), rows.shape[0],
+                                                                      out.data_ptr(), net._stream()))
+            return out
         snrs = self.likelihood.inner_products_batch(rows)
         allreduce_inner_products(snrs)
         return self.likelihood.likelihood_from_inner_products(rows, snrs)
+
+    def check_exchange(self):
+        """Raises if a peer's arrival flag was ever missed (the device-side wait gives up after ~10 s)."""
+        if self.fused:
+            import ctypes
+            from . import _lib
+            net = self.likelihood.device_network
+            status = ctypes.c_int(0)
+            _lib.check(net.lib.bb_exchange_status(net.ptr, ctypes.byref(status)))
+            if status.value:
+                raise _lib.BilbyB200Error(f"frequency-shard exchange: rank {status.value - 1} never arrived")

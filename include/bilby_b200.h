@@ -188,6 +188,28 @@ int bb_project_polarizations_device(bb_handle* h, int det, const double* plus_de
 int bb_noise_weighted_inner_product_device(bb_handle* h, int det, const double* a_dev, const double* b_dev,
                                            double* out_dev, void* stream);
 
+/* ---- Frequency-sharded evaluation with the exchange fused into the kernels ---------
+ * The reference has no multi-device path (bilby/core/sampler/base_sampler.py:772-800 fans single evaluations out
+ * over a process pool); this is the long-signal partition the north star names: every rank (one process per GPU)
+ * owns the bin range set with bb_set_frequency_shard and evaluates all samples on it.  The partial
+ * (Re<d|h>, Im<d|h>, <h|h>) of every (sample, detector) are stored by K1 itself into every rank's exchange buffer
+ * (peer memory over NVLink), a one-warp kernel exchanges arrival flags, and the epilogue sums the partials: no
+ * NCCL call and no host synchronisation on the data path.
+ *   bb_exchange_create : allocates this rank's buffer for up to max_rows samples and returns its 64-byte CUDA IPC
+ *                        handle (ipc_handle_out); world <= 8.
+ *   bb_exchange_connect: ipc_handles = the `world` handles in rank order (gathered by the host code, e.g. with
+ *                        torch.distributed.all_gather); opens the peers' buffers.
+ *   bb_log_likelihood_ratio_sharded_device: collective - every rank calls it with the same rows; out_dev [n] holds
+ *                        the full likelihood on every rank (same marginalisations as bb_log_likelihood_ratio_device
+ *                        except time / calibration marginalisation and the reduced-order likelihoods).
+ *   bb_exchange_status : 0, or 1 + r when rank r's arrival flag was not seen within ~10 s (the wait gives up
+ *                        instead of hanging the device; the results of that call are invalid). */
+int bb_exchange_create(bb_handle* h, int world, int rank, long max_rows, void* ipc_handle_out);
+int bb_exchange_connect(bb_handle* h, const void* ipc_handles);
+int bb_log_likelihood_ratio_sharded_device(bb_handle* h, const double* params_dev, long n, double* out_dev, void* stream);
+int bb_exchange_status(bb_handle* h, int* status_out);
+int bb_exchange_destroy(bb_handle* h);
+
 /* ---- Reduced-order likelihoods ------------------------------------
  * Once one of the two set-up calls below has succeeded, bb_inner_products[_cal]_device and
  * bb_log_likelihood_ratio[_cal]_{device,host} evaluate that likelihood instead of the full-grid one

@@ -27,9 +27,27 @@ def main():
     got = sharded.log_likelihood_ratio_rows(rows).cpu().numpy()
     err = np.max(np.abs(got - full)) / np.max(np.abs(full))
     assert err < 1e-10, err
+    # the same with the exchange fused into the kernels (peer-memory stores + flag round, csrc/bb_exchange.cuh);
+    # several back-to-back calls exercise both buffer parities
+    fused = FrequencyShardedLikelihood(like, rank, world, fused_max_rows=512)
+    assert fused.fused
+    for it in range(5):
+        sub = rows[: 256 - 16 * it]
+        got_f = fused.log_likelihood_ratio_rows(sub).cpu().numpy()
+        err_f = np.max(np.abs(got_f - full[: 256 - 16 * it])) / np.max(np.abs(full))
+        assert err_f < 1e-10, (it, err_f)
+    fused.check_exchange()
+    phase = bb.gw.GravitationalWaveTransient(
+        ifos, wfg, phase_marginalization=True,
+        priors=bb.core.prior.PriorDict(dict(phase=bb.core.prior.Uniform(0, 2 * np.pi, "phase"))))
+    full_p = phase.log_likelihood_ratio_batch(rows).cpu().numpy()
+    fused_p = FrequencyShardedLikelihood(phase, rank, world, fused_max_rows=256)
+    got_p = fused_p.log_likelihood_ratio_rows(rows).cpu().numpy()
+    assert np.max(np.abs(got_p - full_p)) / np.max(np.abs(full_p)) < 1e-10
+    fused_p.check_exchange()
     dist.barrier()
     if rank == 0:
-        print("FREQ_SHARD_OK", world, err)
+        print("FREQ_SHARD_OK", world, err, "fused", err_f)
     dist.destroy_process_group()
 
 
