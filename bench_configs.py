@@ -352,6 +352,15 @@ def main():
         raise SystemExit("bench_configs.py needs a CUDA device (bilby_b200 has no CPU path)")
     if args.config == "recon":
         return recon_bench(args.batch or 20000, args.steps)
+    # N > 1 (torchrun): samples are independent units -> every rank evaluates its own batch of draws (weak scaling,
+    # no data-path collective); value = all ranks' evaluations / max-over-ranks device time
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        hb.DRAW_SEED += rank
     n = args.batch or DEFAULT_BATCH[args.config]
     like, rows_np, cal_np, flop, desc = build(args.config, n)
     net = like.device_network
@@ -366,40 +375,60 @@ def main():
     def step_device():
         return like._evaluate_device(rows_dev, cal_dev)
 
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
     for _ in range(max(3, args.warmup)):
         out = step_device()
-    torch.cuda.synchronize()
+    barrier()
     _lib.check(lib.bb_profile_enable(net.ptr, 1))
     torch.cuda.cudart().cudaProfilerStart()        # `ncu --profile-from-start off` skips the set-up kernels
     launches0 = lib.bb_launch_count(net.ptr)
-    clocks = hb.ClockSampler(0)
+    clocks = hb.ClockSampler(local)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
         out = step_device()
     e1.record(stream)
-    torch.cuda.synchronize()
+    barrier()
     torch.cuda.cudart().cudaProfilerStop()
-    ms_total = e0.elapsed_time(e1)
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = lib.bb_launch_count(net.ptr) - launches0
     k_ms, k_n = ctypes.c_double(0.0), ctypes.c_long(0)
     _lib.check(lib.bb_profile_read(net.ptr, ctypes.byref(k_ms), ctypes.byref(k_n)))
     _lib.check(lib.bb_profile_enable(net.ptr, 0))
     # end to end through the host entry point
     like.log_likelihood_ratio_rows_host(rows_np, cal_np)
+    barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         res = like.log_likelihood_ratio_rows_host(rows_np, cal_np)
-    e2e_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
     clock_info = clocks.stop()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    n_all = n * world
     total_flop, units = flop(rows_np)
     k_avg = k_ms.value / max(1, k_n.value) * (k_n.value / args.steps)       # dominant-kernel time per step
     achieved = total_flop / (k_avg * 1e-3) / 1e12 if k_avg > 0 else 0.0
     fin = np.isfinite(res)
-    line = dict(metric="log-likelihood evals/sec", config=dict(desc, batch=n), value=n * args.steps / (ms_total * 1e-3),
-                unit="evals/s", n_gpus=1, steps=args.steps, warmup=max(3, args.warmup), ms_per_step=ms_total / args.steps,
+    line = dict(metric="log-likelihood evals/sec", config=dict(desc, batch=n, partition=f"samples x{world}"),
+                value=n_all * args.steps / (ms_total * 1e-3),
+                unit="evals/s", n_gpus=world, scaling="weak", steps=args.steps, warmup=max(3, args.warmup), ms_per_step=ms_total / args.steps,
                 dtype="f64", data="synthetic", clocks=clock_info,
-                e2e=dict(value=n * args.steps / (e2e_ms * 1e-3), unit="evals/s", ms_per_step=e2e_ms / args.steps,
+                e2e=dict(value=n_all * args.steps / (e2e_ms * 1e-3), unit="evals/s", ms_per_step=e2e_ms / args.steps,
                          h2d_bytes_per_step=int(rows_np.nbytes + (cal_np.nbytes if cal_np is not None else 0)),
                          d2h_bytes_per_step=n * 8),
                 gpu_launches=int(launches),
