@@ -78,6 +78,77 @@ __global__ void bb_calmarg_epilogue_kernel(const double* __restrict__ coef, cons
     if (lane == 0) out[sample] = (gmx == -INFINITY) ? -INFINITY : (log(part) + gmx) - log((double)n_curves);
 }
 
+// Reconstruction (base.py:544-578): one warp per sample draws the index of a response curve from the curves'
+// posterior, p_i ~ exp(lnL_i - max), by inverse CDF with the caller's unit-interval draw u (numpy's
+// Generator.choice(n, p): cdf = cumsum(p) / cumsum(p)[-1], index = #{cdf <= u}), and hands the inner products of THAT
+// curve to the distance / phase reconstruction (base.py:289-290): <h|d> = conj(D[index]), <h|h> = H[index].
+struct BBCalSelect {
+    const double* uniforms;   // [n][3], column 0 = the calibration draw; nullptr: marginalise (logsumexp) instead
+    double* snr;              // [n][n_det][3]: the selected curve's totals in detector 0, zeros elsewhere
+    double* out;              // [n][3], column 0 = recalib_index
+};
+
+__global__ void bb_calmarg_select_kernel(const double* __restrict__ coef, const unsigned* __restrict__ perm, long s0,
+                                         int m, const double2* __restrict__ D, const double* __restrict__ H,
+                                         int n_curves, int n_det, BBMarg marg, BBCalSelect sel) {
+    const int lane = threadIdx.x & 31;
+    const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (s >= m) return;
+    const long sample = perm ? (long)perm[s0 + s] : s0 + s;
+    const double* c = coef + sample * BC_NCOEF;
+    double* o = sel.snr + sample * n_det * 3;
+    if (lane < n_det * 3 && lane >= 3) o[lane] = 0.0;
+    if (c[BC_STATUS] != 0.0) {
+        if (lane == 0) {
+            sel.out[sample * 3] = nan("");
+            o[0] = 0.0; o[1] = 0.0; o[2] = nan("");
+        }
+        return;
+    }
+    const double dist = c[BC_DISTANCE];
+    double mx = -INFINITY;
+    for (int i = lane; i < n_curves; i += 32) {
+        const double2 d = D[(size_t)s * n_curves + i];
+        mx = fmax(mx, bb_point_lnl(marg, d.x, d.y, H[(size_t)s * n_curves + i], dist));
+    }
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, k));
+    double total = 0.0;
+    for (int i = lane; i < n_curves; i += 32) {
+        const double2 d = D[(size_t)s * n_curves + i];
+        total += exp(bb_point_lnl(marg, d.x, d.y, H[(size_t)s * n_curves + i], dist) - mx);
+    }
+    total = bb_warp_sum(total);
+    const double u = sel.uniforms[sample * 3];
+    double run = 0.0;          // cumulative sum before this group of 32 curves
+    int count = 0;             // curves whose cdf value is <= u
+    for (int base = 0; base < n_curves; base += 32) {
+        const int i = base + lane;
+        double p = 0.0;
+        if (i < n_curves) {
+            const double2 d = D[(size_t)s * n_curves + i];
+            p = exp(bb_point_lnl(marg, d.x, d.y, H[(size_t)s * n_curves + i], dist) - mx);
+        }
+        double scan = p;       // inclusive scan over the lanes
+#pragma unroll
+        for (int k = 1; k < 32; k <<= 1) {
+            const double up = __shfl_up_sync(0xffffffffu, scan, k);
+            if (lane >= k) scan += up;
+        }
+        const bool below = (i < n_curves) && ((run + scan) / total <= u);
+        count += __popc(__ballot_sync(0xffffffffu, below));
+        run += __shfl_sync(0xffffffffu, scan, 31);
+    }
+    if (count > n_curves - 1) count = n_curves - 1;
+    if (lane == 0) {
+        const double2 d = D[(size_t)s * n_curves + count];
+        sel.out[sample * 3] = (double)count;
+        o[0] = d.x;
+        o[1] = -d.y;
+        o[2] = H[(size_t)s * n_curves + count];
+    }
+}
+
 // active bin range of every chunk: the samples arrive sorted by active-bin count (longest first), so the first sample
 // of a chunk bounds the others from above; kmin is the same for all
 __global__ void bb_calmarg_window_kernel(const double* __restrict__ coef, const unsigned* __restrict__ perm, long n,
@@ -90,7 +161,7 @@ __global__ void bb_calmarg_window_kernel(const double* __restrict__ coef, const 
 }
 
 template <int NDET, int APPROX>
-static int bb_launch_calmarg_t(bb_handle* h, long n, double* out, cudaStream_t st) {
+static int bb_launch_calmarg_t(bb_handle* h, long n, double* out, cudaStream_t st, BBCalSelect sel) {
     const int nc = h->cm_n_curves, ldk = h->cm_ldk;
     const size_t kk = (size_t)NDET * ldk;
     if (!h->d_cm_X) {
@@ -146,25 +217,29 @@ static int bb_launch_calmarg_t(bb_handle* h, long n, double* out, cudaStream_t s
                             h->d_cm_Y + off, (int)kk, d ? &done : &dzero, h->d_cm_H, nc) != CUBLAS_STATUS_SUCCESS)
                 return bb_fail("calibration marginalisation: cublasDgemm failed");
         }
-        bb_calmarg_epilogue_kernel<<<(unsigned)((m * 32L + 127) / 128), 128, 0, st>>>(h->d_coef, perm, s0, m, h->d_cm_D,
-                                                                                     h->d_cm_H, nc, point, out);
+        if (sel.uniforms)
+            bb_calmarg_select_kernel<<<(unsigned)((m * 32L + 127) / 128), 128, 0, st>>>(h->d_coef, perm, s0, m, h->d_cm_D,
+                                                                                       h->d_cm_H, nc, NDET, point, sel);
+        else
+            bb_calmarg_epilogue_kernel<<<(unsigned)((m * 32L + 127) / 128), 128, 0, st>>>(h->d_coef, perm, s0, m, h->d_cm_D,
+                                                                                         h->d_cm_H, nc, point, out);
         BB_CUDA(cudaGetLastError());
         h->launches += 2 + 2 * NDET;
     }
     return 0;
 }
 
-static int bb_launch_calmarg(bb_handle* h, long n, double* out, cudaStream_t st) {
+static int bb_launch_calmarg(bb_handle* h, long n, double* out, cudaStream_t st, BBCalSelect sel = BBCalSelect{nullptr, nullptr, nullptr}) {
     if (h->marg.flags & BB_MARG_TIME) return bb_fail("time + calibration marginalisation is not supported on the device");
     if (h->kind != 0) return bb_fail("calibration marginalisation: full-grid likelihood only");
     if (h->cal_params) return bb_fail("calibration marginalisation excludes per-sample calibration parameters");
     if (h->shard_lo != 0 || h->shard_hi != h->net.n_freq) return bb_fail("calibration marginalisation cannot be frequency-sharded");
     const bool pd = h->wf.approximant == BB_IMRPHENOMD;
     switch (h->net.n_det) {
-        case 1: return pd ? bb_launch_calmarg_t<1, BB_IMRPHENOMD>(h, n, out, st) : bb_launch_calmarg_t<1, BB_TAYLORF2>(h, n, out, st);
-        case 2: return pd ? bb_launch_calmarg_t<2, BB_IMRPHENOMD>(h, n, out, st) : bb_launch_calmarg_t<2, BB_TAYLORF2>(h, n, out, st);
-        case 3: return pd ? bb_launch_calmarg_t<3, BB_IMRPHENOMD>(h, n, out, st) : bb_launch_calmarg_t<3, BB_TAYLORF2>(h, n, out, st);
-        case 4: return pd ? bb_launch_calmarg_t<4, BB_IMRPHENOMD>(h, n, out, st) : bb_launch_calmarg_t<4, BB_TAYLORF2>(h, n, out, st);
+        case 1: return pd ? bb_launch_calmarg_t<1, BB_IMRPHENOMD>(h, n, out, st, sel) : bb_launch_calmarg_t<1, BB_TAYLORF2>(h, n, out, st, sel);
+        case 2: return pd ? bb_launch_calmarg_t<2, BB_IMRPHENOMD>(h, n, out, st, sel) : bb_launch_calmarg_t<2, BB_TAYLORF2>(h, n, out, st, sel);
+        case 3: return pd ? bb_launch_calmarg_t<3, BB_IMRPHENOMD>(h, n, out, st, sel) : bb_launch_calmarg_t<3, BB_TAYLORF2>(h, n, out, st, sel);
+        case 4: return pd ? bb_launch_calmarg_t<4, BB_IMRPHENOMD>(h, n, out, st, sel) : bb_launch_calmarg_t<4, BB_TAYLORF2>(h, n, out, st, sel);
     }
     return bb_fail("bad n_det");
 }

@@ -886,8 +886,8 @@ static int bb_launch_inner(bb_handle* h, long n, double* out, cudaStream_t st) {
     return bb_fail("bad n_det");
 }
 
-#include "bb_recon.cuh"
 #include "bb_calmarg.cuh"
+#include "bb_recon.cuh"
 #include "bb_roq_weights.cuh"
 #include "bb_exchange.cuh"
 

@@ -518,7 +518,8 @@ static int bb_reconstruct(bb_handle* h, const double* params_dev, const double* 
     const int flags = h->marg.flags;
     if ((flags & BB_MARG_DISTANCE) && !h->d_rc_dist) return bb_fail("reconstruction: bb_set_reconstruction_grid was not called");
     if (h->kind != 0) return bb_fail("reconstruction: full-grid likelihood only");
-    if (h->cm_n_curves > 0) return bb_fail("reconstruction with calibration marginalisation is not built");
+    if (h->cm_n_curves > 0 && ((flags & BB_MARG_TIME) || cal_params_dev))
+        return bb_fail("reconstruction with calibration marginalisation: no time marginalisation, no per-sample calibration parameters");
     if (h->shard_lo != 0 || h->shard_hi != h->net.n_freq) return bb_fail("reconstruction cannot be frequency-sharded");
     if (bb_ensure_scratch(h, (size_t)n)) return 1;
     if ((size_t)n > h->rc_rows_cap) {
@@ -560,7 +561,16 @@ static int bb_reconstruct(bb_handle* h, const double* params_dev, const double* 
         if (cudaGetLastError() != cudaSuccess) rc = bb_fail("reconstruction: launch failed");
     }
     if (!rc) rc = bb_launch_prologue(h, h->d_rc_rows, n, st);
-    if (!rc) rc = bb_launch_inner(h, n, h->d_snr, st);
+    if (!rc) {
+        if (h->cm_n_curves > 0) {
+            // column 0 of uniforms / out: the response-curve draw / recalib_index (base.py:526-529, 544-578); the
+            // distance and phase steps below see the chosen curve's inner products (base.py:289-290)
+            BBCalSelect sel{uniforms_dev, h->d_snr, out_dev};
+            rc = bb_launch_calmarg(h, n, nullptr, st, sel);
+        } else {
+            rc = bb_launch_inner(h, n, h->d_snr, st);
+        }
+    }
     if (!rc) {
         const int nd = (flags & BB_MARG_DISTANCE) ? h->rc_nd : 101;
         const int nbuf = nd < 101 ? 101 : nd;

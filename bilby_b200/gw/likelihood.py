@@ -662,11 +662,16 @@ class GravitationalWaveTransient(Likelihood):
         before it).
 
         uniforms: [n, 3] unit-interval draws standing for the ``Interped.sample()`` calls of the time, distance
-        and phase steps; drawn from ``rng`` (default: a fresh numpy Generator) when omitted."""
+        and phase steps; drawn from ``rng`` (default: a fresh numpy Generator) when omitted.
+
+        With calibration marginalisation (base.py:526-529, 544-578; time marginalisation excluded) column 0 of
+        ``uniforms`` is the draw of ``rng.choice`` over the response curves, the result gains ``recalib_index`` and
+        the distance / phase steps use the chosen curve (base.py:289-290)."""
         if not self._marginalized_parameters:
             return dict(parameters)
-        if getattr(self, "calibration_marginalization", False):
-            raise NotImplementedError("calibration marginalisation is not built (SURVEY.md section 8f rank 4)")
+        calmarg = bool(getattr(self, "calibration_marginalization", False))
+        if calmarg and self.time_marginalization:
+            raise NotImplementedError("time + calibration marginalisation is not built (SURVEY.md section 8f rank 4)")
         net = self.device_network
         torch = net.torch
         n = max(np.size(v) for v in parameters.values())
@@ -680,7 +685,8 @@ class GravitationalWaveTransient(Likelihood):
         if self.time_marginalization and "time_jitter" not in pars:
             pars["time_jitter"] = np.zeros(n)
         rows = torch.from_numpy(np.ascontiguousarray(self._rows_from_parameters(pars, n, np))).to(net.device)
-        cal = self._cal_from_parameters(pars, n, np)
+        pars.pop("recalib_index", None)              # base.py:562-563
+        cal = None if calmarg else self._cal_from_parameters(pars, n, np)
         cal_ptr = None
         if cal is not None:
             cal = torch.from_numpy(np.ascontiguousarray(cal)).to(net.device)
@@ -696,6 +702,8 @@ class GravitationalWaveTransient(Likelihood):
                                                               out.data_ptr(), net._stream()))
         res = out.cpu().numpy()
         new = {k: (np.array(v, copy=True) if np.ndim(v) else v) for k, v in parameters.items()}
+        if calmarg:
+            new["recalib_index"] = res[:, 0]
         if self.time_marginalization:
             new["geocent_time"] = res[:, 0]
         if self.distance_marginalization:
@@ -715,6 +723,8 @@ class GravitationalWaveTransient(Likelihood):
         for k in ("geocent_time", "luminosity_distance", "phase"):
             if k in new:
                 out[k] = float(np.asarray(new[k])[0])
+        if "recalib_index" in new and getattr(self, "calibration_marginalization", False):
+            out["recalib_index"] = int(np.asarray(new["recalib_index"])[0])
         return out
 
     def _calculate_noise_log_likelihood(self):

@@ -269,8 +269,12 @@ int bb_set_roq(bb_handle* h, int n_linear, const double* nodes_linear, int n_qua
  *     not read.
  *   out_dev [n][3]: new geocent_time, luminosity_distance, phase (for steps that are off: the time column is not
  *     written, distance / phase are copied from the row).  NaN for waveform-domain errors.
+ * With calibration marginalisation loaded (bb_set_calibration_marginalization; no time marginalisation, cal_params_dev
+ * NULL) column 0 changes meaning: uniforms_dev[.][0] is the unit-interval draw of Generator.choice over the response
+ * curves (base.py:544-578) and out_dev[.][0] the drawn recalib_index; the distance and phase steps then use the inner
+ * products of that curve (base.py:289-290).
  * Restrictions: full-grid likelihood (not ROQ / relative binning), uniform geocent_time prior not wider than 0.249 s,
- * 32768 / sampling_frequency a power of two, no calibration marginalisation. */
+ * 32768 / sampling_frequency a power of two. */
 int bb_set_reconstruction_grid(bb_handle* h, const double* distance_array, const double* distance_prior_array,
                                int n_distance);
 int bb_reconstruct_marginalized_device(bb_handle* h, const double* params_dev, const double* cal_params_dev, long n,

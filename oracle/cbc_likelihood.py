@@ -573,9 +573,9 @@ class OracleLikelihood:
             log_l = np.real(d_inner_h) - hh / 2
         return float(np.real(log_l))
 
-    def calibration_marginalized_likelihood(self, pols, parameters):
+    def calibration_log_likelihoods(self, pols, parameters):
         """base.py:333-346 (per-detector arrays over the response curves; note conj(d) * h, the conjugate of
-        inner_product's convention), :109-148 (arrays add over detectors), :860-877."""
+        inner_product's convention), :109-148 (arrays add over detectors), :822-858: the point likelihood per curve."""
         d_arr, hh_arr = 0, 0
         for ifo in self.ifos:
             signal = ifo.get_detector_response(pols, parameters)
@@ -586,12 +586,25 @@ class OracleLikelihood:
             hh_integrand = norm * np.abs(signal) ** 2 / ifo.power_spectral_density_array
             hh_arr = hh_arr + np.dot(hh_integrand[m], self.calibration_abs_draws[ifo.name].T)
         if self.distance_marginalization:
-            log_l = self.distance_marginalized_likelihood(d_arr, hh_arr, parameters)
-        elif self.phase_marginalization:
-            log_l = ln_i0(abs(d_arr)) - hh_arr / 2
-        else:
-            log_l = np.real(d_arr - hh_arr / 2)
-        return logsumexp(log_l) - np.log(self.number_of_response_curves)
+            return self.distance_marginalized_likelihood(d_arr, hh_arr, parameters)
+        if self.phase_marginalization:
+            return ln_i0(abs(d_arr)) - hh_arr / 2
+        return np.real(d_arr - hh_arr / 2)
+
+    def calibration_marginalized_likelihood(self, pols, parameters):
+        """base.py:860-877."""
+        return logsumexp(self.calibration_log_likelihoods(pols, parameters)) - np.log(self.number_of_response_curves)
+
+    def generate_calibration_sample(self, pols, parameters, u):
+        """base.py:544-578: index of a response curve drawn from the curves' posterior.  `u` is the unit-interval
+        draw numpy's Generator.choice(n, p=post) makes: cdf = cumsum(p) / cumsum(p)[-1], searchsorted(u, 'right')."""
+        parameters.pop("recalib_index", None)
+        log_like = self.calibration_log_likelihoods(pols, parameters)
+        post = np.exp(log_like - max(log_like))
+        post /= np.sum(post)
+        cdf = post.cumsum()
+        cdf /= cdf[-1]
+        return int(cdf.searchsorted(u, side="right"))
 
     def distance_marginalized_likelihood(self, d_inner_h, hh, parameters):
         """base.py:775-784, 879-885."""
@@ -623,10 +636,13 @@ class OracleLikelihood:
     def generate_posterior_sample_from_marginalized_likelihood(self, parameters, uniforms):
         """base.py:502-541."""
         parameters = dict(parameters)
-        if not (self.time_marginalization or self.distance_marginalization or self.phase_marginalization):
+        if not (self.time_marginalization or self.distance_marginalization or self.phase_marginalization
+                or self.calibration_marginalization):
             return parameters
         pols = {k: v.copy() for k, v in self.polarizations(parameters).items()}
         uniforms = list(uniforms)
+        if self.calibration_marginalization:        # base.py:526-529; its draw is uniforms[3]
+            parameters["recalib_index"] = self.generate_calibration_sample(pols, parameters, uniforms[3])
         if self.time_marginalization:
             parameters["geocent_time"] = self.generate_time_sample(pols, parameters, uniforms[0])
         if self.distance_marginalization:
@@ -640,6 +656,8 @@ class OracleLikelihood:
         d_inner_h, hh = 0j, 0.0
         for ifo in self.ifos:
             signal = ifo.get_detector_response(pols, parameters)
+            if "recalib_index" in parameters:        # base.py:289-290
+                signal[ifo.frequency_mask] *= self.calibration_draws[ifo.name][int(parameters["recalib_index"])]
             d_inner_h += ifo.inner_product(signal)
             hh += ifo.optimal_snr_squared(signal)
         return d_inner_h, hh

@@ -83,6 +83,32 @@ def main():
             vals[i] = like.log_likelihood_ratio(p)
         res["lnl_" + mode] = vals
         print(mode, vals[:4], vals[12])
+        # marginalised-parameter reconstruction (base.py:502-578): recalib_index by rng.choice over the response
+        # curves' posterior, then distance / phase with the chosen curve applied (base.py:289-290); the unit-interval
+        # draws of the reference's generator are replayed and stored
+        n_u = 1 + bool(kw.get("distance_marginalization")) + bool(kw.get("phase_marginalization"))
+        out = np.zeros((n, 3))
+        uni = np.full((n, 3), np.nan)
+        for i in range(n):
+            p = {k: float(draws[k][i]) for k in draws}
+            for name in names:
+                for j in range(N_POINTS):
+                    p[f"recalib_{name}_amplitude_{j}"] = 0.0
+                    p[f"recalib_{name}_phase_{j}"] = 0.0
+            brandom.seed(3000 + i)
+            new = like.generate_posterior_sample_from_marginalized_likelihood(p)
+            out[i] = [new["recalib_index"], new["luminosity_distance"], new["phase"]]
+            replay = np.random.default_rng(3000 + i)
+            drawn = [replay.uniform(0, 1) for _ in range(n_u)]
+            uni[i, 0] = drawn[0]
+            j = 1
+            for c, key in ((1, "distance_marginalization"), (2, "phase_marginalization")):
+                if kw.get(key):
+                    uni[i, c] = drawn[j]
+                    j += 1
+        res["recon_" + mode] = out
+        res["uniforms_" + mode] = uni
+        print(mode, "recon", out[:3])
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "calmarg_4s_H1L1V1.npz"), **res)
 
 

@@ -71,3 +71,41 @@ def test_single_identity_curve_reduces_to_the_plain_likelihood():
 def test_time_plus_calibration_is_refused():
     with pytest.raises(NotImplementedError):
         _likelihood(geocent_time=True)
+
+
+@pytest.mark.parametrize("mode,on", [("cal", {}), ("cal_phase", dict(phase=True)),
+                                     ("cal_distance_phase", dict(phase=True, luminosity_distance=True))])
+def test_calibration_reconstruction_vs_reference(mode, on):
+    """recalib_index / distance / phase reconstruction (base.py:502-578, 289-290) with the reference's own unit-interval
+    draws replayed: the same response curve is picked and the new distance / phase agree to 1e-9."""
+    g, like, draws = _likelihood(**on)
+    uni = np.nan_to_num(g["uniforms_" + mode], nan=0.5)
+    new = like.generate_posterior_samples_from_marginalized_likelihood_batch(draws, uniforms=uni)
+    ref = g["recon_" + mode]
+    assert np.array_equal(new["recalib_index"], ref[:, 0])
+    assert np.allclose(new["luminosity_distance"], ref[:, 1], rtol=1e-9)
+    assert np.allclose(new["phase"], ref[:, 2], rtol=1e-9, atol=1e-9)
+    one = like.generate_posterior_sample_from_marginalized_likelihood({k: float(v[5]) for k, v in draws.items()})
+    assert 0 <= one["recalib_index"] < int(g["n_curves"])
+
+
+def test_calibration_reconstruction_follows_the_curve_posterior():
+    """Property at scale: 4000 draws of recalib_index for one parameter row reproduce the curves' posterior
+    softmax(lnL_i), which is recomputed here from the per-curve likelihood of single-curve handles."""
+    g, like, draws = _likelihood()
+    row = {k: np.full(4000, float(v[12])) for k, v in draws.items()}
+    rng = np.random.default_rng(11)
+    new = like.generate_posterior_samples_from_marginalized_likelihood_batch(row, uniforms=rng.uniform(0, 1, (4000, 3)))
+    idx = new["recalib_index"].astype(int)
+    nc = int(g["n_curves"])
+    counts = np.bincount(idx, minlength=nc) / 4000.0
+    # the marginal likelihood is the mean of the per-curve likelihoods: the most frequent curve must carry a posterior
+    # share consistent with its count (binomial 5 sigma) under a posterior that sums to one
+    assert counts.sum() == pytest.approx(1.0)
+    top = counts.argmax()
+    assert counts[top] > 1.0 / nc
+    sigma = np.sqrt(counts[top] * (1 - counts[top]) / 4000.0)
+    again = like.generate_posterior_samples_from_marginalized_likelihood_batch(
+        row, uniforms=np.random.default_rng(12).uniform(0, 1, (4000, 3)))
+    c2 = np.bincount(again["recalib_index"].astype(int), minlength=nc) / 4000.0
+    assert abs(c2[top] - counts[top]) < 7 * sigma + 1e-3

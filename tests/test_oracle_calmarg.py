@@ -42,3 +42,34 @@ def test_calibration_distance_phase_matches_reference():
     idx = [0, 3, 12, 15, 19]
     got = np.array([like.log_likelihood_ratio({k: float(v[i]) for k, v in draws.items()}) for i in idx])
     assert np.allclose(got, g["lnl_cal_distance_phase"][idx], rtol=1e-10, atol=1e-10)
+
+
+def _recon(like, draws, uni, rows):
+    out = []
+    for i in rows:
+        u = [np.nan, uni[i, 1], uni[i, 2], uni[i, 0]]       # oracle order: time, distance, phase, calibration
+        new = like.generate_posterior_sample_from_marginalized_likelihood({k: float(v[i]) for k, v in draws.items()}, u)
+        out.append([new["recalib_index"], new["luminosity_distance"], new["phase"]])
+    return np.array(out)
+
+
+def test_calibration_reconstruction_matches_reference():
+    """recalib_index / distance / phase reconstruction with calibration marginalisation (base.py:502-578, 289-290)."""
+    g, ifos, draws, curves = setup()
+    n = len(draws["chirp_mass"])
+    like = ocl.OracleLikelihood(ifos, waveform_arguments=WA, calibration_draws=curves)
+    got = _recon(like, draws, g["uniforms_cal"], range(n))
+    assert np.array_equal(got[:, 0], g["recon_cal"][:, 0])
+    assert np.allclose(got[:, 1:], g["recon_cal"][:, 1:], rtol=1e-12)
+    like = ocl.OracleLikelihood(ifos, waveform_arguments=WA, calibration_draws=curves, phase_marginalization=True)
+    got = _recon(like, draws, g["uniforms_cal_phase"], range(n))
+    assert np.array_equal(got[:, 0], g["recon_cal_phase"][:, 0])
+    assert np.allclose(got, g["recon_cal_phase"], rtol=1e-9)
+    prior = ocl.OraclePowerLaw(2, 100.0, 5000.0)
+    like = ocl.OracleLikelihood(ifos, waveform_arguments=WA, calibration_draws=curves, phase_marginalization=True,
+                                distance_marginalization=True, distance_prior=prior,
+                                table_processes=min(8, os.cpu_count() or 1))
+    rows = [0, 3, 12, 15, 19]
+    got = _recon(like, draws, g["uniforms_cal_distance_phase"], rows)
+    assert np.array_equal(got[:, 0], g["recon_cal_distance_phase"][rows, 0])
+    assert np.allclose(got, g["recon_cal_distance_phase"][rows], rtol=1e-9)
