@@ -98,10 +98,15 @@ def build(config, n):
                                                     number_of_response_curves=n_curves, priors=PriorDict(pri))
             rows = like.pack(draws)
             ldk = (len(ifos[0].frequency_array) + 7) // 8 * 8
-            per = (8 + 2) * 3 * ldk * n_curves
 
             def flop_cm(rows_):
-                return float(len(rows_)) * per, float(3 * ldk)
+                # algorithmic: (8 + 2) flop per (ACTIVE bin, detector, curve) - bins above the waveform's cut-off
+                # 0.2 / (M t_sun) contribute nothing (the contraction is trimmed to each chunk's active window)
+                msec_ = (rows_[:, 0] + rows_[:, 1]) * hb.MTSUN
+                fmp_ = np.minimum(fs / 2, 0.2 / msec_)
+                k1_ = np.minimum(np.floor(fmp_ / df), np.floor(fs / 2 / df) + 1)
+                bins_ = np.maximum(k1_ - np.ceil(20.0 / df), 0)
+                return float(np.sum(bins_)) * (8 + 2) * 3 * n_curves, float(np.mean(bins_) * 3)
             return like, rows, None, flop_cm, dict(
                 workload=f"SURVEY 8f rank 4: calibration marginalisation over {n_curves} CubicSpline(10) response curves + "
                          "phase marginalisation, BBH 4s@2048Hz H1L1V1 IMRPhenomD: [batch x 3*4104] x [3*4104 x 1000] "

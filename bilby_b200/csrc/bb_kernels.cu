@@ -160,25 +160,54 @@ __device__ __forceinline__ void bb_wave(const double* c, double f, double u, dou
 // ------------------------------------------------------------------------------------------------
 // K0: prologue
 // ------------------------------------------------------------------------------------------------
-__global__ void bb_prologue_kernel(const double* __restrict__ params, long n, BBNetwork net,
+#define BB_K0_THREADS 128
+__global__ void __launch_bounds__(BB_K0_THREADS) bb_prologue_kernel(const double* __restrict__ params, long n, BBNetwork net,
                                    BBWaveformConfig wf, double* __restrict__ coef, unsigned* __restrict__ keys,
                                    unsigned* __restrict__ index) {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    double p[BB_NPARAM];
-#pragma unroll
-    for (int k = 0; k < BB_NPARAM; ++k) p[k] = params[i * BB_NPARAM + k];
-    BBQnmTable qnm = {bb_qnm_x, bb_qnm_fring, bb_qnm_fring_d2, bb_qnm_fdamp, bb_qnm_fdamp_d2, BB_QNM_N};
+    // The record is built in registers and leaves through shared memory: a thread storing its own 672-byte record
+    // double by double touches 32 sectors per instruction (lg_throttle-bound, 1.75 x DRAM write amplification in the
+    // first capture, profiles/r1d_k0*); staged in two halves (44 + 40 doubles, both sector-aligned; row stride 45
+    // doubles = conflict-free) the block writes whole sectors with consecutive lanes on consecutive doubles.
+    __shared__ double stage[BB_K0_THREADS * 45];
+    const int tid = threadIdx.x;
+    const long blk0 = (long)blockIdx.x * blockDim.x;
+    const long i = blk0 + tid;
+    const bool live = i < n;
+    const int nrec = (int)min((long)blockDim.x, n - blk0);
     double c[BC_NCOEF];
-    if (wf.approximant == BB_IMRPHENOMD) bb_phenomd_prologue(p, net, wf, qnm, bb_phenomd_fit, c);
-    else bb_taylorf2_prologue(p, net, wf, c);
-    double* dst = coef + i * BC_NCOEF;
-    for (int k = 0; k < BC_NCOEF; ++k) dst[k] = c[k];
-    if (keys) {
-        // descending active-bin count: blocks of K1 then hold samples of equal length, longest first
-        const unsigned count = (unsigned)(c[BC_KMAX] - c[BC_KMIN]);
-        keys[i] = (1u << 24) - min(count, (1u << 24) - 1u);
-        index[i] = (unsigned)i;
+    if (live) {
+        double p[BB_NPARAM];
+#pragma unroll
+        for (int k = 0; k < BB_NPARAM; ++k) p[k] = params[i * BB_NPARAM + k];
+        BBQnmTable qnm = {bb_qnm_x, bb_qnm_fring, bb_qnm_fring_d2, bb_qnm_fdamp, bb_qnm_fdamp_d2, BB_QNM_N};
+        if (wf.approximant == BB_IMRPHENOMD) bb_phenomd_prologue(p, net, wf, qnm, bb_phenomd_fit, c);
+        else bb_taylorf2_prologue(p, net, wf, c);
+        if (keys) {
+            // descending active-bin count: blocks of K1 then hold samples of equal length, longest first
+            const unsigned count = (unsigned)(c[BC_KMAX] - c[BC_KMIN]);
+            keys[i] = (1u << 24) - min(count, (1u << 24) - 1u);
+            index[i] = (unsigned)i;
+        }
+    }
+    static_assert(BC_NCOEF == 84, "K0 stages the record as 44 + 40 doubles");
+    if (live) {
+#pragma unroll
+        for (int k = 0; k < 44; ++k) stage[tid * 45 + k] = c[k];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < nrec * 44; idx += blockDim.x) {
+        const int rec = idx / 44, j = idx - rec * 44;
+        coef[(blk0 + rec) * BC_NCOEF + j] = stage[rec * 45 + j];
+    }
+    __syncthreads();
+    if (live) {
+#pragma unroll
+        for (int k = 0; k < 40; ++k) stage[tid * 45 + k] = c[44 + k];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < nrec * 40; idx += blockDim.x) {
+        const int rec = idx / 40, j = idx - rec * 40;
+        coef[(blk0 + rec) * BC_NCOEF + 44 + j] = stage[rec * 45 + j];
     }
 }
 
@@ -799,7 +828,7 @@ static int bb_launch_prologue(bb_handle* h, const double* params_dev, long n, cu
             wf.antenna_time = h->roq_ref_time;
         }
     }
-    const int threads = 128;
+    const int threads = BB_K0_THREADS;
     const bool sort = n > BB_K1_SB && h->kind == 0;
     bb_prologue_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(
         params_dev, n, h->net, wf, h->d_coef, sort ? h->d_keys : nullptr, h->d_index);

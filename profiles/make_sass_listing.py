@@ -25,9 +25,13 @@ KERNELS = {   # label -> (mangled-name regex, keep full listing)
     "k4r_series_fine": (r"_Z21bb_series_fine_kernel", False),
     "kr_recon_time": (r"_Z20bb_recon_time_kernel", False),
     "kr_recon_distance_phase": (r"_Z30bb_recon_distance_phase_kernel", False),
-    "k5_relbin_3det_taylorf2": (r"_Z16bb_relbin_kernelILi3ELi1ELb0E", False),
+    "k5_relbin_3det_taylorf2": (r"_Z16bb_relbin_kernelILi3ELi1ELb0ELb1E", False),
+    "k5_multiband_3det_taylorf2": (r"_Z16bb_relbin_kernelILi3ELi1ELb0ELb0E", False),
     "k5t_relbin_time_marg_3det_imrphenomd": (r"_Z26bb_relbin_time_marg_kernelILi3ELi0ELb0E", False),
-    "k6_roq_3det_taylorf2": (r"_Z13bb_roq_kernelILi3ELi1ELb0E", False),
+    "k6_roq_3det_taylorf2": (r"_Z13bb_roq_kernelILi3ELi1ELb0E", True),
+    "kx_exchange_signal": (r"_Z25bb_exchange_signal_kernel", True),
+    "kx_exchange_epilogue": (r"_Z27bb_exchange_epilogue_kernel", False),
+    "kc_calmarg_select": (r"_Z24bb_calmarg_select_kernel", False),
     "k7_roq_hlinear_3det_taylorf2": (r"_Z21bb_roq_hlinear_kernelILi3ELi1ELb0E", False),
     "k7_roq_time_marg_3det": (r"_Z23bb_roq_time_marg_kernelILi3E", False),
     "kt_distance_table": (r"_Z24bb_distance_table_kernel", False),
