@@ -66,7 +66,7 @@ def build(config, n):
     from bilby_b200.gw import conversion, source
     from bilby_b200.workloads import INJECTION, draw_bbh_prior
     rng = np.random.default_rng(hb.DRAW_SEED)
-    if config in ("cfg0", "cfg2", "calmarg"):
+    if config in ("cfg0", "cfg2", "calmarg", "calmarg_time"):
         duration = 8.0 if config == "cfg2" else 4.0
         names = ["H1", "L1"] if config == "cfg0" else ["H1", "L1", "V1"]
         fs = 2048.0
@@ -80,7 +80,7 @@ def build(config, n):
         draws = draw_bbh_prior(n, rng)
         df = 1.0 / duration
         msec = None
-        if config == "calmarg":
+        if config in ("calmarg", "calmarg_time"):
             from bilby_b200.core.prior import Gaussian
             from bilby_b200.core.utils import random as bb_random
             bb_random.seed(hb.NOISE_SEED)
@@ -94,8 +94,15 @@ def build(config, n):
                     for kind in ("amplitude", "phase"):
                         key = f"recalib_{ifo.name}_{kind}_{i}"
                         pri[key] = Gaussian(0.0, 0.05, key)
+            tm = config == "calmarg_time"
+            if tm:
+                pri["geocent_time"] = Uniform(T_INJ - 0.1, T_INJ + 0.1, "geocent_time")
             like = bb.gw.GravitationalWaveTransient(ifos, wfg, phase_marginalization=True, calibration_marginalization=True,
+                                                    time_marginalization=tm, jitter_time=True,
                                                     number_of_response_curves=n_curves, priors=PriorDict(pri))
+            if tm:
+                draws["geocent_time"] = np.full(n, float(start))
+                draws["time_jitter"] = rng.uniform(-1 / fs, 1 / fs, n)
             rows = like.pack(draws)
             ldk = (len(ifos[0].frequency_array) + 7) // 8 * 8
 
@@ -106,7 +113,20 @@ def build(config, n):
                 fmp_ = np.minimum(fs / 2, 0.2 / msec_)
                 k1_ = np.minimum(np.floor(fmp_ / df), np.floor(fs / 2 / df) + 1)
                 bins_ = np.maximum(k1_ - np.ceil(20.0 / df), 0)
+                if tm:
+                    # per (sample, curve): series = sum_det X C on the active bins (8 flop each), one 4096-point
+                    # transform (5 N log2 N), 120 flop per time inside the prior; <h|h> per curve as above
+                    nfft = int(round(duration * fs / 2))
+                    per_pair = 5.0 * nfft * np.log2(nfft) + 120.0 * int(0.2 * fs / 2)
+                    return (float(np.sum(bins_)) * (8 + 2) * 3 * n_curves + len(rows_) * n_curves * per_pair,
+                            float(np.mean(bins_) * 3))
                 return float(np.sum(bins_)) * (8 + 2) * 3 * n_curves, float(np.mean(bins_) * 3)
+            if tm:
+                return like, rows, None, flop_cm, dict(
+                    workload=f"SURVEY 8f rank 4: time + calibration (+ phase) marginalisation over {n_curves} CubicSpline(10) "
+                             "response curves, BBH 4s@2048Hz H1L1V1 IMRPhenomD: one 4096-point transform per (sample, curve)",
+                    kernel="bb_calmarg_series_kernel + cublas DGEMM + bb_calmarg_time_kernel + bb_calmarg_lse_kernel",
+                    bound="shared memory / FP64 (in-shared-memory FFT per response curve)", n_curves=n_curves)
             return like, rows, None, flop_cm, dict(
                 workload=f"SURVEY 8f rank 4: calibration marginalisation over {n_curves} CubicSpline(10) response curves + "
                          "phase marginalisation, BBH 4s@2048Hz H1L1V1 IMRPhenomD: [batch x 3*4104] x [3*4104 x 1000] "
@@ -278,7 +298,7 @@ def build(config, n):
 
 
 DEFAULT_BATCH = dict(calmarg=16384, cfg0=1_000_000, cfg2=100_000, cfg3=8192, cfg4_relbin=1_000_000, cfg4_roq=1_000_000,
-                     cfg4_roq_time=65536, mb=65536)
+                     cfg4_roq_time=65536, mb=65536, calmarg_time=1024)
 
 
 def recon_bench(n, steps):

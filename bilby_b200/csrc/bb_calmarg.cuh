@@ -149,6 +149,79 @@ __global__ void bb_calmarg_select_kernel(const double* __restrict__ coef, const 
     }
 }
 
+// Time + calibration marginalisation (base.py:305-323, 860-866, 794-820): one CTA per (sample, response curve).
+//   series_c[k] = sum_det X_det[k] C_det,c[k]  (X = h conj(d)/S with 4/T, from bb_calmarg_series_kernel; zero outside
+//   the chunk's active window), in-shared-memory FFT (bb_tm_fft_dif), weighted logsumexp over the times inside the
+//   geocent_time prior with <h|h>_c from the DGEMM (bb_tm_finish) -> L[s][c]; bb_calmarg_lse_kernel then takes
+//   logsumexp_c L - log(n_curves).
+template <int NDET>
+__global__ void __launch_bounds__(BB_TM_THREADS, 1)
+bb_calmarg_time_kernel(const double* __restrict__ coef, const unsigned* __restrict__ perm, long s0, int m,
+                       const double2* __restrict__ Xs, const double2* __restrict__ C, const double* __restrict__ H,
+                       int n_curves, int ldk, int k_lo, int k_hi, int nfft, int log2n,
+                       const double2* __restrict__ twiddle, BBMarg marg, double start_time, double duration,
+                       double* __restrict__ L) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double2* X = reinterpret_cast<double2*>(smem_raw);
+    int plan_a, plan_b, ps;
+    bb_tm_plan(log2n, &plan_a, &plan_b, &ps);
+    double* red = reinterpret_cast<double*>(X + bb_tm_series_elems(nfft, ps));      // [32]
+    const int tid = threadIdx.x;
+    const size_t kk = (size_t)NDET * ldk;
+    const long pairs = (long)m * n_curves;
+    for (long pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
+        const int s = (int)(pair / n_curves), c = (int)(pair - (long)s * n_curves);
+        const long sample = perm ? (long)perm[s0 + s] : s0 + s;
+        const double* rec = coef + sample * BC_NCOEF;
+        __syncthreads();
+        if (rec[BC_STATUS] != 0.0) {
+            if (tid == 0) L[pair] = -DBL_MAX;
+            continue;
+        }
+        for (int k = tid; k < nfft; k += BB_TM_THREADS) {
+            double vr = 0.0, vi = 0.0;
+            if (k >= k_lo && k < k_hi) {
+#pragma unroll
+                for (int d = 0; d < NDET; ++d) {
+                    const double2 x = Xs[((size_t)s * NDET + d) * ldk + k];
+                    const double2 q = C[(size_t)c * kk + (size_t)d * ldk + k];
+                    vr = fma(x.x, q.x, fma(-x.y, q.y, vr));
+                    vi = fma(x.x, q.y, fma(x.y, q.x, vi));
+                }
+            }
+            X[bb_tm_pos(k, ps)] = make_double2(vr, vi);
+        }
+        __syncthreads();
+        bb_tm_fft_dif(X, nfft, log2n, twiddle);
+        bb_tm_finish(X, nfft, log2n, marg, H[pair], rec[BC_DISTANCE], rec[BC_JITTER], start_time, duration, red,
+                     L + pair);
+    }
+}
+
+// one warp per sample: logsumexp over the curves of the per-curve (time-marginalised) likelihoods
+__global__ void bb_calmarg_lse_kernel(const double* __restrict__ coef, const unsigned* __restrict__ perm, long s0,
+                                      int m, const double* __restrict__ L, int n_curves, double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (s >= m) return;
+    const long sample = perm ? (long)perm[s0 + s] : s0 + s;
+    if (coef[sample * BC_NCOEF + BC_STATUS] != 0.0) {
+        if (lane == 0) out[sample] = -DBL_MAX;
+        return;
+    }
+    double mx = -INFINITY;
+    for (int i = lane; i < n_curves; i += 32) mx = fmax(mx, L[(size_t)s * n_curves + i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    double sum = 0.0;
+    for (int i = lane; i < n_curves; i += 32) {
+        const double l = L[(size_t)s * n_curves + i];
+        if (l != -INFINITY) sum += exp(l - mx);
+    }
+    sum = bb_warp_sum(sum);
+    if (lane == 0) out[sample] = (mx == -INFINITY) ? -INFINITY : (log(sum) + mx) - log((double)n_curves);
+}
+
 // active bin range of every chunk: the samples arrive sorted by active-bin count (longest first), so the first sample
 // of a chunk bounds the others from above; kmin is the same for all
 __global__ void bb_calmarg_window_kernel(const double* __restrict__ coef, const unsigned* __restrict__ perm, long n,
@@ -175,6 +248,21 @@ static int bb_launch_calmarg_t(bb_handle* h, long n, double* out, cudaStream_t s
     const double done = 1.0, dzero = 0.0;
     BBMarg point = h->marg;
     point.flags &= ~BB_MARG_TIME;
+    const bool time_marg = (h->marg.flags & BB_MARG_TIME) != 0;
+    int tm_log2n = 0, tm_per_sm = 1;
+    size_t tm_smem = 0;
+    if (time_marg) {
+        if (sel.uniforms) return bb_fail("reconstruction with time + calibration marginalisation is not supported");
+        while ((1 << tm_log2n) < h->nfft) ++tm_log2n;
+        int pa, pb, ps;
+        bb_tm_plan(tm_log2n, &pa, &pb, &ps);
+        tm_smem = bb_tm_series_elems(h->nfft, ps) * sizeof(double2) + 32 * sizeof(double);
+        if (tm_smem > 227 * 1024) return bb_fail("time + calibration marginalisation: series does not fit shared memory");
+        BB_CUDA(cudaFuncSetAttribute(bb_calmarg_time_kernel<NDET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tm_smem));
+        tm_per_sm = (int)((227 * 1024) / (tm_smem + 1024));
+        if (tm_per_sm < 1) tm_per_sm = 1;
+        if (tm_per_sm > 4) tm_per_sm = 4;
+    }
     // contraction window per chunk (needs the sorted order; one small read-back per call)
     const int n_chunks = (int)((n + BB_CM_CHUNK - 1) / BB_CM_CHUNK);
     const unsigned* perm = (h->perm_valid && !getenv("BB_CM_NOTRIM")) ? h->d_perm : nullptr;
@@ -208,7 +296,7 @@ static int bb_launch_calmarg_t(bb_handle* h, long n, double* out, cudaStream_t s
         // per detector: D^T [nc x m] (+)= C_d [kw x nc]^T  X_d [kw x m]   (column-major views of the row-major buffers)
         for (int d = 0; d < NDET; ++d) {
             const size_t off = (size_t)d * ldk + k_lo;
-            if (cublasZgemm(h->cublas, CUBLAS_OP_T, CUBLAS_OP_N, nc, m, kw, &one,
+            if (!time_marg && cublasZgemm(h->cublas, CUBLAS_OP_T, CUBLAS_OP_N, nc, m, kw, &one,
                             reinterpret_cast<const cuDoubleComplex*>(h->d_cm_C + off), (int)kk,
                             reinterpret_cast<const cuDoubleComplex*>(h->d_cm_X + off), (int)kk, d ? &one : &zero,
                             reinterpret_cast<cuDoubleComplex*>(h->d_cm_D), nc) != CUBLAS_STATUS_SUCCESS)
@@ -217,7 +305,17 @@ static int bb_launch_calmarg_t(bb_handle* h, long n, double* out, cudaStream_t s
                             h->d_cm_Y + off, (int)kk, d ? &done : &dzero, h->d_cm_H, nc) != CUBLAS_STATUS_SUCCESS)
                 return bb_fail("calibration marginalisation: cublasDgemm failed");
         }
-        if (sel.uniforms)
+        if (time_marg) {
+            // the per-curve likelihoods go to the (unused) <d|h> buffer
+            double* L = reinterpret_cast<double*>(h->d_cm_D);
+            long grid_t = (long)m * nc;
+            if (grid_t > (long)h->sm_count * tm_per_sm) grid_t = (long)h->sm_count * tm_per_sm;
+            bb_calmarg_time_kernel<NDET><<<(unsigned)grid_t, BB_TM_THREADS, tm_smem, st>>>(
+                h->d_coef, perm, s0, m, h->d_cm_X, h->d_cm_C, h->d_cm_H, nc, ldk, k_lo, k_hi, h->nfft, tm_log2n,
+                h->d_twiddle, h->marg, h->net.start_time, h->net.duration, L);
+            BB_CUDA(cudaGetLastError());
+            bb_calmarg_lse_kernel<<<(unsigned)((m * 32L + 127) / 128), 128, 0, st>>>(h->d_coef, perm, s0, m, L, nc, out);
+        } else if (sel.uniforms)
             bb_calmarg_select_kernel<<<(unsigned)((m * 32L + 127) / 128), 128, 0, st>>>(h->d_coef, perm, s0, m, h->d_cm_D,
                                                                                        h->d_cm_H, nc, NDET, point, sel);
         else
@@ -230,7 +328,12 @@ static int bb_launch_calmarg_t(bb_handle* h, long n, double* out, cudaStream_t s
 }
 
 static int bb_launch_calmarg(bb_handle* h, long n, double* out, cudaStream_t st, BBCalSelect sel = BBCalSelect{nullptr, nullptr, nullptr}) {
-    if (h->marg.flags & BB_MARG_TIME) return bb_fail("time + calibration marginalisation is not supported on the device");
+    if (h->marg.flags & BB_MARG_TIME) {
+        // base.py:305-323; with distance marginalisation the reference itself fails (shape mismatch in base.py:775-784)
+        if (h->marg.flags & BB_MARG_DISTANCE)
+            return bb_fail("time + calibration + distance marginalisation is not defined by the reference (shape mismatch)");
+        if (h->nfft == 0) return bb_fail("time marginalisation needs n_freq - 1 to be a power of two");
+    }
     if (h->kind != 0) return bb_fail("calibration marginalisation: full-grid likelihood only");
     if (h->cal_params) return bb_fail("calibration marginalisation excludes per-sample calibration parameters");
     if (h->shard_lo != 0 || h->shard_hi != h->net.n_freq) return bb_fail("calibration marginalisation cannot be frequency-sharded");

@@ -166,13 +166,32 @@ __device__ __forceinline__ void bb_relbin_edge_sample(const double* rec, const d
     double2 carry[NDET];
 #pragma unroll
     for (int d = 0; d < NDET; ++d) carry[d] = make_double2(0.0, 0.0);
+    // node tables of the NEXT row are requested before the current row is evaluated (the multi-banded likelihood
+    // streams hundreds of rows per sample from L2)
+    // (only there: with the two rows of a relative-binning sample the extra registers cost more than they hide)
+    constexpr bool PREFETCH = !CROSS;
+    const int j0 = lane < ne ? lane : ne - 1;
+    double nf = 0.0, nu = 0.0, nlf = 0.0, nq = 0.0;
+    if (PREFETCH) { nf = rb.edges.f[j0]; nu = rb.edges.u[j0]; nlf = rb.edges.lf[j0]; nq = rb.edges.q34[j0]; }
     for (int base = 0; base < ne; base += 32) {
         const int j = base + lane;
-        const int jj = j < ne ? j : ne - 1;
-        const double f = rb.edges.f[jj];
-        double A, ph;
-        bb_wave<APPROX>(rec, f, rb.edges.u[jj], rb.edges.lf[jj], rb.edges.q34[jj], &A, &ph);
         const bool more = base + 32 < ne;
+        double f, u, lfj, q34;
+        if (PREFETCH) {
+            f = nf; u = nu; lfj = nlf; q34 = nq;
+            if (more) {
+                const int jn = j + 32 < ne ? j + 32 : ne - 1;
+                nf = rb.edges.f[jn];
+                nu = rb.edges.u[jn];
+                nlf = rb.edges.lf[jn];
+                nq = rb.edges.q34[jn];
+            }
+        } else {
+            const int jj = j < ne ? j : ne - 1;
+            f = rb.edges.f[jj]; u = rb.edges.u[jj]; lfj = rb.edges.lf[jj]; q34 = rb.edges.q34[jj];
+        }
+        double A, ph;
+        bb_wave<APPROX>(rec, f, u, lfj, q34, &A, &ph);
 #pragma unroll
         for (int d = 0; d < NDET; ++d) {
             const double* cd = rec + BC_DET + BC_DSTRIDE * d;
@@ -182,7 +201,7 @@ __device__ __forceinline__ void bb_relbin_edge_sample(const double* rec, const d
             if (CAL) {
                 double amp1, cr, ci;
                 bb_cal_factor(cal + d * 4 * grid.n_points, grid.n_points, grid.l0[d], grid.inv_delta[d],
-                              rb.edges.lf[jj], &amp1, &cr, &ci);
+                              lfj, &amp1, &cr, &ci);
                 const double tr = amp1 * (hr * cr - hi * ci), ti = amp1 * (hr * ci + hi * cr);
                 hr = tr;
                 hi = ti;

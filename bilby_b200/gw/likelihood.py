@@ -190,9 +190,11 @@ class GravitationalWaveTransient(Likelihood):
             self._marginalized_parameters.append("luminosity_distance")
 
         if self.calibration_marginalization:           # base.py:225-229
-            if self.time_marginalization:
-                raise NotImplementedError("time + calibration marginalisation (one FFT per response curve, "
-                                          "base.py:305-323) is not built")
+            if self.time_marginalization and self.distance_marginalization:
+                # the reference itself fails here: distance_marginalized_likelihood (base.py:775-784) broadcasts the
+                # [n_curves, n_times] array against the [n_curves] optimal SNRs
+                raise ValueError("time + calibration + distance marginalisation is not defined by the reference "
+                                 "(shape mismatch in base.py:775-784)")
             self.number_of_response_curves = number_of_response_curves
             self.starting_index = starting_index
             self._setup_calibration_marginalization(calibration_lookup_table, priors)

@@ -456,8 +456,9 @@ class OracleLikelihood:
         # calibration marginalisation (base.py:1037-1051): {detector name: complex [n_curves, n_masked_bins]}
         self.calibration_marginalization = calibration_draws is not None
         if self.calibration_marginalization:
-            if time_marginalization:
-                raise NotImplementedError("time + calibration marginalisation is not restated")
+            if time_marginalization and distance_marginalization:
+                # the reference itself fails here (base.py:775-784 broadcasts [n_curves, n_times] against [n_curves])
+                raise ValueError("time + calibration + distance marginalisation: shape mismatch in the reference")
             self.calibration_draws = {k: np.asarray(v) for k, v in calibration_draws.items()}
             self.calibration_abs_draws = {k: np.abs(v) ** 2 for k, v in self.calibration_draws.items()}
             self.number_of_response_curves = len(next(iter(self.calibration_draws.values())))
@@ -575,16 +576,35 @@ class OracleLikelihood:
 
     def calibration_log_likelihoods(self, pols, parameters):
         """base.py:333-346 (per-detector arrays over the response curves; note conj(d) * h, the conjugate of
-        inner_product's convention), :109-148 (arrays add over detectors), :822-858: the point likelihood per curve."""
+        inner_product's convention), :109-148 (arrays add over detectors), :822-858: the point likelihood per curve.
+        With time marginalisation (base.py:305-323, 860-866): one transform of the calibrated integrand per curve,
+        [n_curves, N - 1], then the time-marginalised likelihood per curve (base.py:794-820, 786-792)."""
         d_arr, hh_arr = 0, 0
         for ifo in self.ifos:
             signal = ifo.get_detector_response(pols, parameters)
             m = ifo.frequency_mask
             norm = 4 / self.duration
             integrand = norm * ifo.frequency_domain_strain.conj() * signal / ifo.power_spectral_density_array
-            d_arr = d_arr + np.dot(integrand[m], self.calibration_draws[ifo.name].T)
+            if self.time_marginalization:
+                tiled = np.tile(integrand, (self.number_of_response_curves, 1)).T          # [N, n_curves]
+                tiled[m] *= self.calibration_draws[ifo.name].T
+                d_arr = d_arr + np.fft.fft(tiled[0:-1], axis=0).T
+            else:
+                d_arr = d_arr + np.dot(integrand[m], self.calibration_draws[ifo.name].T)
             hh_integrand = norm * np.abs(signal) ** 2 / ifo.power_spectral_density_array
             hh_arr = hh_arr + np.dot(hh_integrand[m], self.calibration_abs_draws[ifo.name].T)
+        if self.time_marginalization:
+            times = self._times
+            if self.jitter_time:
+                times = times + parameters["time_jitter"]
+            tmask = (times >= self.time_prior.minimum) & (times <= self.time_prior.maximum)
+            arr = d_arr[:, tmask]
+            time_prior_array = self.time_prior.prob(times[tmask]) * self._delta_tc
+            if self.phase_marginalization:
+                log_l = ln_i0(abs(arr)) - hh_arr[:, np.newaxis] / 2
+            else:
+                log_l = arr.real - hh_arr[:, np.newaxis] / 2
+            return logsumexp(log_l, b=time_prior_array, axis=-1)
         if self.distance_marginalization:
             return self.distance_marginalized_likelihood(d_arr, hh_arr, parameters)
         if self.phase_marginalization:

@@ -37,8 +37,14 @@ def main():
     for k in draws:
         res["param_" + k] = draws[k]
 
-    def priors(phase=False, distance=False):
+    t_inj = inj["geocent_time"]
+    jitter = np.random.default_rng(7).uniform(-1 / 2048.0, 1 / 2048.0, n)
+    res["param_time_jitter"] = jitter
+
+    def priors(phase=False, distance=False, time=False):
         pri = {}
+        if time:
+            pri["geocent_time"] = Uniform(t_inj - 0.1, t_inj + 0.1, "geocent_time")
         for name in names:
             for i in range(N_POINTS):
                 pri[f"recalib_{name}_amplitude_{i}"] = Gaussian(0.0, 0.05, f"recalib_{name}_amplitude_{i}")
@@ -52,7 +58,11 @@ def main():
     first = None
     for mode, kw in (("cal", {}), ("cal_phase", dict(phase_marginalization=True)),
                      ("cal_distance_phase", dict(phase_marginalization=True, distance_marginalization=True,
-                                                 distance_marginalization_lookup_table="/tmp/golden_dp_lookup.npz"))):
+                                                 distance_marginalization_lookup_table="/tmp/golden_dp_lookup.npz")),
+                     # time + calibration (base.py:305-323): one FFT per response curve; with distance marginalisation
+                     # the reference itself raises a shape mismatch, so only these two exist
+                     ("cal_time", dict(time_marginalization=True, jitter_time=True)),
+                     ("cal_time_phase", dict(time_marginalization=True, jitter_time=True, phase_marginalization=True))):
         brandom.seed(424242)
         for ifo in ifos:     # build_calibration_lookup resets the model to the identity (calibration.py:552)
             ifo.calibration_model = bilby.gw.detector.calibration.CubicSpline(
@@ -60,7 +70,8 @@ def main():
                 maximum_frequency=ifo.maximum_frequency, n_points=N_POINTS)
         like = bilby.gw.likelihood.GravitationalWaveTransient(
             ifos, wfg, calibration_marginalization=True, number_of_response_curves=N_CURVES,
-            priors=priors(kw.get("phase_marginalization", False), kw.get("distance_marginalization", False)), **kw)
+            priors=priors(kw.get("phase_marginalization", False), kw.get("distance_marginalization", False),
+                          kw.get("time_marginalization", False)), **kw)
         if first is None:
             first = like
             for name in names:
@@ -80,9 +91,14 @@ def main():
                 for j in range(N_POINTS):
                     p[f"recalib_{name}_amplitude_{j}"] = 0.0
                     p[f"recalib_{name}_phase_{j}"] = 0.0
+            if kw.get("time_marginalization"):
+                p["geocent_time"] = float(start_time)
+                p["time_jitter"] = float(jitter[i])
             vals[i] = like.log_likelihood_ratio(p)
         res["lnl_" + mode] = vals
         print(mode, vals[:4], vals[12])
+        if kw.get("time_marginalization"):
+            continue          # the reconstruction below is pinned for the modes without time marginalisation
         # marginalised-parameter reconstruction (base.py:502-578): recalib_index by rng.choice over the response
         # curves' posterior, then distance / phase with the chosen curve applied (base.py:289-290); the unit-interval
         # draws of the reference's generator are replayed and stored

@@ -68,9 +68,25 @@ def test_single_identity_curve_reduces_to_the_plain_likelihood():
     assert np.abs(a - b).max() < 1e-9 * np.abs(b).max()
 
 
-def test_time_plus_calibration_is_refused():
-    with pytest.raises(NotImplementedError):
-        _likelihood(geocent_time=True)
+@pytest.mark.parametrize("mode,on", [("cal_time", dict(geocent_time=True)),
+                                     ("cal_time_phase", dict(geocent_time=True, phase=True))])
+def test_time_plus_calibration_vs_reference(mode, on):
+    """base.py:305-323, 860-866: one transform of the calibrated integrand per response curve (bb_calmarg_time_kernel)."""
+    g, like, draws = _likelihood(**on)
+    d = dict(draws)
+    d["geocent_time"] = np.full_like(d["chirp_mass"], float(g["start_time"]))
+    lnl = like.log_likelihood_ratio_batch(d)
+    ref = g["lnl_" + mode]
+    plain_g, plain, _ = _build("noise_H1L1V1")
+    snr = plain.compute_snrs_batch({k: v for k, v in draws.items() if k != "time_jitter"})
+    rho2 = sum(snr[f"{ifo.name}_optimal_snr"] ** 2 for ifo in plain.interferometers)
+    err = np.abs(lnl - ref) / np.maximum(np.abs(ref), 0.5 * rho2)
+    assert err.max() < RTOL, err.max()
+
+
+def test_time_calibration_distance_is_refused_like_the_reference():
+    with pytest.raises(ValueError):
+        _likelihood(geocent_time=True, luminosity_distance=True, phase=True)
 
 
 @pytest.mark.parametrize("mode,on", [("cal", {}), ("cal_phase", dict(phase=True)),

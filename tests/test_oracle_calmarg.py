@@ -73,3 +73,19 @@ def test_calibration_reconstruction_matches_reference():
     got = _recon(like, draws, g["uniforms_cal_distance_phase"], rows)
     assert np.array_equal(got[:, 0], g["recon_cal_distance_phase"][rows, 0])
     assert np.allclose(got, g["recon_cal_distance_phase"][rows], rtol=1e-9)
+
+
+def test_time_plus_calibration_matches_reference():
+    """base.py:305-323, 860-866: one transform of the calibrated integrand per response curve."""
+    g, ifos, draws, curves = setup()
+    t_inj = ocl.INJECTION["geocent_time"]
+    rows = [0, 3, 12, 15, 19]
+    for mode, kw in (("cal_time", {}), ("cal_time_phase", dict(phase_marginalization=True))):
+        like = ocl.OracleLikelihood(ifos, waveform_arguments=WA, calibration_draws=curves, time_marginalization=True,
+                                    jitter_time=True, time_prior=ocl.OracleUniform(t_inj - 0.1, t_inj + 0.1), **kw)
+        got = []
+        for i in rows:
+            p = {k: float(v[i]) for k, v in draws.items()}
+            p["geocent_time"] = float(g["start_time"])
+            got.append(like.log_likelihood_ratio(p))
+        assert np.allclose(got, g["lnl_" + mode][rows], rtol=1e-10, atol=1e-10), mode
