@@ -154,8 +154,9 @@ __global__ void bb_calmarg_select_kernel(const double* __restrict__ coef, const 
 //   the chunk's active window), in-shared-memory FFT (bb_tm_fft_dif), weighted logsumexp over the times inside the
 //   geocent_time prior with <h|h>_c from the DGEMM (bb_tm_finish) -> L[s][c]; bb_calmarg_lse_kernel then takes
 //   logsumexp_c L - log(n_curves).
+#define BB_CMT_THREADS 256      // two CTAs per SM: the fill of one pair overlaps the transform of the other
 template <int NDET>
-__global__ void __launch_bounds__(BB_TM_THREADS, 1)
+__global__ void __launch_bounds__(BB_CMT_THREADS, 2)
 bb_calmarg_time_kernel(const double* __restrict__ coef, const unsigned* __restrict__ perm, long s0, int m,
                        const double2* __restrict__ Xs, const double2* __restrict__ C, const double* __restrict__ H,
                        int n_curves, int ldk, int k_lo, int k_hi, int nfft, int log2n,
@@ -178,7 +179,7 @@ bb_calmarg_time_kernel(const double* __restrict__ coef, const unsigned* __restri
             if (tid == 0) L[pair] = -DBL_MAX;
             continue;
         }
-        for (int k = tid; k < nfft; k += BB_TM_THREADS) {
+        for (int k = tid; k < nfft; k += BB_CMT_THREADS) {
             double vr = 0.0, vi = 0.0;
             if (k >= k_lo && k < k_hi) {
 #pragma unroll
@@ -192,8 +193,8 @@ bb_calmarg_time_kernel(const double* __restrict__ coef, const unsigned* __restri
             X[bb_tm_pos(k, ps)] = make_double2(vr, vi);
         }
         __syncthreads();
-        bb_tm_fft_dif(X, nfft, log2n, twiddle);
-        bb_tm_finish(X, nfft, log2n, marg, H[pair], rec[BC_DISTANCE], rec[BC_JITTER], start_time, duration, red,
+        bb_tm_fft_dif<BB_CMT_THREADS>(X, nfft, log2n, twiddle);
+        bb_tm_finish<BB_CMT_THREADS>(X, nfft, log2n, marg, H[pair], rec[BC_DISTANCE], rec[BC_JITTER], start_time, duration, red,
                      L + pair);
     }
 }
@@ -261,7 +262,7 @@ static int bb_launch_calmarg_t(bb_handle* h, long n, double* out, cudaStream_t s
         BB_CUDA(cudaFuncSetAttribute(bb_calmarg_time_kernel<NDET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tm_smem));
         tm_per_sm = (int)((227 * 1024) / (tm_smem + 1024));
         if (tm_per_sm < 1) tm_per_sm = 1;
-        if (tm_per_sm > 4) tm_per_sm = 4;
+        if (tm_per_sm > 2) tm_per_sm = 2;
     }
     // contraction window per chunk (needs the sorted order; one small read-back per call)
     const int n_chunks = (int)((n + BB_CM_CHUNK - 1) / BB_CM_CHUNK);
@@ -310,7 +311,7 @@ static int bb_launch_calmarg_t(bb_handle* h, long n, double* out, cudaStream_t s
             double* L = reinterpret_cast<double*>(h->d_cm_D);
             long grid_t = (long)m * nc;
             if (grid_t > (long)h->sm_count * tm_per_sm) grid_t = (long)h->sm_count * tm_per_sm;
-            bb_calmarg_time_kernel<NDET><<<(unsigned)grid_t, BB_TM_THREADS, tm_smem, st>>>(
+            bb_calmarg_time_kernel<NDET><<<(unsigned)grid_t, BB_CMT_THREADS, tm_smem, st>>>(
                 h->d_coef, perm, s0, m, h->d_cm_X, h->d_cm_C, h->d_cm_H, nc, ldk, k_lo, k_hi, h->nfft, tm_log2n,
                 h->d_twiddle, h->marg, h->net.start_time, h->net.duration, L);
             BB_CUDA(cudaGetLastError());

@@ -110,13 +110,14 @@ __device__ __forceinline__ void bb_tm_radix2_tail(double2* X, int nfft, int log2
 }
 
 // In-place decimation-in-frequency FFT (natural order in, bit-reversed order out: output j is at index bitrev(j)).
+template <int NT = BB_TM_THREADS>
 __device__ __forceinline__ void bb_tm_fft_dif(double2* X, int nfft, int log2n, const double2* __restrict__ twiddle) {
     int a, b, ps;
     bb_tm_plan(log2n, &a, &b, &ps);
     int s = 0;
-    for (int i = 0; i < a; ++i, s += 4) bb_tm_pass<4>(X, nfft, s, ps, twiddle);
-    for (int i = 0; i < b; ++i, s += 3) bb_tm_pass<3>(X, nfft, s, ps, twiddle);
-    bb_tm_radix2_tail(X, nfft, log2n, s, ps, twiddle);
+    for (int i = 0; i < a; ++i, s += 4) bb_tm_pass<4, NT>(X, nfft, s, ps, twiddle);
+    for (int i = 0; i < b; ++i, s += 3) bb_tm_pass<3, NT>(X, nfft, s, ps, twiddle);
+    bb_tm_radix2_tail<NT>(X, nfft, log2n, s, ps, twiddle);
 }
 
 // After the FFT of the series in shared memory: the weighted logsumexp over the times inside the geocent_time
