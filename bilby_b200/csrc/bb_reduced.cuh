@@ -388,15 +388,26 @@ bb_roq_kernel(const double* __restrict__ coef, long n, BBRoqDev rq, const double
             // (4 DFMA) instead of five complex multiply-accumulates (20 DFMA) and 30 running sums per lane.
             bb_interp5_coeffs(a, ck[d]);
         }
+        // source of pass 0 per detector and the advance per pass, computed once per sample; the usual case (all five
+        // times of every detector inside the weights) is one branch-free sequence of NDET bulk copies
+        bool all_in = true;
+        const double2* wsrc[NDET];
+#pragma unroll
+        for (int d = 0; d < NDET; ++d) {
+            all_in = all_in && inb[d];
+            wsrc[d] = rq.W2 + ((size_t)d * n_pass * rq.n_time + (size_t)max(first[d], 0)) * 32;
+        }
+        const size_t wstride = (size_t)rq.n_time * 32;
         auto stage_fill = [&](int pass) {
             if (lane == 0) {
                 bb_mbar_expect_tx(bar, (unsigned)(NDET * 5 * 32 * sizeof(double2)));
+                if (all_in) {
 #pragma unroll
-                for (int d = 0; d < NDET; ++d) {
-                    const double2* blk = rq.W2 + ((size_t)d * n_pass + pass) * rq.n_time * 32;
-                    if (inb[d]) {
-                        bb_bulk_g2s(wst + d * 5 * 32, blk + (size_t)first[d] * 32, 5 * 32 * sizeof(double2), bar);
-                    } else {
+                    for (int d = 0; d < NDET; ++d)
+                        bb_bulk_g2s(wst + d * 5 * 32, wsrc[d] + (size_t)pass * wstride, 5 * 32 * sizeof(double2), bar);
+                } else {
+                    for (int d = 0; d < NDET; ++d) {
+                        const double2* blk = rq.W2 + ((size_t)d * n_pass + pass) * rq.n_time * 32;
                         for (int k = 0; k < 5; ++k) {
                             const int i = min(max(first[d] + k, 0), rq.n_time - 1);
                             bb_bulk_g2s(wst + (d * 5 + k) * 32, blk + (size_t)i * 32, 32 * sizeof(double2), bar);
