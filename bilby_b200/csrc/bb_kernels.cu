@@ -242,6 +242,30 @@ __device__ __forceinline__ double bb_warp_sum(double v) {
     return v;
 }
 
+// Eight sums over the warp with 9 double shuffles instead of 40: each butterfly step keeps half of the values (which
+// half depends on the lane's bit) and sends the other half.  Lane l returns the total of value index (l >> 2) & 7, i.e.
+// lanes 0, 4, ..., 28 hold totals 0 .. 7.
+__device__ __forceinline__ double bb_warp_sum8(const double* v, int lane) {
+    const unsigned full = 0xffffffffu;
+    const bool h1 = (lane & 16) != 0, h2 = (lane & 8) != 0, h3 = (lane & 4) != 0;
+    double a[4], b[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double send = h1 ? v[i] : v[i + 4], keep = h1 ? v[i + 4] : v[i];
+        a[i] = keep + __shfl_xor_sync(full, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const double send = h2 ? a[i] : a[i + 2], keep = h2 ? a[i + 2] : a[i];
+        b[i] = keep + __shfl_xor_sync(full, send, 8);
+    }
+    const double send = h3 ? b[0] : b[1], keep = h3 ? b[1] : b[0];
+    double c = keep + __shfl_xor_sync(full, send, 4);
+    c += __shfl_xor_sync(full, c, 2);
+    c += __shfl_xor_sync(full, c, 1);
+    return c;
+}
+
 #include "bb_k1.cuh"
 
 // calibration prologue: node values -> (values, spline coefficients) per (sample, detector, amplitude|phase)

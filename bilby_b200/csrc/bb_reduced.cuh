@@ -252,14 +252,26 @@ bb_relbin_kernel(const double* __restrict__ coef, long n, BBRelbinDev rb, const 
 #pragma unroll
         for (int d = 0; d < NDET; ++d) acc[d][0] = acc[d][1] = acc[d][2] = 0.0;
         bb_relbin_edge_sample<NDET, APPROX, CAL, CROSS>(rec, cal, grid, rb, lane, acc);
+        if (NDET == 3) {
+            // nine sums: eight through the halving butterfly (lane 4 q ends with quantity q = 3 d + c), one plain
+            const double* flat = &acc[0][0];
+            const double t8 = bb_warp_sum8(flat, lane);
+            const double t9 = bb_warp_sum(flat[8]);
+            const bool bad = rec[BC_STATUS] != 0.0;
+            double* o = out + s * NDET * 3;
+            const int q = lane >> 2;
+            if ((lane & 3) == 0) o[q] = (bad && (q % 3 == 2)) ? nan("") : t8;
+            if (lane == 1) o[8] = bad ? nan("") : t9;
+        } else {
 #pragma unroll
-        for (int d = 0; d < NDET; ++d) {
-            const double sr = bb_warp_sum(acc[d][0]), si = bb_warp_sum(acc[d][1]), sh = bb_warp_sum(acc[d][2]);
-            if (lane == 0) {
-                double* o = out + (s * NDET + d) * 3;
-                o[0] = sr;
-                o[1] = si;
-                o[2] = (rec[BC_STATUS] != 0.0) ? nan("") : sh;
+            for (int d = 0; d < NDET; ++d) {
+                const double sr = bb_warp_sum(acc[d][0]), si = bb_warp_sum(acc[d][1]), sh = bb_warp_sum(acc[d][2]);
+                if (lane == 0) {
+                    double* o = out + (s * NDET + d) * 3;
+                    o[0] = sr;
+                    o[1] = si;
+                    o[2] = (rec[BC_STATUS] != 0.0) ? nan("") : sh;
+                }
             }
         }
         __syncwarp();       // every lane is done with this slot before it is refilled two samples later
