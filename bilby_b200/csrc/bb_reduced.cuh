@@ -282,7 +282,7 @@ bb_relbin_kernel(const double* __restrict__ coef, long n, BBRelbinDev rb, const 
 // K6: ROQ at one coalescence time per sample (roq.py:467-549)
 // ------------------------------------------------------------------------------------------------
 // <h|h>_d = |K_d|^2 sum_j |h22(f_j)|^2 |C_d(f_j)|^2 w_d[j] over the quadratic nodes (roq.py:504-507)
-template <int NDET, int APPROX, bool CAL>
+template <int NDET, int APPROX, bool CAL, bool REDUCE = true>
 __device__ __forceinline__ void bb_roq_quadratic(const double* rec, const double* cal, const BBCalGrid& grid,
                                                  const BBRoqDev& rq, int lane, double* hq) {
 #pragma unroll
@@ -305,8 +305,10 @@ __device__ __forceinline__ void bb_roq_quadratic(const double* rec, const double
             hq[d] += w;
         }
     }
+    if (REDUCE) {
 #pragma unroll
-    for (int d = 0; d < NDET; ++d) hq[d] = bb_warp_sum(hq[d]) * rec[BC_DET + BC_DSTRIDE * d + 3];
+        for (int d = 0; d < NDET; ++d) hq[d] = bb_warp_sum(hq[d]) * rec[BC_DET + BC_DSTRIDE * d + 3];
+    }
 }
 
 // the cubic interpolation through five neighbouring ROQ times (roq.py:576-602 / 644-651, LIGO-T2100224)
@@ -431,7 +433,7 @@ bb_roq_kernel(const double* __restrict__ coef, long n, BBRoqDev rq, const double
         __syncwarp();
         stage_fill(0);
         double hq[NDET];
-        bb_roq_quadratic<NDET, APPROX, CAL>(rec, cal, grid, rq, lane, hq);
+        bb_roq_quadratic<NDET, APPROX, CAL, NDET != 3>(rec, cal, grid, rq, lane, hq);      // NDET == 3: lane partials
         double2 acc[NDET];
 #pragma unroll
         for (int d = 0; d < NDET; ++d) acc[d] = make_double2(0.0, 0.0);
@@ -474,16 +476,40 @@ bb_roq_kernel(const double* __restrict__ coef, long n, BBRoqDev rq, const double
             __syncwarp();                                       // every lane has read the stage
             if (pass + 1 < n_pass) stage_fill(pass + 1);
         }
-#pragma unroll
-        for (int d = 0; d < NDET; ++d) {
-            const double kr = rec[BC_DET + BC_DSTRIDE * d], ki = rec[BC_DET + BC_DSTRIDE * d + 1];
-            const double sr = bb_warp_sum(acc[d].x), si = bb_warp_sum(acc[d].y);
-            if (lane == 0) {
-                double* o = out + (s * NDET + d) * 3;
+        if (NDET == 3) {
+            // nine sums (3 x Re / Im of the contraction, 3 quadratic) through the halving butterfly: lane 4 q ends with
+            // quantity q of {Re0, Im0, Re1, Im1, Re2, Im2, Q0, Q1}; Q2 by a plain reduction
+            const double v[8] = {acc[0].x, acc[0].y, acc[1].x, acc[1].y, acc[2].x, acc[2].y, hq[0], hq[1]};
+            const double t8 = bb_warp_sum8(v, lane);
+            const double q2 = bb_warp_sum(hq[2]);
+            const double im = __shfl_down_sync(0xffffffffu, t8, 4);          // lane 8 d: Re_d here, Im_d from lane 8 d + 4
+            const bool bad = rec[BC_STATUS] != 0.0;
+            double* o = out + s * NDET * 3;
+            if ((lane & 7) == 0 && lane < 24) {
+                const int d = lane >> 3;
+                const double kr = rec[BC_DET + BC_DSTRIDE * d], ki = rec[BC_DET + BC_DSTRIDE * d + 1];
+                const bool in = d == 0 ? inb[0] : (d == 1 ? inb[1] : inb[2]);
                 // conj(K) * sum; out of the ROQ time window: d_inner_h += log(False) (roq.py:532-533)
-                o[0] = inb[d] ? kr * sr + ki * si : -INFINITY;
-                o[1] = kr * si - ki * sr;
-                o[2] = (rec[BC_STATUS] != 0.0) ? nan("") : hq[d];
+                o[3 * d] = in ? kr * t8 + ki * im : -INFINITY;
+                o[3 * d + 1] = kr * im - ki * t8;
+            }
+            if (lane == 24 || lane == 28) {
+                const int d = (lane - 24) >> 2;
+                o[3 * d + 2] = bad ? nan("") : t8 * rec[BC_DET + BC_DSTRIDE * d + 3];
+            }
+            if (lane == 1) o[8] = bad ? nan("") : q2 * rec[BC_DET + BC_DSTRIDE * 2 + 3];
+        } else {
+#pragma unroll
+            for (int d = 0; d < NDET; ++d) {
+                const double kr = rec[BC_DET + BC_DSTRIDE * d], ki = rec[BC_DET + BC_DSTRIDE * d + 1];
+                const double sr = bb_warp_sum(acc[d].x), si = bb_warp_sum(acc[d].y);
+                if (lane == 0) {
+                    double* o = out + (s * NDET + d) * 3;
+                    // conj(K) * sum; out of the ROQ time window: d_inner_h += log(False) (roq.py:532-533)
+                    o[0] = inb[d] ? kr * sr + ki * si : -INFINITY;
+                    o[1] = kr * si - ki * sr;
+                    o[2] = (rec[BC_STATUS] != 0.0) ? nan("") : hq[d];
+                }
             }
         }
         __syncwarp();
