@@ -160,22 +160,21 @@ __device__ __forceinline__ void bb_wave(const double* c, double f, double u, dou
 // ------------------------------------------------------------------------------------------------
 // K0: prologue
 // ------------------------------------------------------------------------------------------------
-#define BB_K0_THREADS 128
+#define BB_K0_THREADS 64
 __global__ void __launch_bounds__(BB_K0_THREADS) bb_prologue_kernel(const double* __restrict__ params, long n, BBNetwork net,
                                    BBWaveformConfig wf, double* __restrict__ coef, unsigned* __restrict__ keys,
                                    unsigned* __restrict__ index) {
-    // The record is built in registers and leaves through shared memory: a thread storing its own 672-byte record
-    // double by double touches 32 sectors per instruction (lg_throttle-bound, 1.75 x DRAM write amplification in the
-    // first capture, profiles/r1d_k0*); staged in two halves (44 + 40 doubles, both sector-aligned; row stride 45
-    // doubles = conflict-free) the block writes whole sectors with consecutive lanes on consecutive doubles.
-    __shared__ double stage[BB_K0_THREADS * 45];
+    // The record is built directly in shared memory (row stride 85 doubles = conflict-free for per-thread access) and
+    // leaves with consecutive lanes on consecutive doubles.  A per-thread record is 672 bytes: as a local array it
+    // lived in local memory (1.3 KB of extra L1/L2 traffic per sample), and stored double by double from each thread it
+    // touched 32 sectors per instruction (lg_throttle-bound, 1.75 x DRAM write amplification, profiles/r1d_k0*).
+    __shared__ double stage[BB_K0_THREADS * 85];
     const int tid = threadIdx.x;
     const long blk0 = (long)blockIdx.x * blockDim.x;
     const long i = blk0 + tid;
-    const bool live = i < n;
     const int nrec = (int)min((long)blockDim.x, n - blk0);
-    double c[BC_NCOEF];
-    if (live) {
+    if (i < n) {
+        double* c = stage + tid * 85;
         double p[BB_NPARAM];
 #pragma unroll
         for (int k = 0; k < BB_NPARAM; ++k) p[k] = params[i * BB_NPARAM + k];
@@ -189,25 +188,11 @@ __global__ void __launch_bounds__(BB_K0_THREADS) bb_prologue_kernel(const double
             index[i] = (unsigned)i;
         }
     }
-    static_assert(BC_NCOEF == 84, "K0 stages the record as 44 + 40 doubles");
-    if (live) {
-#pragma unroll
-        for (int k = 0; k < 44; ++k) stage[tid * 45 + k] = c[k];
-    }
     __syncthreads();
-    for (int idx = tid; idx < nrec * 44; idx += blockDim.x) {
-        const int rec = idx / 44, j = idx - rec * 44;
-        coef[(blk0 + rec) * BC_NCOEF + j] = stage[rec * 45 + j];
-    }
-    __syncthreads();
-    if (live) {
-#pragma unroll
-        for (int k = 0; k < 40; ++k) stage[tid * 45 + k] = c[44 + k];
-    }
-    __syncthreads();
-    for (int idx = tid; idx < nrec * 40; idx += blockDim.x) {
-        const int rec = idx / 40, j = idx - rec * 40;
-        coef[(blk0 + rec) * BC_NCOEF + 44 + j] = stage[rec * 45 + j];
+    double* dst = coef + blk0 * BC_NCOEF;
+    for (int idx = tid; idx < nrec * BC_NCOEF; idx += blockDim.x) {
+        const int rec = idx / BC_NCOEF, j = idx - rec * BC_NCOEF;
+        dst[idx] = stage[rec * 85 + j];
     }
 }
 
@@ -1174,7 +1159,7 @@ extern "C" int bb_frequency_sequence_strain_device(bb_handle* h, const double* p
     wf.no_time_shift = 1;
     wf.f_min = first_frequency;
     wf.add_jitter = 0;
-    bb_prologue_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(params_dev, n, h->net, wf, h->d_coef, nullptr, nullptr);
+    bb_prologue_kernel<<<(unsigned)((n + BB_K0_THREADS - 1) / BB_K0_THREADS), BB_K0_THREADS, 0, st>>>(params_dev, n, h->net, wf, h->d_coef, nullptr, nullptr);
     h->launches++;
     h->perm_valid = false;
     dim3 grid((n_nodes + 127) / 128, (unsigned)n);
