@@ -100,6 +100,7 @@ struct bb_handle {
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     double2* d_series = nullptr;           // K4a -> K4b scratch: two chunks of series (time marginalisation)
     size_t series_cap = 0;                 // elements
+    size_t slotrec_cap = 0;                // doubles
     double* d_slotrec = nullptr;           // per-slot records handed from K4a to K4b
     // marginalised-parameter reconstruction (bb_recon.cuh)
     double *d_rc_dist = nullptr, *d_rc_prior = nullptr;   // distance grid and prior on it
