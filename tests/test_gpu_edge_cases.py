@@ -60,3 +60,26 @@ def test_domain_errors_inside_a_batch_keep_their_neighbours():
         assert bad[4] == np.nan_to_num(-np.inf), name
         keep = np.arange(9) != 4
         assert np.array_equal(bad[keep], good[keep]), name
+
+
+def test_distance_scaling_is_exact_at_scale():
+    """Size-independent property at 50000 draws per class: doubling the luminosity distance halves <d|h> and quarters
+    <h|h> EXACTLY (a power-of-two factor commutes with every rounding in the kernels), for the full grid, relative
+    binning (edge form), ROQ (row combination + bulk-copy staging) and multi-banding."""
+    import torch
+    for name, like, draws in _likelihoods():
+        n = len(draws["chirp_mass"])
+        reps = 50000 // n + 1
+        rng = np.random.default_rng(17)
+        big = {k: np.tile(v, reps)[:50000].copy() for k, v in draws.items()}
+        # decorrelate the copies a little so that the batch is not 50000 / n identical blocks
+        big["luminosity_distance"] *= rng.uniform(0.8, 1.25, 50000)
+        big["psi"] = big["psi"] + rng.uniform(-0.1, 0.1, 50000)
+        s1 = like.inner_products_batch(torch.from_numpy(like.pack(big)).cuda()).cpu().numpy()
+        big["luminosity_distance"] *= 2.0
+        s2 = like.inner_products_batch(torch.from_numpy(like.pack(big)).cuda()).cpu().numpy()
+        fin = np.isfinite(s1[..., 0])
+        assert np.array_equal(np.isfinite(s2[..., 0]), fin), name
+        assert np.array_equal(s2[..., 0][fin] * 2.0, s1[..., 0][fin]), name
+        assert np.array_equal(s2[..., 1] * 2.0, s1[..., 1]), name
+        assert np.array_equal(s2[..., 2] * 4.0, s1[..., 2]), name
