@@ -4,11 +4,14 @@
 //   K6 bb_roq_kernel           ROQ, one coalescence time per sample  <- bilby/gw/likelihood/roq.py:467-602
 //   K7 bb_roq_hlinear_kernel + ZGEMM + bb_roq_time_marg_kernel   ROQ time marginalisation  <- roq.py:535-651
 //
-// All three evaluate the source model on a frequency SEQUENCE (bin edges / ROQ nodes), the device form of
+//   K5 (no neighbour term)    multi-banding  <- bilby/gw/likelihood/multiband.py:728-765 (bb_set_multiband)
+//
+// All evaluate the source model on a frequency SEQUENCE (bin edges / ROQ nodes / banded points), the device form of
 // bilby/gw/source.py:1068-1140: every node is evaluated with the per-sample coefficient record written by
 // K0 (no f_min / f_max masking).  One warp owns one sample; lanes stride over the nodes; the node tables
 // (f, f^-1/6, ln f, f^3/4) and the per-node data are read through L1/L2 (they are a few hundred KB and shared
-// by every sample); partial sums stay in registers; one warp-shuffle reduction per sample.
+// by every sample; K6 stages its ROQ weights with cp.async.bulk); partial sums stay in registers; the per-sample
+// sums are reduced with a halving butterfly (bb_warp_sum8).
 #pragma once
 
 #define BB_RED_THREADS 256
