@@ -162,6 +162,7 @@ __device__ __forceinline__ void bb_wave(const double* c, double f, double u, dou
 // K0: prologue
 // ------------------------------------------------------------------------------------------------
 #define BB_K0_THREADS 64
+template <int APPROX>
 __global__ void __launch_bounds__(BB_K0_THREADS) bb_prologue_kernel(const double* __restrict__ params, long n, BBNetwork net,
                                    BBWaveformConfig wf, double* __restrict__ coef, unsigned* __restrict__ keys,
                                    unsigned* __restrict__ index) {
@@ -179,9 +180,12 @@ __global__ void __launch_bounds__(BB_K0_THREADS) bb_prologue_kernel(const double
         double p[BB_NPARAM];
 #pragma unroll
         for (int k = 0; k < BB_NPARAM; ++k) p[k] = params[i * BB_NPARAM + k];
-        BBQnmTable qnm = {bb_qnm_x, bb_qnm_fring, bb_qnm_fring_d2, bb_qnm_fdamp, bb_qnm_fdamp_d2, BB_QNM_N};
-        if (wf.approximant == BB_IMRPHENOMD) bb_phenomd_prologue(p, net, wf, qnm, bb_phenomd_fit, c);
-        else bb_taylorf2_prologue(p, net, wf, c);
+        if (APPROX == BB_IMRPHENOMD) {
+            BBQnmTable qnm = {bb_qnm_x, bb_qnm_fring, bb_qnm_fring_d2, bb_qnm_fdamp, bb_qnm_fdamp_d2, BB_QNM_N};
+            bb_phenomd_prologue(p, net, wf, qnm, bb_phenomd_fit, c);
+        } else {
+            bb_taylorf2_prologue(p, net, wf, c);
+        }
         if (keys) {
             // descending active-bin count: blocks of K1 then hold samples of equal length, longest first
             const unsigned count = (unsigned)(c[BC_KMAX] - c[BC_KMIN]);
@@ -840,8 +844,12 @@ static int bb_launch_prologue(bb_handle* h, const double* params_dev, long n, cu
     }
     const int threads = BB_K0_THREADS;
     const bool sort = n > BB_K1_SB && h->kind == 0;
-    bb_prologue_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(
-        params_dev, n, h->net, wf, h->d_coef, sort ? h->d_keys : nullptr, h->d_index);
+    if (wf.approximant == BB_IMRPHENOMD)
+        bb_prologue_kernel<BB_IMRPHENOMD><<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(
+            params_dev, n, h->net, wf, h->d_coef, sort ? h->d_keys : nullptr, h->d_index);
+    else
+        bb_prologue_kernel<BB_TAYLORF2><<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(
+            params_dev, n, h->net, wf, h->d_coef, sort ? h->d_keys : nullptr, h->d_index);
     h->launches++;
     BB_CUDA(cudaGetLastError());
     if (h->cal_params) {
@@ -1174,7 +1182,10 @@ extern "C" int bb_frequency_sequence_strain_device(bb_handle* h, const double* p
     wf.no_time_shift = 1;
     wf.f_min = first_frequency;
     wf.add_jitter = 0;
-    bb_prologue_kernel<<<(unsigned)((n + BB_K0_THREADS - 1) / BB_K0_THREADS), BB_K0_THREADS, 0, st>>>(params_dev, n, h->net, wf, h->d_coef, nullptr, nullptr);
+    if (wf.approximant == BB_IMRPHENOMD)
+        bb_prologue_kernel<BB_IMRPHENOMD><<<(unsigned)((n + BB_K0_THREADS - 1) / BB_K0_THREADS), BB_K0_THREADS, 0, st>>>(params_dev, n, h->net, wf, h->d_coef, nullptr, nullptr);
+    else
+        bb_prologue_kernel<BB_TAYLORF2><<<(unsigned)((n + BB_K0_THREADS - 1) / BB_K0_THREADS), BB_K0_THREADS, 0, st>>>(params_dev, n, h->net, wf, h->d_coef, nullptr, nullptr);
     h->launches++;
     h->perm_valid = false;
     dim3 grid((n_nodes + 127) / 128, (unsigned)n);

@@ -14,7 +14,8 @@ ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 LIB = os.path.join(ROOT, "bilby_b200", "_lib", "libbilby_b200.so")
 OUT = os.path.join(ROOT, "profiles", "sass")
 KERNELS = {   # label -> (mangled-name regex, keep full listing)
-    "k0_prologue": (r"_Z18bb_prologue_kernel", False),
+    "k0_prologue_imrphenomd": (r"_Z18bb_prologue_kernelILi0E", False),
+    "k0_prologue_taylorf2": (r"_Z18bb_prologue_kernelILi1E", False),
     "k1_inner_product_3det_imrphenomd": (r"_Z23bb_inner_product_kernelILi3ELi0ELb0E", True),
     "k1_inner_product_3det_imrphenomd_cal": (r"_Z23bb_inner_product_kernelILi3ELi0ELb1E", False),
     "k1_inner_product_3det_taylorf2": (r"_Z23bb_inner_product_kernelILi3ELi1ELb0E", False),
