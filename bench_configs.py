@@ -135,6 +135,7 @@ def build(config, n):
         if config == "cfg0":
             like = bb.gw.GravitationalWaveTransient(ifos, wfg)
             rows = like.pack(draws)
+            like._bench_draws = draws
             cal = None
             per_bin, extra = 240 + 30 * 2, 10
             work = "configs[0]: BBH 4s@2048Hz H1+L1 IMRPhenomD, no marginalisation"
@@ -154,6 +155,7 @@ def build(config, n):
                     draws[f"recalib_{name}_amplitude_{i}"] = crng.normal(0, 0.05, n)
                     draws[f"recalib_{name}_phase_{i}"] = crng.normal(0, 0.05, n)
             rows = like.pack(draws)
+            like._bench_draws = draws
             cal = like._cal_from_parameters(draws, n, np)
             per_bin = 240 + 70 * 3
             n_prior = int(0.2 * fs / 2)
@@ -183,7 +185,8 @@ def build(config, n):
     n_masked = int(ifos[0].frequency_mask.sum())
     if config == "cfg3":
         like = bb.gw.GravitationalWaveTransient(ifos, wfg_full)
-        rows = like.pack(bns_draws(n, rng))
+        like._bench_draws = bns_draws(n, rng)
+        rows = like.pack(like._bench_draws)
         per = (170 + 30 * 3) * n_masked
         return like, rows, None, (lambda r: (float(len(r)) * per, float(n_masked))), dict(
             workload="configs[3]: BNS TaylorF2+tides 128s@4096Hz H1L1V1 (259585 masked bins/detector), no "
@@ -198,7 +201,9 @@ def build(config, n):
                                       parameter_conversion=conv, waveform_arguments=dict(wa))
         like = bb.gw.likelihood.RelativeBinningGravitationalWaveTransient(ifos, wfg, fiducial_parameters=fid,
                                                                           epsilon=0.5, chi=1)
-        rows = like.pack(bns_draws(n, rng, narrow=True))
+        like._bench_draws = bns_draws(n, rng, narrow=True)
+        like._bench_fiducial = fid
+        rows = like.pack(like._bench_draws)
         ne = len(like.bin_freqs)
         per = (170 + 105 * 3) * ne
         return like, rows, None, (lambda r: (float(len(r)) * per, float(ne))), dict(
@@ -293,6 +298,9 @@ def build(config, n):
                 "H1L1V1")
         kernel = "bb_roq_kernel<3,TaylorF2>"
     rows = like.pack(draws)
+    like._bench_draws = draws
+    like._bench_basis = dict(linear_matrix=bl, quadratic_matrix=bq, frequency_nodes_linear=freqs[nl],
+                             frequency_nodes_quadratic=freqs[nq])
     return like, rows, None, (lambda r: (float(len(r)) * per, float(n_lin))), dict(
         workload=work, kernel=kernel, n_linear=n_lin, n_quadratic=n_quad, n_time=n_time)
 

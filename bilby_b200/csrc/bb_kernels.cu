@@ -645,6 +645,18 @@ extern "C" void bb_destroy(bb_handle* h) {
     delete h;
 }
 
+// The calibration staging buffers are sized [rows][n_det][..][n_points]: a handle re-configured with more detectors or
+// spline nodes at the same batch size must not reuse them (their capacities count rows, not doubles).
+static int bb_calmarg_upload(bb_handle* h, int n_curves, const double* curves);
+static void bb_cal_buffers_reset(bb_handle* h) {
+    cudaFree(h->d_calrec);
+    cudaFree(h->d_calpar);
+    if (h->h_calpar) cudaFreeHost(h->h_calpar);
+    h->d_calrec = h->d_calpar = h->h_calpar = nullptr;
+    h->calrec_cap = h->calpar_cap = 0;
+    h->cal_params = nullptr;
+}
+
 extern "C" int bb_set_network(bb_handle* h, int n_det, int n_freq, double duration, double sampling_frequency,
                               double start_time, const double* detector_tensors, const double* vertices,
                               const double* strain, const double* psd, const unsigned char* mask) {
@@ -653,6 +665,8 @@ extern "C" int bb_set_network(bb_handle* h, int n_det, int n_freq, double durati
     if (n_freq < 2) return bb_fail("bb_set_network: n_freq too small");
     BB_CUDA(cudaSetDevice(h->device));
     bb_reduced_clear(h);          // reduced-order set-ups refer to the previous network's data
+    if (h->have_network && h->net.n_det != n_det) bb_cal_buffers_reset(h);
+    if (h->cm_n_curves) bb_calmarg_upload(h, 0, nullptr);   // response curves live on the previous frequency grid
     BBNetwork& net = h->net;
     net.n_det = n_det;
     net.n_freq = n_freq;
@@ -1282,6 +1296,7 @@ extern "C" int bb_set_calibration(bb_handle* h, int n_points, const double* log1
     if (n_points == 0) { h->cal.n_points = 0; return 0; }
     if (n_points < 4 || n_points > BB_NCAL_MAX) return bb_fail("bb_set_calibration: n_points must be in [4, 32]");
     BB_CUDA(cudaSetDevice(h->device));
+    if (h->cal.n_points != n_points) bb_cal_buffers_reset(h);
     h->cal.n_points = n_points;
     h->cal.shared = 1;
     for (int d = 0; d < h->net.n_det; ++d) {

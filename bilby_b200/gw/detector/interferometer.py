@@ -22,6 +22,7 @@ class _StrainData:
     """The attributes of InterferometerStrainData the likelihood path reads."""
 
     def __init__(self, minimum_frequency, maximum_frequency, notch_list=None):
+        self.__dict__["_version"] = 0
         self.duration = None
         self.sampling_frequency = None
         self.start_time = None
@@ -30,6 +31,15 @@ class _StrainData:
         self.notch_list = list(notch_list or [])
         self._frequency_domain_strain = None
         self.window_factor = 1
+
+    def __setattr__(self, name, value):
+        """Every change of the data, the band or the notches bumps ``_version``: the device tiles built from this
+        object (Interferometer._device, GravitationalWaveTransient.device_network) are rebuilt on the next call."""
+        old = self.__dict__.get(name, self)
+        changed = old is not value and not (np.isscalar(value) and np.isscalar(old) and old == value)
+        object.__setattr__(self, name, value)
+        if changed:
+            self.__dict__["_version"] += 1
 
     @property
     def minimum_frequency(self):
@@ -91,6 +101,7 @@ class Interferometer:
     def __init__(self, name, power_spectral_density, minimum_frequency, maximum_frequency, length, latitude,
                  longitude, elevation, xarm_azimuth, yarm_azimuth, xarm_tilt=0., yarm_tilt=0.,
                  calibration_model=None):
+        self.__dict__["_own_version"] = 0
         self.name = name
         self.geometry = InterferometerGeometry(length, latitude, longitude, elevation, xarm_azimuth, yarm_azimuth,
                                                xarm_tilt, yarm_tilt)
@@ -98,9 +109,23 @@ class Interferometer:
         self._calibration_model = Recalibrate() if calibration_model is None else calibration_model
         self.strain_data = _StrainData(minimum_frequency, maximum_frequency)
         self.meta_data = dict(name=name)
-        self._data_version = 0
         self.reference_time = None
         self._handle = None
+
+    def __setattr__(self, name, value):
+        object.__setattr__(self, name, value)
+        if name in ("power_spectral_density", "strain_data", "geometry", "reference_time"):
+            self.__dict__["_own_version"] += 1
+
+    @property
+    def _data_version(self):
+        """Identity of everything the device tiles are built from (PSD object, strain, band, notches, calibration
+        model): replaced or edited inputs are re-uploaded on the next evaluation."""
+        return self._own_version + self.strain_data._version
+
+    @_data_version.setter
+    def _data_version(self, value):
+        self.__dict__["_own_version"] = value - self.strain_data._version
 
     def __repr__(self):
         return f"Interferometer(name='{self.name}', minimum_frequency={self.minimum_frequency}, " \

@@ -155,11 +155,12 @@ class GravitationalWaveTransient(Likelihood):
         self._net = None
         self._net_versions = None
         self._cal_points = 0
-        priors = self.priors
+        # base.py:166, 183-229: self.priors is a COPY that keeps the Prior objects; the side effects below land on the
+        # caller's dict (the one the sampler receives), exactly like the reference.
 
         if self.time_marginalization:
             self._check_marginalized_prior_is_set(key="geocent_time")
-            self._time_prior = self.priors["geocent_time"]
+            self._check_time_prior_is_uniform()
             self._setup_time_marginalization()
             priors["geocent_time"] = float(self.interferometers.start_time)
             if self.jitter_time:
@@ -250,6 +251,15 @@ class GravitationalWaveTransient(Likelihood):
             else:
                 raise ValueError(f"Prior not provided for {key}: the reference would fall back to BBHPriorDict "
                                  "(astropy); supply the prior explicitly")
+
+    def _check_time_prior_is_uniform(self):
+        """The device applies the weight prior.prob(t) * delta_tc of base.py:794-806 as delta_tc / (max - min) inside
+        [minimum, maximum]: exact for a Uniform prior only, so anything else is refused instead of mis-weighted."""
+        prior = self.priors["geocent_time"]
+        if not isinstance(prior, Uniform) or not (np.isfinite(prior.minimum) and np.isfinite(prior.maximum)):
+            raise NotImplementedError(
+                "time marginalisation on the device needs a Uniform geocent_time prior with finite bounds "
+                f"(got {prior!r}); the reference weights by prior.prob(times) for any prior (base.py:794-806)")
 
     def _setup_time_marginalization(self):
         self._delta_tc = 2 / self.waveform_generator.sampling_frequency
@@ -358,6 +368,7 @@ class GravitationalWaveTransient(Likelihood):
         if self._net is None or self._net_versions != self._versions():
             self._net = DeviceNetwork(self.interferometers, self._device_index)
             self._net_versions = self._versions()
+            self._recon_grid_set = False
             self._configure()
         return self._net
 
@@ -388,7 +399,7 @@ class GravitationalWaveTransient(Likelihood):
             flags |= _params.MARG_TIME
         tmin = tmax = 0.0
         if self.time_marginalization:
-            tmin, tmax = float(self._time_prior.minimum), float(self._time_prior.maximum)
+            tmin, tmax = float(self.priors["geocent_time"].minimum), float(self.priors["geocent_time"].maximum)
         if self.distance_marginalization:
             s = self._dist_spline
             _lib.check(net.lib.bb_set_marginalization(
@@ -630,7 +641,9 @@ class GravitationalWaveTransient(Likelihood):
         (base.py:260-354, scalar quantities)."""
         net = self.device_network
         rows = net.torch.from_numpy(np.ascontiguousarray(self._rows_from_parameters(parameters, 1, np))).to(net.device)
-        s = self.inner_products_batch(rows)[0].cpu().numpy()
+        cal = self._cal_from_parameters(parameters, 1, np)
+        cal = None if cal is None else net.torch.from_numpy(np.ascontiguousarray(cal)).to(net.device)
+        s = self.inner_products_batch(rows, cal)[0].cpu().numpy()
         out = []
         for d in range(net.n_det):
             dih = complex(s[d, 0], s[d, 1])

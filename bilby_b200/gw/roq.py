@@ -37,7 +37,6 @@ class ROQGravitationalWaveTransient(GravitationalWaveTransient):
                             "binary_neutron_star_roq")
         self._delta_tc = delta_tc
         self._roq_host = None
-        self._full_time_prior = priors["geocent_time"] if priors is not None and "geocent_time" in priors else None
         super().__init__(interferometers=interferometers, waveform_generator=waveform_generator, priors=priors,
                          distance_marginalization=distance_marginalization,
                          phase_marginalization=phase_marginalization, time_marginalization=time_marginalization,
@@ -167,13 +166,23 @@ class ROQGravitationalWaveTransient(GravitationalWaveTransient):
         n = int(2 ** np.ceil(np.log2(n)))
         return duration / n
 
+    def _roq_time_prior(self):
+        """roq.py:747-765: the ROQ time grid spans the prior on ``{time_reference}_time`` (the detector the sampler
+        times the signal at), not necessarily the geocentre."""
+        key = f"{self.time_reference}_time"
+        prior = None if self.priors is None else self.priors.get(key)
+        if prior is None or not hasattr(prior, "minimum"):
+            raise KeyError(f"ROQGravitationalWaveTransient needs a prior on {key!r} to place the ROQ time samples "
+                           "(roq.py:747-765)")
+        return prior
+
     def _set_weights(self, linear_basis, quadratic_basis):
         """roq.py:736-767 (time grid), 802-837 (basis / data frequency overlap), 849-916 (linear), 976-1004
         (quadratic).  Bases: [n_basis, n_basis_freq]."""
         time_space = self._get_time_resolution()
         duration = self.interferometers.duration
         start_time = self.interferometers.start_time
-        prior = self._full_time_prior
+        prior = self._roq_time_prior()
         number_of_time_samples = int(duration / time_space)
         crossing = 2 * RADIUS_OF_EARTH / SPEED_OF_LIGHT + 5 * time_space
         start_idx = max(0, int(np.floor((prior.minimum - crossing - start_time) / time_space)))
@@ -309,7 +318,7 @@ class ROQGravitationalWaveTransient(GravitationalWaveTransient):
         n_marg, t0, dtc, tref = 0, 0.0, 0.0, 0.0
         if self.time_marginalization:
             n_marg = len(self._times)
-            t0 = float(self._full_time_prior.minimum)
+            t0 = float(self.priors["geocent_time"].minimum)
             dtc = float(self._delta_tc)
             tref = float(self._beam_pattern_reference_time)
         _lib.check(net.lib.bb_set_roq(

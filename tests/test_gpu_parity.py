@@ -124,13 +124,25 @@ def test_time_marginalised_vs_reference(tag, mode, tmp_path):
 
 
 def test_priors_side_effects_match_reference():
-    """base.py:183-223: the priors dict is mutated when marginalising."""
+    """base.py:166, 183-223: the CALLER's priors dict is mutated when marginalising (it is what the sampler gets);
+    likelihood.priors is a copy that keeps the Prior objects."""
+    from bilby_b200.core.prior import Prior, Gaussian, PriorDict
+    priors = _priors(phase=True, geocent_time=True, luminosity_distance=True)
     g, like, _ = _build("zero_H1L1", time_marginalization=True, phase_marginalization=True,
-                        priors=_priors(phase=True, geocent_time=True))
-    assert like.priors["phase"] == 0.0
-    assert like.priors["geocent_time"] == float(g["start_time"])
-    assert like.priors["time_jitter"].maximum == 1 / 2048.0
-    assert like.marginalized_parameters == ["geocent_time", "phase"]
+                        distance_marginalization=True, priors=priors)
+    assert priors["phase"] == 0.0
+    assert priors["geocent_time"] == float(g["start_time"])
+    assert priors["time_jitter"].maximum == 1 / 2048.0 and priors["time_jitter"].boundary == "periodic"
+    assert priors["luminosity_distance"] == float(like._ref_dist)
+    for key in ("phase", "geocent_time", "luminosity_distance"):
+        assert isinstance(like.priors[key], Prior), key
+    assert "time_jitter" not in like.priors
+    assert like.marginalized_parameters == ["geocent_time", "phase", "luminosity_distance"]
+    # a non-uniform time prior would be mis-weighted by the device: refused, not silently accepted
+    bad = _priors(geocent_time=True)
+    bad["geocent_time"] = Gaussian(1126259642.413, 0.01, "geocent_time")
+    with pytest.raises(NotImplementedError):
+        _build("zero_H1L1", time_marginalization=True, priors=PriorDict(bad))
 
 
 def test_device_entry_equals_host_entry_and_is_order_independent():
