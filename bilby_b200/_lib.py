@@ -67,6 +67,7 @@ def load():
         "bb_set_calibration_marginalization": (i, [vp, i, vp]),
         "bb_build_roq_linear_weights": (i, [i, i, i, vp, i, vp, vp, lng, lng, i, d, vp]),
         "bb_reconstruct_marginalized_device": (i, [vp, vp, vp, lng, vp, vp, vp]),
+        "bb_contract_device": (i, [vp, i, i, i, i, i, lng, lng, i, lng, lng, lng, d, vp, lng, vp, lng, i, vp, lng, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is missing
@@ -88,7 +89,7 @@ EXPORTED_SYMBOLS = (
     "bb_launch_count", "bb_set_reconstruction_grid", "bb_reconstruct_marginalized_device",
     "bb_set_calibration_marginalization", "bb_build_roq_linear_weights", "bb_set_multiband",
     "bb_exchange_create", "bb_exchange_connect", "bb_log_likelihood_ratio_sharded_device", "bb_exchange_status",
-    "bb_exchange_destroy")
+    "bb_exchange_destroy", "bb_contract_device")
 
 
 def check(rc):

@@ -31,7 +31,7 @@ def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
     cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + \
-          [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB, "-lcublas", "-lpthread"]
+          [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB, "-lpthread"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

@@ -9,10 +9,13 @@
 //
 // over the n_curves response curves drawn once at set-up (base.py:1037-1051, calibration.py:503-591).  This is the one
 // place on the path where the arithmetic is a dense contraction over the frequency axis: per chunk of samples
-//   X [chunk][n_det * ldk] (complex) , Y [chunk][n_det * ldk] (real)      <- bb_calmarg_series_kernel
-//   D = X C^T (ZGEMM) , H = Y A^T (DGEMM)  with C, A = [n_curves][n_det * ldk]   <- cuBLAS (FP64 tensor path, DMMA)
+//   X_det [chunk x ldk] (complex) , Y_det [chunk x ldk] (real)             <- bb_calmarg_series_kernel
+//   D = sum_det X_det C_det^T , H = sum_det Y_det A_det^T  with C_det, A_det = [n_curves x ldk]
+//                                                 <- bb_gemm.cuh (FP64 tensor path, mma.sync.m8n8k4.f64 = DMMA)
 //   lnL                                                                           <- bb_calmarg_epilogue_kernel
-// The detectors are concatenated along the contraction axis, so the sum over detectors comes out of the GEMM.
+// The detectors are K-segments of one GEMM, so the sum over detectors comes out of the contraction.  All four operands
+// live in the GEMM's packed layout (bb_pk: row tiles x slabs of 16 bins), written that way by the series kernel / the
+// upload.
 #pragma once
 
 #define BB_CM_CHUNK 2048
@@ -20,7 +23,7 @@
 template <int NDET, int APPROX>
 __global__ void bb_calmarg_series_kernel(const double* __restrict__ coef, const unsigned* __restrict__ perm, long s0,
                                          int m, BBTiles tiles, int n_freq, double df, int ldk, int k_lo, int k_hi,
-                                         double2* __restrict__ X, double* __restrict__ Y) {
+                                         double2* __restrict__ X, size_t x_stride, double* __restrict__ Y, size_t y_stride) {
     const int s = blockIdx.y;
     const int k = k_lo + blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= m || k >= k_hi) return;
@@ -43,8 +46,8 @@ __global__ void bb_calmarg_series_kernel(const double* __restrict__ coef, const 
             x = make_double2(hr * dd.x + hi * dd.y, hi * dd.x - hr * dd.y);                           // h conj(d) / S
             y = (hr * hr + hi * hi) * tiles.is[(size_t)d * tiles.n_pad + k];
         }
-        X[((size_t)s * NDET + d) * ldk + k] = x;
-        Y[((size_t)s * NDET + d) * ldk + k] = y;
+        X[d * x_stride + bb_pk(s, k, BB_GEMM_TR_A(true), ldk >> 4)] = x;
+        Y[d * y_stride + bb_pk(s, k, BB_GEMM_TR_A(false), ldk >> 4)] = y;
     }
 }
 
@@ -158,8 +161,8 @@ __global__ void bb_calmarg_select_kernel(const double* __restrict__ coef, const 
 template <int NDET>
 __global__ void __launch_bounds__(BB_CMT_THREADS, 2)
 bb_calmarg_time_kernel(const double* __restrict__ coef, const unsigned* __restrict__ perm, long s0, int m,
-                       const double2* __restrict__ Xs, const double2* __restrict__ C, const double* __restrict__ H,
-                       int n_curves, int ldk, int k_lo, int k_hi, int nfft, int log2n,
+                       const double2* __restrict__ Xs, size_t x_stride, const double2* __restrict__ C, size_t c_stride,
+                       const double* __restrict__ H, int n_curves, int ldk, int k_lo, int k_hi, int nfft, int log2n,
                        const double2* __restrict__ twiddle, BBMarg marg, double start_time, double duration,
                        double* __restrict__ L) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -168,7 +171,7 @@ bb_calmarg_time_kernel(const double* __restrict__ coef, const unsigned* __restri
     bb_tm_plan(log2n, &plan_a, &plan_b, &ps);
     double* red = reinterpret_cast<double*>(X + bb_tm_series_elems(nfft, ps));      // [32]
     const int tid = threadIdx.x;
-    const size_t kk = (size_t)NDET * ldk;
+    const long S = ldk >> 4;
     const long pairs = (long)m * n_curves;
     for (long pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
         const int s = (int)(pair / n_curves), c = (int)(pair - (long)s * n_curves);
@@ -184,8 +187,8 @@ bb_calmarg_time_kernel(const double* __restrict__ coef, const unsigned* __restri
             if (k >= k_lo && k < k_hi) {
 #pragma unroll
                 for (int d = 0; d < NDET; ++d) {
-                    const double2 x = Xs[((size_t)s * NDET + d) * ldk + k];
-                    const double2 q = C[(size_t)c * kk + (size_t)d * ldk + k];
+                    const double2 x = Xs[d * x_stride + bb_pk(s, k, BB_GEMM_TR_A(true), S)];
+                    const double2 q = C[d * c_stride + bb_pk(c, k, BB_GEMM_TR_B, S)];
                     vr = fma(x.x, q.x, fma(-x.y, q.y, vr));
                     vi = fma(x.x, q.y, fma(x.y, q.x, vi));
                 }
@@ -237,16 +240,16 @@ __global__ void bb_calmarg_window_kernel(const double* __restrict__ coef, const 
 template <int NDET, int APPROX>
 static int bb_launch_calmarg_t(bb_handle* h, long n, double* out, cudaStream_t st, BBCalSelect sel) {
     const int nc = h->cm_n_curves, ldk = h->cm_ldk;
-    const size_t kk = (size_t)NDET * ldk;
+    const size_t x_stride = bb_pk_elems(BB_CM_CHUNK, ldk, BB_GEMM_TR_A(true)), y_stride = bb_pk_elems(BB_CM_CHUNK, ldk, BB_GEMM_TR_A(false));
+    const size_t c_stride = bb_pk_elems(nc, ldk, BB_GEMM_TR_B);
     if (!h->d_cm_X) {
-        BB_CUDA(cudaMalloc(&h->d_cm_X, (size_t)BB_CM_CHUNK * kk * sizeof(double2)));
-        BB_CUDA(cudaMalloc(&h->d_cm_Y, (size_t)BB_CM_CHUNK * kk * sizeof(double)));
+        BB_CUDA(cudaMalloc(&h->d_cm_X, NDET * x_stride * sizeof(double2)));
+        BB_CUDA(cudaMalloc(&h->d_cm_Y, NDET * y_stride * sizeof(double)));
+        BB_CUDA(cudaMemsetAsync(h->d_cm_X, 0, NDET * x_stride * sizeof(double2), st));
+        BB_CUDA(cudaMemsetAsync(h->d_cm_Y, 0, NDET * y_stride * sizeof(double), st));
         BB_CUDA(cudaMalloc(&h->d_cm_D, (size_t)BB_CM_CHUNK * nc * sizeof(double2)));
         BB_CUDA(cudaMalloc(&h->d_cm_H, (size_t)BB_CM_CHUNK * nc * sizeof(double)));
     }
-    if (cublasSetStream(h->cublas, st) != CUBLAS_STATUS_SUCCESS) return bb_fail("cublasSetStream failed");
-    const cuDoubleComplex one = make_cuDoubleComplex(1.0, 0.0), zero = make_cuDoubleComplex(0.0, 0.0);
-    const double done = 1.0, dzero = 0.0;
     BBMarg point = h->marg;
     point.flags &= ~BB_MARG_TIME;
     const bool time_marg = (h->marg.flags & BB_MARG_TIME) != 0;
@@ -283,28 +286,39 @@ static int bb_launch_calmarg_t(bb_handle* h, long n, double* out, cudaStream_t s
         const int m = (int)((n - s0) < BB_CM_CHUNK ? (n - s0) : BB_CM_CHUNK);
         int k_lo = 0, k_hi = ldk;
         if (perm) {
-            k_lo = win[2 * c] & ~7;
-            k_hi = (win[2 * c + 1] + 7) & ~7;
+            k_lo = win[2 * c] & ~15;                 // whole slabs of 16 bins
+            k_hi = (win[2 * c + 1] + 15) & ~15;
             if (k_lo < 0) k_lo = 0;
             if (k_hi > ldk) k_hi = ldk;
-            if (k_hi <= k_lo) k_hi = k_lo + 8 <= ldk ? k_lo + 8 : ldk;
+            if (k_hi <= k_lo) k_hi = k_lo + 16 <= ldk ? k_lo + 16 : ldk;
         }
         const int kw = k_hi - k_lo;
         dim3 grid((kw + 127) / 128, (unsigned)m);
         bb_calmarg_series_kernel<NDET, APPROX><<<grid, 128, 0, st>>>(h->d_coef, perm, s0, m, bb_tiles(h), h->net.n_freq,
-                                                                   h->net.df, ldk, k_lo, k_hi, h->d_cm_X, h->d_cm_Y);
+                                                                   h->net.df, ldk, k_lo, k_hi, h->d_cm_X, x_stride, h->d_cm_Y, y_stride);
         BB_CUDA(cudaGetLastError());
-        // per detector: D^T [nc x m] (+)= C_d [kw x nc]^T  X_d [kw x m]   (column-major views of the row-major buffers)
-        for (int d = 0; d < NDET; ++d) {
-            const size_t off = (size_t)d * ldk + k_lo;
-            if (!time_marg && cublasZgemm(h->cublas, CUBLAS_OP_T, CUBLAS_OP_N, nc, m, kw, &one,
-                            reinterpret_cast<const cuDoubleComplex*>(h->d_cm_C + off), (int)kk,
-                            reinterpret_cast<const cuDoubleComplex*>(h->d_cm_X + off), (int)kk, d ? &one : &zero,
-                            reinterpret_cast<cuDoubleComplex*>(h->d_cm_D), nc) != CUBLAS_STATUS_SUCCESS)
-                return bb_fail("calibration marginalisation: cublasZgemm failed");
-            if (cublasDgemm(h->cublas, CUBLAS_OP_T, CUBLAS_OP_N, nc, m, kw, &done, h->d_cm_A + off, (int)kk,
-                            h->d_cm_Y + off, (int)kk, d ? &done : &dzero, h->d_cm_H, nc) != CUBLAS_STATUS_SUCCESS)
-                return bb_fail("calibration marginalisation: cublasDgemm failed");
+        // D[s][c] = sum_det sum_k X_det[s][k] C_det[c][k] (complex) and H[s][c] = sum_det sum_k Y_det[s][k] A_det[c][k]
+        // (real): the detectors are K-segments of ONE DMMA GEMM each (bb_gemm.cuh), trimmed to the chunk's active bins
+        {
+            BBGemmArgs ga{};
+            ga.slabs_a = ga.slabs_b = ldk >> 4;
+            ga.slab0 = k_lo >> 4; ga.n_slabs = kw >> 4;
+            ga.ldc = nc;
+            ga.M = m; ga.N = nc; ga.n_seg = NDET; ga.n_batch = 1; ga.accumulate = 0; ga.alpha = 1.0;
+            if (!time_marg) {
+                for (int d = 0; d < NDET; ++d) {
+                    ga.A[d] = h->d_cm_X + d * x_stride;
+                    ga.B[d] = h->d_cm_C + d * c_stride;
+                }
+                ga.C = reinterpret_cast<double*>(h->d_cm_D);
+                if (bb_gemm_nt(true, ga, h->sm_count, st)) return 1;
+            }
+            for (int d = 0; d < NDET; ++d) {
+                ga.A[d] = h->d_cm_Y + d * y_stride;
+                ga.B[d] = h->d_cm_A + d * c_stride;
+            }
+            ga.C = h->d_cm_H;
+            if (bb_gemm_nt(false, ga, h->sm_count, st)) return 1;
         }
         if (time_marg) {
             // the per-curve likelihoods go to the (unused) <d|h> buffer
@@ -312,7 +326,7 @@ static int bb_launch_calmarg_t(bb_handle* h, long n, double* out, cudaStream_t s
             long grid_t = (long)m * nc;
             if (grid_t > (long)h->sm_count * tm_per_sm) grid_t = (long)h->sm_count * tm_per_sm;
             bb_calmarg_time_kernel<NDET><<<(unsigned)grid_t, BB_CMT_THREADS, tm_smem, st>>>(
-                h->d_coef, perm, s0, m, h->d_cm_X, h->d_cm_C, h->d_cm_H, nc, ldk, k_lo, k_hi, h->nfft, tm_log2n,
+                h->d_coef, perm, s0, m, h->d_cm_X, x_stride, h->d_cm_C, c_stride, h->d_cm_H, nc, ldk, k_lo, k_hi, h->nfft, tm_log2n,
                 h->d_twiddle, h->marg, h->net.start_time, h->net.duration, L);
             BB_CUDA(cudaGetLastError());
             bb_calmarg_lse_kernel<<<(unsigned)((m * 32L + 127) / 128), 128, 0, st>>>(h->d_coef, perm, s0, m, L, nc, out);
@@ -323,7 +337,7 @@ static int bb_launch_calmarg_t(bb_handle* h, long n, double* out, cudaStream_t s
             bb_calmarg_epilogue_kernel<<<(unsigned)((m * 32L + 127) / 128), 128, 0, st>>>(h->d_coef, perm, s0, m, h->d_cm_D,
                                                                                          h->d_cm_H, nc, point, out);
         BB_CUDA(cudaGetLastError());
-        h->launches += 2 + 2 * NDET;
+        h->launches += 2 + (time_marg ? 2 : 2);
     }
     return 0;
 }
@@ -356,20 +370,19 @@ static int bb_calmarg_upload(bb_handle* h, int n_curves, const double* curves) {
     h->cm_n_curves = 0;
     if (n_curves <= 0) return 0;
     if (!curves) return bb_fail("bb_set_calibration_marginalization: null curves");
-    if (!h->cublas && cublasCreate(&h->cublas) != CUBLAS_STATUS_SUCCESS) return bb_fail("cublasCreate failed");
     const int n_det = h->net.n_det, nf = h->net.n_freq;
-    const int ldk = (nf + 7) & ~7;
-    const size_t kk = (size_t)n_det * ldk;
-    std::vector<double2> C((size_t)n_curves * kk, make_double2(0.0, 0.0));
-    std::vector<double> A((size_t)n_curves * kk, 0.0);
+    const int ldk = (nf + 15) & ~15;                       // whole slabs of 16 bins
+    const long S = ldk >> 4;
+    const size_t c_stride = bb_pk_elems(n_curves, ldk, BB_GEMM_TR_B);
+    std::vector<double2> C((size_t)n_det * c_stride, make_double2(0.0, 0.0));
+    std::vector<double> A((size_t)n_det * c_stride, 0.0);
     for (int d = 0; d < n_det; ++d)
         for (int c = 0; c < n_curves; ++c) {
             const double* src = curves + ((size_t)d * n_curves + c) * nf * 2;
-            double2* dc = C.data() + (size_t)c * kk + (size_t)d * ldk;
-            double* da = A.data() + (size_t)c * kk + (size_t)d * ldk;
             for (int k = 0; k < nf; ++k) {
-                dc[k] = make_double2(src[2 * k], src[2 * k + 1]);
-                da[k] = src[2 * k] * src[2 * k] + src[2 * k + 1] * src[2 * k + 1];
+                const size_t o = (size_t)d * c_stride + bb_pk(c, k, BB_GEMM_TR_B, S);
+                C[o] = make_double2(src[2 * k], src[2 * k + 1]);
+                A[o] = src[2 * k] * src[2 * k] + src[2 * k + 1] * src[2 * k + 1];
             }
         }
     BB_CUDA(cudaMalloc(&h->d_cm_C, C.size() * sizeof(double2)));

@@ -10,7 +10,6 @@
 //   KT bb_distance_table_kernel  lookup table build
 //   KW bb_strain_kernel          polarisations / detector response on the full grid (injection, tests)
 #include <cuda_runtime.h>
-#include <cublas_v2.h>
 #include <cub/device/device_radix_sort.cuh>
 #include <float.h>
 #include <stdio.h>
@@ -128,7 +127,6 @@ struct bb_handle {
     double2 *d_roq_V = nullptr, *d_roq_Y = nullptr;
     double* d_roq_hh = nullptr;
     size_t roq_chunk = 0;
-    cublasHandle_t cublas = nullptr;
     cudaStream_t stream = nullptr;
     int sm_count = 148;
     long launches = 0;
@@ -580,6 +578,7 @@ static BBTiles bb_tiles(const bb_handle* h) {
     return t;
 }
 
+#include "bb_gemm.cuh"
 #include "bb_timemarg.cuh"
 #include "bb_timemarg_split.cuh"
 #include "bb_reduced.cuh"
@@ -625,7 +624,6 @@ extern "C" void bb_destroy(bb_handle* h) {
     cudaFree(h->d_mask); cudaFree(h->d_twiddle);
     cudaFree(h->d_calM); cudaFree(h->d_calrec); cudaFree(h->d_calpar); cudaFree(h->d_params_sky);
     bb_reduced_clear(h);
-    if (h->cublas) cublasDestroy(h->cublas);
     cudaFree(h->d_keys); cudaFree(h->d_keys_out); cudaFree(h->d_index); cudaFree(h->d_perm); cudaFree(h->d_sort_tmp);
     if (h->h_params) cudaFreeHost(h->h_params);
     if (h->h_out) cudaFreeHost(h->h_out);
@@ -1337,6 +1335,55 @@ extern "C" int bb_log_likelihood_ratio_cal_host(bb_handle* h, const double* para
     if (!params_host || !out_host || !cal_params_host) return bb_fail("bb_log_likelihood_ratio_cal_host: null buffer");
     if (h->cal.n_points < 4) return bb_fail("bb_log_likelihood_ratio_cal_host: bb_set_calibration was not called");
     return bb_host_pipeline(h, params_host, cal_params_host, n, out_host);
+}
+
+extern "C" int bb_contract_device(bb_handle* h, int is_complex, int m, int n, int k, int n_seg, long seg_stride_a,
+                                  long seg_stride_b, int n_batch, long batch_stride_a, long batch_stride_b,
+                                  long batch_stride_c, double alpha, const double* a, long lda, const double* b, long ldb,
+                                  int accumulate, double* c, long ldc, void* stream) {
+    if (!h || !a || !b || !c) return bb_fail("bb_contract_device: null argument");
+    if (n_seg < 1 || n_seg > BB_GEMM_MAX_SEG || n_batch < 1 || m < 1 || n < 1 || k < 1)
+        return bb_fail("bb_contract_device: bad shape");
+    BB_CUDA(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    // row-major operands from outside the library: pack them into the GEMM's layout first (bb_gemm.cuh)
+    const bool cplx = is_complex != 0;
+    const size_t esz = cplx ? sizeof(double2) : sizeof(double);
+    const size_t pa = bb_pk_elems(m, k, BB_GEMM_TR_A(cplx)), pb = bb_pk_elems(n, k, BB_GEMM_TR_B);
+    char *A = nullptr, *B = nullptr;
+    BB_CUDA(cudaMalloc(&A, pa * esz * n_seg * n_batch));
+    if (cudaMalloc(&B, pb * esz * n_seg * n_batch) != cudaSuccess) { cudaFree(A); return bb_fail("bb_contract_device: out of memory"); }
+    BBGemmArgs g{};
+    for (int s = 0; s < n_seg; ++s) {
+        for (int bt = 0; bt < n_batch; ++bt) {
+            const size_t oa = ((size_t)s * n_batch + bt) * pa, ob = ((size_t)s * n_batch + bt) * pb;
+            if (cplx) {
+                bb_gemm_pack_kernel<double2><<<1024, 256, 0, st>>>(reinterpret_cast<const double2*>(a) + s * seg_stride_a + bt * batch_stride_a,
+                                                                  m, k, lda, BB_GEMM_TR_A(true), reinterpret_cast<double2*>(A) + oa);
+                bb_gemm_pack_kernel<double2><<<1024, 256, 0, st>>>(reinterpret_cast<const double2*>(b) + s * seg_stride_b + bt * batch_stride_b,
+                                                                  n, k, ldb, BB_GEMM_TR_B, reinterpret_cast<double2*>(B) + ob);
+            } else {
+                bb_gemm_pack_kernel<double><<<1024, 256, 0, st>>>(a + s * seg_stride_a + bt * batch_stride_a, m, k, lda,
+                                                                 BB_GEMM_TR_A(false), reinterpret_cast<double*>(A) + oa);
+                bb_gemm_pack_kernel<double><<<1024, 256, 0, st>>>(b + s * seg_stride_b + bt * batch_stride_b, n, k, ldb,
+                                                                 BB_GEMM_TR_B, reinterpret_cast<double*>(B) + ob);
+            }
+        }
+        g.A[s] = A + (size_t)s * n_batch * pa * esz;
+        g.B[s] = B + (size_t)s * n_batch * pb * esz;
+    }
+    g.C = c;
+    g.ldc = ldc;
+    g.slabs_a = g.slabs_b = (k + 15) / 16;
+    g.slab0 = 0; g.n_slabs = (k + 15) / 16;
+    g.batch_a = (long)pa; g.batch_b = (long)pb; g.batch_c = batch_stride_c;
+    g.M = m; g.N = n; g.n_seg = n_seg; g.n_batch = n_batch; g.accumulate = accumulate; g.alpha = alpha;
+    int rc = bb_gemm_nt(cplx, g, h->sm_count, st);
+    cudaStreamSynchronize(st);
+    cudaFree(A);
+    cudaFree(B);
+    h->launches += 1 + 2 * n_seg * n_batch;
+    return rc;
 }
 
 extern "C" int bb_profile_enable(bb_handle* h, int on) {

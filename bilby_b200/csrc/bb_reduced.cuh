@@ -49,7 +49,7 @@ struct BBRelbinDev {
 
 struct BBRoqDev {
     BBNodes lin, quad;
-    const double2* W;         // [n_det][n_time][n_lin]
+    const double2* W;         // [n_det] packed [n_time x n_lin] (bb_gemm.cuh bb_pk, tiles of 128 times): K7's GEMM operand
     const double2* W2;        // [n_det][ceil(n_lin/32)][n_time][32] node-blocked copy for K6, zero beyond n_lin
     const double* wq;         // [n_det][n_quad]
     int n_time;
@@ -529,7 +529,7 @@ bb_roq_kernel(const double* __restrict__ coef, long n, BBRoqDev rq, const double
 template <int NDET, int APPROX, bool CAL>
 __global__ void __launch_bounds__(BB_RED_THREADS)
 bb_roq_hlinear_kernel(const double* __restrict__ coef, long s_begin, long n, BBRoqDev rq,
-                      const double* __restrict__ calrec, BBCalGrid grid, double2* __restrict__ V /* [NDET][n][nl] */,
+                      const double* __restrict__ calrec, BBCalGrid grid, double2* __restrict__ V /* [NDET] packed [n x n_lin] */,
                       double* __restrict__ hh /* [n] */) {
     extern __shared__ __align__(16) double red_smem[];
     const int cal_len = CAL ? NDET * 4 * grid.n_points : 0;
@@ -537,8 +537,13 @@ bb_roq_hlinear_kernel(const double* __restrict__ coef, long s_begin, long n, BBR
     double* rec = red_smem + (size_t)warp * (BC_NCOEF + cal_len);
     double* cal = rec + BC_NCOEF;
     const int nl = rq.lin.n;
+    const long S = (nl + 15) / 16;                                   // V is written packed: the GEMM's A operand
+    const size_t vstride = (size_t)((n + 63) / 64) * S * 64 * BB_PK;
     for (long s = (long)blockIdx.x * BB_RED_WARPS + warp; s < n; s += (long)gridDim.x * BB_RED_WARPS) {
         bb_red_load<CAL>(rec, cal, coef, calrec, s_begin + s, cal_len, lane);
+        if (nl + lane < S * 16)                                      // zero K tail of the last slab
+#pragma unroll
+            for (int d = 0; d < NDET; ++d) V[d * vstride + bb_pk(s, nl + lane, 64, S)] = make_double2(0.0, 0.0);
         double hq[NDET];
         bb_roq_quadratic<NDET, APPROX, CAL>(rec, cal, grid, rq, lane, hq);
         if (lane == 0) {
@@ -566,7 +571,7 @@ bb_roq_hlinear_kernel(const double* __restrict__ coef, long s_begin, long n, BBR
                     zi = ti;
                 }
                 const double kr = rec[BC_DET + BC_DSTRIDE * d], ki = rec[BC_DET + BC_DSTRIDE * d + 1];
-                V[((size_t)d * n + s) * nl + j] = make_double2(kr * zr + ki * zi, kr * zi - ki * zr);   // conj(K) conj(h)
+                V[d * vstride + bb_pk(s, j, 64, S)] = make_double2(kr * zr + ki * zi, kr * zi - ki * zr);   // conj(K) conj(h)
             }
         }
     }

@@ -194,7 +194,18 @@ extern "C" int bb_set_roq(bb_handle* h, int n_linear, const double* nodes_linear
     h->rq = rq;
     if (bb_upload_nodes(h, nodes_linear, n_linear, &rq->lin)) return 1;
     if (bb_upload_nodes(h, nodes_quadratic, n_quadratic, &rq->quad)) return 1;
-    if (bb_red_upload(h, (const double2*)weights_linear, (size_t)nd * n_time * n_linear, &rq->W)) return 1;
+    {
+        // K7's GEMM operand, packed (bb_gemm.cuh bb_pk: tiles of 128 ROQ times x slabs of 16 nodes, zero padded)
+        const long S = (n_linear + 15) / 16;
+        const size_t per_det = bb_pk_elems(n_time, n_linear, BB_GEMM_TR_B);
+        std::vector<double2> wp((size_t)nd * per_det, make_double2(0.0, 0.0));
+        const double2* w = (const double2*)weights_linear;
+        for (int d = 0; d < nd; ++d)
+            for (int t = 0; t < n_time; ++t)
+                for (int j = 0; j < n_linear; ++j)
+                    wp[(size_t)d * per_det + bb_pk(t, j, BB_GEMM_TR_B, S)] = w[((size_t)d * n_time + t) * n_linear + j];
+        if (bb_red_upload(h, wp.data(), wp.size(), &rq->W)) return 1;
+    }
     {
         // node-blocked copy for K6: W2[d][p][t][l] = W[d][t][32 p + l]
         const int nblk = (n_linear + 31) / 32;
@@ -219,9 +230,6 @@ extern "C" int bb_set_roq(bb_handle* h, int n_linear, const double* nodes_linear
     for (int i = 0; i < n_linear; ++i) fmin = nodes_linear[i] < fmin ? nodes_linear[i] : fmin;
     for (int i = 0; i < n_quadratic; ++i) fmin = nodes_quadratic[i] < fmin ? nodes_quadratic[i] : fmin;
     h->roq_fmin = fmin;           // first of the unique (sorted) nodes: f_min of the sequence call
-    if (!h->cublas) {
-        if (cublasCreate(&h->cublas) != CUBLAS_STATUS_SUCCESS) return bb_fail("bb_set_roq: cublasCreate failed");
-    }
     h->kind = 2;
     return 0;
 }
@@ -275,15 +283,14 @@ static int bb_launch_roq_time_marg_t(bb_handle* h, long n, double* out, cudaStre
         cudaFree(h->d_roq_V); cudaFree(h->d_roq_Y); cudaFree(h->d_roq_hh);
         h->d_roq_V = h->d_roq_Y = nullptr;
         h->d_roq_hh = nullptr;
-        BB_CUDA(cudaMalloc(&h->d_roq_V, (size_t)NDET * chunk * nl * sizeof(double2)));
+        BB_CUDA(cudaMalloc(&h->d_roq_V, (size_t)NDET * bb_pk_elems((long)chunk, nl, BB_GEMM_TR_A(true)) * sizeof(double2)));
+        BB_CUDA(cudaMemsetAsync(h->d_roq_V, 0, (size_t)NDET * bb_pk_elems((long)chunk, nl, BB_GEMM_TR_A(true)) * sizeof(double2), st));
         BB_CUDA(cudaMalloc(&h->d_roq_Y, (size_t)NDET * chunk * nt * sizeof(double2)));
         BB_CUDA(cudaMalloc(&h->d_roq_hh, chunk * sizeof(double)));
         h->roq_chunk = chunk;
     }
     const size_t smem = (size_t)BB_RED_WARPS * (BC_NCOEF + (CAL ? NDET * 4 * h->cal.n_points : 0)) * sizeof(double);
     BB_CUDA(cudaFuncSetAttribute(bb_roq_hlinear_kernel<NDET, APPROX, CAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (cublasSetStream(h->cublas, st) != CUBLAS_STATUS_SUCCESS) return bb_fail("cublasSetStream failed");
-    const cuDoubleComplex one = make_cuDoubleComplex(1.0, 0.0), zero = make_cuDoubleComplex(0.0, 0.0);
     BBProfScope prof(h, st);
     for (long s0 = 0; s0 < n; s0 += (long)chunk) {
         const long m = (n - s0) < (long)chunk ? (n - s0) : (long)chunk;
@@ -292,14 +299,20 @@ static int bb_launch_roq_time_marg_t(bb_handle* h, long n, double* out, cudaStre
             h->d_coef, s0, m, rq, h->d_calrec, h->cal, h->d_roq_V, h->d_roq_hh);
         h->launches++;
         BB_CUDA(cudaGetLastError());
-        for (int d = 0; d < NDET; ++d) {
-            // row-major Y_d[m][nt] = V_d[m][nl] W_d[nt][nl]^T  ==  column-major Y^T (nt x m) = Wcm^T (nt x nl) Vcm (nl x m)
-            const cublasStatus_t cs = cublasZgemm(
-                h->cublas, CUBLAS_OP_T, CUBLAS_OP_N, nt, (int)m, nl, &one,
-                (const cuDoubleComplex*)(rq.W + (size_t)d * nt * nl), nl,
-                (const cuDoubleComplex*)(h->d_roq_V + (size_t)d * m * nl), nl, &zero,
-                (cuDoubleComplex*)(h->d_roq_Y + (size_t)d * m * nt), nt);
-            if (cs != CUBLAS_STATUS_SUCCESS) return bb_fail("cublasZgemm failed");
+        {
+            // Y_d[s][t] = sum_i V_d[s][i] W_d[t][i] for every detector: one batched DMMA GEMM (bb_gemm.cuh)
+            BBGemmArgs ga{};
+            ga.A[0] = h->d_roq_V;
+            ga.B[0] = rq.W;
+            ga.C = reinterpret_cast<double*>(h->d_roq_Y);
+            ga.slabs_a = ga.slabs_b = (nl + 15) / 16;
+            ga.slab0 = 0; ga.n_slabs = (nl + 15) / 16;
+            ga.batch_a = (long)bb_pk_elems(m, nl, BB_GEMM_TR_A(true));
+            ga.batch_b = (long)bb_pk_elems(nt, nl, BB_GEMM_TR_B);
+            ga.batch_c = (long)m * nt;
+            ga.ldc = nt;
+            ga.M = (int)m; ga.N = nt; ga.n_seg = 1; ga.n_batch = NDET; ga.accumulate = 0; ga.alpha = 1.0;
+            if (bb_gemm_nt(true, ga, h->sm_count, st)) return 1;
             h->launches++;
         }
         bb_roq_time_marg_kernel<NDET><<<(unsigned)grid, BB_RED_THREADS, 0, st>>>(

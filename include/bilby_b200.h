@@ -289,6 +289,18 @@ int bb_reconstruct_marginalized_device(bb_handle* h, const double* params_dev, c
  * per-sample calibration parameters are refused.  n_curves = 0 switches it off. */
 int bb_set_calibration_marginalization(bb_handle* h, int n_curves, const double* curves);
 
+/* The dense FP64 contraction of the path on the tensor cores (mma.sync.m8n8k4.f64, csrc/bb_gemm.cuh): what the
+ * reference writes as `linear_matrix @ conj(h_linear)` (bilby/gw/likelihood/roq.py:604-651), the calibration-curve
+ * products of bilby/gw/likelihood/base.py:305-346 and the per-basis-element inverse FFTs of roq.py:849-918.
+ *   C[batch][m][n] (+)= alpha * sum_seg sum_k A_seg[batch][m][k] * B_seg[batch][n][k]
+ * A [m x k] and B [n x k] are K-contiguous row-major, C [m x n] row-major; is_complex: elements are (re, im) pairs.
+ * Leading dimensions and strides are in elements; device memory.  (Inside the library the operands are produced
+ * directly in the kernel's packed tile layout; this entry packs row-major inputs first, then synchronises.) */
+int bb_contract_device(bb_handle* h, int is_complex, int m, int n, int k, int n_seg, long seg_stride_a, long seg_stride_b,
+                       int n_batch, long batch_stride_a, long batch_stride_b, long batch_stride_c, double alpha,
+                       const double* a, long lda, const double* b, long ldb, int accumulate, double* c, long ldc,
+                       void* stream);
+
 /* Set-up artefact builder (no handle needed): the linear ROQ weights of n_det detectors sharing one basis,
  * ROQGravitationalWaveTransient._set_weights_linear (bilby/gw/likelihood/roq.py:849-918) - one zero-padded inverse FFT
  * of data * conj(basis_b) / PSD per basis element, of which only the time samples [lo, lo + n_win) are kept.
