@@ -11,8 +11,8 @@ SURVEY.md section 8d / DESIGN.md section 4).  Used for the ncu captures under pr
   cfg3          configs[3]: BNS TaylorF2+tides 128 s @ 4096 Hz H1L1V1             (K0 + K1<TaylorF2>)
   cfg4_relbin   configs[4]: relative binning for the 128 s BNS                     (K0 + K5)
   cfg4_roq      configs[4]: ROQ for the 128 s BNS, synthetic basis                 (K0 + K6)
-  cfg4_roq_time configs[4]: ROQ with time marginalisation (dense contraction)      (K0 + K7: hlinear + ZGEMM + epilogue)
-  calmarg       SURVEY 8f rank 4: calibration (1000 curves) + phase marginalisation, 4 s H1L1V1  (K0 + series + ZGEMM/DGEMM)
+  cfg4_roq_time configs[4]: ROQ with time marginalisation (dense contraction)      (K0 + K7: hlinear + DMMA contraction + epilogue)
+  calmarg       SURVEY 8f rank 4: calibration (1000 curves) + phase marginalisation, 4 s H1L1V1  (K0 + series + DMMA contractions)
   recon         SURVEY 8f rank 2: marginalised-parameter reconstruction, 4 s H1L1V1, time + distance + phase
 """
 import argparse
@@ -125,13 +125,13 @@ def build(config, n):
                 return like, rows, None, flop_cm, dict(
                     workload=f"SURVEY 8f rank 4: time + calibration (+ phase) marginalisation over {n_curves} CubicSpline(10) "
                              "response curves, BBH 4s@2048Hz H1L1V1 IMRPhenomD: one 4096-point transform per (sample, curve)",
-                    kernel="bb_calmarg_series_kernel + cublas DGEMM + bb_calmarg_time_kernel + bb_calmarg_lse_kernel",
+                    kernel="bb_calmarg_series_kernel + bb_gemm_nt_kernel<real> (DMMA) + bb_calmarg_time_kernel + bb_calmarg_lse_kernel",
                     bound="shared memory / FP64 (in-shared-memory FFT per response curve)", n_curves=n_curves)
             return like, rows, None, flop_cm, dict(
                 workload=f"SURVEY 8f rank 4: calibration marginalisation over {n_curves} CubicSpline(10) response curves + "
                          "phase marginalisation, BBH 4s@2048Hz H1L1V1 IMRPhenomD: [batch x 3*4104] x [3*4104 x 1000] "
-                         "ZGEMM + DGEMM per chunk", kernel="bb_calmarg_series_kernel + cublas ZGEMM/DGEMM + epilogue",
-                bound="FP64 tensor path (DMMA) through cuBLAS", n_curves=n_curves)
+                         "complex + real contraction per chunk", kernel="bb_calmarg_series_kernel + bb_gemm_nt_kernel<complex>, <real> (DMMA) + epilogue",
+                bound="fp64 tensor (DMMA)", n_curves=n_curves)
         if config == "cfg0":
             like = bb.gw.GravitationalWaveTransient(ifos, wfg)
             rows = like.pack(draws)
@@ -291,7 +291,14 @@ def build(config, n):
         per = (170 + 20) * n_lin + 100 * n_quad + 8 * n_time * n_lin * 3 + len(like._times) * (3 * 40 + 100)
         work = (f"configs[4]: ROQ (synthetic basis N_l={n_lin}, N_q={n_quad}, {n_time} ROQ times) + time&phase "
                 f"marginalisation ({len(like._times)} times) for the 128s BNS: dense W conj(h) contraction")
-        kernel = "bb_roq_hlinear_kernel + cublas ZGEMM + bb_roq_time_marg_kernel"
+        kernel = "bb_roq_hlinear_kernel + bb_gemm_nt_kernel<complex> (DMMA) || bb_roq_time_marg_kernel (aux stream)"
+        # rows of W the device contracts: only those a time inside the prior (+- light travel time) can touch
+        dmax = max(float(np.linalg.norm(ifo.vertex)) for ifo in ifos) / 299792458.0
+        ts = like.weights["time_samples"]
+        step = ts[1] - ts[0]
+        r_lo = max(0, int(np.floor((T_INJ - 0.05 - start - dmax - ts[0]) / step)) - 3)
+        r_hi = min(n_time - 1, int(np.floor((T_INJ + 0.05 - start + dmax - ts[0]) / step)) + 3)
+        n_rows = r_hi - (r_lo // 64) * 64 + 1
     else:
         per = (170 + 60 + 120) * n_lin + (100 + 6) * n_quad
         work = (f"configs[4]: ROQ (synthetic basis N_l={n_lin}, N_q={n_quad}, {n_time} ROQ times) for the 128s BNS, "
@@ -301,11 +308,13 @@ def build(config, n):
     like._bench_draws = draws
     like._bench_basis = dict(linear_matrix=bl, quadratic_matrix=bq, frequency_nodes_linear=freqs[nl],
                              frequency_nodes_quadratic=freqs[nq])
+    extra = dict(bound="fp64 tensor (DMMA)", n_time_contracted=n_rows,
+                 executed_gemm_flop_per_eval=8.0 * n_rows * n_lin * 3) if tm else {}
     return like, rows, None, (lambda r: (float(len(r)) * per, float(n_lin))), dict(
-        workload=work, kernel=kernel, n_linear=n_lin, n_quadratic=n_quad, n_time=n_time)
+        workload=work, kernel=kernel, n_linear=n_lin, n_quadratic=n_quad, n_time=n_time, **extra)
 
 
-DEFAULT_BATCH = dict(calmarg=16384, cfg0=1_000_000, cfg2=100_000, cfg3=8192, cfg4_relbin=1_000_000, cfg4_roq=1_000_000,
+DEFAULT_BATCH = dict(calmarg=75776, cfg0=1_000_000, cfg2=100_000, cfg3=8192, cfg4_relbin=1_000_000, cfg4_roq=1_000_000,
                      cfg4_roq_time=65536, mb=65536, calmarg_time=1024)
 
 
@@ -403,7 +412,8 @@ def main():
     cal_dev = torch.from_numpy(np.ascontiguousarray(cal_np)).cuda() if cal_np is not None else None
     stream = torch.cuda.current_stream()
     peak = ctypes.c_double(0.0)
-    _lib.check(lib.bb_fp64_peak(net.ptr, ctypes.byref(peak)))
+    tensor_bound = "DMMA" in desc.get("bound", "")
+    _lib.check((lib.bb_fp64_tensor_peak if tensor_bound else lib.bb_fp64_peak)(net.ptr, ctypes.byref(peak)))
 
     def step_device():
         return like._evaluate_device(rows_dev, cal_dev)
@@ -465,11 +475,12 @@ def main():
                          h2d_bytes_per_step=int(rows_np.nbytes + (cal_np.nbytes if cal_np is not None else 0)),
                          d2h_bytes_per_step=n * 8),
                 gpu_launches=int(launches),
-                roofline=dict(bound="fp64", achieved=achieved, peak=peak.value, unit="TFLOP/s",
+                roofline=dict(bound="fp64 tensor" if tensor_bound else "fp64", achieved=achieved, peak=peak.value, unit="TFLOP/s",
                               frac=achieved / peak.value if peak.value else None, kernel=desc["kernel"],
                               kernel_ms_per_step=k_avg, kernel_share_of_step=k_avg / (ms_total / args.steps),
                               algorithmic_flop_per_step=total_flop, units_per_eval=units,
-                              peak_source="in-run DFMA stream kernel (bb_fp64_peak)"),
+                              peak_source="in-run DMMA stream kernel (bb_fp64_tensor_peak)" if tensor_bound
+                              else "in-run DFMA stream kernel (bb_fp64_peak)"),
                 checksum_lnl=float(np.sum(res[fin])), finite_fraction=float(fin.mean()))
     print(json.dumps(line))
 

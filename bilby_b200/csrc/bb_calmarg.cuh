@@ -18,7 +18,9 @@
 // upload.
 #pragma once
 
-#define BB_CM_CHUNK 2048
+// samples per chunk: 148 x 64, so that the complex GEMM (64-row tiles, 16 column tiles for 1000 curves) and the real one
+// (128-row tiles) both split into whole waves of 2 x 148 CTAs (2048 lost 13 % to a half-empty last wave)
+#define BB_CM_CHUNK 9472
 
 template <int NDET, int APPROX>
 __global__ void bb_calmarg_series_kernel(const double* __restrict__ coef, const unsigned* __restrict__ perm, long s0,
@@ -155,7 +157,7 @@ __global__ void bb_calmarg_select_kernel(const double* __restrict__ coef, const 
 // Time + calibration marginalisation (base.py:305-323, 860-866, 794-820): one CTA per (sample, response curve).
 //   series_c[k] = sum_det X_det[k] C_det,c[k]  (X = h conj(d)/S with 4/T, from bb_calmarg_series_kernel; zero outside
 //   the chunk's active window), in-shared-memory FFT (bb_tm_fft_dif), weighted logsumexp over the times inside the
-//   geocent_time prior with <h|h>_c from the DGEMM (bb_tm_finish) -> L[s][c]; bb_calmarg_lse_kernel then takes
+//   geocent_time prior with <h|h>_c from the real contraction (bb_tm_finish) -> L[s][c]; bb_calmarg_lse_kernel then takes
 //   logsumexp_c L - log(n_curves).
 #define BB_CMT_THREADS 256      // two CTAs per SM: the fill of one pair overlaps the transform of the other
 template <int NDET>
@@ -240,15 +242,22 @@ __global__ void bb_calmarg_window_kernel(const double* __restrict__ coef, const 
 template <int NDET, int APPROX>
 static int bb_launch_calmarg_t(bb_handle* h, long n, double* out, cudaStream_t st, BBCalSelect sel) {
     const int nc = h->cm_n_curves, ldk = h->cm_ldk;
-    const size_t x_stride = bb_pk_elems(BB_CM_CHUNK, ldk, BB_GEMM_TR_A(true)), y_stride = bb_pk_elems(BB_CM_CHUNK, ldk, BB_GEMM_TR_A(false));
-    const size_t c_stride = bb_pk_elems(nc, ldk, BB_GEMM_TR_B);
-    if (!h->d_cm_X) {
+    long cap = n < BB_CM_CHUNK ? (n + 127) / 128 * 128 : BB_CM_CHUNK;        // rows the scratch buffers hold
+    if (cap < h->cm_cap) cap = h->cm_cap;
+    const size_t x_stride = bb_pk_elems(cap, ldk, BB_GEMM_TR_A(true)), y_stride = bb_pk_elems(cap, ldk, BB_GEMM_TR_A(false));
+    const size_t c_stride = bb_pk_elems(nc, ldk, BB_GEMM_TR_B), a_stride = bb_pk_elems(nc, ldk, BB_GEMM_TR_B_OF(false));
+    if (!h->d_cm_X || cap > h->cm_cap) {
+        cudaFree(h->d_cm_X); cudaFree(h->d_cm_Y); cudaFree(h->d_cm_D); cudaFree(h->d_cm_H);
+        h->d_cm_X = h->d_cm_D = nullptr;
+        h->d_cm_Y = h->d_cm_H = nullptr;
+        h->cm_cap = 0;
         BB_CUDA(cudaMalloc(&h->d_cm_X, NDET * x_stride * sizeof(double2)));
         BB_CUDA(cudaMalloc(&h->d_cm_Y, NDET * y_stride * sizeof(double)));
         BB_CUDA(cudaMemsetAsync(h->d_cm_X, 0, NDET * x_stride * sizeof(double2), st));
         BB_CUDA(cudaMemsetAsync(h->d_cm_Y, 0, NDET * y_stride * sizeof(double), st));
-        BB_CUDA(cudaMalloc(&h->d_cm_D, (size_t)BB_CM_CHUNK * nc * sizeof(double2)));
-        BB_CUDA(cudaMalloc(&h->d_cm_H, (size_t)BB_CM_CHUNK * nc * sizeof(double)));
+        BB_CUDA(cudaMalloc(&h->d_cm_D, (size_t)cap * nc * sizeof(double2)));
+        BB_CUDA(cudaMalloc(&h->d_cm_H, (size_t)cap * nc * sizeof(double)));
+        h->cm_cap = cap;
     }
     BBMarg point = h->marg;
     point.flags &= ~BB_MARG_TIME;
@@ -315,7 +324,7 @@ static int bb_launch_calmarg_t(bb_handle* h, long n, double* out, cudaStream_t s
             }
             for (int d = 0; d < NDET; ++d) {
                 ga.A[d] = h->d_cm_Y + d * y_stride;
-                ga.B[d] = h->d_cm_A + d * c_stride;
+                ga.B[d] = h->d_cm_A + d * a_stride;
             }
             ga.C = h->d_cm_H;
             if (bb_gemm_nt(false, ga, h->sm_count, st)) return 1;
@@ -368,21 +377,21 @@ static int bb_calmarg_upload(bb_handle* h, int n_curves, const double* curves) {
     cudaFree(h->d_cm_C); cudaFree(h->d_cm_A); cudaFree(h->d_cm_X); cudaFree(h->d_cm_Y); cudaFree(h->d_cm_D); cudaFree(h->d_cm_H);
     h->d_cm_C = nullptr; h->d_cm_A = nullptr; h->d_cm_X = nullptr; h->d_cm_Y = nullptr; h->d_cm_D = nullptr; h->d_cm_H = nullptr;
     h->cm_n_curves = 0;
+    h->cm_cap = 0;
     if (n_curves <= 0) return 0;
     if (!curves) return bb_fail("bb_set_calibration_marginalization: null curves");
     const int n_det = h->net.n_det, nf = h->net.n_freq;
     const int ldk = (nf + 15) & ~15;                       // whole slabs of 16 bins
     const long S = ldk >> 4;
-    const size_t c_stride = bb_pk_elems(n_curves, ldk, BB_GEMM_TR_B);
+    const size_t c_stride = bb_pk_elems(n_curves, ldk, BB_GEMM_TR_B), a_stride = bb_pk_elems(n_curves, ldk, BB_GEMM_TR_B_OF(false));
     std::vector<double2> C((size_t)n_det * c_stride, make_double2(0.0, 0.0));
-    std::vector<double> A((size_t)n_det * c_stride, 0.0);
+    std::vector<double> A((size_t)n_det * a_stride, 0.0);
     for (int d = 0; d < n_det; ++d)
         for (int c = 0; c < n_curves; ++c) {
             const double* src = curves + ((size_t)d * n_curves + c) * nf * 2;
             for (int k = 0; k < nf; ++k) {
-                const size_t o = (size_t)d * c_stride + bb_pk(c, k, BB_GEMM_TR_B, S);
-                C[o] = make_double2(src[2 * k], src[2 * k + 1]);
-                A[o] = src[2 * k] * src[2 * k] + src[2 * k + 1] * src[2 * k + 1];
+                C[(size_t)d * c_stride + bb_pk(c, k, BB_GEMM_TR_B, S)] = make_double2(src[2 * k], src[2 * k + 1]);
+                A[(size_t)d * a_stride + bb_pk(c, k, BB_GEMM_TR_B_OF(false), S)] = src[2 * k] * src[2 * k] + src[2 * k + 1] * src[2 * k + 1];
             }
         }
     BB_CUDA(cudaMalloc(&h->d_cm_C, C.size() * sizeof(double2)));

@@ -13,11 +13,14 @@
 // here at 37.1 TFLOP/s (tools/micro/dmma_peak.cu) = the nominal 148 SM x 64 FMA/clk.  One DMMA occupies a
 // sub-partition's FP64 pipe for 16 cycles, so the issue slots are nearly free and the kernel is built to keep two
 // independent DMMAs in flight per sub-partition:
-//   * persistent CTAs (one per SM) of 8 warps, no producer warp: the warp that is last to finish a stage refills it;
-//   * CTA tile 64 x 128 complex (warp tile 32 x 32 = 4 x 4 fragments, 4 DMMAs per fragment pair and k-step:
-//     re += ar br, re += (-ai) bi, im += ar bi, im += ai br: 128 accumulator registers) or 128 x 128 real (warp tile
-//     64 x 32 = 8 x 4 fragments; the 64 x 64 warp tile spills);
-//   * K slabs of 16 staged through a 3-deep shared-memory ring (61 KB per stage) by two bulk copies per stage
+//   * persistent CTAs of 4 warps, TWO per SM, no producer warp: the warp that is last to finish a stage refills it.
+//     Two independent CTAs per SM because the tile epilogue (stores from the fragments) and the slab hand-overs leave
+//     the tensor pipe idle for ~12k cycles per tile when all warps of an SM belong to one CTA (K = 256: 32.9 TFLOP/s
+//     with one 8-warp CTA, tools/gemm_shapes.py); with two CTAs one computes while the other stores;
+//   * CTA tile 64 x 64 complex (warp tile 32 x 32 = 4 x 4 fragments, 4 DMMAs per fragment pair and k-step:
+//     re += ar br, re += (-ai) bi, im += ar bi, im += ai br: 128 accumulator registers) or 128 x 64 real (warp tile
+//     64 x 32 = 8 x 4 fragments);
+//   * K slabs of 16 staged through a 2-deep shared-memory ring (40 KB per stage) by two bulk copies per stage
 //     (cp.async.bulk -> SASS UBLKCP, completion on the stage's mbarrier, SYNCS) of operands that are stored PACKED
 //     (bb_pk below); rows are padded to a pitch = 64 (complex) / 32 (real) mod 128 bytes so that the fragment loads
 //     (LDS.128 / LDS.64) are bank-conflict free;
@@ -28,8 +31,7 @@
 
 #define BB_GEMM_MAX_SEG 4
 #define BB_GEMM_BK 16
-#define BB_GEMM_STAGES 3
-#define BB_GEMM_CONSUMERS 8
+#define BB_GEMM_CONSUMERS 4
 #define BB_GEMM_THREADS (BB_GEMM_CONSUMERS * 32)
 #define BB_PK 20          // packed row pitch in ELEMENTS: 16 of a K slab + 4 of padding (320 B complex, 160 B real)
 
@@ -57,20 +59,25 @@ struct BBGemmArgs {
     int M, N, n_seg, n_batch;
     int accumulate;                     // 0: C = alpha A B^T, 1: C += alpha A B^T
     double alpha;
+    int skew_from;                      // CTAs with blockIdx >= skew_from start half a tile late (set by bb_gemm_nt)
 };
 
 template <bool CPLX>
 struct BBGemmCfg {
     static constexpr int ELT = CPLX ? 16 : 8;                 // bytes per element
-    static constexpr int FM = CPLX ? 4 : 8, FN = 4;             // fragments (8 x 8) per warp tile
-    static constexpr int WM = 2, WN = 4;                      // warps per CTA tile
-    static constexpr int BM = WM * FM * 8, BN = WN * FN * 8;  // 64 x 128 complex, 128 x 128 real
+    static constexpr int FM = CPLX ? 4 : 8, FN = 4;             // fragments (8 x 8) per warp tile (real 8 x 8 spills)
+    static constexpr int WM = 2, WN = 2;                      // warps per CTA tile
+    static constexpr int BM = WM * FM * 8, BN = WN * FN * 8;  // 64 x 64 complex, 128 x 64 real
     static constexpr int STRIDE = BB_PK * ELT;                // 320 / 160 bytes: = 64 / 32 mod 128 (conflict-free fragments)
-    static constexpr int STAGE_BYTES = (BM + BN) * STRIDE;    // 61440 complex, 40960 real
-    static constexpr int SMEM = BB_GEMM_STAGES * STAGE_BYTES + BB_GEMM_STAGES * 16 + 128;
+    static constexpr int STAGE_BYTES = (BM + BN) * STRIDE;    // 40960 complex, 30720 real
+    // ring depth: a real slab holds half the DMMAs of a complex one (4096 cycles of pipe time), too short to cover the
+    // refill latency with two stages
+    static constexpr int STAGES = CPLX ? 2 : 3;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + STAGES * 16 + 128;
 };
 #define BB_GEMM_TR_A(cplx) ((cplx) ? 64 : 128)
-#define BB_GEMM_TR_B 128
+#define BB_GEMM_TR_B_OF(cplx) 64
+#define BB_GEMM_TR_B 64          // complex operands (the real one is only used by the calibration marginalisation)
 
 __device__ __forceinline__ void bb_dmma(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -81,15 +88,15 @@ __device__ __forceinline__ void bb_mbar_arrive(unsigned long long* bar) {
 }
 
 template <bool CPLX>
-__global__ void __launch_bounds__(BB_GEMM_THREADS, 1) bb_gemm_nt_kernel(BBGemmArgs g) {
+__global__ void __launch_bounds__(BB_GEMM_THREADS, 2) bb_gemm_nt_kernel(BBGemmArgs g) {
     using Cfg = BBGemmCfg<CPLX>;
     extern __shared__ __align__(128) unsigned char gemm_smem[];
     unsigned char* stages = gemm_smem;
-    unsigned long long* full = reinterpret_cast<unsigned long long*>(gemm_smem + BB_GEMM_STAGES * Cfg::STAGE_BYTES);
-    int* done = reinterpret_cast<int*>(full + BB_GEMM_STAGES);          // warps finished with each stage
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(gemm_smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    int* done = reinterpret_cast<int*>(full + Cfg::STAGES);          // warps finished with each stage
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
-        for (int s = 0; s < BB_GEMM_STAGES; ++s) {
+        for (int s = 0; s < Cfg::STAGES; ++s) {
             bb_mbar_init(&full[s], 1);
             done[s] = 0;
         }
@@ -97,6 +104,14 @@ __global__ void __launch_bounds__(BB_GEMM_THREADS, 1) bb_gemm_nt_kernel(BBGemmAr
     }
     __syncthreads();
 
+    // The two CTAs of an SM start together and run at the same rate, so their epilogues would coincide and leave the
+    // tensor pipe idle: the second wave of CTAs starts half a tile late (and stays half a tile out of step).
+    if ((int)blockIdx.x >= g.skew_from) {
+        // half a tile, but no more than a few epilogues' worth (long-K tiles dwarf their epilogue anyway)
+        const long long half = (long long)g.n_slabs * g.n_seg * 4096;
+        const long long t0 = clock64(), wait = half < 40000 ? half : 40000;
+        while (clock64() - t0 < wait) __nanosleep(1000);
+    }
     const int tiles_m = (g.M + Cfg::BM - 1) / Cfg::BM, tiles_n = (g.N + Cfg::BN - 1) / Cfg::BN;
     const long tiles_mn = (long)tiles_m * tiles_n;
     const long n_tiles = tiles_mn * g.n_batch;
@@ -113,7 +128,7 @@ __global__ void __launch_bounds__(BB_GEMM_THREADS, 1) bb_gemm_nt_kernel(BBGemmAr
         const long r = p_tile - (long)b * tiles_mn;
         const int tm = (int)(r / tiles_n), tn = (int)(r - (long)tm * tiles_n);       // n fastest: the A tile is reused from L2
         const int seg = p_sl / g.n_slabs, ks = g.slab0 + (p_sl - seg * g.n_slabs);
-        const int stage = (int)(p_it % BB_GEMM_STAGES);
+        const int stage = (int)(p_it % Cfg::STAGES);
         unsigned char* sa = stages + (size_t)stage * Cfg::STAGE_BYTES;
         unsigned char* sb = sa + Cfg::BM * Cfg::STRIDE;
         if (lane == 0) {
@@ -131,7 +146,7 @@ __global__ void __launch_bounds__(BB_GEMM_THREADS, 1) bb_gemm_nt_kernel(BBGemmAr
         ++p_it;
         if (++p_sl == n_slabs) { p_sl = 0; p_tile += gridDim.x; }
     };
-    for (int s = 0; s < BB_GEMM_STAGES; ++s) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
         if (warp == 0) issue();
         advance();
     }
@@ -154,13 +169,16 @@ __global__ void __launch_bounds__(BB_GEMM_THREADS, 1) bb_gemm_nt_kernel(BBGemmAr
                 for (int c = 0; c < (CPLX ? 4 : 2); ++c) acc[i][j][c] = 0.0;
 
         for (int sl = 0; sl < n_slabs; ++sl, ++it) {
-            const int stage = (int)(it % BB_GEMM_STAGES);
-            const unsigned par = (unsigned)((it / BB_GEMM_STAGES) & 1);
+            const int stage = (int)(it % Cfg::STAGES);
+            const unsigned par = (unsigned)((it / Cfg::STAGES) & 1);
             bb_mbar_wait(&full[stage], par);
             const unsigned char* sa = stages + (size_t)stage * Cfg::STAGE_BYTES
                                       + (size_t)(wm * Cfg::FM * 8 + gq) * Cfg::STRIDE + tq * Cfg::ELT;
             const unsigned char* sb = stages + (size_t)stage * Cfg::STAGE_BYTES + Cfg::BM * Cfg::STRIDE
                                       + (size_t)(wn * Cfg::FN * 8 + gq) * Cfg::STRIDE + tq * Cfg::ELT;
+            // (fetching the fragments of k-step ks + 1 under the DMMAs of k-step ks - a second register set - measured the
+            // same: the other CTA's warp on the sub-partition already covers the LDS latency; 186 instead of 230 registers
+            // leave room for a co-resident epilogue kernel)
 #pragma unroll 1
             for (int ks = 0; ks < BB_GEMM_BK / 4; ++ks) {
                 if (CPLX) {
@@ -171,14 +189,17 @@ __global__ void __launch_bounds__(BB_GEMM_THREADS, 1) bb_gemm_nt_kernel(BBGemmAr
 #pragma unroll
                     for (int j = 0; j < Cfg::FN; ++j)
                         bb[j] = *reinterpret_cast<const double2*>(sb + j * 8 * Cfg::STRIDE + ks * 4 * Cfg::ELT);
+                    // 32 independent DMMAs, then the 32 that depend on them
 #pragma unroll
-                    for (int i = 0; i < Cfg::FM; ++i) {
-                        const double nai = -a[i].y;
+                    for (int i = 0; i < Cfg::FM; ++i)
 #pragma unroll
                         for (int j = 0; j < Cfg::FN; ++j) {
                             bb_dmma(acc[i][j][0], acc[i][j][1], a[i].x, bb[j].x);
                             bb_dmma(acc[i][j][2], acc[i][j][3], a[i].x, bb[j].y);
                         }
+#pragma unroll
+                    for (int i = 0; i < Cfg::FM; ++i) {
+                        const double nai = -a[i].y;
 #pragma unroll
                         for (int j = 0; j < Cfg::FN; ++j) {
                             bb_dmma(acc[i][j][0], acc[i][j][1], nai, bb[j].y);
@@ -186,19 +207,20 @@ __global__ void __launch_bounds__(BB_GEMM_THREADS, 1) bb_gemm_nt_kernel(BBGemmAr
                         }
                     }
                 } else {
-                    double bb[Cfg::FN];
+                    double a[Cfg::FM], bb[Cfg::FN];
+#pragma unroll
+                    for (int i = 0; i < Cfg::FM; ++i)
+                        a[i] = *reinterpret_cast<const double*>(sa + i * 8 * Cfg::STRIDE + ks * 4 * Cfg::ELT);
 #pragma unroll
                     for (int j = 0; j < Cfg::FN; ++j)
                         bb[j] = *reinterpret_cast<const double*>(sb + j * 8 * Cfg::STRIDE + ks * 4 * Cfg::ELT);
 #pragma unroll
-                    for (int i = 0; i < Cfg::FM; ++i) {
-                        const double a = *reinterpret_cast<const double*>(sa + i * 8 * Cfg::STRIDE + ks * 4 * Cfg::ELT);
+                    for (int i = 0; i < Cfg::FM; ++i)
 #pragma unroll
-                        for (int j = 0; j < Cfg::FN; ++j) bb_dmma(acc[i][j][0], acc[i][j][1], a, bb[j]);
-                    }
+                        for (int j = 0; j < Cfg::FN; ++j) bb_dmma(acc[i][j][0], acc[i][j][1], a[i], bb[j]);
                 }
             }
-            // this warp is done reading the stage; the last of the 8 warps refills it with the slab STAGES ahead
+            // this warp is done reading the stage; the last of the 4 warps refills it with the slab STAGES ahead
             __syncwarp();
             int prev = 0;
             if (lane == 0) prev = atomicAdd(&done[stage], 1);
@@ -212,6 +234,27 @@ __global__ void __launch_bounds__(BB_GEMM_THREADS, 1) bb_gemm_nt_kernel(BBGemmAr
 
         // ---- epilogue: fragment (i, j): rows m0 + wm*FM*8 + i*8 + gq, columns n0 + wn*FN*8 + j*8 + 2 tq + {0, 1}
         double* cbase = g.C + (size_t)b * g.batch_c * (CPLX ? 2 : 1);
+        if (!g.accumulate && g.alpha == 1.0 && m0 + Cfg::BM <= g.M && n0 + Cfg::BN <= g.N) {
+            // interior tile: no bounds checks, constant offsets from one row pointer
+            constexpr int W = CPLX ? 2 : 1;
+            double* p0 = cbase + ((size_t)(m0 + wm * Cfg::FM * 8 + gq) * g.ldc + (n0 + wn * Cfg::FN * 8 + 2 * tq)) * W;
+            const size_t row8 = (size_t)8 * g.ldc * W;
+#pragma unroll
+            for (int i = 0; i < Cfg::FM; ++i) {
+                double* p = p0 + i * row8;
+#pragma unroll
+                for (int j = 0; j < Cfg::FN; ++j) {
+                    if (CPLX) {
+                        *reinterpret_cast<double2*>(p + j * 16) = make_double2(acc[i][j][0], acc[i][j][2]);
+                        *reinterpret_cast<double2*>(p + j * 16 + 2) = make_double2(acc[i][j][1], acc[i][j][3]);
+                    } else {
+                        p[j * 8] = acc[i][j][0];           // (16-byte alignment of a real row is not guaranteed)
+                        p[j * 8 + 1] = acc[i][j][1];
+                    }
+                }
+            }
+            continue;
+        }
 #pragma unroll
         for (int i = 0; i < Cfg::FM; ++i) {
             const int m = m0 + (wm * Cfg::FM + i) * 8 + gq;
@@ -264,9 +307,11 @@ static int bb_gemm_nt(bool cplx, const BBGemmArgs& g, int sm_count, cudaStream_t
     else BB_CUDA(cudaFuncSetAttribute(bb_gemm_nt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int bm = cplx ? BBGemmCfg<true>::BM : BBGemmCfg<false>::BM, bn = cplx ? BBGemmCfg<true>::BN : BBGemmCfg<false>::BN;
     long tiles = (long)((g.M + bm - 1) / bm) * ((g.N + bn - 1) / bn) * g.n_batch;
-    const unsigned grid = (unsigned)(tiles < sm_count ? tiles : sm_count);
-    if (cplx) bb_gemm_nt_kernel<true><<<grid, BB_GEMM_THREADS, smem, st>>>(g);
-    else bb_gemm_nt_kernel<false><<<grid, BB_GEMM_THREADS, smem, st>>>(g);
+    const unsigned grid = (unsigned)(tiles < 2L * sm_count ? tiles : 2L * sm_count);       // two CTAs per SM
+    BBGemmArgs ga = g;
+    ga.skew_from = (tiles >= 4L * sm_count) ? sm_count : (int)grid;      // only when every CTA has several tiles
+    if (cplx) bb_gemm_nt_kernel<true><<<grid, BB_GEMM_THREADS, smem, st>>>(ga);
+    else bb_gemm_nt_kernel<false><<<grid, BB_GEMM_THREADS, smem, st>>>(ga);
     BB_CUDA(cudaGetLastError());
     return 0;
 }

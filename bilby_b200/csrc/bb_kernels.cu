@@ -109,6 +109,7 @@ struct bb_handle {
     double2* d_fine = nullptr;
     // calibration marginalisation (bb_calmarg.cuh)
     int cm_n_curves = 0, cm_ldk = 0;
+    long cm_cap = 0;                       // samples the calibration-marginalisation scratch buffers hold
     double2 *d_cm_C = nullptr, *d_cm_X = nullptr, *d_cm_D = nullptr;
     double *d_cm_A = nullptr, *d_cm_Y = nullptr, *d_cm_H = nullptr;
     cudaStream_t aux = nullptr;            // K4b runs here, beside K4a on the caller's stream
@@ -126,7 +127,7 @@ struct bb_handle {
     double roq_fmin = 0.0, rb_fmin = 0.0;
     double2 *d_roq_V = nullptr, *d_roq_Y = nullptr;
     double* d_roq_hh = nullptr;
-    size_t roq_chunk = 0;
+    size_t roq_chunk = 0, roq_y_elems = 0;
     cudaStream_t stream = nullptr;
     int sm_count = 148;
     long launches = 0;
@@ -1349,7 +1350,7 @@ extern "C" int bb_contract_device(bb_handle* h, int is_complex, int m, int n, in
     // row-major operands from outside the library: pack them into the GEMM's layout first (bb_gemm.cuh)
     const bool cplx = is_complex != 0;
     const size_t esz = cplx ? sizeof(double2) : sizeof(double);
-    const size_t pa = bb_pk_elems(m, k, BB_GEMM_TR_A(cplx)), pb = bb_pk_elems(n, k, BB_GEMM_TR_B);
+    const size_t pa = bb_pk_elems(m, k, BB_GEMM_TR_A(cplx)), pb = bb_pk_elems(n, k, BB_GEMM_TR_B_OF(cplx));
     char *A = nullptr, *B = nullptr;
     BB_CUDA(cudaMalloc(&A, pa * esz * n_seg * n_batch));
     if (cudaMalloc(&B, pb * esz * n_seg * n_batch) != cudaSuccess) { cudaFree(A); return bb_fail("bb_contract_device: out of memory"); }
@@ -1366,7 +1367,7 @@ extern "C" int bb_contract_device(bb_handle* h, int is_complex, int m, int n, in
                 bb_gemm_pack_kernel<double><<<1024, 256, 0, st>>>(a + s * seg_stride_a + bt * batch_stride_a, m, k, lda,
                                                                  BB_GEMM_TR_A(false), reinterpret_cast<double*>(A) + oa);
                 bb_gemm_pack_kernel<double><<<1024, 256, 0, st>>>(b + s * seg_stride_b + bt * batch_stride_b, n, k, ldb,
-                                                                 BB_GEMM_TR_B, reinterpret_cast<double*>(B) + ob);
+                                                                 BB_GEMM_TR_B_OF(false), reinterpret_cast<double*>(B) + ob);
             }
         }
         g.A[s] = A + (size_t)s * n_batch * pa * esz;
@@ -1412,35 +1413,61 @@ extern "C" int bb_profile_read(bb_handle* h, double* k1_ms, long* k1_launches) {
     return 0;
 }
 
-// register-resident DFMA stream: 8 independent chains per thread
+// register-resident DFMA stream: 16 independent chains per thread, 4 rounds per loop trip (the round-1 probe - 8
+// chains, one round per trip - read 33.9 TFLOP/s; this one reads what tools/micro/dmma_peak.cu reads, ~36 TFLOP/s)
 __global__ void bb_fp64_peak_kernel(double* out, int iters, double a, double b) {
-    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
-    for (int i = 0; i < iters; ++i) {
-        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
-        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    double x[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = threadIdx.x + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[i] = fma(x[i], a, b);
     }
-    const double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += x[i];
     if (s == 12345.678) out[0] = s;   // never true; keeps the chains alive
 }
 
-extern "C" int bb_fp64_peak(bb_handle* h, double* tflops) {
+// register-resident DMMA stream (mma.sync.m8n8k4.f64): 16 independent accumulator pairs per warp
+__global__ void bb_fp64_tensor_peak_kernel(double* out, int iters, double a, double b) {
+    double c[16][2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i][0] = c[i][1] = 0.0;
+    a += threadIdx.x * 1e-3;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) bb_dmma(c[i][0], c[i][1], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += c[i][0] + c[i][1];
+    if (s == 12345.678) out[0] = s;
+}
+
+static int bb_peak_probe(bb_handle* h, bool tensor, double* tflops) {
     if (!h || !tflops) return bb_fail("bb_fp64_peak: null argument");
     BB_CUDA(cudaSetDevice(h->device));
     double* d = nullptr;
     BB_CUDA(cudaMalloc(&d, sizeof(double)));
-    const int iters = 20000, threads = 256, blocks = h->sm_count * 8;
+    const int iters = tensor ? 20000 : 5000, threads = tensor ? 256 : 512, blocks = h->sm_count * (tensor ? 1 : 2);
     cudaEvent_t e0, e1;
     BB_CUDA(cudaEventCreate(&e0));
     BB_CUDA(cudaEventCreate(&e1));
     double best = 0.0;
     for (int rep = 0; rep < 4; ++rep) {
         BB_CUDA(cudaEventRecord(e0));
-        bb_fp64_peak_kernel<<<blocks, threads>>>(d, iters, 0.999999, 1e-9);
+        if (tensor) bb_fp64_tensor_peak_kernel<<<blocks, threads>>>(d, iters, 0.999999, 1e-9);
+        else bb_fp64_peak_kernel<<<blocks, threads>>>(d, iters, 0.999999, 1e-9);
         BB_CUDA(cudaEventRecord(e1));
         BB_CUDA(cudaEventSynchronize(e1));
         float ms = 0.f;
         BB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-        const double flops = 2.0 * 8.0 * (double)iters * threads * blocks;
+        // DFMA: 2 flop x 64 per thread and trip; DMMA m8n8k4: 512 flop per warp instruction, 16 per trip
+        const double flops = tensor ? 512.0 * 16.0 * (double)iters * (threads / 32) * blocks
+                                    : 2.0 * 64.0 * (double)iters * threads * blocks;
         const double tf = flops / (ms * 1e-3) / 1e12;
         if (rep > 0 && tf > best) best = tf;
     }
@@ -1450,5 +1477,8 @@ extern "C" int bb_fp64_peak(bb_handle* h, double* tflops) {
     *tflops = best;
     return 0;
 }
+
+extern "C" int bb_fp64_peak(bb_handle* h, double* tflops) { return bb_peak_probe(h, false, tflops); }
+extern "C" int bb_fp64_tensor_peak(bb_handle* h, double* tflops) { return bb_peak_probe(h, true, tflops); }
 
 extern "C" long bb_launch_count(bb_handle* h) { return h ? h->launches : 0; }

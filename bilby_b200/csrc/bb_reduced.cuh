@@ -2,7 +2,7 @@
 //
 //   K5 bb_relbin_kernel        relative binning  <- bilby/gw/likelihood/relative.py:365-430
 //   K6 bb_roq_kernel           ROQ, one coalescence time per sample  <- bilby/gw/likelihood/roq.py:467-602
-//   K7 bb_roq_hlinear_kernel + ZGEMM + bb_roq_time_marg_kernel   ROQ time marginalisation  <- roq.py:535-651
+//   K7 bb_roq_hlinear_kernel + bb_gemm_nt_kernel + bb_roq_time_marg_kernel   ROQ time marginalisation  <- roq.py:535-651
 //
 //   K5 (no neighbour term)    multi-banding  <- bilby/gw/likelihood/multiband.py:728-765 (bb_set_multiband)
 //
@@ -522,7 +522,7 @@ bb_roq_kernel(const double* __restrict__ coef, long n, BBRoqDev rq, const double
 // ------------------------------------------------------------------------------------------------
 // K7: ROQ time marginalisation (roq.py:535-549, 604-651; base.py:794-820)
 //   (a) bb_roq_hlinear_kernel : V_d[s][i] = conj(h_linear_d[i]) for every sample, <h|h> per sample
-//   (b) ZGEMM per detector    : Y_d[s][t] = sum_i W_d[t][i] V_d[s][i]      (the dense all-times contraction)
+//   (b) bb_gemm_nt_kernel (DMMA): Y_d[s][t] = sum_i W_d[t][i] V_d[s][i]      (the dense all-times contraction)
 //   (c) bb_roq_time_marg_kernel: five-sample interpolation at the likelihood's time grid, sum over detectors,
 //                                point likelihood, logsumexp with the time prior
 // ------------------------------------------------------------------------------------------------
@@ -580,13 +580,15 @@ bb_roq_hlinear_kernel(const double* __restrict__ coef, long s_begin, long n, BBR
 template <int NDET>
 __global__ void __launch_bounds__(BB_RED_THREADS)
 bb_roq_time_marg_kernel(const double* __restrict__ coef, long s_begin, long n, BBRoqDev rq,
-                        const double2* __restrict__ Y /* [NDET][n][n_time] */, const double* __restrict__ hh,
+                        const double2* __restrict__ Y /* [NDET][n][n_row]: ROQ rows row0 .. row0 + n_row - 1 */, int row0,
+                        int n_row, const double* __restrict__ hh,
                         BBMarg marg, double start_time, double* __restrict__ out) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double ts0 = (double)rq.time_start_index * rq.time_step;
     const double ts1 = (double)(rq.time_start_index + 1) * rq.time_step;
     const double space = ts1 - ts0;
-    for (long s = (long)blockIdx.x * BB_RED_WARPS + warp; s < n; s += (long)gridDim.x * BB_RED_WARPS) {
+    const int wpb = blockDim.x >> 5;          // launched with one warp per CTA so that it fits beside the GEMM's CTAs
+    for (long s = (long)blockIdx.x * wpb + warp; s < n; s += (long)gridDim.x * wpb) {
         const double* rec = coef + (s_begin + s) * BC_NCOEF;
         if (rec[BC_STATUS] != 0.0) {
             if (lane == 0) out[s_begin + s] = -DBL_MAX;
@@ -611,7 +613,7 @@ bb_roq_time_marg_kernel(const double* __restrict__ coef, long s_begin, long n, B
                 const double per = (ifo_t - ts0) / space;
                 const double fl = floor(per);
                 long c = (long)fl;
-                const double2* y = Y + ((size_t)d * n + s) * rq.n_time;
+                const double2* y = Y + ((size_t)d * n + s) * n_row - row0;
                 double2 v[5];
 #pragma unroll
                 for (int k = 0; k < 5; ++k) {

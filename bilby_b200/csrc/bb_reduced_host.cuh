@@ -13,6 +13,7 @@ static void bb_reduced_clear(bb_handle* h) {
     h->d_roq_V = h->d_roq_Y = nullptr;
     h->d_roq_hh = nullptr;
     h->roq_chunk = 0;
+    h->roq_y_elems = 0;
     h->kind = 0;
 }
 
@@ -275,51 +276,93 @@ static int bb_launch_roq_time_marg_t(bb_handle* h, long n, double* out, cudaStre
     const BBRoqDev& rq = *h->rq;
     if (rq.n_marg < 1) return bb_fail("ROQ time marginalisation: bb_set_roq was called without a time grid");
     const int nl = rq.lin.n, nt = rq.n_time;
-    // chunk the batch so that Y [NDET][chunk][n_time] stays below ~2 GB
-    size_t chunk = (size_t)(2.0e9 / ((double)NDET * nt * sizeof(double2)));
+    // ROQ rows any sample can touch.  Only times with t + jitter inside the geocent_time prior contribute (base.py:799-806)
+    // and the detector time is (t + jitter) - start + delay with |delay| <= |vertex| / c, so the five-point stencils stay
+    // inside [tmin - start - dmax, tmax - start + dmax]: the reference contracts all n_time rows (roq.py:604-651), the
+    // weights span twice the light-crossing time (roq.py:747-765), a quarter of them is never read.
+    double dmax = 0.0;
+    for (int d = 0; d < NDET; ++d) {
+        const double* v = h->net.vertex[d];
+        const double r = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]) / BB_C_SI;
+        dmax = r > dmax ? r : dmax;
+    }
+    dmax *= 1.0 + 1e-9;
+    const double ts0 = (double)rq.time_start_index * rq.time_step, space = (double)(rq.time_start_index + 1) * rq.time_step - ts0;
+    long r_lo = (long)floor((h->marg.time_min - h->net.start_time - dmax - ts0) / space) - 3;
+    long r_hi = (long)floor((h->marg.time_max - h->net.start_time + dmax - ts0) / space) + 3;
+    if (r_lo < 0) r_lo = 0;
+    if (r_hi > nt - 1) r_hi = nt - 1;
+    if (getenv("BB_ROQ_NOTRIM") || r_hi < r_lo) { r_lo = 0; r_hi = nt - 1; }
+    const int row0 = (int)(r_lo / BB_GEMM_TR_B) * BB_GEMM_TR_B;          // whole row tiles of the packed weights
+    const int nrow = (int)(r_hi - row0 + 1);
+    // chunk the batch so that one Y buffer [NDET][chunk][nrow] stays below ~1 GB; two buffers: the interpolation +
+    // logsumexp kernel of chunk c runs on the auxiliary stream under the GEMM of chunk c + 1
+    size_t chunk = (size_t)(1.0e9 / ((double)NDET * nrow * sizeof(double2)));
+    chunk = chunk / 64 * 64;
     if (chunk > (size_t)n) chunk = (size_t)n;
     if (chunk < 1) chunk = 1;
-    if (chunk > h->roq_chunk) {
+    const size_t v_elems = (size_t)NDET * bb_pk_elems((long)chunk, nl, BB_GEMM_TR_A(true));
+    const size_t y_elems = (size_t)NDET * chunk * nrow;
+    if (chunk > h->roq_chunk || y_elems > h->roq_y_elems) {
         cudaFree(h->d_roq_V); cudaFree(h->d_roq_Y); cudaFree(h->d_roq_hh);
         h->d_roq_V = h->d_roq_Y = nullptr;
         h->d_roq_hh = nullptr;
-        BB_CUDA(cudaMalloc(&h->d_roq_V, (size_t)NDET * bb_pk_elems((long)chunk, nl, BB_GEMM_TR_A(true)) * sizeof(double2)));
-        BB_CUDA(cudaMemsetAsync(h->d_roq_V, 0, (size_t)NDET * bb_pk_elems((long)chunk, nl, BB_GEMM_TR_A(true)) * sizeof(double2), st));
-        BB_CUDA(cudaMalloc(&h->d_roq_Y, (size_t)NDET * chunk * nt * sizeof(double2)));
-        BB_CUDA(cudaMalloc(&h->d_roq_hh, chunk * sizeof(double)));
+        h->roq_chunk = 0;
+        BB_CUDA(cudaMalloc(&h->d_roq_V, v_elems * sizeof(double2)));
+        BB_CUDA(cudaMemsetAsync(h->d_roq_V, 0, v_elems * sizeof(double2), st));
+        BB_CUDA(cudaMalloc(&h->d_roq_Y, 2 * y_elems * sizeof(double2)));
+        BB_CUDA(cudaMalloc(&h->d_roq_hh, 2 * chunk * sizeof(double)));
         h->roq_chunk = chunk;
+        h->roq_y_elems = y_elems;
+    }
+    const int n_chunks = (int)((n + (long)chunk - 1) / (long)chunk);
+    if (!h->aux) BB_CUDA(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
+    while ((int)h->tm_events.size() < 2 * n_chunks) {
+        cudaEvent_t e;
+        BB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->tm_events.push_back(e);
     }
     const size_t smem = (size_t)BB_RED_WARPS * (BC_NCOEF + (CAL ? NDET * 4 * h->cal.n_points : 0)) * sizeof(double);
     BB_CUDA(cudaFuncSetAttribute(bb_roq_hlinear_kernel<NDET, APPROX, CAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     BBProfScope prof(h, st);
-    for (long s0 = 0; s0 < n; s0 += (long)chunk) {
+    for (int c = 0; c < n_chunks; ++c) {
+        const long s0 = (long)c * (long)chunk;
         const long m = (n - s0) < (long)chunk ? (n - s0) : (long)chunk;
         const long grid = bb_red_grid(h, m);
+        double2* Y = h->d_roq_Y + (size_t)(c & 1) * h->roq_y_elems;
+        double* hh = h->d_roq_hh + (size_t)(c & 1) * h->roq_chunk;
+        if (c >= 2) BB_CUDA(cudaStreamWaitEvent(st, h->tm_events[2 * (c - 2) + 1], 0));      // Y / hh buffer free again
         bb_roq_hlinear_kernel<NDET, APPROX, CAL><<<(unsigned)grid, BB_RED_THREADS, smem, st>>>(
-            h->d_coef, s0, m, rq, h->d_calrec, h->cal, h->d_roq_V, h->d_roq_hh);
-        h->launches++;
+            h->d_coef, s0, m, rq, h->d_calrec, h->cal, h->d_roq_V, hh);
         BB_CUDA(cudaGetLastError());
         {
-            // Y_d[s][t] = sum_i V_d[s][i] W_d[t][i] for every detector: one batched DMMA GEMM (bb_gemm.cuh)
+            // Y_d[s][t - row0] = sum_i V_d[s][i] W_d[t][i] for every detector: one batched DMMA GEMM (bb_gemm.cuh)
             BBGemmArgs ga{};
             ga.A[0] = h->d_roq_V;
-            ga.B[0] = rq.W;
-            ga.C = reinterpret_cast<double*>(h->d_roq_Y);
+            ga.B[0] = rq.W + (size_t)(row0 / BB_GEMM_TR_B) * ((nl + 15) / 16) * BB_GEMM_TR_B * BB_PK;
+            ga.C = reinterpret_cast<double*>(Y);
             ga.slabs_a = ga.slabs_b = (nl + 15) / 16;
             ga.slab0 = 0; ga.n_slabs = (nl + 15) / 16;
             ga.batch_a = (long)bb_pk_elems(m, nl, BB_GEMM_TR_A(true));
             ga.batch_b = (long)bb_pk_elems(nt, nl, BB_GEMM_TR_B);
-            ga.batch_c = (long)m * nt;
-            ga.ldc = nt;
-            ga.M = (int)m; ga.N = nt; ga.n_seg = 1; ga.n_batch = NDET; ga.accumulate = 0; ga.alpha = 1.0;
+            ga.batch_c = (long)m * nrow;
+            ga.ldc = nrow;
+            ga.M = (int)m; ga.N = nrow; ga.n_seg = 1; ga.n_batch = NDET; ga.accumulate = 0; ga.alpha = 1.0;
             if (bb_gemm_nt(true, ga, h->sm_count, st)) return 1;
-            h->launches++;
         }
-        bb_roq_time_marg_kernel<NDET><<<(unsigned)grid, BB_RED_THREADS, 0, st>>>(
-            h->d_coef, s0, m, rq, h->d_roq_Y, h->d_roq_hh, h->marg, h->net.start_time, out);
-        h->launches++;
+        BB_CUDA(cudaEventRecord(h->tm_events[2 * c], st));
+        BB_CUDA(cudaStreamWaitEvent(h->aux, h->tm_events[2 * c], 0));
+        // 128-thread CTAs (14K registers): one becomes resident per SM in what the next chunk's GEMM (2 x 128 threads x
+        // 192 registers) leaves free
+        const long grid_e = (m + 3) / 4 < 4L * h->sm_count ? (m + 3) / 4 : 4L * h->sm_count;
+        bb_roq_time_marg_kernel<NDET><<<(unsigned)grid_e, 128, 0, h->aux>>>(
+            h->d_coef, s0, m, rq, Y, row0, nrow, hh, h->marg, h->net.start_time, out);
         BB_CUDA(cudaGetLastError());
+        BB_CUDA(cudaEventRecord(h->tm_events[2 * c + 1], h->aux));
+        h->launches += 3;
     }
+    BB_CUDA(cudaStreamWaitEvent(st, h->tm_events[2 * (n_chunks - 1) + 1], 0));      // join
+    if (n_chunks > 1) BB_CUDA(cudaStreamWaitEvent(st, h->tm_events[2 * (n_chunks - 2) + 1], 0));
     return 0;
 }
 

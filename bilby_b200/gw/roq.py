@@ -5,7 +5,8 @@ inverse FFT per basis element and detector (roq.py:849-916), quadratic weights (
 loaded from an .npz file written by ``save_weights``.  Evaluation on the device:
   K6 ``bb_roq_kernel``          waveform at the nodes, <h|h> from the quadratic weights, <d|h> at the five ROQ
                                 times around the detector arrival time + cubic interpolation (roq.py:467-602)
-  K7 hlinear + ZGEMM + epilogue time marginalisation: the dense all-times contraction W conj(h) (roq.py:604-651)
+  K7 hlinear + DMMA contraction (csrc/bb_gemm.cuh) + epilogue: time marginalisation, the dense all-times contraction
+     W conj(h) (roq.py:604-651)
 Single linear / quadratic basis given as ndarray, .npy file or precomputed weights; multi-basis selection and
 multibanded bases ship only as .hdf5 (h5py is not a dependency here) and raise NotImplementedError.
 """
@@ -237,7 +238,7 @@ class ROQGravitationalWaveTransient(GravitationalWaveTransient):
                 self.weights[ifo.name + "_linear"] = [lw]
 
     def _linear_weights_device(self, d_over_s, basis, bin_index, n_time, lo, hi, duration):
-        """roq.py:849-918 on the device (bb_build_roq_linear_weights: the wanted time samples as one ZGEMM against an
+        """roq.py:849-918 on the device (bb_build_roq_linear_weights: the wanted time samples as one DMMA contraction (csrc/bb_gemm.cuh) against an
         exact phase matrix).  Returns None when the process has no CUDA device."""
         try:
             import torch

@@ -319,6 +319,8 @@ int bb_build_roq_linear_weights(int device, int n_det, int n_freq_sel, const dou
 int bb_profile_enable(bb_handle* h, int on);
 int bb_profile_read(bb_handle* h, double* k1_ms, long* k1_launches);
 int bb_fp64_peak(bb_handle* h, double* tflops);
+/* The same for the FP64 tensor path (mma.sync.m8n8k4.f64 stream): the denominator of the dense contractions. */
+int bb_fp64_tensor_peak(bb_handle* h, double* tflops);
 
 /* Number of kernel launches issued through this handle so far (bench.py's gpu_launches claim). */
 long bb_launch_count(bb_handle* h);

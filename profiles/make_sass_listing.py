@@ -36,6 +36,8 @@ KERNELS = {   # label -> (mangled-name regex, keep full listing)
     "k7_roq_hlinear_3det_taylorf2": (r"_Z21bb_roq_hlinear_kernelILi3ELi1ELb0E", False),
     "k7_roq_time_marg_3det": (r"_Z23bb_roq_time_marg_kernelILi3E", False),
     "kt_distance_table": (r"_Z24bb_distance_table_kernel", False),
+    "kg_gemm_complex_dmma": (r"_Z17bb_gemm_nt_kernelILb1E", True),
+    "kg_gemm_real_dmma": (r"_Z17bb_gemm_nt_kernelILb0E", False),
 }
 
 
