@@ -287,12 +287,21 @@ def gpu_run(args):
         pass
     roofline = dict(bound="fp64", achieved=achieved, peak=peak.value, unit="TFLOP/s",
                     frac=achieved / peak.value if peak.value else None, traffic=traffic,
+                    traffic_source="profiles/k1_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one "
+                                   "`ncu --set full` capture of this kernel, scaled to this batch (not measured in this run)",
                     kernel="bb_inner_product_kernel<3>", kernel_ms=k1_avg_ms,
                     kernel_share_of_step=k1_ms.value / (e0.elapsed_time(e1)) if k1_n.value else None,
                     algorithmic_flop_per_launch=bins * FLOP_PER_BIN, active_bins_per_eval=bins / n,
                     peak_source="in-run DFMA stream kernel (bb_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
                     hbm_peak_gbs=peaks.get("hbm_gbs"),
                     algorithmic_hbm_bytes_per_launch=n * (16 + 1) * 8)
+
+    # ---- the other BASELINE.json configurations (and, for N > 1, the frequency-sharded long signal) in the same run
+    del like, net, rows_dev, out_dev
+    torch.cuda.empty_cache()
+    extra = None
+    if not args.no_extra:
+        extra = run_extra(args, world, rank, local_rank, dist if world > 1 else None)
 
     if rank != 0:
         if world > 1:
@@ -324,10 +333,60 @@ def gpu_run(args):
                 clocks=clock_info,
                 e2e=dict(value=e2e_value, unit="evals/s", h2d_bytes_per_step=n * 16 * 8, d2h_bytes_per_step=n * 8,
                          ms_per_step=e2e_ms / args.steps, api="bb_log_likelihood_ratio_host (C ABI, pinned host buffers)"),
-                gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, checksum_lnl=lnl_sum)
+                gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, checksum_lnl=lnl_sum, extra=extra)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+EXTRA_CONFIGS = ("cfg0", "cfg2", "cfg3", "cfg4_relbin", "cfg4_roq", "cfg4_roq_time")
+
+
+def run_extra(args, world, rank, local_rank, dist):
+    """every BASELINE.json configuration under the driver's eyes.  Same JSON line, key `extra`:
+    per configuration the device-resident value, the end-to-end value through the host entry point, the roofline of
+    its dominant kernel and (N = 1) the CPU baseline from the oracle port on a bounded sample; for N > 1 also
+    configs[3] with the frequency axis sharded over the N GPUs (strong scaling), through the fused peer-memory exchange
+    and through one NCCL all-reduce."""
+    import bench_configs as bc
+    out = dict(note="steps=3, warmup=3 per configuration; value = device-resident, e2e = host buffers through the C ABI; "
+                    "weak scaling over samples (every rank its own batch) unless stated", configs={})
+    for cfg in EXTRA_CONFIGS:
+        try:
+            line = bc.run_config(cfg, bc.DEFAULT_BATCH[cfg], 3, 3, world, rank, local_rank, dist, clocks=False)
+        except Exception as exc:      # pragma: no cover - reported, never hidden
+            line = dict(error=repr(exc)) if rank == 0 else None
+        if rank != 0:
+            continue
+        if "error" not in line:
+            r = line["roofline"]
+            line = dict(workload=line["config"]["workload"], batch_per_gpu=line["config"]["batch"], value=line["value"],
+                        unit=line["unit"], ms_per_step=line["ms_per_step"],
+                        e2e=dict(value=line["e2e"]["value"], h2d_bytes_per_step=line["e2e"]["h2d_bytes_per_step"],
+                                 d2h_bytes_per_step=line["e2e"]["d2h_bytes_per_step"]),
+                        gpu_launches=line["gpu_launches"], checksum_lnl=line["checksum_lnl"],
+                        roofline=dict(bound=r["bound"], achieved=r["achieved"], peak=r["peak"], unit=r["unit"], frac=r["frac"],
+                                      kernel=r["kernel"], kernel_share_of_step=r["kernel_share_of_step"],
+                                      peak_source=r["peak_source"]),
+                        **{k: line["config"][k] for k in ("n_time_contracted", "executed_gemm_flop_per_eval") if k in line["config"]})
+            if world == 1 and not args.no_cpu_baseline:
+                cmd = [sys.executable, os.path.join(ROOT, "bench_cpu.py"), "--config", cfg]
+                try:
+                    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+                    cpu = json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1])
+                    line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+                except Exception as exc:      # pragma: no cover
+                    line["cpu_baseline"] = dict(value=None, kind="port", sample=f"failed: {exc}")
+        out["configs"][cfg] = line
+    if world > 1:
+        shard = {}
+        for exchange in ("fused", "nccl"):
+            try:
+                shard[exchange] = bc.run_frequency_sharded(8192, 3, 3, world, rank, dist, exchange=exchange)
+            except Exception as exc:      # pragma: no cover
+                shard[exchange] = dict(error=repr(exc))
+        out["frequency_sharded_configs3"] = shard
+    return out if rank == 0 else None
 
 
 def reference_run(args):
@@ -362,6 +421,7 @@ def main():
     ap.add_argument("--cpu-evals", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quiet-json", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other configurations (headline line only)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_run(args)

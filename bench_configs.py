@@ -33,6 +33,7 @@ T_INJ = 1126259642.413
 BNS_INJ = dict(mass_1=1.5, mass_2=1.3, chi_1=0.02, chi_2=0.01, luminosity_distance=100.0, theta_jn=0.4, psi=2.659,
                phase=1.3, geocent_time=T_INJ, ra=1.375, dec=-1.2108, lambda_1=400.0, lambda_2=600.0)
 NOISE_SEED = 88170235
+_ROQ_BASIS = {}
 
 
 def bns_draws(n, rng, narrow=False):
@@ -66,6 +67,15 @@ def build(config, n):
     from bilby_b200.gw import conversion, source
     from bilby_b200.workloads import INJECTION, draw_bbh_prior
     rng = np.random.default_rng(hb.DRAW_SEED)
+    if config == "cfg1":        # the headline configuration of bench.py, here for profiling captures
+        like = hb.build_likelihood()
+        rows = hb.draw_rows(like, n, hb.DRAW_SEED)
+        df = 0.25
+
+        def flop1(rows_):
+            bins = hb.active_bins(rows_, df, 4097)
+            return bins * hb.FLOP_PER_BIN + len(rows_) * hb.EPILOGUE_FLOP, bins / len(rows_)
+        return like, rows, None, flop1, dict(workload=hb.WORKLOAD, kernel="bb_inner_product_kernel<3,IMRPhenomD>")
     if config in ("cfg0", "cfg2", "calmarg", "calmarg_time"):
         duration = 8.0 if config == "cfg2" else 4.0
         names = ["H1", "L1"] if config == "cfg0" else ["H1", "L1", "V1"]
@@ -263,8 +273,11 @@ def build(config, n):
         idx = torch.tensor(nodes, device=v.device)
         b = v @ torch.linalg.inv(v[idx, :])
         return b.cpu().numpy(), nodes
-    bl, nl = interpolant(hp, n_lin)
-    bq, nq = interpolant((hp.abs() ** 2).to(torch.complex128), n_quad)
+    key = (n_lin, n_quad, n_train, len(freqs))
+    if key not in _ROQ_BASIS:           # the two ROQ configurations of one process share the synthetic basis
+        _ROQ_BASIS.clear()
+        _ROQ_BASIS[key] = interpolant(hp, n_lin) + interpolant((hp.abs() ** 2).to(torch.complex128), n_quad)
+    bl, nl, bq, nq = _ROQ_BASIS[key]
     del hp
     torch.cuda.empty_cache()
     wfg = bb.gw.WaveformGenerator(duration=duration, sampling_frequency=fs, start_time=start,
@@ -314,7 +327,7 @@ def build(config, n):
         workload=work, kernel=kernel, n_linear=n_lin, n_quadratic=n_quad, n_time=n_time, **extra)
 
 
-DEFAULT_BATCH = dict(calmarg=75776, cfg0=1_000_000, cfg2=100_000, cfg3=8192, cfg4_relbin=1_000_000, cfg4_roq=1_000_000,
+DEFAULT_BATCH = dict(calmarg=75776, cfg0=1_000_000, cfg1=1_000_000, cfg2=100_000, cfg3=8192, cfg4_relbin=1_000_000, cfg4_roq=1_000_000,
                      cfg4_roq_time=65536, mb=65536, calmarg_time=1024)
 
 
@@ -381,30 +394,19 @@ def recon_bench(n, steps):
                           max_rel_diff_vs_oracle=err)))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--config", required=True, choices=sorted(DEFAULT_BATCH) + ["recon"])
-    ap.add_argument("--batch", type=int, default=0)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    args = ap.parse_args()
+def run_config(config, n, steps, warmup, world=1, rank=0, local=0, dist=None, clocks=True):
+    """Times one configuration on this rank's GPU (process group, if any, already initialised by the caller).
+    Returns the JSON-able line on rank 0, None elsewhere.  N > 1: samples are independent units -> every rank evaluates
+    its own batch of draws (weak scaling, no data-path collective); value = all ranks' evaluations / max-over-ranks
+    device time."""
     import torch
     from bilby_b200 import _lib
-    if not torch.cuda.is_available():
-        raise SystemExit("bench_configs.py needs a CUDA device (bilby_b200 has no CPU path)")
-    if args.config == "recon":
-        return recon_bench(args.batch or 20000, args.steps)
-    # N > 1 (torchrun): samples are independent units -> every rank evaluates its own batch of draws (weak scaling,
-    # no data-path collective); value = all ranks' evaluations / max-over-ranks device time
-    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        hb.DRAW_SEED += rank
-    n = args.batch or DEFAULT_BATCH[args.config]
-    like, rows_np, cal_np, flop, desc = build(args.config, n)
+    seed0 = hb.DRAW_SEED
+    hb.DRAW_SEED = seed0 + rank
+    try:
+        like, rows_np, cal_np, flop, desc = build(config, n)
+    finally:
+        hb.DRAW_SEED = seed0
     net = like.device_network
     lib = net.lib
     rows_np = np.ascontiguousarray(rows_np)
@@ -414,6 +416,7 @@ def main():
     peak = ctypes.c_double(0.0)
     tensor_bound = "DMMA" in desc.get("bound", "")
     _lib.check((lib.bb_fp64_tensor_peak if tensor_bound else lib.bb_fp64_peak)(net.ptr, ctypes.byref(peak)))
+    warmup = max(3, warmup)
 
     def step_device():
         return like._evaluate_device(rows_dev, cal_dev)
@@ -430,16 +433,16 @@ def main():
             return float(t.item())
         return ms
 
-    for _ in range(max(3, args.warmup)):
+    for _ in range(warmup):
         out = step_device()
     barrier()
     _lib.check(lib.bb_profile_enable(net.ptr, 1))
     torch.cuda.cudart().cudaProfilerStart()        # `ncu --profile-from-start off` skips the set-up kernels
     launches0 = lib.bb_launch_count(net.ptr)
-    clocks = hb.ClockSampler(local)
+    sampler = hb.ClockSampler(local) if clocks else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         out = step_device()
     e1.record(stream)
     barrier()
@@ -453,36 +456,121 @@ def main():
     like.log_likelihood_ratio_rows_host(rows_np, cal_np)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         res = like.log_likelihood_ratio_rows_host(rows_np, cal_np)
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
-    clock_info = clocks.stop()
+    clock_info = sampler.stop() if sampler else None
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+    del like, net, rows_dev, cal_dev, out
+    torch.cuda.empty_cache()
     if rank != 0:
-        return
+        return None
     n_all = n * world
     total_flop, units = flop(rows_np)
-    k_avg = k_ms.value / max(1, k_n.value) * (k_n.value / args.steps)       # dominant-kernel time per step
+    k_avg = k_ms.value / max(1, k_n.value) * (k_n.value / steps)       # dominant-kernel time per step
     achieved = total_flop / (k_avg * 1e-3) / 1e12 if k_avg > 0 else 0.0
     fin = np.isfinite(res)
-    line = dict(metric="log-likelihood evals/sec", config=dict(desc, batch=n, partition=f"samples x{world}"),
-                value=n_all * args.steps / (ms_total * 1e-3),
-                unit="evals/s", n_gpus=world, scaling="weak", steps=args.steps, warmup=max(3, args.warmup), ms_per_step=ms_total / args.steps,
+    return dict(metric="log-likelihood evals/sec", config=dict(desc, batch=n, partition=f"samples x{world}"),
+                value=n_all * steps / (ms_total * 1e-3),
+                unit="evals/s", n_gpus=world, scaling="weak", steps=steps, warmup=warmup, ms_per_step=ms_total / steps,
                 dtype="f64", data="synthetic", clocks=clock_info,
-                e2e=dict(value=n_all * args.steps / (e2e_ms * 1e-3), unit="evals/s", ms_per_step=e2e_ms / args.steps,
+                e2e=dict(value=n_all * steps / (e2e_ms * 1e-3), unit="evals/s", ms_per_step=e2e_ms / steps,
                          h2d_bytes_per_step=int(rows_np.nbytes + (cal_np.nbytes if cal_np is not None else 0)),
                          d2h_bytes_per_step=n * 8),
                 gpu_launches=int(launches),
                 roofline=dict(bound="fp64 tensor" if tensor_bound else "fp64", achieved=achieved, peak=peak.value, unit="TFLOP/s",
                               frac=achieved / peak.value if peak.value else None, kernel=desc["kernel"],
-                              kernel_ms_per_step=k_avg, kernel_share_of_step=k_avg / (ms_total / args.steps),
+                              kernel_ms_per_step=k_avg, kernel_share_of_step=k_avg / (ms_total / steps),
                               algorithmic_flop_per_step=total_flop, units_per_eval=units,
                               peak_source="in-run DMMA stream kernel (bb_fp64_tensor_peak)" if tensor_bound
                               else "in-run DFMA stream kernel (bb_fp64_peak)"),
                 checksum_lnl=float(np.sum(res[fin])), finite_fraction=float(fin.mean()))
-    print(json.dumps(line))
+
+
+def run_frequency_sharded(n, steps, warmup, world, rank, dist, exchange="fused"):
+    """configs[3] with the frequency axis in `world` contiguous shards (strong scaling: every rank evaluates ALL n
+    samples on its bin range; fused peer-memory exchange or one NCCL all-reduce; replicated epilogue)."""
+    import torch
+    from bilby_b200.parallel import FrequencyShardedLikelihood
+    like, rows_np, _, flop, desc = build("cfg3", n)
+    rows = torch.from_numpy(np.ascontiguousarray(rows_np)).cuda()
+    check = like.log_likelihood_ratio_batch(rows[:256]).cpu().numpy()          # unsharded, before the shard is set
+    sharded = FrequencyShardedLikelihood(like, rank, world, fused_max_rows=n if exchange == "fused" else 0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, warmup)):
+        out = sharded.log_likelihood_ratio_rows(rows)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = sharded.log_likelihood_ratio_rows(rows)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    snrs = like.inner_products_batch(rows)
+    barrier()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    for _ in range(steps):
+        if world > 1:
+            dist.all_reduce(snrs)
+    a1.record()
+    barrier()
+    ar = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ar, op=dist.ReduceOp.MAX)
+    sharded.check_exchange()
+    err = float(np.max(np.abs(out[:256].cpu().numpy() - check)) / np.max(np.abs(check)))
+    fused = bool(sharded.fused)
+    k_begin, k_end = sharded.k_begin, sharded.k_end
+    del sharded, like, rows, out, snrs
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    total_flop, _ = flop(rows_np)
+    t = float(ms.item()) * 1e-3 / steps
+    return dict(metric="log-likelihood evals/sec (TaylorF2+tides 128 s H1L1V1, frequency-sharded)", value=n / t,
+                unit="evals/s", n_gpus=world, steps=steps, warmup=max(3, warmup), ms_per_step=t * 1e3, scaling="strong",
+                config=dict(workload=desc["workload"], batch=n,
+                            partition=f"frequency axis in {world} contiguous shards, bins [{k_begin}, {k_end}) on rank 0; "
+                                      f"exchange of {n * 3 * 3 * 8} bytes per rank per step",
+                            exchange=("fused into K1 (peer-memory stores over NVLink + flag round)" if fused
+                                      else "NCCL all-reduce")),
+                exchange_us_per_step_nccl_allreduce_alone=1e3 * float(ar.item()) / steps,
+                algorithmic_tflops=total_flop / t / 1e12, max_rel_diff_vs_unsharded=err)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", required=True, choices=sorted(DEFAULT_BATCH) + ["recon"])
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    args = ap.parse_args()
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench_configs.py needs a CUDA device (bilby_b200 has no CPU path)")
+    if args.config == "recon":
+        return recon_bench(args.batch or 20000, args.steps)
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    line = run_config(args.config, args.batch or DEFAULT_BATCH[args.config], args.steps, args.warmup, world, rank, local, dist)
+    if world > 1:
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line))
 
 
 if __name__ == "__main__":

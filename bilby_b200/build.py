@@ -25,11 +25,14 @@ def _newest_source_mtime():
 
 
 def build(force=False, verbose=False):
+    """BB_NVCC_EXTRA (extra nvcc flags, e.g. -DBB_K1_UNROLL=2) and BB_LIB_OUT (output path) serve kernel experiments."""
+    global LIB
+    LIB = os.environ.get("BB_LIB_OUT", LIB)
     os.makedirs(LIB_DIR, exist_ok=True)
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_source_mtime():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + os.environ.get("BB_NVCC_EXTRA", "").split()
     cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + \
           [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB, "-lpthread"]
     res = subprocess.run(cmd, capture_output=True, text=True)

@@ -16,7 +16,14 @@
 // generic per-lane path.  Partial sums stay in registers; one warp-shuffle reduction per sample.
 #pragma once
 
+#ifndef BB_K1_THREADS
 #define BB_K1_THREADS 512
+#endif
+#ifndef BB_K1_UNROLL
+#define BB_K1_UNROLL 1
+#endif
+#define BB_PRAGMA_(x) _Pragma(#x)
+#define BB_UNROLL(n) BB_PRAGMA_(unroll n)
 #define BB_K1_WARPS (BB_K1_THREADS / 32)
 #define BB_K1_SB BB_K1_WARPS               // samples per block (one per warp)
 #define BB_K1_CHUNK 512                    // bins per tile
@@ -27,6 +34,8 @@ struct K1Tile {
     double u[BB_K1_CHUNK];
     double lf[BB_K1_CHUNK];
     double q34[BB_K1_CHUNK];
+    double rf[BB_K1_CHUNK];
+    double u7[BB_K1_CHUNK];
     double2 ds[NDET][BB_K1_CHUNK];
     double is[NDET][BB_K1_CHUNK];
 };
@@ -69,6 +78,8 @@ __device__ __forceinline__ void bb_k1_issue_tile(K1Tile<NDET>& t, unsigned long 
     bb_bulk_g2s(t.u, g.u + c0, BB_K1_CHUNK * 8, bar);
     bb_bulk_g2s(t.lf, g.lf + c0, BB_K1_CHUNK * 8, bar);
     bb_bulk_g2s(t.q34, g.q34 + c0, BB_K1_CHUNK * 8, bar);
+    bb_bulk_g2s(t.rf, g.rf + c0, BB_K1_CHUNK * 8, bar);
+    bb_bulk_g2s(t.u7, g.u7 + c0, BB_K1_CHUNK * 8, bar);
 #pragma unroll
     for (int d = 0; d < NDET; ++d) {
         bb_bulk_g2s(t.ds[d], g.ds + (size_t)d * g.n_pad + c0, BB_K1_CHUNK * 16, bar);
@@ -84,14 +95,18 @@ struct K1PhIns { double q[13]; };
 struct K1PhInt { double q[4]; };
 struct K1PhMr { double q[7]; };
 
+// Every eval works from the tile's per-bin columns: f, u = f^(-1/6) (inspiral only: t = u^2 = f^(-1/3), x = f t^2 =
+// f^(1/3)), rf = 1/f, ln f, f^(3/4).  The amplitude prefactor a0 is folded into the region's coefficients when they
+// are loaded; the common factor f^(-7/6) comes from the tile (K1Tile::u7).
 template <int AR>
 struct K1Amp;
 template <>
 struct K1Amp<0> {
     K1AmpIns c;
     __device__ __forceinline__ void load(const double* r) {
+        const double a0 = r[BC_A0];
 #pragma unroll
-        for (int i = 0; i < 10; ++i) c.k[i] = r[BC_AINS + i];
+        for (int i = 0; i < 10; ++i) c.k[i] = r[BC_AINS + i] * a0;
     }
     __device__ __forceinline__ void begin(double f0, double dfrow) {}
     __device__ __forceinline__ void next() {}
@@ -106,8 +121,9 @@ template <>
 struct K1Amp<1> {
     K1AmpInt c;
     __device__ __forceinline__ void load(const double* r) {
+        const double a0 = r[BC_A0];
 #pragma unroll
-        for (int i = 0; i < 5; ++i) c.k[i] = r[BC_AINT + i];
+        for (int i = 0; i < 5; ++i) c.k[i] = r[BC_AINT + i] * a0;
         c.f1 = r[BC_AINT_F1];
         c.invw = r[BC_AINT_INVW];
     }
@@ -124,16 +140,18 @@ struct K1Amp<1> {
 template <>
 struct K1Amp<2> {
     K1AmpMr c;
+    double a0;
     __device__ __forceinline__ void load(const double* r) {
         c.frd = r[BC_MR_FRD];
         c.wl2 = r[BC_MR_WL2];
         c.g = r[BC_MR_G];
         c.lam = r[BC_MR_LAM];
+        a0 = r[BC_A0];
     }
-    // exp(-lam (f - f_RD)) advances from row to row by one multiplication (rows are equally spaced in f)
+    // a0 g exp(-lam (f - f_RD)) advances from row to row by one multiplication (rows are equally spaced in f)
     double e, ratio;
     __device__ __forceinline__ void begin(double f0, double dfrow) {
-        e = c.g * exp(-c.lam * (f0 - c.frd));
+        e = a0 * c.g * exp(-c.lam * (f0 - c.frd));
         ratio = exp(-c.lam * dfrow);
     }
     __device__ __forceinline__ void next() { e *= ratio; }
@@ -143,6 +161,7 @@ struct K1Amp<2> {
     }
 };
 
+// phase in half turns; NEEDS_X: the region's formulas use x = f^(1/3), t = f^(-1/3)
 template <int PR>
 struct K1Ph;
 template <>
@@ -152,7 +171,7 @@ struct K1Ph<0> {
 #pragma unroll
         for (int i = 0; i < 13; ++i) c.q[i] = r[BC_PINS + i];
     }
-    __device__ __forceinline__ double eval(double f, double t, double x, double lf, double q34) const {
+    __device__ __forceinline__ double eval(double f, double t, double x, double rf, double lf, double q34) const {
         const double* q = c.q;
         double pos = q[6];
         pos = pos * x + q[5]; pos = pos * x + q[4]; pos = pos * x + q[3]; pos = pos * x + q[2]; pos = pos * x + q[1];
@@ -168,9 +187,8 @@ struct K1Ph<1> {
 #pragma unroll
         for (int i = 0; i < 4; ++i) c.q[i] = r[BC_PINT + i];
     }
-    __device__ __forceinline__ double eval(double f, double t, double x, double lf, double q34) const {
-        const double t3 = t * t * t;
-        return c.q[0] + c.q[1] * f + c.q[2] * (t3 * t3 * t3) + c.q[3] * lf;
+    __device__ __forceinline__ double eval(double f, double t, double x, double rf, double lf, double q34) const {
+        return c.q[0] + c.q[1] * f + c.q[2] * (rf * rf * rf) + c.q[3] * lf;
     }
 };
 template <>
@@ -180,8 +198,8 @@ struct K1Ph<2> {
 #pragma unroll
         for (int i = 0; i < 7; ++i) c.q[i] = r[BC_PMR + i];
     }
-    __device__ __forceinline__ double eval(double f, double t, double x, double lf, double q34) const {
-        return c.q[0] + c.q[1] * f + c.q[2] * (t * t * t) + c.q[3] * q34 + c.q[4] * bb_atan((f - c.q[5]) * c.q[6]);
+    __device__ __forceinline__ double eval(double f, double t, double x, double rf, double lf, double q34) const {
+        return c.q[0] + c.q[1] * f + c.q[2] * rf + c.q[3] * q34 + c.q[4] * bb_atan((f - c.q[5]) * c.q[6]);
     }
 };
 
@@ -195,12 +213,15 @@ struct K1State {
     BBCalGrid grid;
 };
 
-template <int NDET, bool CAL>
+template <int NDET, bool CAL, bool MASKED = true>
 __device__ __forceinline__ void bb_k1_accumulate(K1State<NDET>& st, const K1Tile<NDET>& tile, int i, bool act,
                                                  double A, double ph) {
     double sn, cs;
-    bb_sincospi(act ? ph : 0.0, &sn, &cs);
-    A = act ? A : 0.0;
+    if (MASKED) {           // rows cut by the band edges: lanes outside [kmin, kmax) contribute exactly zero
+        ph = act ? ph : 0.0;
+        A = act ? A : 0.0;
+    }
+    bb_sincospi(ph, &sn, &cs);
     const double zr = A * cs, zi = A * sn;      // A e^{+i Phi} = conj(h22 incl. geocentric shift)
     const double A2 = A * A;
     BBCalW cw;
@@ -231,7 +252,34 @@ __device__ __forceinline__ void bb_k1_accumulate(K1State<NDET>& st, const K1Tile
     }
 }
 
-// rows [r0, r1) of one chunk, all inside amplitude region AR and phase region PR
+// rows [r0, r1) of one chunk, all inside amplitude region AR and phase region PR.  MASKED: the rows may contain lanes
+// outside [kmin, kmax) (only the first and the last row of a sample); interior rows skip the selects.
+template <int NDET, int AR, int PR, bool CAL, bool MASKED>
+__device__ __forceinline__ void bb_k1_rows_pd_m(K1State<NDET>& st, const K1Tile<NDET>& tile, K1Amp<AR>& amp,
+                                                const K1Ph<PR>& phs, int r0, int r1, int c0, int lane, int kmin,
+                                                int kmax, double df) {
+    constexpr bool NEEDS_X = (AR == 0) || (PR == 0);
+    double kd = (double)(r0 * BB_ROW + lane);          // bin index as a double: += 32 per row, f = kd * df is exact
+    int i = r0 * BB_ROW + lane - c0;
+    BB_UNROLL(BB_K1_UNROLL)
+    for (int r = r0; r < r1; ++r) {
+        const bool act = !MASKED || ((kd >= (double)kmin) && (kd < (double)kmax));
+        const double f = kd * df;
+        double t = 0.0, x = 0.0;
+        if (NEEDS_X) {
+            const double u = tile.u[i];
+            t = u * u;
+            x = f * t * t;
+        }
+        const double A = amp.eval(f, x) * tile.u7[i];
+        const double ph = phs.eval(f, t, x, tile.rf[i], tile.lf[i], tile.q34[i]);
+        bb_k1_accumulate<NDET, CAL, MASKED>(st, tile, i, act, A, ph);
+        amp.next();
+        kd += (double)BB_ROW;
+        i += BB_ROW;
+    }
+}
+
 template <int NDET, int AR, int PR, bool CAL>
 __device__ __forceinline__ void bb_k1_rows_pd(K1State<NDET>& st, const K1Tile<NDET>& tile, const double* rec, int r0,
                                               int r1, int c0, int lane, int kmin, int kmax, double df) {
@@ -239,18 +287,12 @@ __device__ __forceinline__ void bb_k1_rows_pd(K1State<NDET>& st, const K1Tile<ND
     K1Ph<PR> phs;
     amp.load(rec);
     phs.load(rec);
-    const double a0 = rec[BC_A0];
     amp.begin((double)(r0 * BB_ROW + lane) * df, (double)BB_ROW * df);
-    for (int r = r0; r < r1; ++r) {
-        const int k = r * BB_ROW + lane, i = k - c0;
-        const bool act = (k >= kmin) && (k < kmax);
-        const double f = (double)k * df;
-        const double u = tile.u[i], t = u * u, x = f * t * t;
-        const double A = amp.eval(f, x) * a0 * (u * (t * t * t));
-        const double ph = phs.eval(f, t, x, tile.lf[i], tile.q34[i]);
-        bb_k1_accumulate<NDET, CAL>(st, tile, i, act, A, ph);
-        amp.next();
-    }
+    // rows fully inside [kmin, kmax): [ceil(kmin / 32), floor(kmax / 32))
+    const int ri0 = min(max((kmin + BB_ROW - 1) / BB_ROW, r0), r1), ri1 = max(min(kmax / BB_ROW, r1), ri0);
+    if (r0 < ri0) bb_k1_rows_pd_m<NDET, AR, PR, CAL, true>(st, tile, amp, phs, r0, ri0, c0, lane, kmin, kmax, df);
+    if (ri0 < ri1) bb_k1_rows_pd_m<NDET, AR, PR, CAL, false>(st, tile, amp, phs, ri0, ri1, c0, lane, kmin, kmax, df);
+    if (ri1 < r1) bb_k1_rows_pd_m<NDET, AR, PR, CAL, true>(st, tile, amp, phs, ri1, r1, c0, lane, kmin, kmax, df);
 }
 
 // generic rows: per-lane region selection (rows straddling a region boundary) or TaylorF2

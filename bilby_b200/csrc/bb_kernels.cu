@@ -46,6 +46,8 @@ struct BBTiles {
     const double* u;      // f^(-1/6)            [n_freq]
     const double* lf;     // ln f                [n_freq]
     const double* q34;    // f^(3/4)             [n_freq]
+    const double* rf;     // 1 / f               [n_freq]   (K1: the merger-ringdown and intermediate phase terms)
+    const double* u7;     // f^(-7/6)            [n_freq]   (K1: the amplitude's leading power)
     const double2* ds;    // (4/T) d/S  complex  [n_det][n_pad]
     const double* is;     // (4/T) / S           [n_det][n_pad]
     int n_pad;            // n_freq rounded up to a whole number of K1 tiles (zero padded)
@@ -70,7 +72,7 @@ struct bb_handle {
     BBMarg marg{};
     bool have_network = false;
     int shard_lo = 0, shard_hi = 0;       // bin range owned by this handle
-    double *d_u = nullptr, *d_lf = nullptr, *d_q34 = nullptr, *d_is = nullptr;
+    double *d_u = nullptr, *d_lf = nullptr, *d_q34 = nullptr, *d_is = nullptr, *d_rf = nullptr, *d_u7 = nullptr;
     double2* d_ds = nullptr;
     unsigned char* d_mask = nullptr;
     double2* d_twiddle = nullptr;          // e^{-2 pi i m / nfft}, m < nfft/2 (time marginalisation)
@@ -573,6 +575,8 @@ static BBTiles bb_tiles(const bb_handle* h) {
     t.u = h->d_u;
     t.lf = h->d_lf;
     t.q34 = h->d_q34;
+    t.rf = h->d_rf;
+    t.u7 = h->d_u7;
     t.ds = h->d_ds;
     t.is = h->d_is;
     t.n_pad = h->n_pad;
@@ -620,6 +624,7 @@ extern "C" void bb_destroy(bb_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaFree(h->d_u); cudaFree(h->d_lf); cudaFree(h->d_q34); cudaFree(h->d_is); cudaFree(h->d_ds);
+    cudaFree(h->d_rf); cudaFree(h->d_u7);
     cudaFree(h->d_tx); cudaFree(h->d_ty); cudaFree(h->d_c);
     cudaFree(h->d_coef); cudaFree(h->d_snr); cudaFree(h->d_params); cudaFree(h->d_out);
     cudaFree(h->d_mask); cudaFree(h->d_twiddle);
@@ -683,12 +688,16 @@ extern "C" int bb_set_network(bb_handle* h, int n_det, int n_freq, double durati
     const int n_pad = ((n_freq + BB_K1_CHUNK - 1) / BB_K1_CHUNK) * BB_K1_CHUNK;
     h->n_pad = n_pad;
     std::vector<double> u(n_pad, 0.0), lf(n_pad, 0.0), q34(n_pad, 0.0), is((size_t)n_det * n_pad, 0.0);
+    std::vector<double> rf(n_pad, 0.0), u7(n_pad, 0.0);
     std::vector<double2> ds((size_t)n_det * n_pad, make_double2(0.0, 0.0));
     for (int k = 0; k < n_freq; ++k) {
         const double f = (double)k * net.df;
         u[k] = k ? pow(f, -1.0 / 6.0) : 0.0;
         lf[k] = k ? log(f) : 0.0;
         q34[k] = pow(f, 0.75);
+        rf[k] = k ? 1.0 / f : 0.0;
+        // exactly the product the per-bin code used to form: u * (u^2)^3
+        { const double t = u[k] * u[k]; u7[k] = u[k] * (t * t * t); }
     }
     int k_lo = n_freq, k_hi = -1;
     const double norm = 4.0 / duration;
@@ -707,11 +716,16 @@ extern "C" int bb_set_network(bb_handle* h, int n_det, int n_freq, double durati
     net.k_lo = k_lo;
     net.k_hi = k_hi;
     cudaFree(h->d_u); cudaFree(h->d_lf); cudaFree(h->d_q34); cudaFree(h->d_is); cudaFree(h->d_ds);
-    h->d_u = h->d_lf = h->d_q34 = h->d_is = nullptr;
+    cudaFree(h->d_rf); cudaFree(h->d_u7);
+    h->d_u = h->d_lf = h->d_q34 = h->d_is = h->d_rf = h->d_u7 = nullptr;
     h->d_ds = nullptr;
     BB_CUDA(cudaMalloc(&h->d_u, n_pad * sizeof(double)));
     BB_CUDA(cudaMalloc(&h->d_lf, n_pad * sizeof(double)));
     BB_CUDA(cudaMalloc(&h->d_q34, n_pad * sizeof(double)));
+    BB_CUDA(cudaMalloc(&h->d_rf, n_pad * sizeof(double)));
+    BB_CUDA(cudaMalloc(&h->d_u7, n_pad * sizeof(double)));
+    BB_CUDA(cudaMemcpy(h->d_rf, rf.data(), n_pad * sizeof(double), cudaMemcpyHostToDevice));
+    BB_CUDA(cudaMemcpy(h->d_u7, u7.data(), n_pad * sizeof(double), cudaMemcpyHostToDevice));
     BB_CUDA(cudaMalloc(&h->d_is, (size_t)n_det * n_pad * sizeof(double)));
     BB_CUDA(cudaMalloc(&h->d_ds, (size_t)n_det * n_pad * sizeof(double2)));
     BB_CUDA(cudaMemcpy(h->d_u, u.data(), n_pad * sizeof(double), cudaMemcpyHostToDevice));

@@ -261,7 +261,6 @@ __device__ __forceinline__ int bb_tm_rows_pd(TMState<NDET>& st, const BBTiles& g
     K1Ph<PR> phs;
     amp.load(rec);
     phs.load(rec);
-    const double a0 = rec[BC_A0];
     amp.begin((double)(r * BB_ROW + lane) * df, (double)(BB_TM_WARPS * BB_ROW) * df);
     for (; r < rstop; r += BB_TM_WARPS) {
         const int k = r * BB_ROW + lane;
@@ -269,8 +268,9 @@ __device__ __forceinline__ int bb_tm_rows_pd(TMState<NDET>& st, const BBTiles& g
         const double f = (double)k * df;
         const double u = g.u[k], t = u * u, x = f * t * t;
         const double lfk = g.lf[k];
-        const double A = amp.eval(f, x) * a0 * (u * (t * t * t));
-        const double ph = phs.eval(f, t, x, lfk, g.q34[k]);
+        const double t3 = t * t * t;                    // 1 / f
+        const double A = amp.eval(f, x) * (u * t3);     // a0 is folded into the region's coefficients (bb_k1.cuh)
+        const double ph = phs.eval(f, t, x, t3, lfk, g.q34[k]);
         bb_tm_bin<NDET, CAL>(st, g, rec, X, k, act, nfft, A, ph, lfk);
         amp.next();
     }

@@ -115,15 +115,15 @@ __device__ __forceinline__ void bb_sf_rows_pd(SFState<NDET>& st, const SFTile<ND
     K1Ph<PR> phs;
     amp.load(rec);
     phs.load(rec);
-    const double a0 = rec[BC_A0];
     amp.begin((double)(r0 * BB_ROW + lane) * df, (double)BB_ROW * df);
     for (int r = r0; r < r1; ++r) {
         const int k = r * BB_ROW + lane, i = k - c0;
         const bool act = (k >= kmin) && (k < kmax);
         const double f = (double)k * df;
         const double u = tile.u[i], t = u * u, x = f * t * t;
-        const double A = amp.eval(f, x) * a0 * (u * (t * t * t));
-        const double ph = phs.eval(f, t, x, tile.lf[i], tile.q34[i]);
+        const double t3 = t * t * t;                    // 1 / f
+        const double A = amp.eval(f, x) * (u * t3);     // a0 is folded into the region's coefficients (bb_k1.cuh)
+        const double ph = phs.eval(f, t, x, t3, tile.lf[i], tile.q34[i]);
         bb_sf_bin<NDET, CAL>(st, tile, i, k, act, A, ph);
         amp.next();
     }

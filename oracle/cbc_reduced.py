@@ -315,7 +315,7 @@ class OracleROQ(ocl.OracleLikelihood):
 
     def __init__(self, interferometers, linear_matrix, quadratic_matrix, frequency_nodes_linear,
                  frequency_nodes_quadratic, time_prior, source_model=binary_black_hole_roq, waveform_arguments=None,
-                 time_space=None, delta_tc=None, optimal_snrs=None, **kw):
+                 time_space=None, delta_tc=None, optimal_snrs=None, weights=None, **kw):
         self._roq_delta_tc = delta_tc
         self._roq_time_space = time_space
         self._optimal_snrs = optimal_snrs
@@ -341,7 +341,12 @@ class OracleROQ(ocl.OracleLikelihood):
         self.quadratic_indices = inverse[len(self.frequency_nodes_linear):]
         self.waveform_arguments.update(frequency_nodes=self.frequency_nodes, linear_indices=self.linear_indices,
                                        quadratic_indices=self.quadratic_indices)
-        self._set_weights(np.asarray(linear_matrix).T, np.asarray(quadratic_matrix).T)
+        if weights is not None:
+            # precomputed weights (the reference accepts them too, roq.py:112-122 `weights=`): dict with time_samples,
+            # {IFO}_linear [n_time, n_linear], {IFO}_quadratic [n_quadratic]
+            self.weights = dict(weights)
+        else:
+            self._set_weights(np.asarray(linear_matrix).T, np.asarray(quadratic_matrix).T)
 
     def time_resolution(self):
         if self._roq_time_space is not None:
