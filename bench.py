@@ -296,6 +296,19 @@ def gpu_run(args):
                     hbm_peak_gbs=peaks.get("hbm_gbs"),
                     algorithmic_hbm_bytes_per_launch=n * (16 + 1) * 8)
 
+    # ---- what a stock bilby sampler sees: one parameter dict per call (bilby/core/sampler/base_sampler.py:538-563)
+    scalar_us = None
+    if rank == 0:
+        from bilby_b200.workloads import draw_bbh_prior
+        d1 = draw_bbh_prior(256, np.random.default_rng(DRAW_SEED))
+        dicts = [{k: float(v[i]) for k, v in d1.items()} for i in range(256)]
+        for p in dicts[:16]:
+            like.log_likelihood_ratio(p)
+        t0 = time.perf_counter()
+        for p in dicts:
+            like.log_likelihood_ratio(p)
+        scalar_us = (time.perf_counter() - t0) / len(dicts) * 1e6
+
     # ---- the other BASELINE.json configurations (and, for N > 1, the frequency-sharded long signal) in the same run
     del like, net, rows_dev, out_dev
     torch.cuda.empty_cache()
@@ -333,7 +346,8 @@ def gpu_run(args):
                 clocks=clock_info,
                 e2e=dict(value=e2e_value, unit="evals/s", h2d_bytes_per_step=n * 16 * 8, d2h_bytes_per_step=n * 8,
                          ms_per_step=e2e_ms / args.steps, api="bb_log_likelihood_ratio_host (C ABI, pinned host buffers)"),
-                gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, checksum_lnl=lnl_sum, extra=extra)
+                gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu, checksum_lnl=lnl_sum,
+                scalar_call_us=scalar_us, extra=extra)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
