@@ -7,8 +7,12 @@ loaded from an .npz file written by ``save_weights``.  Evaluation on the device:
                                 times around the detector arrival time + cubic interpolation (roq.py:467-602)
   K7 hlinear + DMMA contraction (csrc/bb_gemm.cuh) + epilogue: time marginalisation, the dense all-times contraction
      W conj(h) (roq.py:604-651)
-Single linear / quadratic basis given as ndarray, .npy file or precomputed weights; multi-basis selection and
-multibanded bases ship only as .hdf5 (h5py is not a dependency here) and raise NotImplementedError.
+Bases: ndarray, .npy file, precomputed weights (dict / .npz), or the reference's hdf5 layout given as nested dicts
+(``{"basis_linear": {"0": {"basis": [n_basis, n_freq], "frequency_nodes": ...}, "1": ...}, "prior_range_linear":
+{"chirp_mass": [n_bases, 2], ...}}``; an .hdf5 file is read into that layout when h5py is importable).  With several
+bases the one whose prior range contains a sample is chosen per sample (roq.py:368-439 _select_prior_ranges /
+_update_basis): a batch is split into groups by (linear, quadratic) basis number, every group runs on its own device
+set-up.  Multibanded bases (roq.py:920-1053) are not supported.
 """
 import os
 
@@ -66,20 +70,20 @@ class ROQGravitationalWaveTransient(GravitationalWaveTransient):
             self._set_weights(linear_matrix, quadratic_matrix)
         self.number_of_bases_linear = len(self.weights[f"{self.interferometers[0].name}_linear"])
         self.number_of_bases_quadratic = len(self.weights[f"{self.interferometers[0].name}_quadratic"])
-        if self.number_of_bases_linear != 1 or self.number_of_bases_quadratic != 1:
-            raise NotImplementedError("multiple ROQ bases (prior-range selection, roq.py:402-439) are not supported")
+        self._cache = dict(parameters=None, basis_number_linear=None, basis_number_quadratic=None)
         self.parameter_conversion = parameter_conversion
-        for basis_type in ("linear", "quadratic"):
-            self._check_frequency_nodes_exist_for_single_basis(basis_type)
-        nodes_l = np.asarray(self.weights["frequency_nodes_linear"][0], dtype=float)
-        nodes_q = np.asarray(self.weights["frequency_nodes_quadratic"][0], dtype=float)
-        unique, inverse = np.unique(np.hstack((nodes_l, nodes_q)), return_inverse=True)
-        wa = self.waveform_generator.waveform_arguments
-        wa["frequency_nodes"] = unique                      # roq.py:206-213
-        wa["linear_indices"] = inverse[:len(nodes_l)]
-        wa["quadratic_indices"] = inverse[len(nodes_l):]
-        self._roq_host = self._pack_host_arrays(nodes_l, nodes_q)
-        self._upload_roq()
+        for basis_type in ("linear", "quadratic"):          # roq.py:198-204
+            if getattr(self, f"number_of_bases_{basis_type}") > 1:
+                self._verify_numbers_of_prior_ranges_and_frequency_nodes(basis_type)
+            else:
+                self._check_frequency_nodes_exist_for_single_basis(basis_type)
+            self._verify_prior_ranges(basis_type)
+        self._views = {}
+        self._roq_pair = (0, 0)
+        self._set_waveform_arguments_for_pair(0, 0)
+        self._roq_host = self._pack_host_arrays(0, 0)
+        if self.number_of_bases_linear == 1 and self.number_of_bases_quadratic == 1:
+            self._upload_roq()
 
     # ---- set-up --------------------------------------------------------------------------------
     @property
@@ -110,17 +114,158 @@ class ROQGravitationalWaveTransient(GravitationalWaveTransient):
 
     @staticmethod
     def _parse_basis(basis, basis_type):
-        """roq.py:333-366 -> ndarray [n_basis, n_freq]."""
+        """roq.py:333-366 -> the reference's hdf5 layout as nested dicts: ``basis_{type}/<i>/basis`` [n_basis, n_freq]
+        (+ ``frequency_nodes``), optional ``prior_range_{type}/<parameter>`` [n_bases, 2]."""
         if isinstance(basis, str):
             fmt = basis.split(".")[-1]
             if fmt == "npy":
-                return np.load(basis)
+                return {f"basis_{basis_type}": {"0": {"basis": np.load(basis)}}}
             if fmt == "hdf5":
-                raise NotImplementedError("hdf5 ROQ bases need h5py, which is not a dependency of bilby_b200")
+                try:
+                    import h5py
+                except ImportError:
+                    raise NotImplementedError("hdf5 ROQ bases need h5py, which is not installed; pass the same layout "
+                                              "as nested dicts of arrays instead") from None
+                with h5py.File(basis, "r") as f:
+                    def rd(g):
+                        return {k: (rd(v) if hasattr(v, "keys") else v[()]) for k, v in g.items()}
+                    out = rd(f)
+                if out.get(f"multiband_{basis_type}", False):
+                    raise NotImplementedError("multibanded ROQ bases (roq.py:920-1053) are not supported")
+                return out
             raise IOError(f"Format {fmt} not recognized.")
         if isinstance(basis, np.ndarray):
-            return basis.T
-        raise TypeError("basis needs to be str or np.ndarray")
+            return {f"basis_{basis_type}": {"0": {"basis": basis.T}}}
+        if isinstance(basis, dict) and f"basis_{basis_type}" in basis:
+            if basis.get(f"multiband_{basis_type}", False):
+                raise NotImplementedError("multibanded ROQ bases (roq.py:920-1053) are not supported")
+            return basis
+        raise TypeError("basis needs to be str, np.ndarray or a dict in the hdf5 layout")
+
+    # ---- several bases (roq.py:218-439)
+    def _verify_numbers_of_prior_ranges_and_frequency_nodes(self, basis_type):
+        """roq.py:218-250."""
+        number_of_bases = getattr(self, f"number_of_bases_{basis_type}")
+        key = f"prior_range_{basis_type}"
+        if key not in self.weights:
+            raise AttributeError(f'For the use of multiple {basis_type} ROQ bases, weights should contain "{key}".')
+        for param_name, ranges in self.weights[key].items():
+            if len(ranges) != number_of_bases:
+                raise ValueError(f'The number of prior ranges for "{param_name}" does not match the number of '
+                                 f"{basis_type} bases")
+        key = f"frequency_nodes_{basis_type}"
+        if key not in self.weights:
+            raise AttributeError(f'For the use of multiple {basis_type} ROQ bases, weights should contain "{key}".')
+        if len(self.weights[key]) != number_of_bases:
+            raise ValueError(f"The number of arrays of frequency nodes does not match the number of {basis_type} bases")
+
+    def _verify_prior_ranges(self, basis_type):
+        """roq.py:252-277: the union of the bases' ranges must cover the prior."""
+        key = f"prior_range_{basis_type}"
+        if key not in self.weights:
+            return
+        for param_name, ranges in self.weights[key].items():
+            ranges = np.asarray(ranges)
+            if self.priors[param_name].minimum < np.min(ranges[:, 0]):
+                raise BilbyROQParamsRangeError(f"Prior minimum of {param_name} {self.priors[param_name].minimum} less "
+                                               f"than ROQ basis bound {np.min(ranges[:, 0])}")
+            if self.priors[param_name].maximum > np.max(ranges[:, 1]):
+                raise BilbyROQParamsRangeError(f"Prior maximum of {param_name} {self.priors[param_name].maximum} "
+                                               f"greater than ROQ basis bound {np.max(ranges[:, 1])}")
+
+    def _select_prior_ranges(self, prior_ranges):
+        """roq.py:368-400: the bases whose ranges intersect the priors."""
+        names = list(prior_ranges.keys())
+        n = len(prior_ranges[names[0]])
+        keep = np.ones(n, dtype=bool)
+        for name in names:
+            if self.priors is None or name not in self.priors:
+                continue
+            r = np.asarray(prior_ranges[name])
+            keep &= (r[:, 1] >= self.priors[name].minimum) & (r[:, 0] <= self.priors[name].maximum)
+        idx = np.arange(n)[keep]
+        return idx, {name: np.asarray(prior_ranges[name])[idx] for name in names}
+
+    def _basis_numbers(self, parameters, n):
+        """Vectorised roq.py:402-429 (_update_basis): per sample the FIRST basis whose range contains it, for the
+        linear and the quadratic family.  parameters: dict of scalars / length-n arrays, converted first
+        (``parameter_conversion``) like the reference."""
+        pars = dict(parameters)
+        if self.parameter_conversion is not None:
+            conv = self.parameter_conversion(pars)
+            pars = conv[0] if isinstance(conv, tuple) else conv
+        out = []
+        for basis_type in ("linear", "quadratic"):
+            nb = getattr(self, f"number_of_bases_{basis_type}")
+            if nb == 1:
+                out.append(np.zeros(n, dtype=int))
+                continue
+            inside = np.ones((n, nb), dtype=bool)
+            for name, ranges in self.weights[f"prior_range_{basis_type}"].items():
+                if name not in pars:
+                    continue
+                v = np.broadcast_to(np.asarray(pars[name], dtype=float), (n,))[:, None]
+                r = np.asarray(ranges)
+                inside &= (r[None, :, 0] <= v) & (r[None, :, 1] >= v)
+            if not np.all(inside.any(axis=1)):
+                raise IndexError(f"a sample lies outside every {basis_type} ROQ basis' prior range")
+            out.append(np.argmax(inside, axis=1))
+        return out[0], out[1]
+
+    def _update_basis(self, parameters):
+        """roq.py:402-439 for one parameter dict."""
+        bl, bq = self._basis_numbers(parameters, 1)
+        self._cache.update(parameters=dict(parameters), basis_number_linear=int(bl[0]), basis_number_quadratic=int(bq[0]))
+        self._set_waveform_arguments_for_pair(int(bl[0]), int(bq[0]))
+
+    def _set_waveform_arguments_for_pair(self, bl, bq):
+        nodes_l = np.asarray(self.weights["frequency_nodes_linear"][bl], dtype=float)
+        nodes_q = np.asarray(self.weights["frequency_nodes_quadratic"][bq], dtype=float)
+        unique, inverse = np.unique(np.hstack((nodes_l, nodes_q)), return_inverse=True)
+        wa = self.waveform_generator.waveform_arguments
+        wa["frequency_nodes"] = unique                      # roq.py:206-213, 433-438
+        wa["linear_indices"] = inverse[:len(nodes_l)]
+        wa["quadratic_indices"] = inverse[len(nodes_l):]
+
+    def _view(self, bl, bq):
+        """This likelihood restricted to ONE (linear, quadratic) basis pair, with its own device set-up."""
+        if (bl, bq) not in self._views:
+            import copy
+            v = copy.copy(self)
+            v.waveform_generator = copy.copy(self.waveform_generator)
+            v.waveform_generator.waveform_arguments = dict(self.waveform_generator.waveform_arguments)
+            v._net, v._net_versions = None, None
+            v.number_of_bases_linear = v.number_of_bases_quadratic = 1
+            v._roq_pair = (bl, bq)
+            v._views = {}
+            v._set_waveform_arguments_for_pair(bl, bq)
+            v._roq_host = self._pack_host_arrays(bl, bq)
+            v._upload_roq()
+            self._views[(bl, bq)] = v
+        return self._views[(bl, bq)]
+
+    def log_likelihood_ratio_batch(self, parameters):
+        if self.number_of_bases_linear == 1 and self.number_of_bases_quadratic == 1:
+            return super().log_likelihood_ratio_batch(parameters)
+        if not isinstance(parameters, dict):
+            raise ValueError("with several ROQ bases the parameters must be a dict (the basis depends on their values)")
+        n = max(np.size(v) for v in parameters.values())
+        host = {k: (np.asarray(v.cpu()) if hasattr(v, "cpu") else v) for k, v in parameters.items()}
+        bl, bq = self._basis_numbers(host, n)
+        out = np.empty(n)
+        for pair in sorted(set(zip(bl.tolist(), bq.tolist()))):
+            idx = np.where((bl == pair[0]) & (bq == pair[1]))[0]
+            sub = {k: (np.asarray(v)[idx] if np.ndim(v) else v) for k, v in host.items()}
+            out[idx] = self._view(*pair).log_likelihood_ratio_batch(sub)
+        return out
+
+    def log_likelihood_ratio(self, parameters):
+        """roq.py:463-465."""
+        if self.number_of_bases_linear == 1 and self.number_of_bases_quadratic == 1:
+            return super().log_likelihood_ratio(parameters)
+        self._update_basis(parameters)
+        return self._view(self._cache["basis_number_linear"], self._cache["basis_number_quadratic"]).log_likelihood_ratio(
+            parameters)
 
     def _check_frequency_nodes_exist_for_single_basis(self, basis_type):
         """roq.py:278-295."""
@@ -177,9 +322,10 @@ class ROQGravitationalWaveTransient(GravitationalWaveTransient):
                            "(roq.py:747-765)")
         return prior
 
-    def _set_weights(self, linear_basis, quadratic_basis):
-        """roq.py:736-767 (time grid), 802-837 (basis / data frequency overlap), 849-916 (linear), 976-1004
-        (quadratic).  Bases: [n_basis, n_basis_freq]."""
+    def _set_weights(self, linear_matrix, quadratic_matrix):
+        """roq.py:736-767 (time grid), 768-792 (basis selection by prior range), 802-837 (basis / data frequency
+        overlap), 849-916 (linear), 976-1004 (quadratic).  linear_matrix / quadratic_matrix: the hdf5 layout as nested
+        dicts (_parse_basis)."""
         time_space = self._get_time_resolution()
         duration = self.interferometers.duration
         start_time = self.interferometers.start_time
@@ -190,11 +336,46 @@ class ROQGravitationalWaveTransient(GravitationalWaveTransient):
         end_idx = min(number_of_time_samples - 1, int(np.ceil((prior.maximum + crossing - start_time) / time_space)))
         self.weights["time_samples"] = np.arange(start_idx, end_idx + 1) * float(time_space)
         logger.info("Using {} ROQ time samples".format(len(self.weights["time_samples"])))
+        # bases inside the prior range, their ranges and nodes (roq.py:768-792)
+        selected = {}
+        for basis_type, matrix in (("linear", linear_matrix), ("quadratic", quadratic_matrix)):
+            key = f"prior_range_{basis_type}"
+            if key in matrix:
+                ranges = {name: np.asarray(matrix[key][name], dtype=float) for name in matrix[key]}
+                idxs, sel = self._select_prior_ranges(ranges)
+                if len(idxs) == 0:
+                    raise BilbyROQParamsRangeError(f"There are no {basis_type} ROQ bases within the prior range.")
+                self.weights[key] = sel
+                selected[basis_type] = [int(i) for i in idxs]
+            else:
+                selected[basis_type] = [0]
+            first = matrix[f"basis_{basis_type}"][str(selected[basis_type][0])]
+            if "frequency_nodes" in first:
+                self.weights[f"frequency_nodes_{basis_type}"] = [
+                    np.asarray(matrix[f"basis_{basis_type}"][str(i)]["frequency_nodes"]) * self.roq_scale_factor
+                    for i in selected[basis_type]]
+        for ifo in self.interferometers:
+            self.weights[ifo.name + "_linear"], self.weights[ifo.name + "_quadratic"] = [], []
+        for i in selected["linear"]:
+            w = self._weights_of_one_basis(np.asarray(linear_matrix["basis_linear"][str(i)]["basis"]), None)
+            for ifo in self.interferometers:
+                self.weights[ifo.name + "_linear"].append(w[ifo.name + "_linear"])
+        for i in selected["quadratic"]:
+            w = self._weights_of_one_basis(None, np.asarray(quadratic_matrix["basis_quadratic"][str(i)]["basis"]))
+            for ifo in self.interferometers:
+                self.weights[ifo.name + "_quadratic"].append(w[ifo.name + "_quadratic"])
+
+    def _weights_of_one_basis(self, linear_basis, quadratic_basis):
+        """Linear (roq.py:849-918) or quadratic (roq.py:976-1004) weights of every detector for ONE basis
+        [n_basis, n_basis_freq]."""
+        duration = self.interferometers.duration
         ts = self.weights["time_samples"]
         space = ts[1] - ts[0]
         n_time = int(duration / space)
         lo, hi = int(ts[0] / space), int(ts[-1] / space)
-        # per detector: overlap of the basis frequencies with the data (roq.py:802-837), then the two weight sets
+        out = {}
+        n_basis_freq = (linear_basis if linear_basis is not None else quadratic_basis).shape[1]
+        # per detector: overlap of the basis frequencies with the data (roq.py:802-837)
         setups = []
         for ifo in self.interferometers:
             mask = ifo.frequency_mask
@@ -205,15 +386,18 @@ class ROQGravitationalWaveTransient(GravitationalWaveTransient):
                 roq_f = roq_f[roq_f >= self.roq_params["flow"] * self.roq_scale_factor]
                 _, ifo_idxs, roq_idxs = np.intersect1d(ifo.frequency_array[mask], roq_f, return_indices=True)
             else:
-                roq_idxs = np.arange(linear_basis.shape[1], dtype=int)
+                roq_idxs = np.arange(n_basis_freq, dtype=int)
                 ifo_idxs = np.arange(int(mask.sum()))
                 if len(ifo_idxs) != len(roq_idxs):
                     raise ValueError("Mismatch between ROQ basis and frequency array for {}".format(ifo.name))
             nonzero = ifo_idxs + int(ifo.minimum_frequency * duration)
             d_over_s = ifo.frequency_domain_strain[mask][ifo_idxs] / ifo.power_spectral_density_array[mask][ifo_idxs]
             setups.append((ifo, roq_idxs, ifo_idxs, nonzero, d_over_s))
-            inv_psd = 1 / ifo.power_spectral_density_array[mask][ifo_idxs]
-            self.weights[ifo.name + "_quadratic"] = [4. / duration * quadratic_basis.real[:, roq_idxs] @ inv_psd]
+            if quadratic_basis is not None:
+                inv_psd = 1 / ifo.power_spectral_density_array[mask][ifo_idxs]
+                out[ifo.name + "_quadratic"] = 4. / duration * quadratic_basis.real[:, roq_idxs] @ inv_psd
+        if linear_basis is None:
+            return out
         # linear weights (roq.py:849-918): on the device, all detectors in one call when they share the frequency set
         same = all(np.array_equal(su[1], setups[0][1]) and np.array_equal(su[3], setups[0][3]) for su in setups)
         groups = [setups] if same else [[su] for su in setups]
@@ -235,7 +419,8 @@ class ROQGravitationalWaveTransient(GravitationalWaveTransient):
                         spec[:, nonzero] = d_over_s[None, :] * basis[sl].conj()
                         lw[:, sl] = _fft.ifft(spec, axis=1, workers=os.cpu_count() or 1)[:, lo:hi + 1].T
                     lw *= 4. * n_time / duration
-                self.weights[ifo.name + "_linear"] = [lw]
+                out[ifo.name + "_linear"] = lw
+        return out
 
     def _linear_weights_device(self, d_over_s, basis, bin_index, n_time, lo, hi, duration):
         """roq.py:849-918 on the device (bb_build_roq_linear_weights: the wanted time samples as one DMMA contraction (csrc/bb_gemm.cuh) against an
@@ -261,42 +446,82 @@ class ROQGravitationalWaveTransient(GravitationalWaveTransient):
         return out
 
     def save_weights(self, filename, format="npz"):
-        """roq.py:1055-1100 (npz flavour)."""
-        if format != "npz":
-            raise IOError(f"Format {format} not supported here (hdf5 needs h5py).")
+        """roq.py:1055-1100.  npz: the reference's single-basis keys; with several bases (which the reference only
+        writes as hdf5) the same keys carry a basis index: ``{IFO}_linear/<i>``, ``frequency_nodes_linear/<i>``,
+        ``prior_range_linear/<parameter>``.  hdf5 (the reference's layout) when h5py is importable."""
+        if format not in ("npz", "hdf5"):
+            raise IOError(f"Format {format} not recognized.")
         if format not in filename:
             filename += "." + format
-        out = dict(time_samples=self.weights["time_samples"])
+        multi = self.number_of_bases_linear > 1 or self.number_of_bases_quadratic > 1
+        flat = dict(time_samples=self.weights["time_samples"])
         for basis_type in ("linear", "quadratic"):
-            for ifo in self.interferometers:
-                key = f"{ifo.name}_{basis_type}"
-                out[key] = self.weights[key][0]
-            key = f"frequency_nodes_{basis_type}"
-            out[key] = self.weights[key][0]
-        np.savez(filename, **out)
+            keys = [f"{ifo.name}_{basis_type}" for ifo in self.interferometers] + [f"frequency_nodes_{basis_type}"]
+            for key in keys:
+                if key not in self.weights:
+                    continue
+                if multi or format == "hdf5":
+                    for i, w in enumerate(self.weights[key]):
+                        flat[f"{key}/{i}"] = np.asarray(w)
+                else:
+                    flat[key] = np.asarray(self.weights[key][0])
+            for name, r in self.weights.get(f"prior_range_{basis_type}", {}).items():
+                flat[f"prior_range_{basis_type}/{name}"] = np.asarray(r)
+        if format == "npz":
+            np.savez(filename, **flat)
+            return
+        try:
+            import h5py
+        except ImportError:
+            raise IOError("hdf5 weight files need h5py, which is not installed; use format='npz'") from None
+        with h5py.File(filename, "w") as f:
+            for key, val in flat.items():
+                f.create_dataset(key, data=val)
 
     def load_weights(self, filename, format=None):
-        """roq.py:1102-1163 (npz flavour)."""
+        """roq.py:1102-1163 (npz: single basis as the reference writes it, or the indexed keys of save_weights; hdf5
+        through h5py when importable).  Bases outside the prior range are dropped (_select_prior_ranges)."""
         if format is None:
             format = filename.split(".")[-1]
-        if format != "npz":
-            raise IOError(f"Format {format} not supported here (hdf5 needs h5py).")
-        f = np.load(filename)
-        weights = dict(time_samples=f["time_samples"])
+        if format not in ("npz", "hdf5"):
+            raise IOError(f"Format {format} not recognized.")
+        if format == "npz":
+            flat = dict(np.load(filename))
+        else:
+            try:
+                import h5py
+            except ImportError:
+                raise IOError("hdf5 weight files need h5py, which is not installed") from None
+            flat = {}
+            with h5py.File(filename, "r") as f:
+                f.visititems(lambda name, obj: flat.__setitem__(name, obj[()]) if hasattr(obj, "shape") else None)
+        weights = dict(time_samples=flat["time_samples"])
         for basis_type in ("linear", "quadratic"):
-            for ifo in self.interferometers:
-                key = f"{ifo.name}_{basis_type}"
-                weights[key] = [f[key]]
-            key = f"frequency_nodes_{basis_type}"
-            if key in f:
-                weights[key] = [f[key]]
+            pr = {k.split("/", 1)[1]: v for k, v in flat.items() if k.startswith(f"prior_range_{basis_type}/")}
+            idxs = None
+            if pr:
+                idxs, sel = self._select_prior_ranges(pr)
+                weights[f"prior_range_{basis_type}"] = sel
+            keys = [f"{ifo.name}_{basis_type}" for ifo in self.interferometers] + [f"frequency_nodes_{basis_type}"]
+            for key in keys:
+                if key in flat:
+                    weights[key] = [flat[key]]
+                    continue
+                n = len([k for k in flat if k.startswith(key + "/")])
+                if n == 0:
+                    continue
+                take = range(n) if idxs is None else idxs
+                weights[key] = [flat[f"{key}/{int(i)}"] for i in take]
         return weights
 
-    def _pack_host_arrays(self, nodes_l, nodes_q):
+    def _pack_host_arrays(self, bl, bq):
+        """Host arrays of bb_set_roq for the (linear basis bl, quadratic basis bq) pair."""
+        nodes_l = np.asarray(self.weights["frequency_nodes_linear"][bl], dtype=float)
+        nodes_q = np.asarray(self.weights["frequency_nodes_quadratic"][bq], dtype=float)
         ts = np.asarray(self.weights["time_samples"], dtype=float)
         names = [ifo.name for ifo in self.interferometers]
-        wl = np.stack([np.asarray(self.weights[n + "_linear"][0], dtype=complex) for n in names])      # [d, t, i]
-        wq = np.stack([np.asarray(self.weights[n + "_quadratic"][0], dtype=float) for n in names])
+        wl = np.stack([np.asarray(self.weights[n + "_linear"][bl], dtype=complex) for n in names])      # [d, t, i]
+        wq = np.stack([np.asarray(self.weights[n + "_quadratic"][bq], dtype=float) for n in names])
         if wl.shape[1] != len(ts) or wl.shape[2] != len(nodes_l) or wq.shape[1] != len(nodes_q):
             raise ValueError("ROQ weights do not match the time samples / frequency nodes")
         # time_samples = arange(start_idx, end_idx + 1) * time_space (roq.py:766): recover both exactly
@@ -334,8 +559,8 @@ class ROQGravitationalWaveTransient(GravitationalWaveTransient):
 
     @property
     def basis_number_linear(self):
-        return 0
+        return self._cache["basis_number_linear"] if self.number_of_bases_linear > 1 else 0
 
     @property
     def basis_number_quadratic(self):
-        return 0
+        return self._cache["basis_number_quadratic"] if self.number_of_bases_quadratic > 1 else 0

@@ -230,3 +230,58 @@ def test_relative_binning_tracks_full_likelihood_at_scale():
     rows2[:, 4] *= 2.0
     rb2 = like.inner_products_batch(rows2)
     assert torch.equal(rb2[..., 2] * 4.0, rb[..., 2]) or ((rb2[..., 2] * 4.0 - rb[..., 2]).abs() / rb[..., 2]).max() < 1e-14
+
+
+def test_roq_multiple_bases_selected_per_sample_vs_oracle(tmp_path):
+    """roq.py:368-439: several linear bases with chirp-mass ranges - every sample must be evaluated with the FIRST basis
+    whose range contains it; compared with the single-basis oracle of that basis.  Also the weight-file round trip
+    with several bases (npz with indexed keys)."""
+    import bilby_b200 as bb
+    from bilby_b200.core.prior import Uniform
+    g, _ = rc.load("roq_bbh_4s_H1L1V1")
+    lin, quad = g["linear_matrix"].astype(complex), g["quadratic_matrix"].astype(complex)     # [n_freq, n_basis]
+    nodes_l, nodes_q = g["frequency_nodes_linear"], g["frequency_nodes_quadratic"]
+    half = lin.shape[1] // 2
+    # basis 0: the golden basis (chirp mass 20-30); basis 1: its first half of elements (chirp mass 29-40); overlap at
+    # 29-30 -> basis 0 wins there (the reference takes the first match)
+    linear = dict(basis_linear={"0": dict(basis=lin.T, frequency_nodes=nodes_l),
+                                "1": dict(basis=lin[:, :half].T, frequency_nodes=nodes_l[:half])},
+                  prior_range_linear=dict(chirp_mass=np.array([[20.0, 30.0], [29.0, 40.0]])))
+    quadratic = dict(basis_quadratic={"0": dict(basis=quad.T, frequency_nodes=nodes_q)})
+    like, draws = _roq_product(g, extra_priors=dict(chirp_mass=Uniform(22.0, 38.0, "chirp_mass")))
+    base_kw = dict(interferometers=like.interferometers, waveform_generator=like.waveform_generator)
+    pri = _priors(geocent_time=Uniform(T_INJ - 0.1, T_INJ + 0.1, "geocent_time"), chirp_mass=Uniform(22.0, 38.0, "chirp_mass"))
+    multi = bb.gw.likelihood.ROQGravitationalWaveTransient(priors=pri, linear_matrix=linear, quadratic_matrix=quadratic,
+                                                           **base_kw)
+    assert multi.number_of_bases_linear == 2 and multi.number_of_bases_quadratic == 1
+    d = {k: v[:-2].copy() for k, v in draws.items() if k != "time_jitter"}          # drop the out-of-window rows
+    n = len(d["chirp_mass"])
+    d["chirp_mass"] = np.linspace(22.5, 37.5, n)
+    got = multi.log_likelihood_ratio_batch(d)
+    o0, _ = rc.roq_oracle(g)
+    o1 = ocr.OracleROQ(o0.ifos, lin[:, :half], quad, nodes_l[:half], nodes_q,
+                       time_prior=ocl.OracleUniform(T_INJ - 0.1, T_INJ + 0.1),
+                       waveform_arguments=dict(waveform_approximant="IMRPhenomD", reference_frequency=20.0),
+                       optimal_snrs=list(g["optimal_snrs"]))
+    use1 = d["chirp_mass"] > 30.0
+    assert use1.any() and (~use1).any()
+    for i in range(n):
+        p = {k: float(v[i]) for k, v in d.items()}
+        ref = (o1 if use1[i] else o0).log_likelihood_ratio(p)
+        assert abs(got[i] - ref) < RTOL * max(1.0, abs(ref), 0.5 * g["optimal_snr_squared"][i].sum()), (i, got[i], ref)
+        if i in (0, n - 1):
+            assert multi.log_likelihood_ratio(p) == got[i]
+            assert multi.basis_number_linear == int(use1[i])
+    # weight files with several bases
+    path = str(tmp_path / "roq_weights_multi.npz")
+    multi.save_weights(path)
+    again = bb.gw.likelihood.ROQGravitationalWaveTransient(priors=_priors(
+        geocent_time=Uniform(T_INJ - 0.1, T_INJ + 0.1, "geocent_time"), chirp_mass=Uniform(22.0, 38.0, "chirp_mass")),
+        weights=path, **base_kw)
+    assert again.number_of_bases_linear == 2
+    assert np.array_equal(again.log_likelihood_ratio_batch(d), got)
+    # a prior inside one basis' range keeps only that basis
+    one = bb.gw.likelihood.ROQGravitationalWaveTransient(priors=_priors(
+        geocent_time=Uniform(T_INJ - 0.1, T_INJ + 0.1, "geocent_time"), chirp_mass=Uniform(31.0, 38.0, "chirp_mass")),
+        weights=path, **base_kw)
+    assert one.number_of_bases_linear == 1 and len(one.weights["frequency_nodes_linear"][0]) == half
