@@ -63,6 +63,8 @@ def load():
         "bb_profile_read": (i, [vp, ctypes.POINTER(d), ctypes.POINTER(lng)]),
         "bb_fp64_peak": (i, [vp, ctypes.POINTER(d)]),
         "bb_fp64_tensor_peak": (i, [vp, ctypes.POINTER(d)]),
+        "bb_build_roq_quadratic_weights": (i, [i, i, i, vp, i, vp, d, vp]),
+        "bb_build_relbin_summary_data": (i, [vp, i, vp, vp, vp, vp]),
         "bb_launch_count": (lng, [vp]),
         "bb_set_reconstruction_grid": (i, [vp, vp, vp, i]),
         "bb_set_calibration_marginalization": (i, [vp, i, vp]),
@@ -90,7 +92,8 @@ EXPORTED_SYMBOLS = (
     "bb_launch_count", "bb_set_reconstruction_grid", "bb_reconstruct_marginalized_device",
     "bb_set_calibration_marginalization", "bb_build_roq_linear_weights", "bb_set_multiband",
     "bb_exchange_create", "bb_exchange_connect", "bb_log_likelihood_ratio_sharded_device", "bb_exchange_status",
-    "bb_exchange_destroy", "bb_contract_device", "bb_fp64_tensor_peak")
+    "bb_exchange_destroy", "bb_contract_device", "bb_fp64_tensor_peak",
+    "bb_build_roq_quadratic_weights", "bb_build_relbin_summary_data")
 
 
 def check(rc):

@@ -963,6 +963,7 @@ static int bb_launch_inner(bb_handle* h, long n, double* out, cudaStream_t st) {
 #include "bb_calmarg.cuh"
 #include "bb_recon.cuh"
 #include "bb_roq_weights.cuh"
+#include "bb_builders.cuh"
 #include "bb_exchange.cuh"
 
 extern "C" int bb_set_calibration_marginalization(bb_handle* h, int n_curves, const double* curves) {

@@ -145,6 +145,7 @@ class RelativeBinningGravitationalWaveTransient(GravitationalWaveTransient):
     def compute_summary_data(self):
         """relative.py:319-363: per bin a0 = <h0|d>, a1 = <h0|d (f - fc)>, b0 = <h0|h0>, b1 = <h0|h0 (f - fc)>."""
         summary_data = dict()
+        starts, centres = [], []
         for ifo in self.interferometers:
             mask = ifo.frequency_mask
             mf = ifo.frequency_array[mask]
@@ -153,22 +154,26 @@ class RelativeBinningGravitationalWaveTransient(GravitationalWaveTransient):
                 raise ValueError("bin edges must lie on the interferometer's masked frequency grid")
             if idx[-1] < len(mf) - 1:
                 idx[-1] += 1                      # the last bin takes the last edge point too
-            strain = ifo.frequency_domain_strain[mask]
-            h0 = np.asarray(self.per_detector_fiducial_waveforms[ifo.name][mask])
-            psd = ifo.power_spectral_density_array[mask]
-            norm = 4 / ifo.duration
-            centre = (mf[idx[:-1]] + mf[idx[1:]]) / 2
-            hd = h0.conj() * strain / psd
-            hh = h0.conj() * h0 / psd
-            a0, a1, b0, b1 = np.zeros((4, self.number_of_bins), dtype=complex)
-            for i in range(self.number_of_bins):
-                sl = slice(idx[i], idx[i + 1])
-                df = mf[sl] - centre[i]
-                a0[i] = norm * np.sum(hd[sl])
-                b0[i] = norm * np.sum(hh[sl])
-                a1[i] = norm * np.sum(hd[sl] * df)
-                b1[i] = norm * np.sum(hh[sl] * df)
-            summary_data[ifo.name] = (a0, a1, b0, b1)
+            first = int(np.argmax(mask))              # masked index -> grid index (the mask is one contiguous band)
+            starts.append((idx + first).astype(np.int32))
+            centres.append((mf[idx[:-1]] + mf[idx[1:]]) / 2)
+        if any(not np.array_equal(s_, starts[0]) for s_ in starts[1:]):
+            raise NotImplementedError("relative binning needs the same frequency band in every interferometer")
+        # the four sums per bin on the device (bb_build_relbin_summary_data) from the data tiles already uploaded
+        net = self.device_network
+        n_det, n_freq = len(self.interferometers), len(self.interferometers[0].frequency_array)
+        fid = np.zeros((n_det, n_freq, 2))
+        for d, ifo in enumerate(self.interferometers):
+            full = np.asarray(self.per_detector_fiducial_waveforms[ifo.name])
+            fid[d, :, 0], fid[d, :, 1] = full.real, full.imag
+        out = np.zeros((n_det, 4, self.number_of_bins, 2))
+        bs = np.ascontiguousarray(starts[0], dtype=np.int32)
+        ce = np.ascontiguousarray(centres[0], dtype=np.float64)
+        _lib.check(net.lib.bb_build_relbin_summary_data(net.ptr, self.number_of_bins, bs.ctypes.data, ce.ctypes.data,
+                                                        fid.ctypes.data, out.ctypes.data))
+        for d, ifo in enumerate(self.interferometers):
+            c = out[d, :, :, 0] + 1j * out[d, :, :, 1]
+            summary_data[ifo.name] = (c[0], c[1], c[2], c[3])
         self.summary_data = summary_data
 
     def _pack_host_arrays(self):

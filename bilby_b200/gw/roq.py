@@ -395,7 +395,8 @@ class ROQGravitationalWaveTransient(GravitationalWaveTransient):
             setups.append((ifo, roq_idxs, ifo_idxs, nonzero, d_over_s))
             if quadratic_basis is not None:
                 inv_psd = 1 / ifo.power_spectral_density_array[mask][ifo_idxs]
-                out[ifo.name + "_quadratic"] = 4. / duration * quadratic_basis.real[:, roq_idxs] @ inv_psd
+                out[ifo.name + "_quadratic"] = self._quadratic_weights_device(
+                    inv_psd, quadratic_basis.real[:, roq_idxs], duration)
         if linear_basis is None:
             return out
         # linear weights (roq.py:849-918): on the device, all detectors in one call when they share the frequency set
@@ -420,6 +421,25 @@ class ROQGravitationalWaveTransient(GravitationalWaveTransient):
                         lw[:, sl] = _fft.ifft(spec, axis=1, workers=os.cpu_count() or 1)[:, lo:hi + 1].T
                     lw *= 4. * n_time / duration
                 out[ifo.name + "_linear"] = lw
+        return out
+
+    def _quadratic_weights_device(self, inv_psd, basis_real, duration):
+        """roq.py:976-1004 on the device (bb_build_roq_quadratic_weights); numpy when the process has no CUDA device
+        (weight files built on a login node)."""
+        try:
+            import torch
+            have = torch.cuda.is_available()
+            dev = (torch.cuda.current_device() if self._device_index is None else int(self._device_index)) if have else 0
+        except ImportError:      # pragma: no cover
+            have = False
+        if not have:
+            return 4. / duration * basis_real @ inv_psd
+        lib = _lib.load()
+        p = np.ascontiguousarray(inv_psd, dtype=np.float64)
+        b = np.ascontiguousarray(basis_real, dtype=np.float64)
+        out = np.empty(b.shape[0])
+        _lib.check(lib.bb_build_roq_quadratic_weights(dev, 1, len(p), p.ctypes.data, b.shape[0], b.ctypes.data,
+                                                      float(duration), out.ctypes.data))
         return out
 
     def _linear_weights_device(self, d_over_s, basis, bin_index, n_time, lo, hi, duration):

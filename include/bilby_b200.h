@@ -311,6 +311,19 @@ int bb_contract_device(bb_handle* h, int is_complex, int m, int n, int k, int n_
 int bb_build_roq_linear_weights(int device, int n_det, int n_freq_sel, const double* d_over_s, int n_basis, const double* basis,
                                 const int* bin_index, long n_time, long lo, int n_win, double duration, double* out);
 
+/* Set-up artefact builder: the quadratic ROQ weights of n_det detectors sharing one basis,
+ * ROQGravitationalWaveTransient._set_weights_quadratic (bilby/gw/likelihood/roq.py:976-1004):
+ *   out[d][b] = (4 / T) sum_j basis_real[b][j] * inv_psd[d][j]       (host arrays in, host array out) */
+int bb_build_roq_quadratic_weights(int device, int n_det, int n_freq_sel, const double* inv_psd, int n_basis,
+                                   const double* basis_real, double duration, double* out);
+
+/* Set-up artefact builder: the summary data of RelativeBinningGravitationalWaveTransient.compute_summary_data
+ * (bilby/gw/likelihood/relative.py:319-363) from the handle's data tiles.  Bin b covers the grid bins
+ * [bin_start[b], bin_start[b + 1]) and has centre frequency centre[b]; fiducial = per-detector fiducial waveform on the
+ * full grid, [n_det][n_freq] complex (re, im), host.  out [n_det][4][n_bins] complex (re, im), host: a0, a1, b0, b1. */
+int bb_build_relbin_summary_data(bb_handle* h, int n_bins, const int* bin_start, const double* centre,
+                                 const double* fiducial, double* out);
+
 /* Measurement hooks (bench.py).  With profiling enabled the handle brackets every launch of the
  * dominant kernel (K1, the fused inner-product kernel) with CUDA events on the launching stream;
  * bb_profile_read synchronises and returns the summed duration and the number of launches since the
