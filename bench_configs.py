@@ -219,17 +219,33 @@ def build(config, n):
         return like, rows, None, (lambda r: (float(len(r)) * per, float(ne))), dict(
             workload=f"configs[4]: relative binning (epsilon=0.5, chi=1, {ne - 1} bins) for the 128s BNS, H1L1V1",
             kernel="bb_relbin_kernel<3,TaylorF2>", n_edges=ne)
-    if config == "mb":
+    if config in ("mb", "mb_time"):
         wfg = bb.gw.WaveformGenerator(duration=duration, sampling_frequency=fs, start_time=start,
                                       frequency_domain_source_model=source.binary_neutron_star_frequency_sequence,
                                       parameter_conversion=conv,
                                       waveform_arguments=dict(waveform_approximant="TaylorF2", reference_frequency=50.0))
         pri = PriorDict(dict(geocent_time=Uniform(T_INJ - 0.1, T_INJ + 0.1, "geocent_time")))
         t0 = time.time()
-        like = bb.gw.likelihood.MBGravitationalWaveTransient(ifos, wfg, reference_chirp_mass=1.15, priors=pri)
+        tm = config == "mb_time"
+        if tm:
+            pri["phase"] = Uniform(0, 2 * np.pi, "phase")
+        like = bb.gw.likelihood.MBGravitationalWaveTransient(ifos, wfg, reference_chirp_mass=1.15, priors=pri,
+                                                             time_marginalization=tm, phase_marginalization=tm)
         npts = len(like.banded_frequency_points)
         sys.stderr.write(f"multi-banding: {like.number_of_bands} bands, {npts} points, set up in {time.time() - t0:.1f} s\n")
-        rows = like.pack(bns_draws(n, rng, narrow=True))
+        draws = bns_draws(n, rng, narrow=True)
+        if tm:
+            draws["geocent_time"] = np.full(n, float(start))
+            draws["time_jitter"] = rng.uniform(-1 / fs, 1 / fs, n)
+            n_times = int(np.ceil(0.2 / like._delta_tc)) + 8
+            rows = like.pack(draws)
+            per = (170 + 78 * 3) * npts + 8.0 * npts * n_times
+            return like, rows, None, (lambda r: (float(len(r)) * per, float(npts))), dict(
+                workload=f"SURVEY 8f rank 4: multi-banded likelihood + time & phase marginalisation ({npts} banded points x "
+                         f"{n_times} times of the {int(like.Nbs[-1]) // 2}-point transform) for the 128s BNS, H1L1V1",
+                kernel="bb_mb_series_kernel + bb_gemm_nt_kernel<complex> (DMMA) + bb_mb_time_marg_kernel",
+                bound="fp64 tensor (DMMA)", n_points=npts, n_times=n_times)
+        rows = like.pack(draws)
         per = (170 + 78 * 3) * npts          # per (point, detector): sincospi 60, K h 6, <d|h> 8, <h|h> 4
         return like, rows, None, (lambda r: (float(len(r)) * per, float(npts))), dict(
             workload=f"SURVEY 8f rank 4: multi-banded likelihood ({like.number_of_bands} bands, {npts} banded points vs "
@@ -328,7 +344,7 @@ def build(config, n):
 
 
 DEFAULT_BATCH = dict(calmarg=75776, cfg0=1_000_000, cfg1=1_000_000, cfg2=100_000, cfg3=8192, cfg4_relbin=1_000_000, cfg4_roq=1_000_000,
-                     cfg4_roq_time=65536, mb=65536, calmarg_time=1024)
+                     cfg4_roq_time=65536, mb=65536, mb_time=16384, calmarg_time=1024)
 
 
 def recon_bench(n, steps):

@@ -84,7 +84,8 @@ struct BBWaveformConfig {
     // evaluated, f_min = first node for the IMRPhenomD domain check, no f_end check for TaylorF2
     int sequence;
     int no_time_shift;    // ROQ: the waveform carries no exp(-2 pi i f (t_c - t_start)) (roq.py:486-502)
-    int fixed_antenna_time;   // ROQ time marginalisation: antenna response / delay at antenna_time (roq.py:478-481)
+    int fixed_antenna_time;   // 1: ROQ time marginalisation: antenna response AND delay at antenna_time (roq.py:478-481);
+                              // 2: multi-banded time marginalisation: antenna response only (Interferometer.reference_time)
     double antenna_time;
 };
 

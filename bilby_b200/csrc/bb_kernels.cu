@@ -130,6 +130,16 @@ struct bb_handle {
     double2 *d_roq_V = nullptr, *d_roq_Y = nullptr;
     double* d_roq_hh = nullptr;
     size_t roq_chunk = 0, roq_y_elems = 0;
+    // multi-banded time marginalisation (bb_set_multiband_time_marginalization)
+    long mb_nfull = 0;                     // length of the reference's full d_h array, Nbs[-1] / 2
+    int* d_mb_idx = nullptr;               // [n_points] index of every banded point in that array
+    double mb_dtc = 0.0, mb_ref_time = 0.0;
+    double2 *d_mb_E = nullptr, *d_mb_V = nullptr, *d_mb_Y = nullptr;
+    double* d_mb_hh = nullptr;
+    long mb_row0 = 0;
+    int mb_nrow = 0;
+    size_t mb_chunk = 0, mb_y_cap = 0;
+    double mb_win[2] = {0.0, 0.0};
     cudaStream_t stream = nullptr;
     int sm_count = 148;
     long launches = 0;
@@ -858,6 +868,10 @@ static int bb_launch_prologue(bb_handle* h, const double* params_dev, long n, cu
     if (h->kind == 1) {
         wf.sequence = 1;
         wf.f_min = h->rb_fmin;
+        if ((h->marg.flags & BB_MARG_TIME) && h->mb_nfull > 0) {
+            wf.fixed_antenna_time = 2;
+            wf.antenna_time = h->mb_ref_time;
+        }
     } else if (h->kind == 2) {
         wf.sequence = 1;
         wf.f_min = h->roq_fmin;

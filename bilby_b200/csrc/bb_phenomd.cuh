@@ -223,6 +223,9 @@ BB_HD void bb_solve5(double a[5][5], double* b) {
 BB_HD double bb_detector_prologue(const double* p, const BBNetwork& net, const BBWaveformConfig& wf, double* coef) {
     const double tc = wf.add_jitter ? p[BB_P_GEOCENT_TIME] + p[BB_P_TIME_JITTER] : p[BB_P_GEOCENT_TIME];
     const double gmst = bb_wrap_2pi(bb_gmst(wf.fixed_antenna_time ? wf.antenna_time : tc));
+    // fixed_antenna_time == 2 (multi-banded time marginalisation, multiband.py:714-726 + interferometer.py:336-355):
+    // the antenna response at the reference time, the delay still at geocent_time
+    const double gmst_delay = (wf.fixed_antenna_time == 2) ? bb_wrap_2pi(bb_gmst(tc)) : gmst;
     const double cfac = cos(p[BB_P_THETA_JN]);
     const double pfac = 0.5 * (1.0 + cfac * cfac);
     for (int d = 0; d < BB_MAX_DET; ++d) {
@@ -230,7 +233,7 @@ BB_HD double bb_detector_prologue(const double* p, const BBNetwork& net, const B
         if (d < net.n_det) {
             double fp, fc;
             bb_antenna(net.detector_tensor[d], p[BB_P_RA], p[BB_P_DEC], p[BB_P_PSI], gmst, &fp, &fc);
-            const double delay = bb_time_delay(net.vertex[d], p[BB_P_RA], p[BB_P_DEC], gmst);
+            const double delay = bb_time_delay(net.vertex[d], p[BB_P_RA], p[BB_P_DEC], gmst_delay);
             // h_det = F+ h+ + Fx hx with h+ = pfac h22, hx = -i cfac h22
             cd[0] = fp * pfac;
             cd[1] = -fc * cfac;

@@ -641,6 +641,124 @@ bb_roq_time_marg_kernel(const double* __restrict__ coef, long s_begin, long n, B
 }
 
 // ------------------------------------------------------------------------------------------------
+// Multi-banded likelihood with time marginalisation (multiband.py:714-726, 789-797).  The reference scatters
+// strain * linear_coeffs of every detector into a zero array of Nbs[-1] / 2 points and takes its FFT; only the banded
+// points are non-zero (1e4 of 2.6e5 for the 128 s signal) and only the times inside the geocent_time prior are used
+// (a few hundred), so the transform is evaluated as a dense contraction instead:
+//   (a) bb_mb_series_kernel   : v_s[p] = sum_det h_det(f_p) L_det[p] for every sample (packed, the GEMM's A operand),
+//                               <h|h> = sum_det sum_p Q_det[p] |h_det(f_p)|^2
+//   (b) bb_gemm_nt_kernel     : D[s][t] = sum_p v_s[p] exp(-2 pi i idx_p (row0 + t) / N)      (FP64 tensor cores)
+//   (c) bb_mb_time_marg_kernel: point likelihood per time, logsumexp with the time prior (base.py:794-820)
+// ------------------------------------------------------------------------------------------------
+template <int NDET, int APPROX, bool CAL>
+__global__ void __launch_bounds__(BB_RED_THREADS)
+bb_mb_series_kernel(const double* __restrict__ coef, long s_begin, long n, BBRelbinDev rb,
+                    const double* __restrict__ calrec, BBCalGrid grid, double2* __restrict__ V /* packed [n x n_points] */,
+                    double* __restrict__ hh /* [n] */) {
+    extern __shared__ __align__(16) double red_smem[];
+    const int cal_len = CAL ? NDET * 4 * grid.n_points : 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* rec = red_smem + (size_t)warp * (BC_NCOEF + cal_len);
+    double* cal = rec + BC_NCOEF;
+    const int ne = rb.edges.n, np = rb.ne_pad;
+    const long S = (ne + 15) / 16;
+    for (long s = (long)blockIdx.x * BB_RED_WARPS + warp; s < n; s += (long)gridDim.x * BB_RED_WARPS) {
+        bb_red_load<CAL>(rec, cal, coef, calrec, s_begin + s, cal_len, lane);
+        double h2 = 0.0;
+        for (int base = 0; base < S * 16; base += 32) {
+            const int j = base + lane;
+            if (j >= S * 16) break;
+            double vr = 0.0, vi = 0.0;
+            if (j < ne) {
+                const double f = rb.edges.f[j], lfj = rb.edges.lf[j];
+                double A, ph;
+                bb_wave<APPROX>(rec, f, rb.edges.u[j], lfj, rb.edges.q34[j], &A, &ph);
+#pragma unroll
+                for (int d = 0; d < NDET; ++d) {
+                    const double* cd = rec + BC_DET + BC_DSTRIDE * d;
+                    double sn, cs;
+                    bb_sincospi(ph + cd[2] * f, &sn, &cs);
+                    double hr = A * (cd[0] * cs + cd[1] * sn), hi = A * (cd[1] * cs - cd[0] * sn);   // K h
+                    if (CAL) {
+                        double amp1, cr, ci;
+                        bb_cal_factor(cal + d * 4 * grid.n_points, grid.n_points, grid.l0[d], grid.inv_delta[d], lfj,
+                                      &amp1, &cr, &ci);
+                        const double tr = amp1 * (hr * cr - hi * ci), ti = amp1 * (hr * ci + hi * cr);
+                        hr = tr;
+                        hi = ti;
+                    }
+                    const double2 c = rb.lin_c[(size_t)d * np + j];         // conj(L)
+                    vr = fma(hr, c.x, fma(hi, c.y, vr));                      // h L
+                    vi = fma(hi, c.x, fma(-hr, c.y, vi));
+                    h2 = fma(rb.quad_e[(size_t)d * np + j], fma(hr, hr, hi * hi), h2);
+                }
+            }
+            V[bb_pk(s, j, 64, S)] = make_double2(vr, vi);                    // zero K tail included
+        }
+        h2 = bb_warp_sum(h2);
+        if (lane == 0) hh[s] = (rec[BC_STATUS] != 0.0) ? nan("") : h2;
+    }
+}
+
+// E[t][p] = exp(-2 pi i idx_p (row0 + t) / N), packed as the GEMM's B operand (phases reduced modulo N in integers: exact)
+__global__ void bb_mb_phase_kernel(const int* __restrict__ idx, int n_points, long row0, int n_row, long n_full,
+                                   double2* __restrict__ E) {
+    const long S = (n_points + 15) / 16;
+    const long total = (long)n_row * S * 16;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long t = i / (S * 16), p = i - t * (S * 16);
+        double2 v = make_double2(0.0, 0.0);
+        if (p < n_points) {
+            const long m = ((long)idx[p] * (row0 + t)) % n_full;
+            double sn, cs;
+            sincospi(-2.0 * (double)m / (double)n_full, &sn, &cs);
+            v = make_double2(cs, sn);
+        }
+        E[bb_pk(t, p, BB_GEMM_TR_B, S)] = v;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+bb_mb_time_marg_kernel(const double* __restrict__ coef, long s_begin, long n, const double2* __restrict__ Y /* [n][n_row] */,
+                       long row0, int n_row, long n_full, double dtc, const double* __restrict__ hh, BBMarg marg,
+                       double start_time, double* __restrict__ out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    for (long s = (long)blockIdx.x * wpb + warp; s < n; s += (long)gridDim.x * wpb) {
+        const double* rec = coef + (s_begin + s) * BC_NCOEF;
+        if (rec[BC_STATUS] != 0.0) {
+            if (lane == 0) out[s_begin + s] = -DBL_MAX;
+            continue;
+        }
+        const double h2 = hh[s], dist = rec[BC_DISTANCE];
+        const double jit = marg.jitter ? rec[BC_JITTER] : 0.0;
+        const double bw = dtc / (marg.time_max - marg.time_min);              // prior.prob(t) * delta_tc
+        // times start + j dtc (+ jitter) inside the prior (base.py:795-806): j in [j_lo, j_hi]
+        long j_lo = (long)ceil((marg.time_min - jit - start_time) / dtc) - 1, j_hi = (long)floor((marg.time_max - jit - start_time) / dtc) + 1;
+        if (j_lo < 0) j_lo = 0;
+        if (j_hi > n_full - 1) j_hi = n_full - 1;
+        bool missing = false;
+        double mx = -INFINITY, sum = 0.0;
+        for (long j = j_lo + lane; j <= j_hi; j += 32) {
+            const double tt = (start_time + (double)j * dtc) + jit;
+            if (tt < marg.time_min || tt > marg.time_max) continue;
+            if (j < row0 || j >= row0 + n_row) { missing = true; continue; }   // outside the contracted window
+            const double2 d = Y[(size_t)s * n_row + (j - row0)];
+            const double l = bb_point_lnl(marg, d.x, d.y, h2, dist);
+            if (l == -INFINITY) continue;
+            if (l > mx) { sum = sum * exp(mx - l) + bw; mx = l; }
+            else sum += bw * exp(l - mx);
+        }
+        double gmx = mx;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) gmx = fmax(gmx, __shfl_xor_sync(0xffffffffu, gmx, o));
+        double part = (mx == -INFINITY) ? 0.0 : sum * exp(mx - gmx);
+        part = bb_warp_sum(part);
+        missing = __any_sync(0xffffffffu, missing);
+        if (lane == 0) out[s_begin + s] = missing ? nan("") : ((gmx == -INFINITY) ? -INFINITY : log(part) + gmx);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K5t: relative binning with time marginalisation (relative.py:380-421): the full-grid waveform is rebuilt
 // as h0_d[k] (r0_b + r1_b (f_k - f_centre,b)), so the series h conj(d)/S is P_d[k] (r0 + r1 (f_k - fc)) with
 // P_d = (4/T) h0_d conj(d_d) / S_d precomputed at set-up.  One CTA per sample; warp 0 evaluates the edges.

@@ -14,6 +14,14 @@ static void bb_reduced_clear(bb_handle* h) {
     h->d_roq_hh = nullptr;
     h->roq_chunk = 0;
     h->roq_y_elems = 0;
+    cudaFree(h->d_mb_idx); cudaFree(h->d_mb_E); cudaFree(h->d_mb_V); cudaFree(h->d_mb_Y); cudaFree(h->d_mb_hh);
+    h->d_mb_idx = nullptr;
+    h->d_mb_E = h->d_mb_V = h->d_mb_Y = nullptr;
+    h->d_mb_hh = nullptr;
+    h->mb_nfull = 0;
+    h->mb_chunk = 0;
+    h->mb_y_cap = 0;
+    h->mb_nrow = 0;
     h->kind = 0;
 }
 
@@ -175,6 +183,28 @@ extern "C" int bb_set_multiband(bb_handle* h, int n_points, const double* freque
     h->rb_fmin = frequencies[0];
     for (int k = 1; k < n_points; ++k) if (frequencies[k] < h->rb_fmin) h->rb_fmin = frequencies[k];
     h->kind = 1;
+    return 0;
+}
+
+extern "C" int bb_set_multiband_time_marginalization(bb_handle* h, long n_full, const int* full_index, double delta_tc,
+                                                     double beam_pattern_reference_time) {
+    if (!h || !h->rb || h->kind != 1 || h->rb->cross_g) return bb_fail("bb_set_multiband_time_marginalization: call bb_set_multiband first");
+    BB_CUDA(cudaSetDevice(h->device));
+    cudaFree(h->d_mb_idx); cudaFree(h->d_mb_E);
+    h->d_mb_idx = nullptr;
+    h->d_mb_E = nullptr;
+    h->mb_nfull = 0;
+    h->mb_nrow = 0;
+    if (n_full <= 0) return 0;
+    if (!full_index || !(delta_tc > 0.0)) return bb_fail("bb_set_multiband_time_marginalization: bad arguments");
+    const int np = h->rb->edges.n;
+    for (int p = 0; p < np; ++p)
+        if (full_index[p] < 0 || full_index[p] >= n_full) return bb_fail("bb_set_multiband_time_marginalization: index outside the full array");
+    BB_CUDA(cudaMalloc(&h->d_mb_idx, (size_t)np * sizeof(int)));
+    BB_CUDA(cudaMemcpy(h->d_mb_idx, full_index, (size_t)np * sizeof(int), cudaMemcpyHostToDevice));
+    h->mb_nfull = n_full;
+    h->mb_dtc = delta_tc;
+    h->mb_ref_time = beam_pattern_reference_time;
     return 0;
 }
 
@@ -367,6 +397,84 @@ static int bb_launch_roq_time_marg_t(bb_handle* h, long n, double* out, cudaStre
 }
 
 template <int NDET, int APPROX, bool CAL>
+static int bb_launch_mb_time_marg_t(bb_handle* h, long n, double* out, cudaStream_t st) {
+    const BBRelbinDev& rb = *h->rb;
+    if (h->mb_nfull <= 0) return bb_fail("multi-banded time marginalisation: bb_set_multiband_time_marginalization was not called");
+    const int np = rb.edges.n;
+    const long S = (np + 15) / 16;
+    const double dtc = h->mb_dtc, start = h->net.start_time;
+    // rows of the transform any sample can use: t_j + jitter inside the prior with |jitter| <= 1 / fs (the reference's
+    // jitter prior is +- 1 / fs, base.py:189-197); a sample that needs a row outside the window gets NaN, never a
+    // silently truncated sum
+    const double jmax = 1.0 / h->net.sampling_frequency;
+    long r_lo = (long)floor((h->marg.time_min - jmax - start) / dtc) - 2, r_hi = (long)ceil((h->marg.time_max + jmax - start) / dtc) + 2;
+    if (r_lo < 0) r_lo = 0;
+    if (r_hi > h->mb_nfull - 1) r_hi = h->mb_nfull - 1;
+    if (r_hi < r_lo) r_hi = r_lo;
+    const int nrow = (int)(r_hi - r_lo + 1);
+    if (!h->d_mb_E || h->mb_row0 != r_lo || h->mb_nrow != nrow) {
+        cudaFree(h->d_mb_E);
+        h->d_mb_E = nullptr;
+        const size_t e_elems = bb_pk_elems(nrow, np, BB_GEMM_TR_B);
+        BB_CUDA(cudaMalloc(&h->d_mb_E, e_elems * sizeof(double2)));
+        BB_CUDA(cudaMemsetAsync(h->d_mb_E, 0, e_elems * sizeof(double2), st));
+        bb_mb_phase_kernel<<<1024, 256, 0, st>>>(h->d_mb_idx, np, r_lo, nrow, h->mb_nfull, h->d_mb_E);
+        BB_CUDA(cudaGetLastError());
+        h->mb_row0 = r_lo;
+        h->mb_nrow = nrow;
+        h->launches++;
+    }
+    size_t chunk = (size_t)(1.0e9 / ((double)S * 16 * 1.25 * sizeof(double2)));
+    chunk = chunk / 64 * 64;
+    if (chunk > (size_t)n) chunk = (size_t)n;
+    if (chunk < 1) chunk = 1;
+    if (chunk > h->mb_chunk) {
+        cudaFree(h->d_mb_V); cudaFree(h->d_mb_Y); cudaFree(h->d_mb_hh);
+        h->d_mb_V = h->d_mb_Y = nullptr;
+        h->d_mb_hh = nullptr;
+        h->mb_chunk = 0;
+        const size_t v_elems = bb_pk_elems((long)chunk, np, BB_GEMM_TR_A(true));
+        BB_CUDA(cudaMalloc(&h->d_mb_V, v_elems * sizeof(double2)));
+        BB_CUDA(cudaMemsetAsync(h->d_mb_V, 0, v_elems * sizeof(double2), st));
+        BB_CUDA(cudaMalloc(&h->d_mb_hh, chunk * sizeof(double)));
+        h->mb_chunk = chunk;
+        h->mb_y_cap = 0;
+    }
+    if (h->mb_chunk * (size_t)nrow > h->mb_y_cap) {
+        cudaFree(h->d_mb_Y);
+        h->d_mb_Y = nullptr;
+        h->mb_y_cap = 0;
+        BB_CUDA(cudaMalloc(&h->d_mb_Y, h->mb_chunk * (size_t)nrow * sizeof(double2)));
+        h->mb_y_cap = h->mb_chunk * (size_t)nrow;
+    }
+    const size_t smem = (size_t)BB_RED_WARPS * (BC_NCOEF + (CAL ? NDET * 4 * h->cal.n_points : 0)) * sizeof(double);
+    BB_CUDA(cudaFuncSetAttribute(bb_mb_series_kernel<NDET, APPROX, CAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BBProfScope prof(h, st);
+    for (long s0 = 0; s0 < n; s0 += (long)chunk) {
+        const long m = (n - s0) < (long)chunk ? (n - s0) : (long)chunk;
+        const long grid = bb_red_grid(h, m);
+        bb_mb_series_kernel<NDET, APPROX, CAL><<<(unsigned)grid, BB_RED_THREADS, smem, st>>>(
+            h->d_coef, s0, m, rb, h->d_calrec, h->cal, h->d_mb_V, h->d_mb_hh);
+        BB_CUDA(cudaGetLastError());
+        BBGemmArgs ga{};
+        ga.A[0] = h->d_mb_V;
+        ga.B[0] = h->d_mb_E;
+        ga.C = reinterpret_cast<double*>(h->d_mb_Y);
+        ga.slabs_a = ga.slabs_b = S;
+        ga.slab0 = 0; ga.n_slabs = (int)S;
+        ga.ldc = nrow;
+        ga.M = (int)m; ga.N = nrow; ga.n_seg = 1; ga.n_batch = 1; ga.accumulate = 0; ga.alpha = 1.0;
+        if (bb_gemm_nt(true, ga, h->sm_count, st)) return 1;
+        const long grid_e = (m + 3) / 4 < 8L * h->sm_count ? (m + 3) / 4 : 8L * h->sm_count;
+        bb_mb_time_marg_kernel<<<(unsigned)grid_e, 128, 0, st>>>(h->d_coef, s0, m, h->d_mb_Y, r_lo, nrow, h->mb_nfull, dtc,
+                                                                  h->d_mb_hh, h->marg, start, out);
+        BB_CUDA(cudaGetLastError());
+        h->launches += 3;
+    }
+    return 0;
+}
+
+template <int NDET, int APPROX, bool CAL>
 static int bb_launch_relbin_time_marg_t(bb_handle* h, long n, double* out, cudaStream_t st) {
     const BBRelbinDev& rb = *h->rb;
     if (!rb.pgrid) return bb_fail("relative binning time marginalisation: bb_set_relative_binning was called without "
@@ -407,6 +515,7 @@ static int bb_launch_reduced_n(bb_handle* h, long n, double* out, cudaStream_t s
         return pd ? FN<NDET, BB_IMRPHENOMD, false>(h, n, out, st) : FN<NDET, BB_TAYLORF2, false>(h, n, out, st);        \
     } while (0)
     if (what == 0) BB_RED_DISPATCH(bb_launch_reduced_t);
+    if (h->kind == 1 && !h->rb->cross_g) BB_RED_DISPATCH(bb_launch_mb_time_marg_t);
     if (h->kind == 1) BB_RED_DISPATCH(bb_launch_relbin_time_marg_t);
     BB_RED_DISPATCH(bb_launch_roq_time_marg_t);
 #undef BB_RED_DISPATCH

@@ -7,8 +7,11 @@ shortened data / PSD of every band (:529-549) and the quadratic coefficients of 
 <d|h> = conj(sum h L), <h|h> = sum |h|^2 Q in kernel K5's edge form (`bb_set_multiband`; one warp per sample, lanes
 over the points); the marginalisations run in the usual epilogue.
 
-Not provided: the IFFT-FFT form of (h, h) (`linear_interpolation=False`), time marginalisation, weights files
-(h5py is absent).
+Time marginalisation (multiband.py:714-726, 789-797): the reference's FFT of the scattered strain * linear_coeffs array is
+evaluated for the times inside the geocent_time prior as a dense contraction on the FP64 tensor cores
+(`bb_set_multiband_time_marginalization`, csrc/bb_reduced.cuh bb_mb_*).
+
+Not provided: the IFFT-FFT form of (h, h) (`linear_interpolation=False`), weights files (h5py is absent).
 """
 import math
 import numbers
@@ -34,8 +37,6 @@ class MBGravitationalWaveTransient(GravitationalWaveTransient):
         if getattr(waveform_generator.frequency_domain_source_model, "_bb_kind", None) != "frequency_sequence":
             raise TypeError("MBGravitationalWaveTransient needs one of the source models "
                             "binary_black_hole_frequency_sequence / binary_neutron_star_frequency_sequence")
-        if time_marginalization:
-            raise NotImplementedError("time marginalisation of the multi-banded likelihood has no device kernel")
         if not linear_interpolation:
             raise NotImplementedError("the IFFT-FFT form of (h, h) has no device kernel (linear_interpolation=True)")
         if isinstance(weights, str):
@@ -43,7 +44,7 @@ class MBGravitationalWaveTransient(GravitationalWaveTransient):
         self._mb_host = None
         super().__init__(interferometers=interferometers, waveform_generator=waveform_generator, priors=priors,
                          distance_marginalization=distance_marginalization,
-                         phase_marginalization=phase_marginalization, time_marginalization=False,
+                         phase_marginalization=phase_marginalization, time_marginalization=time_marginalization,
                          distance_marginalization_lookup_table=distance_marginalization_lookup_table,
                          jitter_time=jitter_time, reference_frame=reference_frame, time_reference=time_reference,
                          device=device)
@@ -59,6 +60,8 @@ class MBGravitationalWaveTransient(GravitationalWaveTransient):
             self.setup_multibanding()
         else:
             self.setup_multibanding_from_weights(weights)
+        if self.time_marginalization:
+            self._setup_time_marginalization_multiband()
         self._mb_host = self._pack_host_arrays()
         self._upload_multiband()
 
@@ -374,6 +377,18 @@ class MBGravitationalWaveTransient(GravitationalWaveTransient):
             else:
                 setattr(self, key, value)
 
+    def _setup_time_marginalization_multiband(self):
+        """multiband.py:714-726."""
+        N = int(self.Nbs[-1]) // 2
+        self._delta_tc = self.durations[0] / N
+        self._times = self.interferometers.start_time + np.arange(N) * self._delta_tc
+        self.time_prior_array = self.priors["geocent_time"].prob(self._times) * self._delta_tc
+        self._full_to_multiband = [int(f * self.durations[0]) for f in self.banded_frequency_points]
+        self._beam_pattern_reference_time = (self.priors["geocent_time"].minimum
+                                             + self.priors["geocent_time"].maximum) / 2
+        for ifo in self.interferometers:
+            ifo.reference_time = self._beam_pattern_reference_time
+
     # ---- device ----------------------------------------------------------------------------------
     def _pack_host_arrays(self):
         n_det, n = len(self.interferometers), len(self.banded_frequency_points)
@@ -390,6 +405,11 @@ class MBGravitationalWaveTransient(GravitationalWaveTransient):
         hst = self._mb_host
         _lib.check(net.lib.bb_set_multiband(net.ptr, len(hst["freqs"]), hst["freqs"].ctypes.data,
                                             hst["linear"].ctypes.data, hst["quadratic"].ctypes.data))
+        if self.time_marginalization:
+            idx = np.ascontiguousarray(self._full_to_multiband, dtype=np.int32)
+            _lib.check(net.lib.bb_set_multiband_time_marginalization(
+                net.ptr, int(self.Nbs[-1]) // 2, idx.ctypes.data, float(self._delta_tc),
+                float(self._beam_pattern_reference_time)))
 
     def _configure(self):
         super()._configure()

@@ -240,6 +240,15 @@ int bb_set_relative_binning(bb_handle* h, int n_edges, const double* bin_freqs, 
 int bb_set_multiband(bb_handle* h, int n_points, const double* frequencies, const double* linear_coeffs,
                      const double* quadratic_coeffs);
 
+/* Time marginalisation of the multi-banded likelihood (MBGravitationalWaveTransient._setup_time_marginalization_multiband
+ * and calculate_snrs, bilby/gw/likelihood/multiband.py:714-726, 789-797): the reference's FFT of the scattered
+ * strain * linear_coeffs array of n_full = Nbs[-1] / 2 points, evaluated for the times inside the geocent_time prior.
+ *   full_index [n_points]: position of every banded point in that array (int(f * durations[0]));  delta_tc = durations[0] / n_full;
+ *   the antenna response is taken at beam_pattern_reference_time (Interferometer.reference_time).  Call after
+ *   bb_set_multiband; needs bb_set_marginalization with BB_MARG_TIME.  n_full = 0 switches it off. */
+int bb_set_multiband_time_marginalization(bb_handle* h, long n_full, const int* full_index, double delta_tc,
+                                          double beam_pattern_reference_time);
+
 /* ROQ: replaces ROQGravitationalWaveTransient.calculate_snrs, _closest_time_indices, _interp_five_samples and
  * _calculate_d_inner_h_array (bilby/gw/likelihood/roq.py:467-651) with the source model binary_*_roq
  * (bilby/gw/source.py:693-721, 802-898) evaluated at the ROQ frequency nodes.

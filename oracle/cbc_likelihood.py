@@ -159,6 +159,7 @@ class OracleInterferometer:
                                                      fill_value=np.inf)(self.frequency_array)
         self.frequency_domain_strain = np.zeros(len(self.frequency_array), dtype=complex)
         self.calibration = None   # or OracleCubicSpline
+        self.reference_time = None   # interferometer.py:336-339: antenna response at this time when set
 
     def set_gaussian_noise(self, rng):
         """psd.py:350-376 + series.py:161-198 semantics, but drawing from a caller-supplied
@@ -187,8 +188,8 @@ class OracleInterferometer:
             mask = self.frequency_mask
         else:
             mask = np.ones(len(frequencies), dtype=bool)
-        fp, fc = self.antenna_response(parameters["ra"], parameters["dec"],
-                                       parameters["geocent_time"], parameters["psi"])
+        antenna_time = parameters["geocent_time"] if self.reference_time is None else self.reference_time
+        fp, fc = self.antenna_response(parameters["ra"], parameters["dec"], antenna_time, parameters["psi"])
         signal = pols["plus"] * mask * fp + pols["cross"] * mask * fc
         time_shift = time_delay_from_geocenter(self.vertex, parameters["ra"], parameters["dec"],
                                                parameters["geocent_time"])

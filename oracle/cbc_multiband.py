@@ -81,6 +81,19 @@ class OracleMultiband(ocl.OracleLikelihood):
         self._setup_waveform_frequency_points()
         self._setup_linear_coefficients()
         self._setup_quadratic_coefficients_linear_interp()
+        if self.time_marginalization:
+            self._setup_time_marginalization_multiband()
+
+    def _setup_time_marginalization_multiband(self):
+        """:714-726."""
+        n = int(self.Nbs[-1]) // 2
+        self._delta_tc = self.durations[0] / n
+        self._times = self.start_time + np.arange(n) * self._delta_tc
+        self._full_d_h = np.zeros(n, dtype=complex)
+        self._full_to_multiband = [int(f * self.durations[0]) for f in self.banded_frequency_points]
+        self._beam_pattern_reference_time = (self.time_prior.minimum + self.time_prior.maximum) / 2
+        for ifo in self.ifos:
+            ifo.reference_time = self._beam_pattern_reference_time
 
     # ---- 0PN time to merger (:322-360)
     def _tau(self, f):
@@ -230,4 +243,12 @@ class OracleMultiband(ocl.OracleLikelihood):
         strain = ifo.get_detector_response(modes, parameters, frequencies=self.banded_frequency_points)
         d_inner_h = np.conj(np.dot(strain, self.linear_coeffs[ifo.name]))
         hh = np.vdot(np.abs(strain) ** 2, self.quadratic_coeffs[ifo.name])
-        return d_inner_h, float(np.real(hh)), None
+        arr = None
+        if self.time_marginalization:                                  # :789-797
+            idx = np.asarray(self._full_to_multiband)
+            self._full_d_h[idx] *= 0
+            for b in range(self.number_of_bands):
+                s0, e0 = self.start_end_idxs[b]
+                self._full_d_h[idx[s0:e0 + 1]] += strain[s0:e0 + 1] * self.linear_coeffs[ifo.name][s0:e0 + 1]
+            arr = np.fft.fft(self._full_d_h)
+        return d_inner_h, float(np.real(hh)), arr

@@ -86,6 +86,24 @@ def multiband(tag, duration, fs, inj, model, grid_model, conversion, approximant
         distance_marginalization=True, distance_marginalization_lookup_table=f"/tmp/golden_mb_{tag}_lookup.npz")
     res["lnl_distance_phase"] = evaluate(like, draws, n)
     res["distance_prior"] = np.array([dmin, dmax])
+    # time marginalisation (multiband.py:714-726, 789-797): geocent_time := start_time, jitter drawn inside its prior
+    tdraws = dict(draws)
+    tdraws["geocent_time"] = np.full(n, float(start_time))
+    pri = PriorDict(dict(geocent_time=Uniform(T_INJ - 0.1, T_INJ + 0.1, "geocent_time")))
+    like = bilby.gw.likelihood.MBGravitationalWaveTransient(
+        ifos, wfg_new(), reference_chirp_mass=ref_mc, priors=pri, time_marginalization=True, jitter_time=True)
+    jmax = float(pri["time_jitter"].maximum)
+    tdraws["time_jitter"] = np.random.default_rng(5).uniform(-jmax, jmax, n)
+    res["param_time_jitter"] = tdraws["time_jitter"]
+    res["time_marg_delta_tc"] = like._delta_tc
+    res["lnl_time"] = evaluate(like, tdraws, n)
+    pri = PriorDict(dict(geocent_time=Uniform(T_INJ - 0.1, T_INJ + 0.1, "geocent_time"), phase=Uniform(0, 2 * np.pi, "phase")))
+    like = bilby.gw.likelihood.MBGravitationalWaveTransient(
+        ifos, wfg_new(), reference_chirp_mass=ref_mc, priors=pri, time_marginalization=True, jitter_time=True,
+        phase_marginalization=True)
+    res["lnl_time_phase"] = evaluate(like, tdraws, n)
+    for ifo in ifos:
+        ifo.reference_time = None
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", f"multiband_{tag}.npz"), **res)
     print(tag, "bands", len(res["durations"]), "points", len(res["banded_frequency_points"]), "lnl",
           res["lnl_none"][:3], res["lnl_full_grid"][:3], res["lnl_distance_phase"][:3])

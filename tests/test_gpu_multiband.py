@@ -110,3 +110,25 @@ def test_multiband_tracks_full_grid_at_scale():
     lnl_full = full.log_likelihood_ratio_batch(d)
     assert np.all(np.isfinite(lnl_mb))
     assert np.max(np.abs(lnl_mb - lnl_full)) < 2e-2
+
+
+@pytest.mark.parametrize("name,bns", [("multiband_bbh_8s_H1L1V1", False), ("multiband_bns_32s_H1L1V1", True)])
+def test_multiband_time_marginalisation_vs_reference(name, bns):
+    """multiband.py:714-726, 789-797 on the device: the reference's FFT of the scattered strain * linear_coeffs array as a
+    dense contraction over the banded points for the times inside the prior (csrc/bb_reduced.cuh bb_mb_* +
+    bb_gemm.cuh), vs lnl_time / lnl_time_phase of the unmodified reference."""
+    from bilby_b200.core.prior import Uniform
+    g, _ = rc.load(name)
+    for key, kw in (("lnl_time", {}), ("lnl_time_phase", dict(phase_marginalization=True))):
+        pri = _priors(phase=Uniform(0, 2 * np.pi, "phase")) if kw else _priors()
+        like, draws = _mb_product(g, bns, time_marginalization=True, jitter_time=True, priors=pri, **kw)
+        assert abs(like._delta_tc - float(g["time_marg_delta_tc"])) < 1e-18
+        if kw:
+            assert pri["geocent_time"] == float(g["start_time"])           # base.py:187: the sampler's prior is pinned
+        d = dict(draws)
+        d["geocent_time"] = np.full(len(d["chirp_mass"]), float(g["start_time"]))
+        lnl = like.log_likelihood_ratio_batch(d)
+        scale = np.maximum(1.0, 0.5 * g["optimal_snr_squared"].sum(axis=1))
+        assert np.max(np.abs(lnl - g[key]) / scale) < RTOL, (key, lnl[:4], g[key][:4])
+        one = like.log_likelihood_ratio({k: float(v[2]) for k, v in d.items()})
+        assert one == lnl[2]

@@ -42,3 +42,21 @@ def test_multiband_vs_reference(name, bns):
                                   distance_prior=ocl.OraclePowerLaw(2, float(dmin), float(dmax)),
                                   lookup_table=rc.distance_phase_table())
     assert np.all(np.abs(_eval(like, draws, n) - g["lnl_distance_phase"][:n]) < 1e-9 * scale)
+
+
+@pytest.mark.parametrize("name,bns", [("multiband_bbh_8s_H1L1V1", False), ("multiband_bns_32s_H1L1V1", True)])
+def test_multiband_time_marginalisation_vs_reference(name, bns):
+    """multiband.py:714-726, 789-797: FFT of the scattered strain * linear_coeffs array, antenna response at the
+    beam-pattern reference time, jitter; golden lnl_time / lnl_time_phase from the unmodified reference."""
+    g, draws = rc.load(name)
+    n = 4
+    tmin, tmax = (float(x) for x in g["geocent_time_prior"])
+    d = dict(draws)
+    d["geocent_time"] = np.full(len(d["chirp_mass"]), float(g["start_time"]))
+    scale = np.maximum(1.0, 0.5 * g["optimal_snr_squared"][:n].sum(axis=1))
+    for key, kw in (("lnl_time", {}), ("lnl_time_phase", dict(phase_marginalization=True))):
+        like, _ = rc.multiband_oracle(g, bns, time_marginalization=True, jitter_time=True,
+                                      time_prior=ocl.OracleUniform(tmin, tmax), **kw)
+        assert abs(like._delta_tc - float(g["time_marg_delta_tc"])) < 1e-18
+        got = _eval(like, d, n, skip=())
+        assert np.all(np.abs(got - g[key][:n]) < 1e-9 * scale), (key, got, g[key][:n])
