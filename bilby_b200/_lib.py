@@ -49,6 +49,8 @@ def load():
         "bb_set_roq": (i, [vp, i, vp, i, vp, i, lng, d, vp, vp, i, d, d, d]),
         "bb_set_multiband": (i, [vp, i, vp, vp, vp]),
         "bb_set_multiband_time_marginalization": (i, [vp, lng, vp, d, d]),
+        "bb_set_multiband_ifft_fft": (i, [vp, i, vp, vp, vp, vp, vp, vp, vp]),
+        "bb_fft_device": (i, [vp, vp, vp, lng, i, vp]),
         "bb_exchange_create": (i, [vp, i, i, lng, vp]),
         "bb_exchange_connect": (i, [vp, vp]),
         "bb_log_likelihood_ratio_sharded_device": (i, [vp, vp, lng, vp, vp]),
@@ -94,7 +96,8 @@ EXPORTED_SYMBOLS = (
     "bb_set_calibration_marginalization", "bb_build_roq_linear_weights", "bb_set_multiband",
     "bb_exchange_create", "bb_exchange_connect", "bb_log_likelihood_ratio_sharded_device", "bb_exchange_status",
     "bb_exchange_destroy", "bb_contract_device", "bb_fp64_tensor_peak",
-    "bb_build_roq_quadratic_weights", "bb_build_relbin_summary_data", "bb_set_multiband_time_marginalization")
+    "bb_build_roq_quadratic_weights", "bb_build_relbin_summary_data", "bb_set_multiband_time_marginalization",
+    "bb_set_multiband_ifft_fft", "bb_fft_device")
 
 
 def check(rc):

@@ -63,6 +63,7 @@ struct BBMarg {
 };
 
 struct BBRelbinDev;
+struct BBMbBand;
 struct BBRoqDev;
 
 struct bb_handle {
@@ -140,6 +141,11 @@ struct bb_handle {
     int mb_nrow = 0;
     size_t mb_chunk = 0, mb_y_cap = 0;
     double mb_win[2] = {0.0, 0.0};
+    // IFFT-FFT form of (h, h) (bb_set_multiband_ifft_fft): bands b >= 1, host copies of the kernel arguments
+    std::vector<struct BBMbBand> mb_bands;
+    double* d_mb_sqrtw = nullptr;
+    double2 *d_mb_Z = nullptr, *d_mb_Z2 = nullptr, *d_mb_Z3 = nullptr;
+    size_t mb_z_cap = 0;
     cudaStream_t stream = nullptr;
     int sm_count = 148;
     long launches = 0;
@@ -594,6 +600,7 @@ static BBTiles bb_tiles(const bb_handle* h) {
 }
 
 #include "bb_gemm.cuh"
+#include "bb_fft.cuh"
 #include "bb_timemarg.cuh"
 #include "bb_timemarg_split.cuh"
 #include "bb_reduced.cuh"
@@ -1413,6 +1420,19 @@ extern "C" int bb_contract_device(bb_handle* h, int is_complex, int m, int n, in
     cudaFree(A);
     cudaFree(B);
     h->launches += 1 + 2 * n_seg * n_batch;
+    return rc;
+}
+
+extern "C" int bb_fft_device(bb_handle* h, const double* in, double* out, long batch, int log2n, void* stream) {
+    if (!h || !in || !out || batch < 1) return bb_fail("bb_fft_device: bad arguments");
+    BB_CUDA(cudaSetDevice(h->device));
+    double2* scratch = nullptr;
+    BB_CUDA(cudaMalloc(&scratch, (size_t)batch * ((size_t)1 << log2n) * sizeof(double2)));
+    const int rc = bb_fft_forward(reinterpret_cast<const double2*>(in), scratch, reinterpret_cast<double2*>(out), batch, log2n,
+                                  h->sm_count, (cudaStream_t)stream);
+    cudaStreamSynchronize((cudaStream_t)stream);
+    cudaFree(scratch);
+    h->launches += 2;
     return rc;
 }
 

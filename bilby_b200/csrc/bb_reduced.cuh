@@ -759,6 +759,97 @@ bb_mb_time_marg_kernel(const double* __restrict__ coef, long s_begin, long n, co
 }
 
 // ------------------------------------------------------------------------------------------------
+// Multi-banded likelihood, IFFT-FFT form of (h, h) (multiband.py:613-646, 766-787; linear_interpolation=False).
+// Per band b >= 1 the reference takes the inverse real transform (M^(b) points) of sqrt(window) * strain, zero-pads it to
+// 2 M^(b) and sums |rfft|^2 against the transform I of the truncated inverse-PSD autocorrelation.  The EVEN bins of that
+// spectrum are the band's points themselves, so their terms (like all of band 0) are per-point weights and ride in
+// quad_e with the linear-interpolation kernel; only the ODD bins need transforms:
+//   Z[m]   = FFT(conj(w))[m],  w = sqrt(window) strain at bins Ks..Ke   -> x[m] = (2 / M) Re Z[m]   (the irfft)
+//   Y[l]   = FFT(x[m] e^{-i pi m / M})[l] = X[2 l + 1]
+//   <h|h> += (4 / That) sum_l |Y[l]|^2 I[2 l + 1],   l < M / 2
+// (bb_fft.cuh for the transforms; these kernels fill, modulate and reduce).
+// ------------------------------------------------------------------------------------------------
+struct BBMbBand {
+    int M, log2M, Ks, Ke, start;      // transform length, band bins, index of the band's first banded point
+    double norm;                      // 4 / That^(b)
+    const double* i_odd;              // [n_det][M / 2]   I^(b)[2 l + 1]
+};
+
+template <int NDET, int APPROX, bool CAL>
+__global__ void __launch_bounds__(BB_RED_THREADS)
+bb_mb_band_fill_kernel(const double* __restrict__ coef, long s_begin, long n, BBRelbinDev rb, BBMbBand band,
+                       const double* __restrict__ sqrt_window, const double* __restrict__ calrec, BBCalGrid grid,
+                       double2* __restrict__ Z /* [n][NDET][M], zeroed */) {
+    extern __shared__ __align__(16) double red_smem[];
+    const int cal_len = CAL ? NDET * 4 * grid.n_points : 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* rec = red_smem + (size_t)warp * (BC_NCOEF + cal_len);
+    double* cal = rec + BC_NCOEF;
+    const int nb = band.Ke - band.Ks + 1;
+    for (long s = (long)blockIdx.x * BB_RED_WARPS + warp; s < n; s += (long)gridDim.x * BB_RED_WARPS) {
+        bb_red_load<CAL>(rec, cal, coef, calrec, s_begin + s, cal_len, lane);
+        for (int q = lane; q < nb; q += 32) {
+            const int j = band.start + q;
+            const double f = rb.edges.f[j], lfj = rb.edges.lf[j], sw = sqrt_window[j];
+            double A, ph;
+            bb_wave<APPROX>(rec, f, rb.edges.u[j], lfj, rb.edges.q34[j], &A, &ph);
+#pragma unroll
+            for (int d = 0; d < NDET; ++d) {
+                const double* cd = rec + BC_DET + BC_DSTRIDE * d;
+                double sn, cs;
+                bb_sincospi(ph + cd[2] * f, &sn, &cs);
+                double hr = A * (cd[0] * cs + cd[1] * sn), hi = A * (cd[1] * cs - cd[0] * sn);   // K h
+                if (CAL) {
+                    double amp1, cr, ci;
+                    bb_cal_factor(cal + d * 4 * grid.n_points, grid.n_points, grid.l0[d], grid.inv_delta[d], lfj,
+                                  &amp1, &cr, &ci);
+                    const double tr = amp1 * (hr * cr - hi * ci), ti = amp1 * (hr * ci + hi * cr);
+                    hr = tr;
+                    hi = ti;
+                }
+                Z[((size_t)s * NDET + d) * band.M + band.Ks + q] = make_double2(sw * hr, -sw * hi);     // conj(w)
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// y[m] = (2 / M) Re Z[m] e^{-i pi m / M}, in place
+__global__ void bb_mb_band_modulate_kernel(double2* __restrict__ Z, long total, int M) {
+    const double scale = 2.0 / (double)M;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int m = (int)(i & (M - 1));
+        double sn, cs;
+        sincospi(-(double)m / (double)M, &sn, &cs);
+        const double x = scale * Z[i].x;
+        Z[i] = make_double2(x * cs, x * sn);
+    }
+}
+
+__global__ void bb_mb_hh_fold_kernel(const double* __restrict__ per_det, long n, int n_det, double* __restrict__ hh) {
+    const long s = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    double t = 0.0;
+    for (int d = 0; d < n_det; ++d) t += per_det[s * n_det + d];
+    hh[s] += t;
+}
+
+// one warp per (sample, detector): target[(s * NDET + d) * stride + offset] += norm sum_l |Y[l]|^2 I_odd[d][l]
+__global__ void bb_mb_band_reduce_kernel(const double2* __restrict__ Y, long n, int n_det, BBMbBand band,
+                                         double* __restrict__ target, int stride, int offset) {
+    const int lane = threadIdx.x & 31;
+    const long w = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= n * n_det) return;
+    const int d = (int)(w % n_det);
+    const double2* y = Y + (size_t)w * band.M;
+    const double* io = band.i_odd + (size_t)d * (band.M / 2);
+    double acc = 0.0;
+    for (int l = lane; l < band.M / 2; l += 32) acc = fma(fma(y[l].x, y[l].x, y[l].y * y[l].y), io[l], acc);
+    acc = bb_warp_sum(acc);
+    if (lane == 0) target[(size_t)w * stride + offset] += band.norm * acc;
+}
+
+// ------------------------------------------------------------------------------------------------
 // K5t: relative binning with time marginalisation (relative.py:380-421): the full-grid waveform is rebuilt
 // as h0_d[k] (r0_b + r1_b (f_k - f_centre,b)), so the series h conj(d)/S is P_d[k] (r0 + r1 (f_k - fc)) with
 // P_d = (4/T) h0_d conj(d_d) / S_d precomputed at set-up.  One CTA per sample; warp 0 evaluates the edges.

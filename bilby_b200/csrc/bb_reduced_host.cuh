@@ -22,6 +22,11 @@ static void bb_reduced_clear(bb_handle* h) {
     h->mb_chunk = 0;
     h->mb_y_cap = 0;
     h->mb_nrow = 0;
+    h->mb_bands.clear();
+    cudaFree(h->d_mb_sqrtw); cudaFree(h->d_mb_Z); cudaFree(h->d_mb_Z2); cudaFree(h->d_mb_Z3);
+    h->d_mb_sqrtw = nullptr;
+    h->d_mb_Z = h->d_mb_Z2 = h->d_mb_Z3 = nullptr;
+    h->mb_z_cap = 0;
     h->kind = 0;
 }
 
@@ -208,6 +213,93 @@ extern "C" int bb_set_multiband_time_marginalization(bb_handle* h, long n_full, 
     return 0;
 }
 
+static long bb_red_grid(const bb_handle* h, long n);
+
+extern "C" int bb_set_multiband_ifft_fft(bb_handle* h, int n_bands, const int* band_m, const int* band_ks,
+                                        const int* band_ke, const int* band_start, const double* band_norm,
+                                        const double* sqrt_window, const double* i_odd) {
+    if (!h || !h->rb || h->kind != 1 || h->rb->cross_g) return bb_fail("bb_set_multiband_ifft_fft: call bb_set_multiband first");
+    BB_CUDA(cudaSetDevice(h->device));
+    h->mb_bands.clear();
+    cudaFree(h->d_mb_sqrtw);
+    h->d_mb_sqrtw = nullptr;
+    if (n_bands <= 0) return 0;
+    if (!band_m || !band_ks || !band_ke || !band_start || !band_norm || !sqrt_window || !i_odd)
+        return bb_fail("bb_set_multiband_ifft_fft: bad arguments");
+    const int nd = h->net.n_det, np = h->rb->edges.n;
+    size_t total = 0;
+    for (int b = 0; b < n_bands; ++b) {
+        const int M = band_m[b];
+        int l2 = 0;
+        while ((1 << l2) < M) ++l2;
+        if ((1 << l2) != M || l2 < 8 || l2 > 18) return bb_fail("bb_set_multiband_ifft_fft: M^(b) must be 2^8 .. 2^18");
+        if (band_ks[b] < 1 || band_ke[b] >= M / 2 || band_ke[b] < band_ks[b] || band_start[b] < 0
+            || band_start[b] + (band_ke[b] - band_ks[b]) >= np)
+            return bb_fail("bb_set_multiband_ifft_fft: band bins outside (0, M / 2) or outside the banded points");
+        total += (size_t)nd * (M / 2);
+    }
+    double* d_io = nullptr;
+    if (bb_red_upload(h, i_odd, total, (const double**)&d_io)) return 1;
+    BB_CUDA(cudaMalloc(&h->d_mb_sqrtw, (size_t)np * sizeof(double)));
+    BB_CUDA(cudaMemcpy(h->d_mb_sqrtw, sqrt_window, (size_t)np * sizeof(double), cudaMemcpyHostToDevice));
+    size_t off = 0;
+    for (int b = 0; b < n_bands; ++b) {
+        BBMbBand bd;
+        bd.M = band_m[b];
+        bd.log2M = 0;
+        while ((1 << bd.log2M) < bd.M) ++bd.log2M;
+        bd.Ks = band_ks[b]; bd.Ke = band_ke[b]; bd.start = band_start[b];
+        bd.norm = band_norm[b];
+        bd.i_odd = d_io + off;
+        off += (size_t)nd * (bd.M / 2);
+        h->mb_bands.push_back(bd);
+    }
+    return 0;
+}
+
+// adds the odd-bin terms of every band b >= 1 to target[(s * NDET + d) * stride + offset], s in [s0, s0 + m)
+template <int NDET, int APPROX, bool CAL>
+static int bb_mb_add_ifft_fft_terms(bb_handle* h, long s0, long m, double* target, int stride, int offset, cudaStream_t st) {
+    const BBRelbinDev& rb = *h->rb;
+    const size_t smem = (size_t)BB_RED_WARPS * (BC_NCOEF + (CAL ? NDET * 4 * h->cal.n_points : 0)) * sizeof(double);
+    BB_CUDA(cudaFuncSetAttribute(bb_mb_band_fill_kernel<NDET, APPROX, CAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int maxM = 0;
+    for (const BBMbBand& bd : h->mb_bands) maxM = bd.M > maxM ? bd.M : maxM;
+    // transforms per pass: three buffers of chunk * NDET * M complex numbers, ~1.5 GB in total
+    long chunk = (long)(0.5e9 / ((double)NDET * maxM * sizeof(double2)));
+    if (chunk > m) chunk = m;
+    if (chunk < 1) chunk = 1;
+    const size_t need = (size_t)chunk * NDET * maxM;
+    if (need > h->mb_z_cap) {
+        cudaFree(h->d_mb_Z); cudaFree(h->d_mb_Z2); cudaFree(h->d_mb_Z3);
+        h->d_mb_Z = h->d_mb_Z2 = h->d_mb_Z3 = nullptr;
+        h->mb_z_cap = 0;
+        BB_CUDA(cudaMalloc(&h->d_mb_Z, need * sizeof(double2)));
+        BB_CUDA(cudaMalloc(&h->d_mb_Z2, need * sizeof(double2)));
+        BB_CUDA(cudaMalloc(&h->d_mb_Z3, need * sizeof(double2)));
+        h->mb_z_cap = need;
+    }
+    for (long c0 = 0; c0 < m; c0 += chunk) {
+        const long mc = (m - c0) < chunk ? (m - c0) : chunk;
+        for (const BBMbBand& bd : h->mb_bands) {
+            const long nt = mc * NDET;
+            const size_t elems = (size_t)nt * bd.M;
+            BB_CUDA(cudaMemsetAsync(h->d_mb_Z, 0, elems * sizeof(double2), st));
+            bb_mb_band_fill_kernel<NDET, APPROX, CAL><<<(unsigned)bb_red_grid(h, mc), BB_RED_THREADS, smem, st>>>(
+                h->d_coef, s0 + c0, mc, rb, bd, h->d_mb_sqrtw, h->d_calrec, h->cal, h->d_mb_Z);
+            BB_CUDA(cudaGetLastError());
+            if (bb_fft_forward(h->d_mb_Z, h->d_mb_Z2, h->d_mb_Z3, nt, bd.log2M, h->sm_count, st)) return 1;
+            bb_mb_band_modulate_kernel<<<(unsigned)(h->sm_count * 8), 256, 0, st>>>(h->d_mb_Z3, (long)elems, bd.M);
+            if (bb_fft_forward(h->d_mb_Z3, h->d_mb_Z2, h->d_mb_Z, nt, bd.log2M, h->sm_count, st)) return 1;
+            bb_mb_band_reduce_kernel<<<(unsigned)((nt * 32 + 255) / 256), 256, 0, st>>>(
+                h->d_mb_Z, mc, NDET, bd, target + (size_t)c0 * NDET * stride, stride, offset);
+            BB_CUDA(cudaGetLastError());
+            h->launches += 7;
+        }
+    }
+    return 0;
+}
+
 extern "C" int bb_set_roq(bb_handle* h, int n_linear, const double* nodes_linear, int n_quadratic,
                           const double* nodes_quadratic, int n_time, long time_start_index, double time_step,
                           const double* weights_linear, const double* weights_quadratic, int n_marg_times,
@@ -286,6 +378,8 @@ static int bb_launch_reduced_t(bb_handle* h, long n, double* out, cudaStream_t s
             BB_CUDA(cudaFuncSetAttribute(bb_relbin_kernel<NDET, APPROX, CAL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             bb_relbin_kernel<NDET, APPROX, CAL, false><<<(unsigned)grid, BB_RED_THREADS, smem, st>>>(
                 h->d_coef, n, *h->rb, h->d_calrec, h->cal, out);
+            // IFFT-FFT form of (h, h): the odd-bin terms of the bands b >= 1 join <h|h> of every detector
+            if (!h->mb_bands.empty() && bb_mb_add_ifft_fft_terms<NDET, APPROX, CAL>(h, 0, n, out, 3, 2, st)) return 1;
         }
     } else {
         const size_t smem_k6 = (size_t)2 * BB_ROQ_WARPS * (BC_NCOEF + (CAL ? NDET * 4 * h->cal.n_points : 0)) * sizeof(double)
@@ -456,6 +550,14 @@ static int bb_launch_mb_time_marg_t(bb_handle* h, long n, double* out, cudaStrea
         bb_mb_series_kernel<NDET, APPROX, CAL><<<(unsigned)grid, BB_RED_THREADS, smem, st>>>(
             h->d_coef, s0, m, rb, h->d_calrec, h->cal, h->d_mb_V, h->d_mb_hh);
         BB_CUDA(cudaGetLastError());
+        if (!h->mb_bands.empty()) {       // IFFT-FFT form of (h, h): odd-bin terms per detector, folded into <h|h>
+            double* tmp = nullptr;
+            BB_CUDA(cudaMallocAsync(&tmp, (size_t)m * NDET * sizeof(double), st));
+            BB_CUDA(cudaMemsetAsync(tmp, 0, (size_t)m * NDET * sizeof(double), st));
+            if (bb_mb_add_ifft_fft_terms<NDET, APPROX, CAL>(h, s0, m, tmp, 1, 0, st)) return 1;
+            bb_mb_hh_fold_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(tmp, m, NDET, h->d_mb_hh);
+            BB_CUDA(cudaFreeAsync(tmp, st));
+        }
         BBGemmArgs ga{};
         ga.A[0] = h->d_mb_V;
         ga.B[0] = h->d_mb_E;

@@ -11,7 +11,11 @@ Time marginalisation (multiband.py:714-726, 789-797): the reference's FFT of the
 evaluated for the times inside the geocent_time prior as a dense contraction on the FP64 tensor cores
 (`bb_set_multiband_time_marginalization`, csrc/bb_reduced.cuh bb_mb_*).
 
-Not provided: the IFFT-FFT form of (h, h) (`linear_interpolation=False`), weights files (h5py is absent).
+IFFT-FFT form of (h, h) (`linear_interpolation=False`, multiband.py:613-646, 766-787): band 0 and the even bins of every
+band's zero-padded spectrum are per-point weights (they ride in the same kernel as the linear-interpolation form); the
+odd bins take two transforms per sample, detector and band on the device (csrc/bb_fft.cuh, bb_mb_band_*).
+
+Not provided: weights files (HDF5; h5py is absent) - the `weights` dict round-trips.
 """
 import math
 import numbers
@@ -37,8 +41,6 @@ class MBGravitationalWaveTransient(GravitationalWaveTransient):
         if getattr(waveform_generator.frequency_domain_source_model, "_bb_kind", None) != "frequency_sequence":
             raise TypeError("MBGravitationalWaveTransient needs one of the source models "
                             "binary_black_hole_frequency_sequence / binary_neutron_star_frequency_sequence")
-        if not linear_interpolation:
-            raise NotImplementedError("the IFFT-FFT form of (h, h) has no device kernel (linear_interpolation=True)")
         if isinstance(weights, str):
             raise NotImplementedError("multiband weights files are HDF5 (h5py is absent): pass the weights dict")
         self._mb_host = None
@@ -200,7 +202,56 @@ class MBGravitationalWaveTransient(GravitationalWaveTransient):
         self._setup_integers()
         self._setup_waveform_frequency_points()
         self._setup_linear_coefficients()
-        self._setup_quadratic_coefficients_linear_interp()
+        if self.linear_interpolation:
+            self._setup_quadratic_coefficients_linear_interp()
+        else:
+            self._setup_quadratic_coefficients_ifft_fft()
+
+    def _setup_quadratic_coefficients_ifft_fft(self):
+        """multiband.py:613-646.  Also folds everything that is a per-point weight into ``quadratic_coeffs`` (see
+        the module docstring): band 0 (multiband.py:771-775) and the even bins of the bands b >= 1."""
+        logger.info("IFFT-FFT algorithm is used for (h, h).")
+        N = int(self.Nbs[-1])
+        Nhatbs = [min(2 * int(Mb), int(Nb)) for Mb, Nb in zip(self.Mbs, self.Nbs)]
+        self.Tbhats = [self.interferometers.duration * Nbhat / Nb for Nb, Nbhat in zip(self.Nbs, Nhatbs)]
+        self.Ibcs = {ifo.name: [] for ifo in self.interferometers}
+        for ifo in self.interferometers:
+            full_inv_psds = np.zeros(N // 2 + 1)
+            psd, mask = ifo.power_spectral_density_array, ifo.frequency_mask
+            full_inv_psds[:len(psd)][mask[:len(full_inv_psds)]] = 1 / psd[mask]
+            for b in range(self.number_of_bands):
+                Imb = np.fft.irfft(full_inv_psds[:int(self.Nbs[b]) // 2 + 1])
+                half_length = Nhatbs[b] // 2
+                Imbc = np.append(Imb[:half_length + 1], Imb[-(Nhatbs[b] - half_length - 1):])
+                self.Ibcs[ifo.name].append(np.fft.rfft(Imbc))
+        self.windows = np.array([])
+        self.square_root_windows = np.array([])
+        for b in range(self.number_of_bands):
+            Ks, Ke = self.Ks_Ke[b]
+            ws = self._get_window_sequence(1. / self.durations[b], Ks, Ke - Ks + 1, b)
+            self.windows = np.append(self.windows, ws)
+            self.square_root_windows = np.append(self.square_root_windows, np.sqrt(ws))
+        self._fold_ifft_fft_point_weights(Nhatbs)
+
+    def _fold_ifft_fft_point_weights(self, Nhatbs=None):
+        if Nhatbs is None:
+            Nhatbs = [min(2 * int(Mb), int(Nb)) for Mb, Nb in zip(self.Mbs, self.Nbs)]
+        self.quadratic_coeffs = {}
+        for ifo in self.interferometers:
+            q = np.zeros(len(self.banded_frequency_points))
+            for b in range(self.number_of_bands):
+                Ks, Ke = (int(x) for x in self.Ks_Ke[b])
+                s0, e0 = (int(x) for x in self.start_end_idxs[b])
+                w = self.windows[s0:e0 + 1]
+                if b == 0:          # multiband.py:771-775: plain inner product on the full grid
+                    q[s0:e0 + 1] = (4. / self.interferometers.duration) * ifo.frequency_mask[Ks:Ke + 1] * w \
+                        / ifo.power_spectral_density_array[Ks:Ke + 1]
+                elif Nhatbs[b] == 2 * int(self.Mbs[b]):
+                    # even bins of the 2 M-point spectrum are the band's points: |sqrt(w) h_k|^2 I[2 k]
+                    q[s0:e0 + 1] = (4. / self.Tbhats[b]) * w * self.Ibcs[ifo.name][b].real[2 * np.arange(Ks, Ke + 1)]
+                else:               # pragma: no cover - Nb >= 2 Mb for every band b >= 1 (multiband.py:428-447)
+                    raise NotImplementedError("IFFT-FFT form with Nhat^(b) != 2 M^(b)")
+            self.quadratic_coeffs[ifo.name] = q
 
     def _tau(self, f):
         """0PN time to merger from frequency f (multiband.py:322-340)."""
@@ -359,6 +410,9 @@ class MBGravitationalWaveTransient(GravitationalWaveTransient):
         out = {key: getattr(self, key) for key in self._WEIGHT_KEYS}
         out["waveform_frequencies"] = self.waveform_generator.waveform_arguments["frequencies"]
         out["quadratic_coeffs"] = self.quadratic_coeffs
+        if not self.linear_interpolation:
+            for key in ("Tbhats", "Ibcs", "windows", "square_root_windows"):
+                out[key] = getattr(self, key)
         return out
 
     def save_weights(self, filename):
@@ -366,8 +420,6 @@ class MBGravitationalWaveTransient(GravitationalWaveTransient):
 
     def setup_multibanding_from_weights(self, weights):
         """multiband.py:689-712 (dict form)."""
-        if not weights.get("linear_interpolation", True):
-            raise NotImplementedError("the IFFT-FFT form of (h, h) has no device kernel")
         self.reference_chirp_mass = weights["reference_chirp_mass"]
         for key, value in weights.items():
             if key == "reference_chirp_mass":
@@ -405,6 +457,21 @@ class MBGravitationalWaveTransient(GravitationalWaveTransient):
         hst = self._mb_host
         _lib.check(net.lib.bb_set_multiband(net.ptr, len(hst["freqs"]), hst["freqs"].ctypes.data,
                                             hst["linear"].ctypes.data, hst["quadratic"].ctypes.data))
+        if not self.linear_interpolation and self.number_of_bands > 1:
+            bands = range(1, self.number_of_bands)
+            ints = lambda vals: np.ascontiguousarray(list(vals), dtype=np.int32)      # noqa: E731
+            m = ints(int(self.Mbs[b]) for b in bands)
+            ks = ints(int(self.Ks_Ke[b][0]) for b in bands)
+            ke = ints(int(self.Ks_Ke[b][1]) for b in bands)
+            st = ints(int(self.start_end_idxs[b][0]) for b in bands)
+            norm = np.ascontiguousarray([4. / self.Tbhats[b] for b in bands], dtype=np.float64)
+            sw = np.ascontiguousarray(self.square_root_windows, dtype=np.float64)
+            i_odd = np.ascontiguousarray(np.concatenate([
+                np.concatenate([self.Ibcs[ifo.name][b].real[1::2][:int(self.Mbs[b]) // 2] for ifo in self.interferometers])
+                for b in bands]), dtype=np.float64)
+            _lib.check(net.lib.bb_set_multiband_ifft_fft(net.ptr, len(m), m.ctypes.data, ks.ctypes.data, ke.ctypes.data,
+                                                         st.ctypes.data, norm.ctypes.data, sw.ctypes.data,
+                                                         i_odd.ctypes.data))
         if self.time_marginalization:
             idx = np.ascontiguousarray(self._full_to_multiband, dtype=np.int32)
             _lib.check(net.lib.bb_set_multiband_time_marginalization(

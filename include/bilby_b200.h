@@ -249,6 +249,22 @@ int bb_set_multiband(bb_handle* h, int n_points, const double* frequencies, cons
 int bb_set_multiband_time_marginalization(bb_handle* h, long n_full, const int* full_index, double delta_tc,
                                           double beam_pattern_reference_time);
 
+/* The IFFT-FFT form of (h, h) of the multi-banded likelihood (linear_interpolation=False; bilby/gw/likelihood/
+ * multiband.py:613-646 _setup_quadratic_coefficients_ifft_fft, :766-787 calculate_snrs).  Band 0 and the even bins of
+ * every band's 2 M-point spectrum are per-point weights and belong in bb_set_multiband's quadratic_coeffs; this call
+ * hands over what the odd bins need, for the bands b >= 1 (n_bands of them):
+ *   band_m[b] = M^(b) (power of two), band_ks / band_ke = Ks_Ke[b], band_start[b] = start_end_idxs[b][0],
+ *   band_norm[b] = 4 / That^(b), sqrt_window [n_points] = square_root_windows,
+ *   i_odd = for every band in turn [n_det][M^(b) / 2] = Ibcs[ifo][b].real[1::2].
+ * n_bands = 0 switches it off (linear-interpolation form). */
+int bb_set_multiband_ifft_fft(bb_handle* h, int n_bands, const int* band_m, const int* band_ks, const int* band_ke,
+                              const int* band_start, const double* band_norm, const double* sqrt_window,
+                              const double* i_odd);
+
+/* Batched complex FFT, `batch` contiguous transforms of 2^log2n points (2^8 .. 2^18), forward sign e^{-2 pi i},
+ * out-of-place, device memory (csrc/bb_fft.cuh: what numpy.fft.fft does in the reference's multiband.py:766-797). */
+int bb_fft_device(bb_handle* h, const double* in, double* out, long batch, int log2n, void* stream);
+
 /* ROQ: replaces ROQGravitationalWaveTransient.calculate_snrs, _closest_time_indices, _interp_five_samples and
  * _calculate_d_inner_h_array (bilby/gw/likelihood/roq.py:467-651) with the source model binary_*_roq
  * (bilby/gw/source.py:693-721, 802-898) evaluated at the ROQ frequency nodes.

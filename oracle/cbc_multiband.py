@@ -56,7 +56,8 @@ class OracleMultiband(ocl.OracleLikelihood):
 
     def __init__(self, interferometers, reference_chirp_mass, source_model=binary_black_hole_frequency_sequence,
                  waveform_arguments=None, highest_mode=2, accuracy_factor=5, time_offset=None, delta_f_end=None,
-                 maximum_banding_frequency=None, minimum_banding_duration=0.0, geocent_time_prior=None, **kw):
+                 maximum_banding_frequency=None, minimum_banding_duration=0.0, geocent_time_prior=None,
+                 linear_interpolation=True, **kw):
         super().__init__(interferometers, source_model=source_model, waveform_arguments=waveform_arguments, **kw)
         self.reference_chirp_mass = reference_chirp_mass
         self.mc_sec = GRAVITATIONAL_CONSTANT * reference_chirp_mass * SOLAR_MASS / SPEED_OF_LIGHT ** 3   # :133-134
@@ -80,7 +81,11 @@ class OracleMultiband(ocl.OracleLikelihood):
         self._setup_integers()
         self._setup_waveform_frequency_points()
         self._setup_linear_coefficients()
-        self._setup_quadratic_coefficients_linear_interp()
+        self.linear_interpolation = linear_interpolation
+        if linear_interpolation:
+            self._setup_quadratic_coefficients_linear_interp()
+        else:
+            self._setup_quadratic_coefficients_ifft_fft()
         if self.time_marginalization:
             self._setup_time_marginalization_multiband()
 
@@ -237,12 +242,59 @@ class OracleMultiband(ocl.OracleLikelihood):
         for name in self.quadratic_coeffs:
             self.quadratic_coeffs[name] = np.concatenate(self.quadratic_coeffs[name])
 
+    def _setup_quadratic_coefficients_ifft_fft(self):
+        """:613-646."""
+        n_full = int(self.Nbs[-1])
+        nhat = [min(2 * int(mb), int(nb)) for mb, nb in zip(self.Mbs, self.Nbs)]
+        self.Tbhats = [self.duration * nh / nb for nb, nh in zip(self.Nbs, nhat)]
+        self.Ibcs = {ifo.name: [] for ifo in self.ifos}
+        self.hbcs = {ifo.name: [] for ifo in self.ifos}
+        self.wths = {ifo.name: [] for ifo in self.ifos}
+        for ifo in self.ifos:
+            inv = np.zeros(n_full // 2 + 1)
+            psd, mask = ifo.power_spectral_density_array, ifo.frequency_mask
+            inv[:len(psd)][mask[:len(inv)]] = 1 / psd[mask]
+            for b in range(self.number_of_bands):
+                imb = np.fft.irfft(inv[:int(self.Nbs[b]) // 2 + 1])
+                half = nhat[b] // 2
+                imbc = np.append(imb[:half + 1], imb[-(nhat[b] - half - 1):])
+                self.Ibcs[ifo.name].append(np.fft.rfft(imbc))
+                self.hbcs[ifo.name].append(np.zeros(nhat[b]))
+                self.wths[ifo.name].append(np.zeros(int(self.Mbs[b]) // 2 + 1, dtype=complex))
+        self.windows, self.square_root_windows = np.array([]), np.array([])
+        for b in range(self.number_of_bands):
+            ks, ke = self.Ks_Ke[b]
+            ws = self._get_window_sequence(1.0 / self.durations[b], ks, ke - ks + 1, b)
+            self.windows = np.append(self.windows, ws)
+            self.square_root_windows = np.append(self.square_root_windows, np.sqrt(ws))
+
+    def _optimal_snr_squared_ifft_fft(self, strain, ifo):
+        """:766-787."""
+        out = 0.0
+        for b in range(self.number_of_bands):
+            ks, ke = self.Ks_Ke[b]
+            s0, e0 = self.start_end_idxs[b]
+            mb = int(self.Mbs[b])
+            if b == 0:
+                out += (4.0 / self.duration) * np.vdot(
+                    np.abs(strain[s0:e0 + 1]) ** 2,
+                    ifo.frequency_mask[ks:ke + 1] * self.windows[s0:e0 + 1] / ifo.power_spectral_density_array[ks:ke + 1])
+            else:
+                self.wths[ifo.name][b][ks:ke + 1] = self.square_root_windows[s0:e0 + 1] * strain[s0:e0 + 1]
+                self.hbcs[ifo.name][b][-mb:] = np.fft.irfft(self.wths[ifo.name][b])
+                thbc = np.fft.rfft(self.hbcs[ifo.name][b])
+                out += (4.0 / self.Tbhats[b]) * np.vdot(np.abs(thbc) ** 2, self.Ibcs[ifo.name][b].real)
+        return out
+
     # ---- evaluation (:728-765)
     def calculate_snrs(self, pols, ifo, parameters):
         modes = {m: v[self.unique_to_original_frequencies] for m, v in pols.items()}
         strain = ifo.get_detector_response(modes, parameters, frequencies=self.banded_frequency_points)
         d_inner_h = np.conj(np.dot(strain, self.linear_coeffs[ifo.name]))
-        hh = np.vdot(np.abs(strain) ** 2, self.quadratic_coeffs[ifo.name])
+        if self.linear_interpolation:
+            hh = np.vdot(np.abs(strain) ** 2, self.quadratic_coeffs[ifo.name])
+        else:
+            hh = self._optimal_snr_squared_ifft_fft(strain, ifo)
         arr = None
         if self.time_marginalization:                                  # :789-797
             idx = np.asarray(self._full_to_multiband)

@@ -86,6 +86,19 @@ def multiband(tag, duration, fs, inj, model, grid_model, conversion, approximant
         distance_marginalization=True, distance_marginalization_lookup_table=f"/tmp/golden_mb_{tag}_lookup.npz")
     res["lnl_distance_phase"] = evaluate(like, draws, n)
     res["distance_prior"] = np.array([dmin, dmax])
+    # the IFFT-FFT form of (h, h) (multiband.py:613-646, 766-787)
+    like = bilby.gw.likelihood.MBGravitationalWaveTransient(
+        ifos, wfg_new(), reference_chirp_mass=ref_mc, priors=PriorDict(dict(geocent_time=tprior)),
+        linear_interpolation=False)
+    res["lnl_ifft_fft"] = evaluate(like, draws, n)
+    hh2 = np.zeros((n, 3))
+    for i in range(n):
+        p = {k: float(v[i]) for k, v in draws.items()}
+        p.update(like.get_sky_frame_parameters(p))
+        pols_i = like.waveform_generator.frequency_domain_strain(p)
+        for j, ifo in enumerate(ifos):
+            hh2[i, j] = like.calculate_snrs(pols_i, ifo, parameters=p).optimal_snr_squared
+    res["optimal_snr_squared_ifft_fft"] = hh2
     # time marginalisation (multiband.py:714-726, 789-797): geocent_time := start_time, jitter drawn inside its prior
     tdraws = dict(draws)
     tdraws["geocent_time"] = np.full(n, float(start_time))

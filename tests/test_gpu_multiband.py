@@ -132,3 +132,39 @@ def test_multiband_time_marginalisation_vs_reference(name, bns):
         assert np.max(np.abs(lnl - g[key]) / scale) < RTOL, (key, lnl[:4], g[key][:4])
         one = like.log_likelihood_ratio({k: float(v[2]) for k, v in d.items()})
         assert one == lnl[2]
+
+
+@pytest.mark.parametrize("log2n,batch", [(8, 5), (9, 3), (13, 4), (14, 6), (15, 2), (18, 1)])
+def test_batched_fft_vs_numpy(log2n, batch):
+    """csrc/bb_fft.cuh (four-step FFT over global memory) vs numpy.fft.fft, the transform of multiband.py:766-797."""
+    import torch
+    from bilby_b200 import _lib
+    h = _lib.Handle()
+    rng = np.random.default_rng(log2n)
+    n = 1 << log2n
+    x = rng.standard_normal((batch, n)) + 1j * rng.standard_normal((batch, n))
+    xd = torch.from_numpy(x).cuda()
+    out = torch.empty_like(xd)
+    _lib.check(h.lib.bb_fft_device(h.ptr, xd.data_ptr(), out.data_ptr(), batch, log2n, None))
+    ref = np.fft.fft(x, axis=1)
+    assert np.max(np.abs(out.cpu().numpy() - ref)) < 1e-13 * np.abs(ref).max() * log2n
+
+
+@pytest.mark.parametrize("name,bns", [("multiband_bbh_8s_H1L1V1", False), ("multiband_bns_32s_H1L1V1", True)])
+def test_multiband_ifft_fft_form_vs_reference(name, bns):
+    """linear_interpolation=False (multiband.py:613-646, 766-787): per-detector <h|h> and lnL vs the unmodified
+    reference, plus the combination with time marginalisation vs the oracle."""
+    import torch
+    g, _ = rc.load(name)
+    like, draws = _mb_product(g, bns, linear_interpolation=False)
+    d = {k: v for k, v in draws.items() if k != "time_jitter"}
+    snr = like.inner_products_batch(torch.from_numpy(like.pack(d)).cuda()).cpu().numpy()
+    hh = g["optimal_snr_squared_ifft_fft"]
+    assert np.max(np.abs(snr[..., 2] - hh) / hh) < RTOL
+    assert np.max(np.abs(snr[..., 0] + 1j * snr[..., 1] - g["d_inner_h"]) / hh) < RTOL
+    lnl = like.log_likelihood_ratio_batch(d)
+    assert np.max(np.abs(lnl - g["lnl_ifft_fft"]) / _scale(g, g["lnl_ifft_fft"])) < RTOL
+    # weights dict round trip keeps the form
+    like2, _ = _mb_product(g, bns, weights=like.weights)
+    assert like2.linear_interpolation is False
+    assert np.array_equal(like2.log_likelihood_ratio_batch(d), lnl)

@@ -60,3 +60,18 @@ def test_multiband_time_marginalisation_vs_reference(name, bns):
         assert abs(like._delta_tc - float(g["time_marg_delta_tc"])) < 1e-18
         got = _eval(like, d, n, skip=())
         assert np.all(np.abs(got - g[key][:n]) < 1e-9 * scale), (key, got, g[key][:n])
+
+
+@pytest.mark.parametrize("name,bns", [("multiband_bbh_8s_H1L1V1", False), ("multiband_bns_32s_H1L1V1", True)])
+def test_multiband_ifft_fft_form_vs_reference(name, bns):
+    """multiband.py:613-646, 766-787 (linear_interpolation=False)."""
+    g, draws = rc.load(name)
+    n = 4
+    like, _ = rc.multiband_oracle(g, bns, linear_interpolation=False)
+    for i in range(n):
+        p = {k: float(v[i]) for k, v in draws.items() if k != "time_jitter"}
+        for d, (_, hh) in enumerate(like.log_likelihood_ratio(p, return_snrs=True)):
+            ref = g["optimal_snr_squared_ifft_fft"][i, d]
+            assert abs(hh - ref) < 1e-9 * ref
+    scale = np.maximum(np.abs(g["lnl_ifft_fft"][:n]), 0.5 * g["optimal_snr_squared"][:n].sum(axis=1))
+    assert np.all(np.abs(_eval(like, draws, n) - g["lnl_ifft_fft"][:n]) < 1e-9 * scale)
