@@ -100,6 +100,24 @@ EXPORTED_SYMBOLS = (
     "bb_set_multiband_ifft_fft", "bb_fft_device")
 
 
+_torch_ops = None
+
+
+def torch_ops():
+    """torch.ops.bilby_b200: the TORCH_LIBRARY shim over the C ABI (csrc/bb_torch.cpp).  Built by bilby_b200.build."""
+    global _torch_ops
+    if _torch_ops is None:
+        import torch
+        load()                                   # the shim links against libbilby_b200.so
+        path = os.path.join(os.path.dirname(LIB_PATH), "libbilby_b200_torch.so")
+        if not os.path.exists(path):
+            from . import build
+            build.build_torch_shim()
+        torch.ops.load_library(path)
+        _torch_ops = torch.ops.bilby_b200
+    return _torch_ops
+
+
 def check(rc):
     if rc != 0:
         raise BilbyB200Error(load().bb_last_error().decode())

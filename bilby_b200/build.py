@@ -11,6 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(LIB_DIR, "libbilby_b200.so")
+TORCH_LIB = os.path.join(LIB_DIR, "libbilby_b200_torch.so")
 SOURCES = ["bb_kernels.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared", "--use_fast_math=false"]
@@ -41,7 +42,26 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed: " + " ".join(cmd))
     if verbose:
         print(res.stdout + res.stderr)
+    if "BB_LIB_OUT" not in os.environ:
+        build_torch_shim()
     return LIB
+
+
+def build_torch_shim():
+    """csrc/bb_torch.cpp -> _lib/libbilby_b200_torch.so: TORCH_LIBRARY ops over the C ABI (g++, ~15 s)."""
+    import torch
+    from torch.utils import cpp_extension
+    tlib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", os.path.join(CSRC, "bb_torch.cpp"), "-o", TORCH_LIB]
+    cmd += [f"-I{i}" for i in cpp_extension.include_paths()] + ["-I/usr/local/cuda/include"]
+    cmd += [f"-L{tlib}", "-ltorch", "-ltorch_cpu", "-lc10", "-lc10_cuda", f"-L{LIB_DIR}", "-lbilby_b200",
+            "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{tlib}",
+            "-D_GLIBCXX_USE_CXX11_ABI=" + str(int(torch._C._GLIBCXX_USE_CXX11_ABI))]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("g++ failed: " + " ".join(cmd))
+    return TORCH_LIB
 
 
 if __name__ == "__main__":

@@ -587,19 +587,15 @@ class GravitationalWaveTransient(Likelihood):
         return out
 
     def _evaluate_device(self, rows, cal=None):
+        """Device rows in, device lnL out, through the TORCH_LIBRARY ops (csrc/bb_torch.cpp -> C ABI) on the current
+        stream of the rows' device."""
         net = self.device_network
-        torch = net.torch
-        out = torch.empty(rows.shape[0], dtype=torch.float64, device=rows.device)
+        ops = _lib.torch_ops()
         if self._cal_points:
             if cal is None:
                 raise ValueError("this likelihood has a calibration model: calibration parameters are required")
-            cal = cal.contiguous()
-            _lib.check(net.lib.bb_log_likelihood_ratio_cal_device(net.ptr, rows.data_ptr(), cal.data_ptr(),
-                                                                  rows.shape[0], out.data_ptr(), net._stream()))
-        else:
-            _lib.check(net.lib.bb_log_likelihood_ratio_device(net.ptr, rows.data_ptr(), rows.shape[0], out.data_ptr(),
-                                                              net._stream()))
-        return out
+            return ops.log_likelihood_ratio_cal(net.ptr.value, rows.contiguous(), cal.contiguous())
+        return ops.log_likelihood_ratio(net.ptr.value, rows.contiguous())
 
     def inner_products_batch(self, rows, cal=None):
         """[n,16] CUDA rows -> [n, n_det, 3] (Re<h|d>, Im<h|d>, <h|h>) per detector (base.py:260-354)."""

@@ -46,3 +46,14 @@ def test_no_cpu_path_fails_loudly():
     ptr = ctypes.c_void_p()
     assert lib.bb_create(0, ctypes.byref(ptr)) != 0
     assert b"no CUDA device" in lib.bb_last_error()
+
+
+def test_torch_library_shim_registers_the_ops():
+    """csrc/bb_torch.cpp: TORCH_LIBRARY(bilby_b200) over the C ABI loads without a GPU and refuses CPU tensors loudly."""
+    import torch
+    from bilby_b200 import _lib
+    ops = _lib.torch_ops()
+    for name in ("log_likelihood_ratio", "log_likelihood_ratio_cal", "inner_products", "likelihood_from_inner_products"):
+        assert hasattr(ops, name), name
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        ops.log_likelihood_ratio(1, torch.zeros((2, 16), dtype=torch.float64))
