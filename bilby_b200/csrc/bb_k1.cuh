@@ -203,12 +203,16 @@ struct K1Ph<2> {
     }
 };
 
-// per-warp running state of one sample
+// per-warp running state of one sample.
+// The detector's phase ramp exp(+2 pi i f dt_d) at bin (row r, lane l) is ramp_d[r0, l] R_d^(r - r0) with R_d the
+// advance over one row, so   sum_r ramp_d[r] t_r = ramp_d[r_last] * sum_r conj(R_d)^(r_last - r) t_r,   t_r = conj(h22) d/S:
+// the sum is a Horner scheme in conj(R_d) over the rows,  acc <- acc conj(R_d) + t_r  (8 FP64 operations per detector
+// and row instead of 12 for rotate + accumulate + advance, and no ramp registers); the lane's ramp at the LAST row
+// multiplies once per sample, where the anchor sincospi used to be.
 template <int NDET>
 struct K1State {
-    double acc[NDET][3];     // sum conj(h/K) d/S (re, im), sum A^2 / S
-    double ramp[NDET][2];    // exp(+2 pi i f dt_d) at this lane's bin of the current row
-    double step[NDET][2];    // its advance over one row
+    double acc[NDET][3];     // Horner accumulators of conj(h/K) d/S (re, im); sum A^2 / S
+    double step[NDET][2];    // R_d = exp(+i pi * 2 dt_d * 32 df)
     const double* cal;       // CAL: this sample's calibration record [NDET][4][n_points] (shared memory)
     BBCalGrid grid;
 };
@@ -228,8 +232,7 @@ __device__ __forceinline__ void bb_k1_accumulate(K1State<NDET>& st, const K1Tile
     if (CAL) cw = bb_cal_weights(st.grid.n_points, st.grid.l0[0], st.grid.inv_delta[0], tile.lf[i]);
 #pragma unroll
     for (int d = 0; d < NDET; ++d) {
-        const double rc = st.ramp[d][0], rs = st.ramp[d][1];
-        double wr = zr * rc - zi * rs, wi = zr * rs + zi * rc;
+        double wr = zr, wi = zi;
         double hw = A2;
         if (CAL) {
             // h_det *= C(f)  =>  conj(h) picks up amp1 (cr - i ci), |h|^2 picks up amp1^2
@@ -243,12 +246,12 @@ __device__ __forceinline__ void bb_k1_accumulate(K1State<NDET>& st, const K1Tile
             hw = A2 * amp1 * amp1;
         }
         const double2 dd = tile.ds[d][i];
-        st.acc[d][0] = fma(wr, dd.x, fma(-wi, dd.y, st.acc[d][0]));
-        st.acc[d][1] = fma(wr, dd.y, fma(wi, dd.x, st.acc[d][1]));
+        // t = w d/S;  acc <- acc conj(R) + t
+        const double tr = fma(wr, dd.x, -wi * dd.y), ti = fma(wr, dd.y, wi * dd.x);
+        const double ar = st.acc[d][0], ai = st.acc[d][1];
+        st.acc[d][0] = fma(ar, st.step[d][0], fma(ai, st.step[d][1], tr));
+        st.acc[d][1] = fma(ai, st.step[d][0], fma(-ar, st.step[d][1], ti));
         st.acc[d][2] = fma(hw, tile.is[d][i], st.acc[d][2]);
-        // advance the ramp to the next row
-        st.ramp[d][0] = rc * st.step[d][0] - rs * st.step[d][1];
-        st.ramp[d][1] = rc * st.step[d][1] + rs * st.step[d][0];
     }
 }
 
@@ -399,8 +402,6 @@ bb_inner_product_kernel(const double* __restrict__ coef, const unsigned* __restr
 #pragma unroll
         for (int d = 0; d < NDET; ++d) {
             st.acc[d][0] = st.acc[d][1] = st.acc[d][2] = 0.0;
-            const double f0 = (double)(row_first * BB_ROW + lane) * df;
-            bb_sincospi(rec[BC_DET + BC_DSTRIDE * d + 2] * f0, &st.ramp[d][1], &st.ramp[d][0]);
             st.step[d][0] = rec[BC_DET + BC_DSTRIDE * d + 4];
             st.step[d][1] = rec[BC_DET + BC_DSTRIDE * d + 5];
         }
@@ -461,8 +462,12 @@ bb_inner_product_kernel(const double* __restrict__ coef, const unsigned* __restr
             const long s = perm ? (long)perm[p0 + warp] : p0 + warp;
 #pragma unroll
             for (int d = 0; d < NDET; ++d) {
-                const double sr = bb_warp_sum(st.acc[d][0]);
-                const double si = bb_warp_sum(st.acc[d][1]);
+                // the lane's ramp at the last row this sample visited closes the Horner sum
+                double rs, rc;
+                bb_sincospi(rec[BC_DET + BC_DSTRIDE * d + 2] * ((double)((row_last - 1) * BB_ROW + lane) * df), &rs, &rc);
+                const double ar = st.acc[d][0], ai = st.acc[d][1];
+                const double sr = bb_warp_sum(ar * rc - ai * rs);
+                const double si = bb_warp_sum(ar * rs + ai * rc);
                 const double sh = bb_warp_sum(st.acc[d][2]);
                 if (lane == 0) {
                     const double kr = rec[BC_DET + BC_DSTRIDE * d], ki = rec[BC_DET + BC_DSTRIDE * d + 1];

@@ -69,8 +69,14 @@ BB_HD void bb_sincospi(double x, double* sn, double* cs) {
     s *= r;
     // x = n/2 + r: rotate by n quarter turns
     const double a = (n & 1) ? c : s, b = (n & 1) ? s : c;
+#ifdef __CUDA_ARCH__
+    // sign flips on the high word (two integer instructions instead of a DADD and two selects each)
+    *sn = __hiloint2double(__double2hiint(a) ^ ((n & 2) << 30), __double2loint(a));
+    *cs = __hiloint2double(__double2hiint(b) ^ (((n + 1) & 2) << 30), __double2loint(b));
+#else
     *sn = (n & 2) ? -a : a;
     *cs = ((n + 1) & 2) ? -b : b;
+#endif
 }
 
 // atan(y), any finite y
@@ -89,6 +95,10 @@ BB_HD double bb_atan(double y) {
 #pragma unroll
     for (int i = 10; i >= 1; --i) p = fma(p, u, BB_KC(bb_kc_atan, i));
     // atan(t) = t + t u p(u) (the leading coefficient is exactly 1)
-    const double r = off + (fma(t * u, p, off_lo) + t);
+    const double r = off + (fma(t * u, p, off_lo) + t);          // >= 0 in every branch
+#ifdef __CUDA_ARCH__
+    return __hiloint2double(__double2hiint(r) ^ (__double2hiint(y) & 0x80000000), __double2loint(r));   // copysign(r, y)
+#else
     return y < 0.0 ? -r : r;
+#endif
 }
