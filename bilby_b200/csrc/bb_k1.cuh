@@ -36,6 +36,9 @@ struct K1Tile {
     double q34[BB_K1_CHUNK];
     double rf[BB_K1_CHUNK];
     double u7[BB_K1_CHUNK];
+    double ff[BB_K1_CHUNK];
+    double t3[BB_K1_CHUNK];
+    double x3[BB_K1_CHUNK];
     double2 ds[NDET][BB_K1_CHUNK];
     double is[NDET][BB_K1_CHUNK];
 };
@@ -80,6 +83,9 @@ __device__ __forceinline__ void bb_k1_issue_tile(K1Tile<NDET>& t, unsigned long 
     bb_bulk_g2s(t.q34, g.q34 + c0, BB_K1_CHUNK * 8, bar);
     bb_bulk_g2s(t.rf, g.rf + c0, BB_K1_CHUNK * 8, bar);
     bb_bulk_g2s(t.u7, g.u7 + c0, BB_K1_CHUNK * 8, bar);
+    bb_bulk_g2s(t.ff, g.ff + c0, BB_K1_CHUNK * 8, bar);
+    bb_bulk_g2s(t.t3, g.t3 + c0, BB_K1_CHUNK * 8, bar);
+    bb_bulk_g2s(t.x3, g.x3 + c0, BB_K1_CHUNK * 8, bar);
 #pragma unroll
     for (int d = 0; d < NDET; ++d) {
         bb_bulk_g2s(t.ds[d], g.ds + (size_t)d * g.n_pad + c0, BB_K1_CHUNK * 16, bar);
@@ -95,9 +101,9 @@ struct K1PhIns { double q[13]; };
 struct K1PhInt { double q[4]; };
 struct K1PhMr { double q[7]; };
 
-// Every eval works from the tile's per-bin columns: f, u = f^(-1/6) (inspiral only: t = u^2 = f^(-1/3), x = f t^2 =
-// f^(1/3)), rf = 1/f, ln f, f^(3/4).  The amplitude prefactor a0 is folded into the region's coefficients when they
-// are loaded; the common factor f^(-7/6) comes from the tile (K1Tile::u7).
+// Every eval works from the tile's per-bin columns: f, t = f^(-1/3) and x = f^(1/3) (inspiral only), rf = 1/f, ln f,
+// f^(3/4): no conversion, multiplication or power per bin.  The amplitude prefactor a0 is folded into the region's
+// coefficients when they are loaded; the common factor f^(-7/6) comes from the tile (K1Tile::u7).
 template <int AR>
 struct K1Amp;
 template <>
@@ -262,23 +268,22 @@ __device__ __forceinline__ void bb_k1_rows_pd_m(K1State<NDET>& st, const K1Tile<
                                                 const K1Ph<PR>& phs, int r0, int r1, int c0, int lane, int kmin,
                                                 int kmax, double df) {
     constexpr bool NEEDS_X = (AR == 0) || (PR == 0);
-    double kd = (double)(r0 * BB_ROW + lane);          // bin index as a double: += 32 per row, f = kd * df is exact
-    int i = r0 * BB_ROW + lane - c0;
+    int k = r0 * BB_ROW + lane;
+    int i = k - c0;
     BB_UNROLL(BB_K1_UNROLL)
     for (int r = r0; r < r1; ++r) {
-        const bool act = !MASKED || ((kd >= (double)kmin) && (kd < (double)kmax));
-        const double f = kd * df;
+        const bool act = !MASKED || ((k >= kmin) && (k < kmax));
+        const double f = tile.ff[i];
         double t = 0.0, x = 0.0;
         if (NEEDS_X) {
-            const double u = tile.u[i];
-            t = u * u;
-            x = f * t * t;
+            t = tile.t3[i];
+            x = tile.x3[i];
         }
         const double A = amp.eval(f, x) * tile.u7[i];
         const double ph = phs.eval(f, t, x, tile.rf[i], tile.lf[i], tile.q34[i]);
         bb_k1_accumulate<NDET, CAL, MASKED>(st, tile, i, act, A, ph);
         amp.next();
-        kd += (double)BB_ROW;
+        if (MASKED) k += BB_ROW;
         i += BB_ROW;
     }
 }
@@ -298,7 +303,40 @@ __device__ __forceinline__ void bb_k1_rows_pd(K1State<NDET>& st, const K1Tile<ND
     if (ri1 < r1) bb_k1_rows_pd_m<NDET, AR, PR, CAL, true>(st, tile, amp, phs, ri1, r1, c0, lane, kmin, kmax, df);
 }
 
-// generic rows: per-lane region selection (rows straddling a region boundary) or TaylorF2
+// TaylorF2 (+ tides): one region, the 15 phase coefficients and the amplitude prefactor in registers, f / t / x / f^(-7/6)
+// from the tile (the generic path re-reads every coefficient from shared memory and forms the powers per bin)
+template <int NDET, bool CAL, bool MASKED>
+__device__ __forceinline__ void bb_k1_rows_tf2_m(K1State<NDET>& st, const K1Tile<NDET>& tile, const double (&q)[BT_NP],
+                                                 double a0, int r0, int r1, int c0, int lane, int kmin, int kmax) {
+    int k = r0 * BB_ROW + lane;
+    int i = k - c0;
+    for (int r = r0; r < r1; ++r) {
+        const bool act = !MASKED || ((k >= kmin) && (k < kmax));
+        const double f = tile.ff[i], t = tile.t3[i], x = tile.x3[i], lf = tile.lf[i];
+        const double A = a0 * tile.u7[i];
+        // the arithmetic of bb_taylorf2_phase, operation for operation
+        const double x2 = x * x, x5 = x2 * x2 * x;
+        double tid = q[8];
+        tid = tid * x + q[7]; tid = tid * x + q[6]; tid = tid * x + q[5]; tid = tid * x2 + q[4];
+        double neg = q[12] * t * t + q[11];
+        neg = neg * t + q[10]; neg = neg * t + q[9];
+        const double ph = q[0] + x * (q[1] + x * q[2]) + q[3] * f + tid * x5 + neg * t + lf * (q[13] + q[14] * x);
+        bb_k1_accumulate<NDET, CAL, MASKED>(st, tile, i, act, A, ph);
+        if (MASKED) k += BB_ROW;
+        i += BB_ROW;
+    }
+}
+
+template <int NDET, bool CAL>
+__device__ __forceinline__ void bb_k1_rows_tf2(K1State<NDET>& st, const K1Tile<NDET>& tile, const double (&q)[BT_NP],
+                                               double a0, int r0, int r1, int c0, int lane, int kmin, int kmax) {
+    const int ri0 = min(max((kmin + BB_ROW - 1) / BB_ROW, r0), r1), ri1 = max(min(kmax / BB_ROW, r1), ri0);
+    if (r0 < ri0) bb_k1_rows_tf2_m<NDET, CAL, true>(st, tile, q, a0, r0, ri0, c0, lane, kmin, kmax);
+    if (ri0 < ri1) bb_k1_rows_tf2_m<NDET, CAL, false>(st, tile, q, a0, ri0, ri1, c0, lane, kmin, kmax);
+    if (ri1 < r1) bb_k1_rows_tf2_m<NDET, CAL, true>(st, tile, q, a0, ri1, r1, c0, lane, kmin, kmax);
+}
+
+// generic rows: per-lane region selection (rows straddling a region boundary)
 template <int NDET, int APPROX, bool CAL>
 __device__ __forceinline__ void bb_k1_rows_generic(K1State<NDET>& st, const K1Tile<NDET>& tile, const double* rec,
                                                    int r0, int r1, int c0, int lane, int kmin, int kmax, double df) {
@@ -409,6 +447,12 @@ bb_inner_product_kernel(const double* __restrict__ coef, const unsigned* __restr
         if (APPROX == BB_IMRPHENOMD) {
             ka1 = (int)rec[BC_KA1]; ka2 = (int)rec[BC_KA2]; kp1 = (int)rec[BC_KP1]; kp2 = (int)rec[BC_KP2];
         }
+        double tq[BT_NP], ta0 = 0.0;
+        if (APPROX == BB_TAYLORF2) {
+#pragma unroll
+            for (int j = 0; j < BT_NP; ++j) tq[j] = rec[BT_P + j];
+            ta0 = rec[BC_A0];
+        }
 
         // ---- stream the tiles
         if (cb1 > cb0 && tid == 0) {
@@ -451,7 +495,7 @@ bb_inner_product_kernel(const double* __restrict__ coef, const unsigned* __restr
                         }
                     }
                 } else {
-                    bb_k1_rows_generic<NDET, APPROX, CAL>(st, tile, rec, r, rend, c0, lane, kmin, kmax, df);
+                    bb_k1_rows_tf2<NDET, CAL>(st, tile, tq, ta0, r, rend, c0, lane, kmin, kmax);
                 }
             }
             __syncthreads();     // everyone is done with this stage before it is refilled

@@ -48,6 +48,9 @@ struct BBTiles {
     const double* q34;    // f^(3/4)             [n_freq]
     const double* rf;     // 1 / f               [n_freq]   (K1: the merger-ringdown and intermediate phase terms)
     const double* u7;     // f^(-7/6)            [n_freq]   (K1: the amplitude's leading power)
+    const double* ff;     // f = k df            [n_freq]   (K1 / K4a: no conversion or multiplication per bin)
+    const double* t3;     // f^(-1/3) = u^2      [n_freq]
+    const double* x3;     // f^(1/3) = (f t) t   [n_freq]
     const double2* ds;    // (4/T) d/S  complex  [n_det][n_pad]
     const double* is;     // (4/T) / S           [n_det][n_pad]
     int n_pad;            // n_freq rounded up to a whole number of K1 tiles (zero padded)
@@ -73,7 +76,8 @@ struct bb_handle {
     BBMarg marg{};
     bool have_network = false;
     int shard_lo = 0, shard_hi = 0;       // bin range owned by this handle
-    double *d_u = nullptr, *d_lf = nullptr, *d_q34 = nullptr, *d_is = nullptr, *d_rf = nullptr, *d_u7 = nullptr;
+    double *d_u = nullptr, *d_lf = nullptr, *d_q34 = nullptr, *d_is = nullptr, *d_rf = nullptr, *d_u7 = nullptr,
+           *d_ff = nullptr, *d_t3 = nullptr, *d_x3 = nullptr;
     double2* d_ds = nullptr;
     unsigned char* d_mask = nullptr;
     double2* d_twiddle = nullptr;          // e^{-2 pi i m / nfft}, m < nfft/2 (time marginalisation)
@@ -171,6 +175,20 @@ __device__ __forceinline__ void bb_wave(const double* c, double f, double u, dou
         *ph = bb_phenomd_phase(c, f, t, x, lf, q34);
     } else {
         *A = bb_taylorf2_amp(c, u, t);
+        *ph = bb_taylorf2_phase(c, f, t, x, lf);
+    }
+}
+
+// the same from precomputed per-node columns t = f^(-1/3), x = f^(1/3), u7 = f^(-7/6) (BBNodes): identical bits, since
+// the columns are formed with bb_wave's operations (t = u u, x = (f t) t, u7 = u (t t t))
+template <int APPROX>
+__device__ __forceinline__ void bb_wave_cols(const double* c, double f, double t, double x, double u7, double lf,
+                                             double q34, double* A, double* ph) {
+    if (APPROX == BB_IMRPHENOMD) {
+        *A = bb_phenomd_amp_core(c, f, x) * c[BC_A0] * u7;
+        *ph = bb_phenomd_phase(c, f, t, x, lf, q34);
+    } else {
+        *A = c[BC_A0] * u7;
         *ph = bb_taylorf2_phase(c, f, t, x, lf);
     }
 }
@@ -593,6 +611,9 @@ static BBTiles bb_tiles(const bb_handle* h) {
     t.q34 = h->d_q34;
     t.rf = h->d_rf;
     t.u7 = h->d_u7;
+    t.ff = h->d_ff;
+    t.t3 = h->d_t3;
+    t.x3 = h->d_x3;
     t.ds = h->d_ds;
     t.is = h->d_is;
     t.n_pad = h->n_pad;
@@ -641,7 +662,7 @@ extern "C" void bb_destroy(bb_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaFree(h->d_u); cudaFree(h->d_lf); cudaFree(h->d_q34); cudaFree(h->d_is); cudaFree(h->d_ds);
-    cudaFree(h->d_rf); cudaFree(h->d_u7);
+    cudaFree(h->d_rf); cudaFree(h->d_u7); cudaFree(h->d_ff); cudaFree(h->d_t3); cudaFree(h->d_x3);
     cudaFree(h->d_tx); cudaFree(h->d_ty); cudaFree(h->d_c);
     cudaFree(h->d_coef); cudaFree(h->d_snr); cudaFree(h->d_params); cudaFree(h->d_out);
     cudaFree(h->d_mask); cudaFree(h->d_twiddle);
@@ -705,7 +726,7 @@ extern "C" int bb_set_network(bb_handle* h, int n_det, int n_freq, double durati
     const int n_pad = ((n_freq + BB_K1_CHUNK - 1) / BB_K1_CHUNK) * BB_K1_CHUNK;
     h->n_pad = n_pad;
     std::vector<double> u(n_pad, 0.0), lf(n_pad, 0.0), q34(n_pad, 0.0), is((size_t)n_det * n_pad, 0.0);
-    std::vector<double> rf(n_pad, 0.0), u7(n_pad, 0.0);
+    std::vector<double> rf(n_pad, 0.0), u7(n_pad, 0.0), ff(n_pad, 0.0), t3(n_pad, 0.0), x3(n_pad, 0.0);
     std::vector<double2> ds((size_t)n_det * n_pad, make_double2(0.0, 0.0));
     for (int k = 0; k < n_freq; ++k) {
         const double f = (double)k * net.df;
@@ -715,6 +736,10 @@ extern "C" int bb_set_network(bb_handle* h, int n_det, int n_freq, double durati
         rf[k] = k ? 1.0 / f : 0.0;
         // exactly the product the per-bin code used to form: u * (u^2)^3
         { const double t = u[k] * u[k]; u7[k] = u[k] * (t * t * t); }
+        // f, t = u^2 and x = (f t) t in the operation order of bb_wave, so both routes give the same bits
+        ff[k] = f;
+        t3[k] = u[k] * u[k];
+        x3[k] = f * t3[k] * t3[k];
     }
     int k_lo = n_freq, k_hi = -1;
     const double norm = 4.0 / duration;
@@ -733,8 +758,8 @@ extern "C" int bb_set_network(bb_handle* h, int n_det, int n_freq, double durati
     net.k_lo = k_lo;
     net.k_hi = k_hi;
     cudaFree(h->d_u); cudaFree(h->d_lf); cudaFree(h->d_q34); cudaFree(h->d_is); cudaFree(h->d_ds);
-    cudaFree(h->d_rf); cudaFree(h->d_u7);
-    h->d_u = h->d_lf = h->d_q34 = h->d_is = h->d_rf = h->d_u7 = nullptr;
+    cudaFree(h->d_rf); cudaFree(h->d_u7); cudaFree(h->d_ff); cudaFree(h->d_t3); cudaFree(h->d_x3);
+    h->d_u = h->d_lf = h->d_q34 = h->d_is = h->d_rf = h->d_u7 = h->d_ff = h->d_t3 = h->d_x3 = nullptr;
     h->d_ds = nullptr;
     BB_CUDA(cudaMalloc(&h->d_u, n_pad * sizeof(double)));
     BB_CUDA(cudaMalloc(&h->d_lf, n_pad * sizeof(double)));
@@ -743,6 +768,12 @@ extern "C" int bb_set_network(bb_handle* h, int n_det, int n_freq, double durati
     BB_CUDA(cudaMalloc(&h->d_u7, n_pad * sizeof(double)));
     BB_CUDA(cudaMemcpy(h->d_rf, rf.data(), n_pad * sizeof(double), cudaMemcpyHostToDevice));
     BB_CUDA(cudaMemcpy(h->d_u7, u7.data(), n_pad * sizeof(double), cudaMemcpyHostToDevice));
+    BB_CUDA(cudaMalloc(&h->d_ff, n_pad * sizeof(double)));
+    BB_CUDA(cudaMalloc(&h->d_t3, n_pad * sizeof(double)));
+    BB_CUDA(cudaMalloc(&h->d_x3, n_pad * sizeof(double)));
+    BB_CUDA(cudaMemcpy(h->d_ff, ff.data(), n_pad * sizeof(double), cudaMemcpyHostToDevice));
+    BB_CUDA(cudaMemcpy(h->d_t3, t3.data(), n_pad * sizeof(double), cudaMemcpyHostToDevice));
+    BB_CUDA(cudaMemcpy(h->d_x3, x3.data(), n_pad * sizeof(double), cudaMemcpyHostToDevice));
     BB_CUDA(cudaMalloc(&h->d_is, (size_t)n_det * n_pad * sizeof(double)));
     BB_CUDA(cudaMalloc(&h->d_ds, (size_t)n_det * n_pad * sizeof(double2)));
     BB_CUDA(cudaMemcpy(h->d_u, u.data(), n_pad * sizeof(double), cudaMemcpyHostToDevice));

@@ -6,9 +6,9 @@
 // __constant__ tables (one LDCU.128 per two coefficients) and are specialised for the argument ranges of this path:
 //
 //   bb_sincospi(x)   |x| < 2^30 half turns; argument reduction x = n/2 + r by the 1.5*2^52 shift (two DADDs), minimax
-//                    polynomials for sin(pi r), cos(pi r) on |r| <= 1/4 (oracle/tools/make_math_coeffs.py; errors
-//                    5.6e-21 / 3.0e-20 before rounding)
-//   bb_atan(y)       three-way reduction at tan(pi/8), tan(3 pi/8), one reciprocal, 12-term minimax polynomial
+//                    polynomials (7 terms) for sin(pi r), cos(pi r) on |r| <= 1/4 (oracle/tools/make_math_coeffs.py;
+//                    errors 2.5e-18 / 4.7e-17 before rounding)
+//   bb_atan(y)       three-way reduction at tan(pi/8), tan(3 pi/8), one reciprocal, 11-term minimax polynomial
 //   bb_rcp_pos(a)    reciprocal of a normal positive number: rcp.approx.ftz.f64 (MUFU.RCP64H) + two Newton steps
 //                    (relative error ~1.5e-16; not correctly rounded, no special cases)
 //
@@ -19,13 +19,13 @@
 #include "math_coeffs.inc"
 
 #ifdef __CUDACC__
-static __constant__ double bb_kc_sinpi_d[8] = {BB_SINPI_COEFFS};
-static __constant__ double bb_kc_cospi_d[8] = {BB_COSPI_COEFFS};
-static __constant__ double bb_kc_atan_d[12] = {BB_ATAN_COEFFS};
+static __constant__ double bb_kc_sinpi_d[BB_SINPI_N] = {BB_SINPI_COEFFS};
+static __constant__ double bb_kc_cospi_d[BB_COSPI_N] = {BB_COSPI_COEFFS};
+static __constant__ double bb_kc_atan_d[BB_ATAN_N] = {BB_ATAN_COEFFS};
 #endif
-static const double bb_kc_sinpi_h[8] = {BB_SINPI_COEFFS};
-static const double bb_kc_cospi_h[8] = {BB_COSPI_COEFFS};
-static const double bb_kc_atan_h[12] = {BB_ATAN_COEFFS};
+static const double bb_kc_sinpi_h[BB_SINPI_N] = {BB_SINPI_COEFFS};
+static const double bb_kc_cospi_h[BB_COSPI_N] = {BB_COSPI_COEFFS};
+static const double bb_kc_atan_h[BB_ATAN_N] = {BB_ATAN_COEFFS};
 #ifdef __CUDA_ARCH__
 #define BB_KC(name, i) name##_d[i]
 #else
@@ -49,9 +49,10 @@ BB_HD double bb_rcp_pos(double a) {
 // sin(pi x), cos(pi x)
 BB_HD void bb_sincospi(double x, double* sn, double* cs) {
 #ifdef __CUDA_ARCH__
-    if (!(fabs(x) < 1073741824.0)) { sincospi(x, sn, cs); return; }      // huge / inf / nan: library path
+    // huge / inf / nan: library path; |x| >= 2^30 tested on the high word (an integer compare, not a DSETP)
+    if ((__double2hiint(x) & 0x7fffffff) >= 0x41d00000) { sincospi(x, sn, cs); return; }
     const double shift = 6755399441055744.0;                              // 1.5 * 2^52
-    const double t = (x + x) + shift;                                     // low word = nearest integer n of 2x
+    const double t = fma(x, 2.0, shift);                                  // low word = nearest integer n of 2x
     const int n = __double2loint(t);
     const double r = fma(t - shift, -0.5, x);                             // exact, |r| <= 1/4
 #else
@@ -60,9 +61,10 @@ BB_HD void bb_sincospi(double x, double* sn, double* cs) {
     const double r = x - 0.5 * n2;
 #endif
     const double u = r * r;
-    double s = BB_KC(bb_kc_sinpi, 7), c = BB_KC(bb_kc_cospi, 7);
+    static_assert(BB_SINPI_N == BB_COSPI_N, "sin / cos polynomials advance together");
+    double s = BB_KC(bb_kc_sinpi, BB_SINPI_N - 1), c = BB_KC(bb_kc_cospi, BB_COSPI_N - 1);
 #pragma unroll
-    for (int i = 6; i >= 0; --i) {
+    for (int i = BB_SINPI_N - 2; i >= 0; --i) {
         s = fma(s, u, BB_KC(bb_kc_sinpi, i));
         c = fma(c, u, BB_KC(bb_kc_cospi, i));
     }
@@ -91,9 +93,9 @@ BB_HD double bb_atan(double y) {
     const double off = big ? 1.57079632679489661923 : (mid ? 0.78539816339744830962 : 0.0);
     const double off_lo = big ? 6.123233995736766e-17 : (mid ? 3.061616997868383e-17 : 0.0);
     const double u = t * t;
-    double p = BB_KC(bb_kc_atan, 11);
+    double p = BB_KC(bb_kc_atan, BB_ATAN_N - 1);
 #pragma unroll
-    for (int i = 10; i >= 1; --i) p = fma(p, u, BB_KC(bb_kc_atan, i));
+    for (int i = BB_ATAN_N - 2; i >= 1; --i) p = fma(p, u, BB_KC(bb_kc_atan, i));
     // atan(t) = t + t u p(u) (the leading coefficient is exactly 1)
     const double r = off + (fma(t * u, p, off_lo) + t);          // >= 0 in every branch
 #ifdef __CUDA_ARCH__

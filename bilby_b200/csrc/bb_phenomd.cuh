@@ -481,7 +481,8 @@ BB_HD void bb_phenomd_prologue(const double* p, const BBNetwork& net, const BBWa
 // per-bin evaluation (the hot path).  Inputs: f [Hz], u = f^(-1/6), lf = ln f, q34 = f^(3/4).
 // Returns amplitude A (>= 0) and total phase in half turns.
 // ---------------------------------------------------------------------------------------------
-BB_HD double bb_phenomd_amp(const double* c, double f, double u, double t, double x) {
+// amplitude without the prefactor a0 f^(-7/6)
+BB_HD double bb_phenomd_amp_core(const double* c, double f, double x) {
     double a;
     if (f < c[BC_FA1]) {
         const double* k = c + BC_AINS;
@@ -497,8 +498,12 @@ BB_HD double bb_phenomd_amp(const double* c, double f, double u, double t, doubl
         const double d = f - c[BC_MR_FRD];
         a = c[BC_MR_G] * exp(-c[BC_MR_LAM] * d) / (d * d + c[BC_MR_WL2]);
     }
+    return a;
+}
+
+BB_HD double bb_phenomd_amp(const double* c, double f, double u, double t, double x) {
     const double t3 = t * t * t;
-    return a * c[BC_A0] * (u * t3);      // f^(-7/6) = u^7 = u * (u^2)^3
+    return bb_phenomd_amp_core(c, f, x) * c[BC_A0] * (u * t3);      // f^(-7/6) = u^7 = u * (u^2)^3
 }
 
 BB_HD double bb_phenomd_phase(const double* c, double f, double t, double x, double lf, double q34) {

@@ -25,6 +25,9 @@ struct BBNodes {
     const double* u;      // f^(-1/6)
     const double* lf;     // ln f
     const double* q34;    // f^(3/4)
+    const double* t3;     // f^(-1/3) = u u
+    const double* x3;     // f^(1/3) = (f t) t
+    const double* u7;     // f^(-7/6) = u (t t t)
     int n;
 };
 
@@ -111,7 +114,7 @@ __device__ __forceinline__ void bb_relbin_sample(const double* rec, const double
         const int jj = act ? j : ne - 1;
         const double f = rb.edges.f[jj];
         double A, ph;
-        bb_wave<APPROX>(rec, f, rb.edges.u[jj], rb.edges.lf[jj], rb.edges.q34[jj], &A, &ph);
+        bb_wave_cols<APPROX>(rec, f, rb.edges.t3[jj], rb.edges.x3[jj], rb.edges.u7[jj], rb.edges.lf[jj], rb.edges.q34[jj], &A, &ph);
         const int b = j - 1;                               // bin whose right edge is j
         const bool have_bin = act && b >= 0;
         const double iw = have_bin ? rb.inv_width[b] : 0.0;
@@ -174,27 +177,33 @@ __device__ __forceinline__ void bb_relbin_edge_sample(const double* rec, const d
     // (only there: with the two rows of a relative-binning sample the extra registers cost more than they hide)
     constexpr bool PREFETCH = !CROSS;
     const int j0 = lane < ne ? lane : ne - 1;
-    double nf = 0.0, nu = 0.0, nlf = 0.0, nq = 0.0;
-    if (PREFETCH) { nf = rb.edges.f[j0]; nu = rb.edges.u[j0]; nlf = rb.edges.lf[j0]; nq = rb.edges.q34[j0]; }
+    double nf = 0.0, nt = 0.0, nx = 0.0, nu7 = 0.0, nlf = 0.0, nq = 0.0;
+    if (PREFETCH) {
+        nf = rb.edges.f[j0]; nt = rb.edges.t3[j0]; nx = rb.edges.x3[j0]; nu7 = rb.edges.u7[j0];
+        nlf = rb.edges.lf[j0]; nq = rb.edges.q34[j0];
+    }
     for (int base = 0; base < ne; base += 32) {
         const int j = base + lane;
         const bool more = base + 32 < ne;
-        double f, u, lfj, q34;
+        double f, t, x, u7, lfj, q34;
         if (PREFETCH) {
-            f = nf; u = nu; lfj = nlf; q34 = nq;
+            f = nf; t = nt; x = nx; u7 = nu7; lfj = nlf; q34 = nq;
             if (more) {
                 const int jn = j + 32 < ne ? j + 32 : ne - 1;
                 nf = rb.edges.f[jn];
-                nu = rb.edges.u[jn];
+                nt = rb.edges.t3[jn];
+                nx = rb.edges.x3[jn];
+                nu7 = rb.edges.u7[jn];
                 nlf = rb.edges.lf[jn];
-                nq = rb.edges.q34[jn];
+                if (APPROX == BB_IMRPHENOMD) nq = rb.edges.q34[jn];
             }
         } else {
             const int jj = j < ne ? j : ne - 1;
-            f = rb.edges.f[jj]; u = rb.edges.u[jj]; lfj = rb.edges.lf[jj]; q34 = rb.edges.q34[jj];
+            f = rb.edges.f[jj]; t = rb.edges.t3[jj]; x = rb.edges.x3[jj]; u7 = rb.edges.u7[jj]; lfj = rb.edges.lf[jj];
+            q34 = (APPROX == BB_IMRPHENOMD) ? rb.edges.q34[jj] : 0.0;
         }
         double A, ph;
-        bb_wave<APPROX>(rec, f, u, lfj, q34, &A, &ph);
+        bb_wave_cols<APPROX>(rec, f, t, x, u7, lfj, q34, &A, &ph);
 #pragma unroll
         for (int d = 0; d < NDET; ++d) {
             const double* cd = rec + BC_DET + BC_DSTRIDE * d;
@@ -294,7 +303,7 @@ __device__ __forceinline__ void bb_roq_quadratic(const double* rec, const double
     for (int j = lane; j < nq; j += 32) {
         const double f = rq.quad.f[j];
         double A, ph;
-        bb_wave<APPROX>(rec, f, rq.quad.u[j], rq.quad.lf[j], rq.quad.q34[j], &A, &ph);
+        bb_wave_cols<APPROX>(rec, f, rq.quad.t3[j], rq.quad.x3[j], rq.quad.u7[j], rq.quad.lf[j], rq.quad.q34[j], &A, &ph);
         const double A2 = A * A;
 #pragma unroll
         for (int d = 0; d < NDET; ++d) {
@@ -447,7 +456,7 @@ bb_roq_kernel(const double* __restrict__ coef, long n, BBRoqDev rq, const double
                 const double f = rq.lin.f[j];
                 double A, ph, sn, cs;
                 lfj = rq.lin.lf[j];
-                bb_wave<APPROX>(rec, f, rq.lin.u[j], lfj, rq.lin.q34[j], &A, &ph);
+                bb_wave_cols<APPROX>(rec, f, rq.lin.t3[j], rq.lin.x3[j], rq.lin.u7[j], lfj, rq.lin.q34[j], &A, &ph);
                 bb_sincospi(ph, &sn, &cs);
                 zr0 = A * cs;                                   // conj(h22) = A e^{+i Phi}
                 zi0 = A * sn;
@@ -555,7 +564,7 @@ bb_roq_hlinear_kernel(const double* __restrict__ coef, long s_begin, long n, BBR
         for (int j = lane; j < nl; j += 32) {
             const double f = rq.lin.f[j];
             double A, ph;
-            bb_wave<APPROX>(rec, f, rq.lin.u[j], rq.lin.lf[j], rq.lin.q34[j], &A, &ph);
+            bb_wave_cols<APPROX>(rec, f, rq.lin.t3[j], rq.lin.x3[j], rq.lin.u7[j], rq.lin.lf[j], rq.lin.q34[j], &A, &ph);
             double sn, cs;
             bb_sincospi(ph, &sn, &cs);
             const double zr0 = A * cs, zi0 = A * sn;
@@ -672,7 +681,7 @@ bb_mb_series_kernel(const double* __restrict__ coef, long s_begin, long n, BBRel
             if (j < ne) {
                 const double f = rb.edges.f[j], lfj = rb.edges.lf[j];
                 double A, ph;
-                bb_wave<APPROX>(rec, f, rb.edges.u[j], lfj, rb.edges.q34[j], &A, &ph);
+                bb_wave_cols<APPROX>(rec, f, rb.edges.t3[j], rb.edges.x3[j], rb.edges.u7[j], lfj, rb.edges.q34[j], &A, &ph);
 #pragma unroll
                 for (int d = 0; d < NDET; ++d) {
                     const double* cd = rec + BC_DET + BC_DSTRIDE * d;
@@ -792,7 +801,7 @@ bb_mb_band_fill_kernel(const double* __restrict__ coef, long s_begin, long n, BB
             const int j = band.start + q;
             const double f = rb.edges.f[j], lfj = rb.edges.lf[j], sw = sqrt_window[j];
             double A, ph;
-            bb_wave<APPROX>(rec, f, rb.edges.u[j], lfj, rb.edges.q34[j], &A, &ph);
+            bb_wave_cols<APPROX>(rec, f, rb.edges.t3[j], rb.edges.x3[j], rb.edges.u7[j], lfj, rb.edges.q34[j], &A, &ph);
 #pragma unroll
             for (int d = 0; d < NDET; ++d) {
                 const double* cd = rec + BC_DET + BC_DSTRIDE * d;

@@ -41,18 +41,25 @@ static int bb_red_upload(bb_handle* h, const T* host, size_t count, const T** de
 }
 
 static int bb_upload_nodes(bb_handle* h, const double* f, int n, BBNodes* out) {
-    std::vector<double> u(n), lf(n), q34(n);
+    std::vector<double> u(n), lf(n), q34(n), t3(n), x3(n), u7(n);
     for (int i = 0; i < n; ++i) {
         if (!(f[i] > 0.0)) return bb_fail("frequency nodes must be positive");
         u[i] = pow(f[i], -1.0 / 6.0);
         lf[i] = log(f[i]);
         q34[i] = pow(f[i], 0.75);
+        // the powers bb_wave forms per node, in its operation order (bb_wave_cols reads them instead)
+        t3[i] = u[i] * u[i];
+        x3[i] = f[i] * t3[i] * t3[i];
+        u7[i] = u[i] * (t3[i] * t3[i] * t3[i]);
     }
     out->n = n;
     if (bb_red_upload(h, f, n, &out->f)) return 1;
     if (bb_red_upload(h, u.data(), n, &out->u)) return 1;
     if (bb_red_upload(h, lf.data(), n, &out->lf)) return 1;
     if (bb_red_upload(h, q34.data(), n, &out->q34)) return 1;
+    if (bb_red_upload(h, t3.data(), n, &out->t3)) return 1;
+    if (bb_red_upload(h, x3.data(), n, &out->x3)) return 1;
+    if (bb_red_upload(h, u7.data(), n, &out->u7)) return 1;
     return 0;
 }
 

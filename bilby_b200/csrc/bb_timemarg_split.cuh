@@ -25,7 +25,10 @@
 
 template <int NDET>
 struct SFTile {
-    double u[BB_SF_CHUNK];
+    double ff[BB_SF_CHUNK];       // f, f^(-1/3), f^(1/3), f^(-7/6): K1's columns (bb_k1.cuh); 1/f = t^3 is formed per bin
+    double t3[BB_SF_CHUNK];       // where a region needs it, so that K4a (79 KB) still fits one SM together with K4b
+    double x3[BB_SF_CHUNK];
+    double u7[BB_SF_CHUNK];
     double lf[BB_SF_CHUNK];
     double q34[BB_SF_CHUNK];
     double2 ds[NDET][BB_SF_CHUNK];
@@ -49,7 +52,10 @@ __host__ __device__ __forceinline__ long bb_sf_pos(int slot, int c, int n_chunks
 template <int NDET>
 __device__ __forceinline__ void bb_sf_issue_tile(SFTile<NDET>& t, unsigned long long* bar, const BBTiles& g, int c0) {
     bb_mbar_expect_tx(bar, (unsigned)sizeof(SFTile<NDET>));
-    bb_bulk_g2s(t.u, g.u + c0, BB_SF_CHUNK * 8, bar);
+    bb_bulk_g2s(t.ff, g.ff + c0, BB_SF_CHUNK * 8, bar);
+    bb_bulk_g2s(t.t3, g.t3 + c0, BB_SF_CHUNK * 8, bar);
+    bb_bulk_g2s(t.x3, g.x3 + c0, BB_SF_CHUNK * 8, bar);
+    bb_bulk_g2s(t.u7, g.u7 + c0, BB_SF_CHUNK * 8, bar);
     bb_bulk_g2s(t.lf, g.lf + c0, BB_SF_CHUNK * 8, bar);
     bb_bulk_g2s(t.q34, g.q34 + c0, BB_SF_CHUNK * 8, bar);
 #pragma unroll
@@ -116,16 +122,17 @@ __device__ __forceinline__ void bb_sf_rows_pd(SFState<NDET>& st, const SFTile<ND
     amp.load(rec);
     phs.load(rec);
     amp.begin((double)(r0 * BB_ROW + lane) * df, (double)BB_ROW * df);
+    int k = r0 * BB_ROW + lane, i = k - c0;
     for (int r = r0; r < r1; ++r) {
-        const int k = r * BB_ROW + lane, i = k - c0;
         const bool act = (k >= kmin) && (k < kmax);
-        const double f = (double)k * df;
-        const double u = tile.u[i], t = u * u, x = f * t * t;
-        const double t3 = t * t * t;                    // 1 / f
-        const double A = amp.eval(f, x) * (u * t3);     // a0 is folded into the region's coefficients (bb_k1.cuh)
-        const double ph = phs.eval(f, t, x, t3, tile.lf[i], tile.q34[i]);
+        const double f = tile.ff[i], t = tile.t3[i], x = tile.x3[i];
+        const double rf = (PR != 0) ? t * t * t : 0.0;          // 1 / f (intermediate and merger-ringdown phase only)
+        const double A = amp.eval(f, x) * tile.u7[i];           // a0 is folded into the region's coefficients (bb_k1.cuh)
+        const double ph = phs.eval(f, t, x, rf, tile.lf[i], tile.q34[i]);
         bb_sf_bin<NDET, CAL>(st, tile, i, k, act, A, ph);
         amp.next();
+        k += BB_ROW;
+        i += BB_ROW;
     }
 }
 
@@ -135,9 +142,16 @@ __device__ __forceinline__ void bb_sf_rows_generic(SFState<NDET>& st, const SFTi
     for (int r = r0; r < r1; ++r) {
         const int k = r * BB_ROW + lane, i = k - c0;
         const bool act = (k >= kmin) && (k < kmax);
-        const double f = (double)k * df;
+        const double f = tile.ff[i];
         double A, ph;
-        bb_wave<APPROX>(rec, f, tile.u[i], tile.lf[i], tile.q34[i], &A, &ph);
+        if (APPROX == BB_TAYLORF2) {
+            A = rec[BC_A0] * tile.u7[i];
+            ph = bb_taylorf2_phase(rec, f, tile.t3[i], tile.x3[i], tile.lf[i]);
+        } else {
+            // rows that straddle a region boundary: u = f^(-1/6) = sqrt(u^2) exactly (the square root of a correctly
+            // rounded square returns the operand)
+            bb_wave<APPROX>(rec, f, sqrt(tile.t3[i]), tile.lf[i], tile.q34[i], &A, &ph);
+        }
         bb_sf_bin<NDET, CAL>(st, tile, i, k, act, A, ph);
     }
 }
