@@ -382,6 +382,7 @@ def run_extra(args, world, rank, local_rank, dist):
                         roofline=dict(bound=r["bound"], achieved=r["achieved"], peak=r["peak"], unit=r["unit"], frac=r["frac"],
                                       kernel=r["kernel"], kernel_share_of_step=r["kernel_share_of_step"],
                                       peak_source=r["peak_source"]),
+                        **({"device_front_end": line["device_front_end"]} if "device_front_end" in line else {}),
                         **{k: line["config"][k] for k in ("n_time_contracted", "executed_gemm_flop_per_eval") if k in line["config"]})
             if world == 1 and not args.no_cpu_baseline:
                 cmd = [sys.executable, os.path.join(ROOT, "bench_cpu.py"), "--config", cfg]

@@ -468,14 +468,25 @@ def run_config(config, n, steps, warmup, world=1, rank=0, local=0, dist=None, cl
     k_ms, k_n = ctypes.c_double(0.0), ctypes.c_long(0)
     _lib.check(lib.bb_profile_read(net.ptr, ctypes.byref(k_ms), ctypes.byref(k_n)))
     _lib.check(lib.bb_profile_enable(net.ptr, 0))
-    # end to end through the host entry point
-    like.log_likelihood_ratio_rows_host(rows_np, cal_np)
+    # end to end through the host entry point, from / to page-locked host buffers (the bench contract's e2e)
+    from bilby_b200.core.utils import pinned_empty
+    rows_pin = pinned_empty(rows_np.shape)
+    rows_pin[...] = rows_np
+    cal_pin = None
+    if cal_np is not None:
+        cal_pin = pinned_empty(np.shape(cal_np))
+        cal_pin[...] = cal_np
+    res = pinned_empty(n)
+    like.log_likelihood_ratio_rows_host(rows_pin, cal_pin, out=res)
     barrier()
     t0 = time.perf_counter()
     for _ in range(steps):
-        res = like.log_likelihood_ratio_rows_host(rows_np, cal_np)
+        like.log_likelihood_ratio_rows_host(rows_pin, cal_pin, out=res)
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
     clock_info = sampler.stop() if sampler else None
+    front = None
+    if config in ("cfg4_relbin", "cfg4_roq"):
+        front = front_end_rate(like, n, steps, stream, torch)
     if world > 1:
         dist.barrier()
     del like, net, rows_dev, cal_dev, out
@@ -501,7 +512,40 @@ def run_config(config, n, steps, warmup, world=1, rank=0, local=0, dist=None, cl
                               algorithmic_flop_per_step=total_flop, units_per_eval=units,
                               peak_source="in-run DMMA stream kernel (bb_fp64_tensor_peak)" if tensor_bound
                               else "in-run DFMA stream kernel (bb_fp64_peak)"),
-                checksum_lnl=float(np.sum(res[fin])), finite_fraction=float(fin.mean()))
+                checksum_lnl=float(np.sum(res[fin])), finite_fraction=float(fin.mean()),
+                **(dict(device_front_end=front) if front else {}))
+
+
+def front_end_rate(like, n, steps, stream, torch):
+    """The device-resident sampling front end (csrc/bb_sampling.cuh) in front of the same likelihood: unit-cube points
+    that already live on the device -> PriorDict.rescale + parameter conversion + rows (one kernel) -> lnL.  The
+    priors are the box bns_draws(narrow=True) samples from; nothing crosses PCIe."""
+    from bilby_b200.core.prior import PriorDict, Uniform, PowerLaw, Sine, Cosine
+    from bilby_b200.core.sampler import BatchedLikelihood
+    mc0 = (1.5 * 1.3) ** 0.6 / 2.8 ** 0.2
+    pri = PriorDict(dict(
+        chirp_mass=Uniform(mc0 * (1 - 1e-4), mc0 * (1 + 1e-4), "chirp_mass"), mass_ratio=Uniform(0.8, 0.95, "mass_ratio"),
+        chi_1=Uniform(-0.05, 0.05, "chi_1"), chi_2=Uniform(-0.05, 0.05, "chi_2"),
+        luminosity_distance=PowerLaw(2, 10.0, 500.0, "luminosity_distance"), theta_jn=Sine(name="theta_jn"),
+        psi=Uniform(0, np.pi, "psi"), phase=Uniform(0, 2 * np.pi, "phase"), ra=Uniform(0, 2 * np.pi, "ra"),
+        dec=Cosine(name="dec"), geocent_time=Uniform(T_INJ - 2e-3, T_INJ + 2e-3, "geocent_time"),
+        lambda_1=Uniform(0, 5000, "lambda_1"), lambda_2=Uniform(0, 5000, "lambda_2")))
+    batched = BatchedLikelihood(like, pri)
+    u = torch.rand((n, batched.ndim), dtype=torch.float64, device="cuda", generator=torch.Generator("cuda").manual_seed(7))
+    for _ in range(3):
+        lnl = batched.log_likelihood_from_unit_cube(u)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        lnl = batched.log_likelihood_from_unit_cube(u)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    fin = torch.isfinite(lnl)
+    return dict(value=n / (ms * 1e-3), unit="evals/s", ms_per_step=ms, finite_fraction=float(fin.double().mean().item()),
+                what="unit-cube points resident on the device -> bb_rows_from_unit_cube_device (prior rescale + "
+                     "conversion + rows) -> lnL; no host<->device traffic")
 
 
 def run_frequency_sharded(n, steps, warmup, world, rank, dist, exchange="fused"):

@@ -74,6 +74,9 @@ def load():
         "bb_build_roq_linear_weights": (i, [i, i, i, vp, i, vp, vp, lng, lng, i, d, vp]),
         "bb_reconstruct_marginalized_device": (i, [vp, vp, vp, lng, vp, vp, vp]),
         "bb_contract_device": (i, [vp, i, i, i, i, i, lng, lng, i, lng, lng, lng, d, vp, lng, vp, lng, i, vp, lng, vp]),
+        "bb_set_sampling_priors": (i, [vp, i, vp, i, vp, vp, i]),
+        "bb_rows_from_unit_cube_device": (i, [vp, vp, lng, vp, vp, vp]),
+        "bb_rows_from_theta_device": (i, [vp, vp, lng, vp, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is missing
@@ -97,7 +100,8 @@ EXPORTED_SYMBOLS = (
     "bb_exchange_create", "bb_exchange_connect", "bb_log_likelihood_ratio_sharded_device", "bb_exchange_status",
     "bb_exchange_destroy", "bb_contract_device", "bb_fp64_tensor_peak",
     "bb_build_roq_quadratic_weights", "bb_build_relbin_summary_data", "bb_set_multiband_time_marginalization",
-    "bb_set_multiband_ifft_fft", "bb_fft_device")
+    "bb_set_multiband_ifft_fft", "bb_fft_device", "bb_set_sampling_priors", "bb_rows_from_unit_cube_device",
+    "bb_rows_from_theta_device")
 
 
 _torch_ops = None

@@ -14,7 +14,10 @@ LIB = os.path.join(LIB_DIR, "libbilby_b200.so")
 TORCH_LIB = os.path.join(LIB_DIR, "libbilby_b200_torch.so")
 SOURCES = ["bb_kernels.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-shared", "--use_fast_math=false"]
+              "-Xcompiler", "-fPIC", "-shared", "--use_fast_math=false",
+              # one soname for the library and every experiment build (BB_LIB_OUT): whichever copy ctypes loads first also
+              # satisfies the torch shim's DT_NEEDED, so the shim never pulls a second copy in beside it
+              "-Xlinker", "-soname=libbilby_b200.so"]
 
 
 def _newest_source_mtime():

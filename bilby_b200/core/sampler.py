@@ -8,6 +8,9 @@ evaluates 1e6 points, so the adaptor below hands *arrays of theta* to ``log_like
 
 * ``BatchedLikelihood``  - theta [n, ndim] (numpy or CUDA tensor) in ``search_parameter_keys`` order + the fixed
   parameters of the prior  ->  lnL [n]; ``log_likelihood(theta)`` keeps the reference's one-point signature.
+  ``rows_from_unit_cube_device`` / ``rows_from_theta_device`` / ``log_likelihood_from_unit_cube`` keep the points
+  on the device: one kernel (csrc/bb_sampling.cuh) does ``PriorDict.rescale``, the waveform generator's parameter
+  conversion and the packing into parameter rows, so theta never crosses PCIe.
 * ``DeviceBatchPool``    - a ``pool`` object for samplers that fan proposals out with ``pool.map(fn, points)``
   (dynesty's ``pool=``/``queue_size=``): the whole iterable is one batch, ``fn`` is never called.
 """
@@ -57,6 +60,112 @@ class BatchedLikelihood:
         """Unit hypercube [n, ndim] -> theta [n, ndim] (base_sampler.py:495-510 prior_transform, vectorised)."""
         u = np.asarray(u, dtype=np.float64)
         return np.stack([self.priors[k].rescale(u[:, j]) for j, k in enumerate(self.search_parameter_keys)], axis=1)
+
+
+    # ---- device-resident front end (include/bilby_b200.h: bb_set_sampling_priors / bb_rows_from_*_device) -----------
+    _PRIOR_KINDS = {"DeltaFunction": 0, "Uniform": 1, "PowerLaw": 2, "LogUniform": 2, "Sine": 3, "Cosine": 4,
+                    "Gaussian": 5, "Normal": 5}
+    SOURCE_KEYS = ("mass_1", "mass_2", "chirp_mass", "mass_ratio", "total_mass", "symmetric_mass_ratio", "chi_1",
+                   "chi_2", "a_1", "a_2", "tilt_1", "tilt_2", "cos_tilt_1", "cos_tilt_2", "luminosity_distance",
+                   "theta_jn", "cos_theta_jn", "psi", "phase", "delta_phase", "ra", "dec", "geocent_time",
+                   "time_jitter", "lambda_1", "lambda_2", "lambda_tilde", "delta_lambda_tilde")
+    _IGNORED_FIXED = ("phi_jl", "phi_12")        # zero for aligned spins (conversion.py:255-257)
+
+    @staticmethod
+    def prior_spec(prior):
+        """(kind, a, b, c) of include/bilby_b200.h bb_prior_spec for one analytic prior."""
+        name = type(prior).__name__
+        if name not in BatchedLikelihood._PRIOR_KINDS:
+            raise NotImplementedError(f"prior class {name} has no device rescale (Uniform, PowerLaw, LogUniform, Sine, "
+                                      "Cosine, Gaussian, DeltaFunction)")
+        kind = BatchedLikelihood._PRIOR_KINDS[name]
+        if kind == 0:
+            return kind, float(prior.peak), 0.0, 0.0
+        if kind == 2:
+            return kind, float(prior.minimum), float(prior.maximum), float(prior.alpha)
+        if kind == 5:
+            return kind, float(prior.mu), float(prior.sigma), 0.0
+        return kind, float(prior.minimum), float(prior.maximum), 0.0
+
+    def _key_index(self, key):
+        like = self.likelihood
+        alias = {}
+        if getattr(like, "reference_frame", "sky") != "sky":
+            alias.update(azimuth="ra", zenith="dec")          # the rows carry (azimuth, zenith) in the sky columns
+        if getattr(like, "time_reference", "geocent") != "geocent":
+            alias[f"{like.time_reference}_time"] = "geocent_time"
+        key = alias.get(key, key)
+        if key not in self.SOURCE_KEYS:
+            raise NotImplementedError(f"parameter '{key}' is not part of the device sampling front end")
+        return self.SOURCE_KEYS.index(key)
+
+    def _device_front_end(self):
+        """Upload the prior table once (bb_set_sampling_priors)."""
+        if getattr(self, "_front_end_ready", None) is self.likelihood.device_network:
+            return self.likelihood.device_network
+        import ctypes
+        from .. import _lib
+        net = self.likelihood.device_network
+        if getattr(self.likelihood, "_cal_points", 0):
+            raise NotImplementedError("calibration parameters are not part of the device sampling front end")
+
+        class Spec(ctypes.Structure):
+            _fields_ = [("kind", ctypes.c_int), ("key", ctypes.c_int), ("a", ctypes.c_double), ("b", ctypes.c_double),
+                        ("c", ctypes.c_double)]
+        specs = (Spec * max(1, self.ndim))()
+        for j, key in enumerate(self.search_parameter_keys):
+            kind, a, b, c = self.prior_spec(self.priors[key])
+            specs[j] = Spec(kind, self._key_index(key), a, b, c)
+        fixed = {k: v for k, v in self.fixed_parameters.items() if k not in self._IGNORED_FIXED}
+        fkeys = (ctypes.c_int * max(1, len(fixed)))(*[self._key_index(k) for k in fixed])
+        fvals = (ctypes.c_double * max(1, len(fixed)))(*[float(v) for v in fixed.values()])
+        wfg = self.likelihood.waveform_generator
+        conv = getattr(getattr(wfg, "parameter_conversion", None), "__name__", "")
+        src = getattr(getattr(wfg, "frequency_domain_source_model", None), "__name__", "")
+        bns = int("neutron_star" in conv or "neutron_star" in src)
+        _lib.check(net.lib.bb_set_sampling_priors(net.ptr, self.ndim, ctypes.cast(specs, ctypes.c_void_p), len(fixed),
+                                                  ctypes.cast(fkeys, ctypes.c_void_p),
+                                                  ctypes.cast(fvals, ctypes.c_void_p), bns))
+        self._front_end_ready = net
+        return net
+
+    def _check_points(self, x):
+        net = self._device_front_end()
+        torch = net.torch
+        if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float64 and x.dim() == 2
+                and x.shape[1] == self.ndim):
+            raise ValueError(f"points must be a CUDA float64 tensor of shape [n, {self.ndim}]")
+        return net, torch, x.contiguous()
+
+    def rows_from_unit_cube_device(self, u, return_theta=False):
+        """Unit hypercube [n, ndim] (CUDA tensor) -> parameter rows [n, 16] (CUDA) in one kernel: PriorDict.rescale
+        (core/prior/dict.py:647-666) + the generator's parameter conversion + packing."""
+        from .. import _lib
+        net, torch, u = self._check_points(u)
+        rows = torch.empty((u.shape[0], 16), dtype=torch.float64, device=u.device)
+        theta = torch.empty_like(u) if return_theta else None
+        _lib.check(net.lib.bb_rows_from_unit_cube_device(net.ptr, u.data_ptr(), u.shape[0],
+                                                         theta.data_ptr() if return_theta else None, rows.data_ptr(),
+                                                         net._stream()))
+        return (rows, theta) if return_theta else rows
+
+    def rows_from_theta_device(self, theta):
+        """Sampled parameters [n, ndim] (CUDA tensor, search_parameter_keys order) -> parameter rows [n, 16]."""
+        from .. import _lib
+        net, torch, theta = self._check_points(theta)
+        rows = torch.empty((theta.shape[0], 16), dtype=torch.float64, device=theta.device)
+        _lib.check(net.lib.bb_rows_from_theta_device(net.ptr, theta.data_ptr(), theta.shape[0], rows.data_ptr(),
+                                                     net._stream()))
+        return rows
+
+    def log_likelihood_from_unit_cube(self, u):
+        """CUDA unit-cube points in, CUDA lnL out; nothing but the kernels' launches touches the host."""
+        lnl = self.likelihood.log_likelihood_ratio_batch(self.rows_from_unit_cube_device(u))
+        return lnl if self.use_ratio else lnl + self.likelihood.noise_log_likelihood()
+
+    def log_likelihood_from_theta_device(self, theta):
+        lnl = self.likelihood.log_likelihood_ratio_batch(self.rows_from_theta_device(theta))
+        return lnl if self.use_ratio else lnl + self.likelihood.noise_log_likelihood()
 
 
 class DeviceBatchPool:

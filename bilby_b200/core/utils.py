@@ -48,3 +48,12 @@ class random:
     @classmethod
     def seed(cls, seed):
         cls.rng = np.random.default_rng(seed)
+
+
+def pinned_empty(shape, dtype="float64"):
+    """numpy array in page-locked host memory (the storage belongs to a torch tensor the array keeps alive): the host
+    entry points copy from / to such buffers directly instead of staging them."""
+    import numpy as np
+    import torch
+    t = torch.empty(tuple(np.atleast_1d(shape)), dtype=getattr(torch, str(np.dtype(dtype)))).pin_memory()
+    return t.numpy()

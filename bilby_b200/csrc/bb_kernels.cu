@@ -128,6 +128,7 @@ struct bb_handle {
     // reduced-order likelihoods (bb_reduced.cuh): 0 full grid, 1 relative binning, 2 ROQ
     int kind = 0;
     std::vector<void*> red_bufs;           // device allocations owned by the current reduced-order set-up
+    struct BBSampling* sampling = nullptr;   // prior table of the sampling front end (bb_sampling.cuh)
     BBRelbinDev* rb = nullptr;             // host copies of the kernel argument structs
     BBRoqDev* rq = nullptr;
     double roq_ref_time = 0.0;
@@ -657,6 +658,7 @@ extern "C" int bb_create(int device, bb_handle** out) {
 }
 
 static void bb_exchange_release(bb_handle* h);
+static void bb_sampling_release(bb_handle* h);
 
 extern "C" void bb_destroy(bb_handle* h) {
     if (!h) return;
@@ -684,6 +686,7 @@ extern "C" void bb_destroy(bb_handle* h) {
     if (h->copy_out) cudaStreamDestroy(h->copy_out);
     if (h->stream) cudaStreamDestroy(h->stream);
     bb_exchange_release(h);
+    bb_sampling_release(h);
     delete h;
 }
 
@@ -1017,6 +1020,7 @@ static int bb_launch_inner(bb_handle* h, long n, double* out, cudaStream_t st) {
 #include "bb_roq_weights.cuh"
 #include "bb_builders.cuh"
 #include "bb_exchange.cuh"
+#include "bb_sampling.cuh"
 
 extern "C" int bb_set_calibration_marginalization(bb_handle* h, int n_curves, const double* curves) {
     if (!h || !h->have_network) return bb_fail("bb_set_calibration_marginalization: network not set");

@@ -17,7 +17,17 @@
 #define BB_RED_THREADS 256
 #define BB_RED_WARPS (BB_RED_THREADS / 32)
 #define BB_ROQ_THREADS 128     // K6: 4 warps per CTA, BB_ROQ_CTAS CTAs per SM (one shared-memory stage of W per warp)
+#ifndef BB_ROQ_CTAS
 #define BB_ROQ_CTAS 4
+#endif
+// K5 leaves the register allocation to ptxas (80 registers for relative binning = 3 CTAs per SM, more for the
+// multi-banded variant, which spills under a 3-CTA bound: 6.2e6 -> 5.3e6 eval/s); BB_RELBIN_CTAS forces a bound for
+// experiments
+#ifdef BB_RELBIN_CTAS
+#define BB_RELBIN_BOUNDS __launch_bounds__(BB_RED_THREADS, BB_RELBIN_CTAS)
+#else
+#define BB_RELBIN_BOUNDS __launch_bounds__(BB_RED_THREADS)
+#endif
 #define BB_ROQ_WARPS (BB_ROQ_THREADS / 32)
 
 struct BBNodes {
@@ -240,7 +250,7 @@ __device__ __forceinline__ void bb_relbin_edge_sample(const double* rec, const d
 }
 
 template <int NDET, int APPROX, bool CAL, bool CROSS>
-__global__ void __launch_bounds__(BB_RED_THREADS)
+__global__ void BB_RELBIN_BOUNDS
 bb_relbin_kernel(const double* __restrict__ coef, long n, BBRelbinDev rb, const double* __restrict__ calrec,
                  BBCalGrid grid, double* __restrict__ out) {
     extern __shared__ __align__(16) double red_smem[];

@@ -367,10 +367,14 @@ extern "C" int bb_set_roq(bb_handle* h, int n_linear, const double* nodes_linear
 // ---- launchers ------------------------------------------------------------------------------------
 static long bb_red_grid(const bb_handle* h, long n) {
     long blocks = (n + BB_RED_WARPS - 1) / BB_RED_WARPS;
-    const long cap = (long)h->sm_count * 8;          // 8 CTAs of 256 threads per SM
+    // 8 CTAs of 256 threads per SM by default (BB_RED_GRID_PER_SM overrides it for experiments)
+    static const long per_sm = [] { const char* e = getenv("BB_RED_GRID_PER_SM"); const long v = e ? atol(e) : 0; return v > 0 ? v : 8L; }();
+    const long cap = (long)h->sm_count * per_sm;
     return blocks < cap ? blocks : cap;
 }
 
+// (Measured: sizing these grids to exactly the resident CTAs - occupancy x SM count, no partial last wave - is SLOWER
+// than the fixed cap of 8 CTAs per SM: relative binning 6.45e8 -> 6.15e8 eval/s, multi-banding 6.25e6 -> 5.70e6.)
 template <int NDET, int APPROX, bool CAL>
 static int bb_launch_reduced_t(bb_handle* h, long n, double* out, cudaStream_t st) {
     const size_t smem = (size_t)2 * BB_RED_WARPS * (BC_NCOEF + (CAL ? NDET * 4 * h->cal.n_points : 0)) * sizeof(double);

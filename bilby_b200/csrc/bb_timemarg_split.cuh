@@ -18,7 +18,15 @@
 #define BB_SF_THREADS (BB_SF_WARPS * 32)
 #define BB_SF_SB BB_SF_WARPS               // samples per block (one per warp)
 #define BB_SF_CHUNK 256                    // bins per tile
+#ifndef BB_SFT_THREADS
 #define BB_SFT_THREADS 128                 // K4b
+#endif
+#ifndef BB_SFT_REGS
+#define BB_SFT_REGS 128
+#endif
+#ifndef BB_SFT_PLAN
+#define BB_SFT_PLAN 0                      // first eight stages: 0 = two radix-16 passes, 1 = radix-8, radix-8, radix-4
+#endif
 #define BB_SF_BLOCKS_PER_CHUNK 296         // sample blocks per pipeline chunk (2 per SM)
 #define BB_SF_SLOTREC 8                    // doubles per slot handed from K4a to K4b
 #define BB_SFT_PRUNE_MAX 640               // widest prior window (in samples) summed directly after two radix-16 passes
@@ -340,7 +348,7 @@ __device__ __forceinline__ void bb_prefetch_l2(const void* p, unsigned bytes) {
 }
 
 // Needs log2n >= 9.  Shared memory: series (padding shift 3), red[32], meta[8], wl[L] (L = nfft / 256).
-__global__ void __maxnreg__(128)
+__global__ void __maxnreg__(BB_SFT_REGS)
 bb_series_fft_kernel(long n, int chunk, int n_chunks, int n_slots, const double2* __restrict__ series,
                      const double* __restrict__ slotrec, int nfft, int log2n, const double2* __restrict__ twiddle,
                      BBMarg marg, double start_time, double duration, double* __restrict__ out) {
@@ -381,8 +389,14 @@ bb_series_fft_kernel(long n, int chunk, int n_chunks, int n_slots, const double2
         }
         const int k0 = (int)meta[1], k1 = min((int)meta[2], nfft);
         const double2* src = series + (size_t)slot * nfft;
+#if BB_SFT_PLAN == 0
         bb_tm_pass_from_global<4, BB_SFT_THREADS>(X, src, k0, k1, nfft, ps, twiddle);
         bb_tm_pass<4, BB_SFT_THREADS>(X, nfft, 4, ps, twiddle);
+#else
+        bb_tm_pass_from_global<3, BB_SFT_THREADS>(X, src, k0, k1, nfft, ps, twiddle);
+        bb_tm_pass<3, BB_SFT_THREADS>(X, nfft, 3, ps, twiddle);
+        bb_tm_pass<2, BB_SFT_THREADS>(X, nfft, 6, ps, twiddle);
+#endif
         int j_lo, j_hi;
         bb_tm_window(marg, meta[4], start_time, duration, nfft, &j_lo, &j_hi);
         if (j_hi - j_lo <= BB_SFT_PRUNE_MAX) {

@@ -570,12 +570,17 @@ class GravitationalWaveTransient(Likelihood):
         rows = np.ascontiguousarray(self._rows_from_parameters(parameters, n, np))
         return self.log_likelihood_ratio_rows_host(rows, self._cal_from_parameters(parameters, n, np))
 
-    def log_likelihood_ratio_rows_host(self, rows, cal=None):
+    def log_likelihood_ratio_rows_host(self, rows, cal=None, out=None):
         """Host rows [n,16] (numpy float64, C order) [+ calibration parameters [n,n_det,2,n_points]] -> numpy
-        lnL; the C ABI's end-to-end entry point."""
+        lnL; the C ABI's end-to-end entry point.  Page-locked buffers (`bilby_b200.core.utils.pinned_empty`, also
+        for `out`) are copied from / to directly; pageable ones pass through the library's staging buffers
+        (one extra host copy: 128 B per sample, which bounds the reduced-order likelihoods)."""
         net = self.device_network
         rows = np.ascontiguousarray(rows, dtype=np.float64)
-        out = np.empty(rows.shape[0])
+        if out is None:
+            out = np.empty(rows.shape[0])
+        elif out.dtype != np.float64 or not out.flags.c_contiguous or out.shape != (rows.shape[0],):
+            raise ValueError("out must be a C-contiguous float64 array of length n")
         if self._cal_points:
             if cal is None:
                 raise ValueError("this likelihood has a calibration model: calibration parameters are required")

@@ -349,6 +349,46 @@ int bb_build_roq_quadratic_weights(int device, int n_det, int n_freq_sel, const 
 int bb_build_relbin_summary_data(bb_handle* h, int n_bins, const int* bin_start, const double* centre,
                                  const double* fiducial, double* out);
 
+/* Device-resident sampling front end (a batched sampler whose points never cross PCIe).
+ * Replaces, per sample, PriorDict.rescale (bilby/core/prior/dict.py:647-666) over analytic priors
+ * (bilby/core/prior/analytical.py: DeltaFunction :45, PowerLaw / LogUniform :107, Uniform :214, Cosine :415, Sine :475,
+ * Gaussian :535), the parameter conversion the waveform generator applies (bilby/gw/conversion.py:182-283
+ * convert_to_lal_binary_black_hole_parameters, :286-348 convert_to_lal_binary_neutron_star_parameters, :1826-1985
+ * generate_component_masses, tidal maps :1187-1264) and the packing into parameter rows (enum bb_param).
+ *   kind      prior class; (a, b, c) = (minimum, maximum, alpha) for PowerLaw (LogUniform: alpha = -1),
+ *             (minimum, maximum) for Uniform / Sine / Cosine, (mu, sigma) for Gaussian, (peak) for DeltaFunction
+ *   key       which sampled parameter the dimension is (enum bb_source_key, bilby's parameter names; with a
+ *             detector-based sky frame / time reference azimuth, zenith and {IFO}_time take the ra, dec and
+ *             geocent_time keys, like the rows)
+ * bb_set_sampling_priors: the sampled dimensions in the sampler's order plus the fixed parameters (DeltaFunction /
+ * float priors, the side effects of the marginalisations); neutron_star selects the tidal conversion.
+ * bb_rows_from_unit_cube_device: unit_dev [n][n_dim] -> rows_dev [n][16] (and theta_dev [n][n_dim] if not NULL);
+ * bb_rows_from_theta_device: theta_dev [n][n_dim] sampled parameters -> rows.  Precessing spins (tilts other than 0
+ * or pi) give NaN spin columns, which the evaluation kernels answer with the waveform-error sentinel. */
+enum bb_prior_kind {
+    BB_PRIOR_DELTA = 0, BB_PRIOR_UNIFORM = 1, BB_PRIOR_POWERLAW = 2, BB_PRIOR_SINE = 3, BB_PRIOR_COSINE = 4,
+    BB_PRIOR_GAUSSIAN = 5
+};
+enum bb_source_key {
+    BB_KEY_MASS_1 = 0, BB_KEY_MASS_2 = 1, BB_KEY_CHIRP_MASS = 2, BB_KEY_MASS_RATIO = 3, BB_KEY_TOTAL_MASS = 4,
+    BB_KEY_SYMMETRIC_MASS_RATIO = 5, BB_KEY_CHI_1 = 6, BB_KEY_CHI_2 = 7, BB_KEY_A_1 = 8, BB_KEY_A_2 = 9,
+    BB_KEY_TILT_1 = 10, BB_KEY_TILT_2 = 11, BB_KEY_COS_TILT_1 = 12, BB_KEY_COS_TILT_2 = 13,
+    BB_KEY_LUMINOSITY_DISTANCE = 14, BB_KEY_THETA_JN = 15, BB_KEY_COS_THETA_JN = 16, BB_KEY_PSI = 17, BB_KEY_PHASE = 18,
+    BB_KEY_DELTA_PHASE = 19, BB_KEY_RA = 20, BB_KEY_DEC = 21, BB_KEY_GEOCENT_TIME = 22, BB_KEY_TIME_JITTER = 23,
+    BB_KEY_LAMBDA_1 = 24, BB_KEY_LAMBDA_2 = 25, BB_KEY_LAMBDA_TILDE = 26, BB_KEY_DELTA_LAMBDA_TILDE = 27,
+    BB_KEY_COUNT = 28
+};
+typedef struct bb_prior_spec {
+    int kind;
+    int key;
+    double a, b, c;
+} bb_prior_spec;
+int bb_set_sampling_priors(bb_handle* h, int n_dim, const bb_prior_spec* specs, int n_fixed, const int* fixed_keys,
+                           const double* fixed_values, int neutron_star);
+int bb_rows_from_unit_cube_device(bb_handle* h, const double* unit_dev, long n, double* theta_dev, double* rows_dev,
+                                  void* stream);
+int bb_rows_from_theta_device(bb_handle* h, const double* theta_dev, long n, double* rows_dev, void* stream);
+
 /* Measurement hooks (bench.py).  With profiling enabled the handle brackets every launch of the
  * dominant kernel (K1, the fused inner-product kernel) with CUDA events on the launching stream;
  * bb_profile_read synchronises and returns the summed duration and the number of launches since the

@@ -61,3 +61,42 @@ def test_one_point_signature_and_plugin_registration():
     assert m, "entry point missing"
     mod = __import__(m.group(1), fromlist=[m.group(2)])
     assert getattr(mod, m.group(2)) is B200Ensemble
+
+
+def test_host_prior_rescale_and_conversion_match_the_reference_goldens():
+    """The host mirror (core/prior.py rescale, gw/conversion.py, gw/_params.py pack_rows) against vectors generated
+    by the UNMODIFIED reference (oracle/tools/make_golden_prior.py); the device kernel is tested against the same
+    file in tests/test_gpu_sampling_front_end.py."""
+    from bilby_b200.core import prior as P
+    from bilby_b200.gw import _params, conversion
+    g = np.load(os.path.join(ROOT, "tests", "golden", "prior_transform.npz"))
+    make = {0: lambda a, b, c: P.DeltaFunction(a), 1: lambda a, b, c: P.Uniform(a, b),
+            2: lambda a, b, c: P.PowerLaw(c, a, b), 3: lambda a, b, c: P.Sine(a, b), 4: lambda a, b, c: P.Cosine(a, b),
+            5: lambda a, b, c: P.Gaussian(a, b)}
+    for case in (str(c) for c in g["case_names"]):
+        keys = [str(k) for k in g[f"{case}_keys"]]
+        spec = g[f"{case}_spec"]
+        u, ref_theta, ref_rows = g[f"{case}_unit"], g[f"{case}_theta"], g[f"{case}_rows"]
+        n = len(u)
+        params = {str(k): float(v) for k, v in zip(g[f"{case}_fixed_keys"], g[f"{case}_fixed_values"])}
+        for j, k in enumerate(keys):
+            pr = make[int(spec[j, 0])](*spec[j, 1:])
+            params[k] = pr.rescale(u[:, j])
+            np.testing.assert_allclose(params[k][2:], ref_theta[2:, j], rtol=1e-13, atol=0, err_msg=f"{case} {k}")
+        convert = (conversion.convert_to_lal_binary_neutron_star_parameters if bool(g[f"{case}_bns"])
+                   else conversion.convert_to_lal_binary_black_hole_parameters)
+        converted, _ = convert(params)
+        rows = _params.pack_rows(converted, n, np)
+        for c, name in enumerate(str(k) for k in g["row_keys"]):
+            np.testing.assert_allclose(rows[2:, c], ref_rows[2:, c], rtol=1e-12, atol=1e-15, err_msg=f"{case} {name}")
+
+
+def test_device_front_end_tables():
+    from bilby_b200.core import prior as P
+    assert BatchedLikelihood.prior_spec(P.PowerLaw(2, 10.0, 500.0)) == (2, 10.0, 500.0, 2.0)
+    assert BatchedLikelihood.prior_spec(P.Gaussian(1.0, 0.5)) == (5, 1.0, 0.5, 0.0)
+    assert BatchedLikelihood.prior_spec(P.DeltaFunction(3.0)) == (0, 3.0, 0.0, 0.0)
+    assert len(BatchedLikelihood.SOURCE_KEYS) == 28 and BatchedLikelihood.SOURCE_KEYS.index("geocent_time") == 22
+    text = open(os.path.join(ROOT, "include", "bilby_b200.h")).read()
+    for i, key in enumerate(BatchedLikelihood.SOURCE_KEYS):          # the header's enum is the same list
+        assert re.search(rf"BB_KEY_{key.upper()} = {i}\b", text), key
