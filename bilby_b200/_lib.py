@@ -113,7 +113,9 @@ def torch_ops():
     if _torch_ops is None:
         import torch
         load()                                   # the shim links against libbilby_b200.so
-        path = os.path.join(os.path.dirname(LIB_PATH), "libbilby_b200_torch.so")
+        # always the in-tree shim: its DT_NEEDED names the soname libbilby_b200.so, which the copy ctypes has already
+        # loaded satisfies (also an experiment build selected with BILBY_B200_LIB)
+        path = os.path.join(_HERE, "_lib", "libbilby_b200_torch.so")
         if not os.path.exists(path):
             from . import build
             build.build_torch_shim()

@@ -367,14 +367,14 @@ extern "C" int bb_set_roq(bb_handle* h, int n_linear, const double* nodes_linear
 // ---- launchers ------------------------------------------------------------------------------------
 static long bb_red_grid(const bb_handle* h, long n) {
     long blocks = (n + BB_RED_WARPS - 1) / BB_RED_WARPS;
-    // 8 CTAs of 256 threads per SM by default (BB_RED_GRID_PER_SM overrides it for experiments)
-    static const long per_sm = [] { const char* e = getenv("BB_RED_GRID_PER_SM"); const long v = e ? atol(e) : 0; return v > 0 ? v : 8L; }();
+    // 32 CTAs of 256 threads per SM (BB_RED_GRID_PER_SM overrides it): 3 are resident, the others start as the first
+    // ones drain.  Measured on relative binning, 1e6 samples: 4 per SM 6.07e8 eval/s, 8: 6.42e8, 16: 6.53e8, 32: 6.59e8,
+    // 64: 6.59e8, one CTA per 8 samples: 6.27e8; exactly the resident CTAs (no partial last wave): 6.15e8
+    static const long per_sm = [] { const char* e = getenv("BB_RED_GRID_PER_SM"); const long v = e ? atol(e) : 0; return v > 0 ? v : 32L; }();
     const long cap = (long)h->sm_count * per_sm;
     return blocks < cap ? blocks : cap;
 }
 
-// (Measured: sizing these grids to exactly the resident CTAs - occupancy x SM count, no partial last wave - is SLOWER
-// than the fixed cap of 8 CTAs per SM: relative binning 6.45e8 -> 6.15e8 eval/s, multi-banding 6.25e6 -> 5.70e6.)
 template <int NDET, int APPROX, bool CAL>
 static int bb_launch_reduced_t(bb_handle* h, long n, double* out, cudaStream_t st) {
     const size_t smem = (size_t)2 * BB_RED_WARPS * (BC_NCOEF + (CAL ? NDET * 4 * h->cal.n_points : 0)) * sizeof(double);
@@ -396,7 +396,8 @@ static int bb_launch_reduced_t(bb_handle* h, long n, double* out, cudaStream_t s
         const size_t smem_k6 = (size_t)2 * BB_ROQ_WARPS * (BC_NCOEF + (CAL ? NDET * 4 * h->cal.n_points : 0)) * sizeof(double)
                                + (size_t)BB_ROQ_WARPS * NDET * 5 * 32 * sizeof(double2) + BB_ROQ_WARPS * sizeof(unsigned long long);
         long grid_k6 = (n + BB_ROQ_WARPS - 1) / BB_ROQ_WARPS;
-        if (grid_k6 > (long)BB_ROQ_CTAS * h->sm_count) grid_k6 = (long)BB_ROQ_CTAS * h->sm_count;
+        static const long k6_per_sm = [] { const char* e = getenv("BB_ROQ_GRID_PER_SM"); const long v = e ? atol(e) : 0; return v > 0 ? v : (long)BB_ROQ_CTAS; }();
+        if (grid_k6 > k6_per_sm * h->sm_count) grid_k6 = k6_per_sm * h->sm_count;
         BB_CUDA(cudaFuncSetAttribute(bb_roq_kernel<NDET, APPROX, CAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k6));
         bb_roq_kernel<NDET, APPROX, CAL><<<(unsigned)grid_k6, BB_ROQ_THREADS, smem_k6, st>>>(
             h->d_coef, n, *h->rq, h->d_calrec, h->cal, out);

@@ -130,15 +130,11 @@ class ROQGravitationalWaveTransient(GravitationalWaveTransient):
                     def rd(g):
                         return {k: (rd(v) if hasattr(v, "keys") else v[()]) for k, v in g.items()}
                     out = rd(f)
-                if out.get(f"multiband_{basis_type}", False):
-                    raise NotImplementedError("multibanded ROQ bases (roq.py:920-1053) are not supported")
                 return out
             raise IOError(f"Format {fmt} not recognized.")
         if isinstance(basis, np.ndarray):
             return {f"basis_{basis_type}": {"0": {"basis": basis.T}}}
         if isinstance(basis, dict) and f"basis_{basis_type}" in basis:
-            if basis.get(f"multiband_{basis_type}", False):
-                raise NotImplementedError("multibanded ROQ bases (roq.py:920-1053) are not supported")
             return basis
         raise TypeError("basis needs to be str, np.ndarray or a dict in the hdf5 layout")
 
@@ -356,14 +352,109 @@ class ROQGravitationalWaveTransient(GravitationalWaveTransient):
                     for i in selected[basis_type]]
         for ifo in self.interferometers:
             self.weights[ifo.name + "_linear"], self.weights[ifo.name + "_quadratic"] = [], []
-        for i in selected["linear"]:
-            w = self._weights_of_one_basis(np.asarray(linear_matrix["basis_linear"][str(i)]["basis"]), None)
+        # roq.py:792-799, 839-847: a multibanded basis lives on its own banded frequency grid
+        if bool(np.asarray(linear_matrix.get("multiband_linear", False))[()]):
+            self._set_weights_linear_multiband(linear_matrix, selected["linear"])
+        else:
+            for i in selected["linear"]:
+                w = self._weights_of_one_basis(np.asarray(linear_matrix["basis_linear"][str(i)]["basis"]), None)
+                for ifo in self.interferometers:
+                    self.weights[ifo.name + "_linear"].append(w[ifo.name + "_linear"])
+        if bool(np.asarray(quadratic_matrix.get("multiband_quadratic", False))[()]):
+            self._set_weights_quadratic_multiband(quadratic_matrix, selected["quadratic"])
+        else:
+            for i in selected["quadratic"]:
+                w = self._weights_of_one_basis(None, np.asarray(quadratic_matrix["basis_quadratic"][str(i)]["basis"]))
+                for ifo in self.interferometers:
+                    self.weights[ifo.name + "_quadratic"].append(w[ifo.name + "_quadratic"])
+
+    @staticmethod
+    def _bands(matrix, basis_type, scale):
+        """Band durations (scaled), [start, end] frequency bins per band, the basis dimension and the highest basis
+        frequency of a multibanded basis (roq.py:934-938 / 1022-1026)."""
+        tbs = np.atleast_1d(np.asarray(matrix[f"durations_s_{basis_type}"], dtype=float)) / scale
+        bins = np.asarray(matrix[f"start_end_frequency_bins_{basis_type}"], dtype=int).reshape(-1, 2)
+        dim = int(np.sum(bins[:, 1] - bins[:, 0] + 1))
+        return tbs, bins, dim, float(np.max(bins[:, 1] / tbs))
+
+    def _set_weights_linear_multiband(self, linear_matrix, basis_idxs):
+        """roq.py:920-974: time-dependent linear weights from a multibanded basis.  Per band b (duration T_b, bins
+        [k0, k1] of spacing 1 / T_b) the over-whitened data d / S goes to the time domain, its last 2 f_high T_b samples
+        come back as D_b[k], and   w[t, i] = sum_b sum_k conj(B_i[b, k]) (4 / T_b) D_b[k] exp(2 pi i f_k (t - T + T_b)).
+        The transforms are host numpy (once per data set); the contraction over the banded points is the library's
+        FP64 tensor-core kernel when a CUDA device is there."""
+        tbs, bins, dim, fhigh = self._bands(linear_matrix, "linear", self.roq_scale_factor)
+        ts = np.asarray(self.weights["time_samples"], dtype=float)
+        shifted = {}
+        for ifo in self.interferometers:
+            mask = ifo.frequency_mask
+            spec = np.zeros(int(fhigh * ifo.duration) + 1, dtype=complex)
+            spec[np.arange(len(ifo.frequency_domain_strain))[mask]] = (
+                ifo.frequency_domain_strain[mask] / ifo.power_spectral_density_array[mask])
+            td = np.fft.irfft(spec)
+            rows = np.zeros((dim, len(ts)), dtype=complex)
+            at = 0
+            for (k0, k1), tb in zip(bins, tbs):
+                fs = np.arange(k0, k1 + 1) / tb
+                db = np.fft.rfft(td[-int(2. * fhigh * tb):])[k0:k1 + 1]
+                rows[at:at + k1 - k0 + 1] = 4. / tb * db[:, None] * np.exp(
+                    2. * np.pi * 1j * fs[:, None] * (ts[None, :] - ifo.duration + tb))
+                at += k1 - k0 + 1
+            shifted[ifo.name] = rows
+        for i in basis_idxs:
+            logger.info(f"Building linear ROQ weights for the {i}-th basis.")
+            basis = np.asarray(linear_matrix["basis_linear"][str(i)]["basis"])
             for ifo in self.interferometers:
-                self.weights[ifo.name + "_linear"].append(w[ifo.name + "_linear"])
-        for i in selected["quadratic"]:
-            w = self._weights_of_one_basis(None, np.asarray(quadratic_matrix["basis_quadratic"][str(i)]["basis"]))
+                self.weights[ifo.name + "_linear"].append(self._contract(shifted[ifo.name].T, basis.conj()))
+
+    def _set_weights_quadratic_multiband(self, quadratic_matrix, basis_idxs):
+        """roq.py:1006-1053: quadratic weights from a multibanded basis,  w[i] = sum_b sum_k B_i[b, k] (4 / T_b)
+        Re rfft(inverse-PSD time series folded to 2 f_high T_b samples)[k]."""
+        tbs, bins, dim, fhigh = self._bands(quadratic_matrix, "quadratic", self.roq_scale_factor)
+        folded = {}
+        for ifo in self.interferometers:
+            mask = ifo.frequency_mask
+            inv = np.zeros(int(fhigh * ifo.duration) + 1)
+            inv[np.arange(len(ifo.power_spectral_density_array))[mask]] = 1. / ifo.power_spectral_density_array[mask]
+            td = np.fft.irfft(inv)
+            vec = np.zeros(dim)
+            at = 0
+            for (k0, k1), tb in zip(bins, tbs):
+                half = int(fhigh * tb)
+                vec[at:at + k1 - k0 + 1] = 4. / tb * np.fft.rfft(np.concatenate([td[:half], td[-half:]]))[k0:k1 + 1].real
+                at += k1 - k0 + 1
+            folded[ifo.name] = vec
+        for i in basis_idxs:
+            logger.info(f"Building quadratic ROQ weights for the {i}-th basis.")
+            basis = np.asarray(quadratic_matrix["basis_quadratic"][str(i)]["basis"]).real
             for ifo in self.interferometers:
-                self.weights[ifo.name + "_quadratic"].append(w[ifo.name + "_quadratic"])
+                self.weights[ifo.name + "_quadratic"].append(basis @ folded[ifo.name])
+
+    def _contract(self, a, b):
+        """a [m, k] @ b [n, k].T (complex): bb_contract_device (DMMA) with a CUDA device, numpy without."""
+        try:
+            import torch
+            if not torch.cuda.is_available():
+                raise RuntimeError
+            net = self.device_network
+        except Exception:
+            return a @ b.T
+        import ctypes
+        from .. import _lib
+        m, k = a.shape
+        n = b.shape[0]
+
+        def dev(x):
+            buf = np.empty(x.shape + (2,))
+            buf[..., 0], buf[..., 1] = x.real, x.imag
+            return torch.from_numpy(buf).to(net.device)
+        ad, bd = dev(np.ascontiguousarray(a)), dev(np.ascontiguousarray(b))
+        cd = torch.empty((m, n, 2), dtype=torch.float64, device=net.device)
+        _lib.check(net.lib.bb_contract_device(net.ptr, 1, m, n, k, 1, 0, 0, 1, 0, 0, 0, 1.0, ad.data_ptr(), k,
+                                              bd.data_ptr(), k, 0, cd.data_ptr(), n, net._stream()))
+        torch.cuda.synchronize(net.device)
+        c = cd.cpu().numpy()
+        return c[..., 0] + 1j * c[..., 1]
 
     def _weights_of_one_basis(self, linear_basis, quadratic_basis):
         """Linear (roq.py:849-918) or quadratic (roq.py:976-1004) weights of every detector for ONE basis

@@ -285,3 +285,47 @@ def test_roq_multiple_bases_selected_per_sample_vs_oracle(tmp_path):
         geocent_time=Uniform(T_INJ - 0.1, T_INJ + 0.1, "geocent_time"), chirp_mass=Uniform(31.0, 38.0, "chirp_mass")),
         weights=path, **base_kw)
     assert one.number_of_bases_linear == 1 and len(one.weights["frequency_nodes_linear"][0]) == half
+
+
+def test_roq_multibanded_basis_vs_reference():
+    """roq.py:920-974, 1006-1053: ROQ weights from a MULTIBANDED basis (three bands of 4 / 2 / 1 s) and the likelihood
+    evaluated with them, against the unmodified reference (oracle/tools/make_golden_roq_multiband.py); the multibanded
+    ROQ likelihood also tracks the reference's full-grid likelihood of the same draws."""
+    import bilby_b200 as bb
+    from bilby_b200.gw import conversion, source
+    from bilby_b200.core.prior import Uniform
+    g, draws = rc.load("roq_multiband_bbh_4s_H1L1V1")
+    fmax = float(g["maximum_frequency"])
+    oifos = rc.oracle_ifos(g, dict(ocl.INJECTION), ocl.lal_binary_black_hole,
+                           dict(waveform_approximant="IMRPhenomD", reference_frequency=20.0, minimum_frequency=20.0),
+                           maximum_frequency=fmax)
+    ifos = _product_ifos(oifos, maximum_frequency=fmax)
+    wfg = bb.gw.WaveformGenerator(
+        duration=float(g["duration"]), sampling_frequency=float(g["sampling_frequency"]),
+        start_time=float(g["start_time"]), frequency_domain_source_model=source.binary_black_hole_roq,
+        parameter_conversion=conversion.convert_to_lal_binary_black_hole_parameters,
+        waveform_arguments=dict(waveform_approximant="IMRPhenomD", reference_frequency=20.0))
+    linear = dict(multiband_linear=np.array(True), durations_s_linear=g["durations_s"],
+                  start_end_frequency_bins_linear=g["start_end_frequency_bins"],
+                  basis_linear={"0": dict(basis=g["basis_linear"].astype(complex),
+                                          frequency_nodes=g["frequency_nodes_linear"])})
+    quadratic = dict(multiband_quadratic=np.array(True), durations_s_quadratic=g["durations_s"],
+                     start_end_frequency_bins_quadratic=g["start_end_frequency_bins"],
+                     basis_quadratic={"0": dict(basis=g["basis_quadratic"].astype(complex),
+                                                frequency_nodes=g["frequency_nodes_quadratic"])})
+    like = bb.gw.likelihood.ROQGravitationalWaveTransient(
+        ifos, wfg, _priors(geocent_time=Uniform(T_INJ - 0.1, T_INJ + 0.1, "geocent_time")),
+        linear_matrix=linear, quadratic_matrix=quadratic)
+    assert np.allclose(like.weights["time_samples"], g["time_samples"], rtol=0, atol=1e-12)
+    for name in ("H1", "L1", "V1"):
+        ref = g[f"weights_{name}_linear"]
+        got = like.weights[f"{name}_linear"][0][::37]
+        assert got.shape == ref.shape
+        assert np.max(np.abs(got - ref)) < 1e-9 * np.abs(ref).max(), name
+        assert np.allclose(like.weights[f"{name}_quadratic"][0], g[f"weights_{name}_quadratic"], rtol=1e-10), name
+    import torch
+    lnl = like.log_likelihood_ratio_batch(draws)
+    hh = like.inner_products_batch(torch.from_numpy(like.pack(draws)).cuda()).cpu().numpy()[..., 2]
+    scale = np.maximum(1.0, 0.5 * hh.sum(axis=1))
+    _close(lnl, g["lnl_none"], scale)
+    assert np.max(np.abs(lnl - g["lnl_full_grid"])) < 5.0            # the approximation itself (20-element basis)
