@@ -273,11 +273,12 @@ def gpu_run(args):
     bins = active_bins(rows_np, df, net.n_freq)
     k1_avg_ms = k1_ms.value / max(1, k1_n.value)
     achieved = bins * FLOP_PER_BIN / (k1_avg_ms * 1e-3) / 1e12 if k1_avg_ms > 0 else 0.0
-    traffic = None
+    traffic, capture = None, {}
     tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            capture = json.load(open(tpath))
+            traffic = capture.get("dram_bytes_per_launch")
         except Exception:
             traffic = None
     peaks = {}
@@ -294,7 +295,13 @@ def gpu_run(args):
                     algorithmic_flop_per_launch=bins * FLOP_PER_BIN, active_bins_per_eval=bins / n,
                     peak_source="in-run DFMA stream kernel (bb_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
                     hbm_peak_gbs=peaks.get("hbm_gbs"),
-                    algorithmic_hbm_bytes_per_launch=n * (16 + 1) * 8)
+                    algorithmic_hbm_bytes_per_launch=n * (16 + 1) * 8,
+                    # `achieved` counts SURVEY section 8d's convention (330 flop per bin: sincos = 60, ...); the kernel
+                    # executes about half as many FP64 operations (recurrences, tile columns, a shared sincospi), so
+                    # frac can exceed 1 while the hardware counter of the same capture shows the pipe half idle
+                    executed=dict(sm__pipe_fp64_cycles_active_pct=capture.get("sm__pipe_fp64_cycles_active_pct"),
+                                  smsp__issue_active_pct=capture.get("smsp__issue_active_pct"),
+                                  source=capture.get("source")))
 
     # ---- what a stock bilby sampler sees: one parameter dict per call (bilby/core/sampler/base_sampler.py:538-563)
     scalar_us = None

@@ -172,8 +172,16 @@ bb_calmarg_time_kernel(const double* __restrict__ coef, const unsigned* __restri
     int plan_a, plan_b, ps;
     bb_tm_plan(log2n, &plan_a, &plan_b, &ps);
     double* red = reinterpret_cast<double*>(X + bb_tm_series_elems(nfft, ps));      // [32]
+    double2* wl = reinterpret_cast<double2*>(red + 32);                              // [nfft / 256] (pruned finish)
     const int tid = threadIdx.x;
     const long S = ldk >> 4;
+    const int Lw = nfft >> 8;
+    if (log2n >= 9) {
+        for (int e = tid; e < Lw; e += BB_CMT_THREADS) {
+            const double2 w = twiddle[(e & (Lw / 2 - 1)) << 8];        // exp(-2 pi i e / L) from the nfft-point table
+            wl[e] = (e < Lw / 2) ? w : make_double2(-w.x, -w.y);
+        }
+    }
     const long pairs = (long)m * n_curves;
     for (long pair = blockIdx.x; pair < pairs; pair += gridDim.x) {
         const int s = (int)(pair / n_curves), c = (int)(pair - (long)s * n_curves);
@@ -198,9 +206,20 @@ bb_calmarg_time_kernel(const double* __restrict__ coef, const unsigned* __restri
             X[bb_tm_pos(k, ps)] = make_double2(vr, vi);
         }
         __syncthreads();
-        bb_tm_fft_dif<BB_CMT_THREADS>(X, nfft, log2n, twiddle);
-        bb_tm_finish<BB_CMT_THREADS>(X, nfft, log2n, marg, H[pair], rec[BC_DISTANCE], rec[BC_JITTER], start_time, duration, red,
-                     L + pair);
+        // K4b's pruned transform (bb_timemarg_split.cuh): eight stages, then only the outputs inside the time prior are
+        // formed by a direct nfft/256-term sum - per (sample, curve) pair 8 instead of log2n stages
+        int j_lo = 0, j_hi = nfft;
+        if (log2n >= 9) bb_tm_window(marg, rec[BC_JITTER], start_time, duration, nfft, &j_lo, &j_hi);
+        if (log2n >= 9 && j_hi - j_lo <= BB_SFT_PRUNE_MAX) {
+            bb_tm_pass<4, BB_CMT_THREADS>(X, nfft, 0, ps, twiddle);
+            bb_tm_pass<4, BB_CMT_THREADS>(X, nfft, 4, ps, twiddle);
+            bb_tm_finish<BB_CMT_THREADS, true>(X, nfft, log2n, marg, H[pair], rec[BC_DISTANCE], rec[BC_JITTER], start_time,
+                                               duration, red, L + pair, wl, ps);
+        } else {
+            bb_tm_fft_dif<BB_CMT_THREADS>(X, nfft, log2n, twiddle);
+            bb_tm_finish<BB_CMT_THREADS>(X, nfft, log2n, marg, H[pair], rec[BC_DISTANCE], rec[BC_JITTER], start_time, duration,
+                                         red, L + pair);
+        }
     }
 }
 
@@ -269,7 +288,7 @@ static int bb_launch_calmarg_t(bb_handle* h, long n, double* out, cudaStream_t s
         while ((1 << tm_log2n) < h->nfft) ++tm_log2n;
         int pa, pb, ps;
         bb_tm_plan(tm_log2n, &pa, &pb, &ps);
-        tm_smem = bb_tm_series_elems(h->nfft, ps) * sizeof(double2) + 32 * sizeof(double);
+        tm_smem = bb_tm_series_elems(h->nfft, ps) * sizeof(double2) + 32 * sizeof(double) + (size_t)(h->nfft >> 8) * sizeof(double2);
         if (tm_smem > 227 * 1024) return bb_fail("time + calibration marginalisation: series does not fit shared memory");
         BB_CUDA(cudaFuncSetAttribute(bb_calmarg_time_kernel<NDET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tm_smem));
         tm_per_sm = (int)((227 * 1024) / (tm_smem + 1024));

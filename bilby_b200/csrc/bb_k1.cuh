@@ -26,26 +26,30 @@
 #define BB_UNROLL(n) BB_PRAGMA_(unroll n)
 #define BB_K1_WARPS (BB_K1_THREADS / 32)
 #define BB_K1_SB BB_K1_WARPS               // samples per block (one per warp)
-#define BB_K1_CHUNK 512                    // bins per tile
-#define BB_K1_ROWS (BB_K1_CHUNK / BB_ROW)
+#define BB_K1_CHUNK 512                    // bins per tile: kernels with a calibration record or four detectors
+#define BB_K1_CHUNK_LARGE 768              // ... and the others (209 KB of tiles: 51.6 instead of 50.7 M eval/s on configs[1];
+                                           // 256-bin tiles: 46.3 M - the per-tile barrier and region set-up are not free)
+#define BB_K1_PAD 1536                     // the frequency axis is padded to a common multiple of both
+template <int NDET, bool CAL>
+struct K1Chunk { static constexpr int value = (!CAL && NDET <= 3) ? BB_K1_CHUNK_LARGE : BB_K1_CHUNK; };
 
-template <int NDET>
+template <int NDET, int CHUNK>
 struct K1Tile {
-    double u[BB_K1_CHUNK];
-    double lf[BB_K1_CHUNK];
-    double q34[BB_K1_CHUNK];
-    double rf[BB_K1_CHUNK];
-    double u7[BB_K1_CHUNK];
-    double ff[BB_K1_CHUNK];
-    double t3[BB_K1_CHUNK];
-    double x3[BB_K1_CHUNK];
-    double2 ds[NDET][BB_K1_CHUNK];
-    double is[NDET][BB_K1_CHUNK];
+    double u[CHUNK];
+    double lf[CHUNK];
+    double q34[CHUNK];
+    double rf[CHUNK];
+    double u7[CHUNK];
+    double ff[CHUNK];
+    double t3[CHUNK];
+    double x3[CHUNK];
+    double2 ds[NDET][CHUNK];
+    double is[NDET][CHUNK];
 };
 
-template <int NDET>
+template <int NDET, int CHUNK>
 struct K1Smem {
-    K1Tile<NDET> tile[2];
+    K1Tile<NDET, CHUNK> tile[2];
     double coef[BB_K1_SB][BC_NCOEF];
     unsigned long long bar[2];
     int krange[2];
@@ -75,21 +79,21 @@ __device__ __forceinline__ void bb_mbar_wait(unsigned long long* bar, unsigned p
         "}" ::"r"(bb_smem_u32(bar)), "r"(parity) : "memory");
 }
 
-template <int NDET>
-__device__ __forceinline__ void bb_k1_issue_tile(K1Tile<NDET>& t, unsigned long long* bar, const BBTiles& g, int c0) {
-    bb_mbar_expect_tx(bar, (unsigned)sizeof(K1Tile<NDET>));
-    bb_bulk_g2s(t.u, g.u + c0, BB_K1_CHUNK * 8, bar);
-    bb_bulk_g2s(t.lf, g.lf + c0, BB_K1_CHUNK * 8, bar);
-    bb_bulk_g2s(t.q34, g.q34 + c0, BB_K1_CHUNK * 8, bar);
-    bb_bulk_g2s(t.rf, g.rf + c0, BB_K1_CHUNK * 8, bar);
-    bb_bulk_g2s(t.u7, g.u7 + c0, BB_K1_CHUNK * 8, bar);
-    bb_bulk_g2s(t.ff, g.ff + c0, BB_K1_CHUNK * 8, bar);
-    bb_bulk_g2s(t.t3, g.t3 + c0, BB_K1_CHUNK * 8, bar);
-    bb_bulk_g2s(t.x3, g.x3 + c0, BB_K1_CHUNK * 8, bar);
+template <int NDET, int CHUNK>
+__device__ __forceinline__ void bb_k1_issue_tile(K1Tile<NDET, CHUNK>& t, unsigned long long* bar, const BBTiles& g, int c0) {
+    bb_mbar_expect_tx(bar, (unsigned)sizeof(K1Tile<NDET, CHUNK>));
+    bb_bulk_g2s(t.u, g.u + c0, CHUNK * 8, bar);
+    bb_bulk_g2s(t.lf, g.lf + c0, CHUNK * 8, bar);
+    bb_bulk_g2s(t.q34, g.q34 + c0, CHUNK * 8, bar);
+    bb_bulk_g2s(t.rf, g.rf + c0, CHUNK * 8, bar);
+    bb_bulk_g2s(t.u7, g.u7 + c0, CHUNK * 8, bar);
+    bb_bulk_g2s(t.ff, g.ff + c0, CHUNK * 8, bar);
+    bb_bulk_g2s(t.t3, g.t3 + c0, CHUNK * 8, bar);
+    bb_bulk_g2s(t.x3, g.x3 + c0, CHUNK * 8, bar);
 #pragma unroll
     for (int d = 0; d < NDET; ++d) {
-        bb_bulk_g2s(t.ds[d], g.ds + (size_t)d * g.n_pad + c0, BB_K1_CHUNK * 16, bar);
-        bb_bulk_g2s(t.is[d], g.is + (size_t)d * g.n_pad + c0, BB_K1_CHUNK * 8, bar);
+        bb_bulk_g2s(t.ds[d], g.ds + (size_t)d * g.n_pad + c0, CHUNK * 16, bar);
+        bb_bulk_g2s(t.is[d], g.is + (size_t)d * g.n_pad + c0, CHUNK * 8, bar);
     }
 }
 
@@ -223,8 +227,8 @@ struct K1State {
     BBCalGrid grid;
 };
 
-template <int NDET, bool CAL, bool MASKED = true>
-__device__ __forceinline__ void bb_k1_accumulate(K1State<NDET>& st, const K1Tile<NDET>& tile, int i, bool act,
+template <int NDET, bool CAL, bool MASKED = true, class TILE>
+__device__ __forceinline__ void bb_k1_accumulate(K1State<NDET>& st, const TILE& tile, int i, bool act,
                                                  double A, double ph) {
     double sn, cs;
     if (MASKED) {           // rows cut by the band edges: lanes outside [kmin, kmax) contribute exactly zero
@@ -263,8 +267,8 @@ __device__ __forceinline__ void bb_k1_accumulate(K1State<NDET>& st, const K1Tile
 
 // rows [r0, r1) of one chunk, all inside amplitude region AR and phase region PR.  MASKED: the rows may contain lanes
 // outside [kmin, kmax) (only the first and the last row of a sample); interior rows skip the selects.
-template <int NDET, int AR, int PR, bool CAL, bool MASKED>
-__device__ __forceinline__ void bb_k1_rows_pd_m(K1State<NDET>& st, const K1Tile<NDET>& tile, K1Amp<AR>& amp,
+template <int NDET, int AR, int PR, bool CAL, bool MASKED, class TILE>
+__device__ __forceinline__ void bb_k1_rows_pd_m(K1State<NDET>& st, const TILE& tile, K1Amp<AR>& amp,
                                                 const K1Ph<PR>& phs, int r0, int r1, int c0, int lane, int kmin,
                                                 int kmax, double df) {
     constexpr bool NEEDS_X = (AR == 0) || (PR == 0);
@@ -288,8 +292,8 @@ __device__ __forceinline__ void bb_k1_rows_pd_m(K1State<NDET>& st, const K1Tile<
     }
 }
 
-template <int NDET, int AR, int PR, bool CAL>
-__device__ __forceinline__ void bb_k1_rows_pd(K1State<NDET>& st, const K1Tile<NDET>& tile, const double* rec, int r0,
+template <int NDET, int AR, int PR, bool CAL, class TILE>
+__device__ __forceinline__ void bb_k1_rows_pd(K1State<NDET>& st, const TILE& tile, const double* rec, int r0,
                                               int r1, int c0, int lane, int kmin, int kmax, double df) {
     K1Amp<AR> amp;
     K1Ph<PR> phs;
@@ -305,8 +309,8 @@ __device__ __forceinline__ void bb_k1_rows_pd(K1State<NDET>& st, const K1Tile<ND
 
 // TaylorF2 (+ tides): one region, the 15 phase coefficients and the amplitude prefactor in registers, f / t / x / f^(-7/6)
 // from the tile (the generic path re-reads every coefficient from shared memory and forms the powers per bin)
-template <int NDET, bool CAL, bool MASKED>
-__device__ __forceinline__ void bb_k1_rows_tf2_m(K1State<NDET>& st, const K1Tile<NDET>& tile, const double (&q)[BT_NP],
+template <int NDET, bool CAL, bool MASKED, class TILE>
+__device__ __forceinline__ void bb_k1_rows_tf2_m(K1State<NDET>& st, const TILE& tile, const double (&q)[BT_NP],
                                                  double a0, int r0, int r1, int c0, int lane, int kmin, int kmax) {
     int k = r0 * BB_ROW + lane;
     int i = k - c0;
@@ -327,8 +331,8 @@ __device__ __forceinline__ void bb_k1_rows_tf2_m(K1State<NDET>& st, const K1Tile
     }
 }
 
-template <int NDET, bool CAL>
-__device__ __forceinline__ void bb_k1_rows_tf2(K1State<NDET>& st, const K1Tile<NDET>& tile, const double (&q)[BT_NP],
+template <int NDET, bool CAL, class TILE>
+__device__ __forceinline__ void bb_k1_rows_tf2(K1State<NDET>& st, const TILE& tile, const double (&q)[BT_NP],
                                                double a0, int r0, int r1, int c0, int lane, int kmin, int kmax) {
     const int ri0 = min(max((kmin + BB_ROW - 1) / BB_ROW, r0), r1), ri1 = max(min(kmax / BB_ROW, r1), ri0);
     if (r0 < ri0) bb_k1_rows_tf2_m<NDET, CAL, true>(st, tile, q, a0, r0, ri0, c0, lane, kmin, kmax);
@@ -337,8 +341,8 @@ __device__ __forceinline__ void bb_k1_rows_tf2(K1State<NDET>& st, const K1Tile<N
 }
 
 // generic rows: per-lane region selection (rows straddling a region boundary)
-template <int NDET, int APPROX, bool CAL>
-__device__ __forceinline__ void bb_k1_rows_generic(K1State<NDET>& st, const K1Tile<NDET>& tile, const double* rec,
+template <int NDET, int APPROX, bool CAL, class TILE>
+__device__ __forceinline__ void bb_k1_rows_generic(K1State<NDET>& st, const TILE& tile, const double* rec,
                                                    int r0, int r1, int c0, int lane, int kmin, int kmax, double df) {
     for (int r = r0; r < r1; ++r) {
         const int k = r * BB_ROW + lane, i = k - c0;
@@ -350,8 +354,8 @@ __device__ __forceinline__ void bb_k1_rows_generic(K1State<NDET>& st, const K1Ti
     }
 }
 
-template <int NDET, bool CAL>
-__device__ __forceinline__ void bb_k1_dispatch_pd(K1State<NDET>& st, const K1Tile<NDET>& tile, const double* rec,
+template <int NDET, bool CAL, class TILE>
+__device__ __forceinline__ void bb_k1_dispatch_pd(K1State<NDET>& st, const TILE& tile, const double* rec,
                                                   int r0, int r1, int c0, int lane, int kmin, int kmax, double df,
                                                   int ar, int pr) {
     const int combo = ar * 3 + pr;
@@ -380,8 +384,9 @@ bb_inner_product_kernel(const double* __restrict__ coef, const unsigned* __restr
                         double df, int shard_lo, int shard_hi, const double* __restrict__ calrec, BBCalGrid grid,
                         double* __restrict__ out, BBPush push) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    K1Smem<NDET>& sm = *reinterpret_cast<K1Smem<NDET>*>(smem_raw);
-    double* sm_cal = reinterpret_cast<double*>(smem_raw + sizeof(K1Smem<NDET>));   // [SB][NDET*4*n_points] (CAL)
+    constexpr int CHUNK = K1Chunk<NDET, CAL>::value;
+    K1Smem<NDET, CHUNK>& sm = *reinterpret_cast<K1Smem<NDET, CHUNK>*>(smem_raw);
+    double* sm_cal = reinterpret_cast<double*>(smem_raw + sizeof(K1Smem<NDET, CHUNK>));   // [SB][NDET*4*n_points] (CAL)
     const int cal_len = CAL ? NDET * 4 * grid.n_points : 0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long n_blocks = (n + BB_K1_SB - 1) / BB_K1_SB;
@@ -422,7 +427,7 @@ bb_inner_product_kernel(const double* __restrict__ coef, const unsigned* __restr
         }
         __syncthreads();
         const int kb0 = sm.krange[0], kb1 = sm.krange[1];
-        const int cb0 = kb0 / BB_K1_CHUNK, cb1 = (kb1 + BB_K1_CHUNK - 1) / BB_K1_CHUNK;   // chunk index range
+        const int cb0 = kb0 / CHUNK, cb1 = (kb1 + CHUNK - 1) / CHUNK;   // chunk index range
 
         // ---- per-warp sample set-up
         const bool have = warp < ns;
@@ -456,21 +461,21 @@ bb_inner_product_kernel(const double* __restrict__ coef, const unsigned* __restr
 
         // ---- stream the tiles
         if (cb1 > cb0 && tid == 0) {
-            bb_k1_issue_tile<NDET>(sm.tile[issued & 1], &sm.bar[issued & 1], tiles, cb0 * BB_K1_CHUNK);
+            bb_k1_issue_tile(sm.tile[issued & 1], &sm.bar[issued & 1], tiles, cb0 * CHUNK);
         }
         for (int cb = cb0; cb < cb1; ++cb) {
             const int stage = issued & 1;
             if (cb + 1 < cb1 && tid == 0) {
                 // the other stage was released by the __syncthreads that ended the previous iteration
-                bb_k1_issue_tile<NDET>(sm.tile[stage ^ 1], &sm.bar[stage ^ 1], tiles, (cb + 1) * BB_K1_CHUNK);
+                bb_k1_issue_tile(sm.tile[stage ^ 1], &sm.bar[stage ^ 1], tiles, (cb + 1) * CHUNK);
             }
             if (stage == 0) { bb_mbar_wait(&sm.bar[0], phase0); phase0 ^= 1; }
             else { bb_mbar_wait(&sm.bar[1], phase1); phase1 ^= 1; }
             ++issued;
-            const K1Tile<NDET>& tile = sm.tile[stage];
-            const int c0 = cb * BB_K1_CHUNK;
+            const K1Tile<NDET, CHUNK>& tile = sm.tile[stage];
+            const int c0 = cb * CHUNK;
             int r = max(row_first, c0 / BB_ROW);
-            const int rend = min(row_last, (c0 + BB_K1_CHUNK) / BB_ROW);
+            const int rend = min(row_last, (c0 + CHUNK) / BB_ROW);
             if (have && r < rend) {
                 if (APPROX == BB_IMRPHENOMD) {
                     // split [r, rend) at the rows that contain a region boundary

@@ -726,7 +726,7 @@ extern "C" int bb_set_network(bb_handle* h, int n_det, int n_freq, double durati
         memcpy(net.detector_tensor[d], detector_tensors + 9 * d, 9 * sizeof(double));
         memcpy(net.vertex[d], vertices + 3 * d, 3 * sizeof(double));
     }
-    const int n_pad = ((n_freq + BB_K1_CHUNK - 1) / BB_K1_CHUNK) * BB_K1_CHUNK;
+    const int n_pad = ((n_freq + BB_K1_PAD - 1) / BB_K1_PAD) * BB_K1_PAD;       // whole tiles of every K1 / K4a tile size
     h->n_pad = n_pad;
     std::vector<double> u(n_pad, 0.0), lf(n_pad, 0.0), q34(n_pad, 0.0), is((size_t)n_det * n_pad, 0.0);
     std::vector<double> rf(n_pad, 0.0), u7(n_pad, 0.0), ff(n_pad, 0.0), t3(n_pad, 0.0), x3(n_pad, 0.0);
@@ -978,7 +978,7 @@ static BBPush bb_exchange_push(bb_handle* h) {
 
 template <int NDET, int APPROX, bool CAL>
 static int bb_launch_inner_t(bb_handle* h, long n, double* out, cudaStream_t st) {
-    const size_t smem = sizeof(K1Smem<NDET>) + (CAL ? (size_t)BB_K1_SB * NDET * 4 * h->cal.n_points * sizeof(double) : 0);
+    const size_t smem = sizeof(K1Smem<NDET, K1Chunk<NDET, CAL>::value>) + (CAL ? (size_t)BB_K1_SB * NDET * 4 * h->cal.n_points * sizeof(double) : 0);
     if (smem > 227 * 1024) return bb_fail("K1: shared memory budget exceeded (too many calibration nodes)");
     BB_CUDA(cudaFuncSetAttribute(bb_inner_product_kernel<NDET, APPROX, CAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long n_blocks = (n + BB_K1_SB - 1) / BB_K1_SB;

@@ -431,28 +431,31 @@ class ROQGravitationalWaveTransient(GravitationalWaveTransient):
                 self.weights[ifo.name + "_quadratic"].append(basis @ folded[ifo.name])
 
     def _contract(self, a, b):
-        """a [m, k] @ b [n, k].T (complex): bb_contract_device (DMMA) with a CUDA device, numpy without."""
+        """a [m, k] @ b [n, k].T (complex): bb_contract_device (DMMA) with a CUDA device, numpy without.  Runs on a bare
+        handle of its own: the likelihood's device state is configured only after the weights exist."""
         try:
             import torch
             if not torch.cuda.is_available():
-                raise RuntimeError
-            net = self.device_network
-        except Exception:
+                return a @ b.T
+        except ImportError:      # pragma: no cover
             return a @ b.T
         import ctypes
         from .. import _lib
+        handle = _lib.Handle(self._device_index)
+        device = torch.device("cuda", handle.device)
         m, k = a.shape
         n = b.shape[0]
 
         def dev(x):
-            buf = np.empty(x.shape + (2,))
-            buf[..., 0], buf[..., 1] = x.real, x.imag
-            return torch.from_numpy(buf).to(net.device)
-        ad, bd = dev(np.ascontiguousarray(a)), dev(np.ascontiguousarray(b))
-        cd = torch.empty((m, n, 2), dtype=torch.float64, device=net.device)
-        _lib.check(net.lib.bb_contract_device(net.ptr, 1, m, n, k, 1, 0, 0, 1, 0, 0, 0, 1.0, ad.data_ptr(), k,
-                                              bd.data_ptr(), k, 0, cd.data_ptr(), n, net._stream()))
-        torch.cuda.synchronize(net.device)
+            # complex128 arrays are (re, im) pairs in memory
+            x = np.ascontiguousarray(x, dtype=np.complex128)
+            return torch.from_numpy(x.view(np.float64).reshape(x.shape + (2,))).to(device)
+        ad, bd = dev(a), dev(b)
+        cd = torch.empty((m, n, 2), dtype=torch.float64, device=device)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        _lib.check(handle.lib.bb_contract_device(handle.ptr, 1, m, n, k, 1, 0, 0, 1, 0, 0, 0, 1.0, ad.data_ptr(), k,
+                                                 bd.data_ptr(), k, 0, cd.data_ptr(), n, stream))
+        torch.cuda.synchronize(device)
         c = cd.cpu().numpy()
         return c[..., 0] + 1j * c[..., 1]
 

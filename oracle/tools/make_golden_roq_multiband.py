@@ -80,7 +80,8 @@ def main():
     res = dict(start_time=start_time, duration=duration, sampling_frequency=fs, detectors=np.array(names),
                noise_seed=NOISE_SEED, maximum_frequency=fmax, durations_s=DURATIONS, start_end_frequency_bins=BINS,
                basis_linear=lin, basis_quadratic=quad, frequency_nodes_linear=fnl, frequency_nodes_quadratic=fnq,
-               time_samples=like.weights["time_samples"])
+               time_samples=like.weights["time_samples"],
+               optimal_snrs=np.array([ifo.meta_data["optimal_SNR"] for ifo in ifos]))
     for k in draws:
         res["param_" + k] = draws[k]
     for ifo in ifos:

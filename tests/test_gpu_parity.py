@@ -153,6 +153,14 @@ def test_device_entry_equals_host_entry_and_is_order_independent():
     host = like.log_likelihood_ratio_rows_host(rows)
     dev = like.log_likelihood_ratio_batch(torch.from_numpy(rows).cuda()).cpu().numpy()
     assert np.array_equal(host, dev)
+    # page-locked buffers are copied from / to directly (no staging copy); same numbers
+    from bilby_b200.core.utils import pinned_empty
+    rows_pin, out_pin = pinned_empty(rows.shape), pinned_empty(len(rows))
+    rows_pin[...] = rows
+    assert like.log_likelihood_ratio_rows_host(rows_pin, out=out_pin) is out_pin
+    assert np.array_equal(out_pin, host)
+    with pytest.raises(ValueError):
+        like.log_likelihood_ratio_rows_host(rows, out=np.empty(len(rows) + 1))
     perm = np.random.default_rng(0).permutation(len(rows))
     dev_p = like.log_likelihood_ratio_batch(torch.from_numpy(rows[perm]).cuda()).cpu().numpy()
     assert np.array_equal(dev_p, dev[perm])

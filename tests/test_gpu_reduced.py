@@ -300,6 +300,8 @@ def test_roq_multibanded_basis_vs_reference():
                            dict(waveform_approximant="IMRPhenomD", reference_frequency=20.0, minimum_frequency=20.0),
                            maximum_frequency=fmax)
     ifos = _product_ifos(oifos, maximum_frequency=fmax)
+    for ifo, snr in zip(ifos, g["optimal_snrs"]):
+        ifo.meta_data["optimal_SNR"] = float(snr)      # what inject_signal records; sets the ROQ time resolution
     wfg = bb.gw.WaveformGenerator(
         duration=float(g["duration"]), sampling_frequency=float(g["sampling_frequency"]),
         start_time=float(g["start_time"]), frequency_domain_source_model=source.binary_black_hole_roq,
