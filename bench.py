@@ -370,11 +370,11 @@ def run_extra(args, world, rank, local_rank, dist):
     configs[3] with the frequency axis sharded over the N GPUs (strong scaling), through the fused peer-memory exchange
     and through one NCCL all-reduce."""
     import bench_configs as bc
-    out = dict(note="steps=3, warmup=3 per configuration; value = device-resident, e2e = host buffers through the C ABI; "
+    out = dict(note="steps=5, warmup=3 per configuration; value = device-resident, e2e = host buffers through the C ABI; "
                     "weak scaling over samples (every rank its own batch) unless stated", configs={})
     for cfg in EXTRA_CONFIGS:
         try:
-            line = bc.run_config(cfg, bc.DEFAULT_BATCH[cfg], 3, 3, world, rank, local_rank, dist, clocks=False)
+            line = bc.run_config(cfg, bc.DEFAULT_BATCH[cfg], 5, 3, world, rank, local_rank, dist, clocks=False)
         except Exception as exc:      # pragma: no cover - reported, never hidden
             line = dict(error=repr(exc)) if rank == 0 else None
         if rank != 0:

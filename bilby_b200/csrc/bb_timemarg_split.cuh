@@ -14,7 +14,9 @@
 // two phases alternate and neither pipe is busy more than half of the time.
 #pragma once
 
+#ifndef BB_SF_WARPS
 #define BB_SF_WARPS 12
+#endif
 #define BB_SF_THREADS (BB_SF_WARPS * 32)
 #define BB_SF_SB BB_SF_WARPS               // samples per block (one per warp)
 #define BB_SF_CHUNK 256                    // bins per tile
@@ -475,13 +477,18 @@ static int bb_launch_time_marg_split_t(bb_handle* h, long n, double* out, cudaSt
             double2* buf = h->d_series + (size_t)(c & 1) * slots_cap * nfft;
             double* srec = h->d_slotrec + (size_t)(c & 1) * slots_cap * BB_SF_SLOTREC;
             if (c >= 2) BB_CUDA(cudaStreamWaitEvent(st, h->tm_events[2 * (c - 2) + 1], 0));
-            const unsigned grid_a = (unsigned)(nb < h->sm_count ? nb : h->sm_count);
+            // BB_K4_FILL_SMS (experiment): SMs given to K4a; K4b gets the rest (with kernels that fill an SM each, the
+            // fill and the transform then run side by side on disjoint SMs instead of sharing every SM)
+            static const int fill_sms = [] { const char* e = getenv("BB_K4_FILL_SMS"); return e ? atoi(e) : 0; }();
+            const long sms_a = (fill_sms > 0 && fill_sms < h->sm_count) ? fill_sms : h->sm_count;
+            const long sms_b = (fill_sms > 0 && fill_sms < h->sm_count) ? h->sm_count - fill_sms : h->sm_count;
+            const unsigned grid_a = (unsigned)(nb < sms_a ? nb : sms_a);
             bb_series_fill_kernel<NDET, APPROX, CAL><<<grid_a, BB_SF_THREADS, smem_a, st>>>(
                 h->d_coef, perm, n, c, n_chunks, n_slots, bb_tiles(h), h->net.df, nfft, nfft, h->d_calrec, h->cal, buf, srec);
             BB_CUDA(cudaGetLastError());
             BB_CUDA(cudaEventRecord(h->tm_events[2 * c], st));
             BB_CUDA(cudaStreamWaitEvent(h->aux, h->tm_events[2 * c], 0));
-            const unsigned grid_b = (unsigned)(n_slots < h->sm_count ? n_slots : h->sm_count);
+            const unsigned grid_b = (unsigned)(n_slots < sms_b ? n_slots : sms_b);
             bb_series_fft_kernel<<<grid_b, BB_SFT_THREADS, smem_b, h->aux>>>(
                 n, c, n_chunks, n_slots, buf, srec, nfft, log2n, h->d_twiddle, h->marg,
                 h->net.start_time, h->net.duration, out);

@@ -2,7 +2,6 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -4 > gpurun_out/r2f_gpu_tests.log; cat gpurun_out/r2f_gpu_tests.log
-for g in 8 16 32; do BB_ROQ_GRID_PER_SM=$g timeout 300 python bench_configs.py --config cfg4_roq 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('k6grid$g', '%.4g' % d['value'], '%.3f' % d['roofline']['frac'])"; done
 ( time timeout 1400 python bench.py > gpurun_out/r2f_bench_n1.json 2> gpurun_out/r2f_bench_n1.err ) 2>&1 | tail -4
 tail -3 gpurun_out/r2f_bench_n1.err
 ( time timeout 600 python bench.py --impl reference > gpurun_out/r2f_bench_ref.json 2> gpurun_out/r2f_bench_ref.err ) 2>&1 | tail -4
