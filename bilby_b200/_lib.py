@@ -77,6 +77,7 @@ def load():
         "bb_set_sampling_priors": (i, [vp, i, vp, i, vp, vp, i]),
         "bb_rows_from_unit_cube_device": (i, [vp, vp, lng, vp, vp, vp]),
         "bb_rows_from_theta_device": (i, [vp, vp, lng, vp, vp]),
+        "bb_math_device": (i, [vp, i, vp, lng, vp, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is missing
@@ -101,7 +102,7 @@ EXPORTED_SYMBOLS = (
     "bb_exchange_destroy", "bb_contract_device", "bb_fp64_tensor_peak",
     "bb_build_roq_quadratic_weights", "bb_build_relbin_summary_data", "bb_set_multiband_time_marginalization",
     "bb_set_multiband_ifft_fft", "bb_fft_device", "bb_set_sampling_priors", "bb_rows_from_unit_cube_device",
-    "bb_rows_from_theta_device")
+    "bb_rows_from_theta_device", "bb_math_device")
 
 
 _torch_ops = None

@@ -1308,6 +1308,33 @@ extern "C" int bb_ln_i0_device(bb_handle* h, const double* x_dev, long n, double
     return 0;
 }
 
+// the device math layer on arrays (test hook: tests/test_gpu_math_layer.py compares it with 50-digit arithmetic)
+__global__ void bb_math_probe_kernel(int function, const double* __restrict__ x, long n, double* __restrict__ out) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (function == 0) {
+        double sn, cs;
+        bb_sincospi(x[i], &sn, &cs);
+        out[2 * i] = sn;
+        out[2 * i + 1] = cs;
+    } else if (function == 1) {
+        out[i] = bb_atan(x[i]);
+    } else {
+        out[i] = bb_rcp_pos(x[i]);
+    }
+}
+
+extern "C" int bb_math_device(bb_handle* h, int function, const double* x_dev, long n, double* out_dev, void* stream) {
+    if (!h) return bb_fail("bb_math_device: null handle");
+    if (function < 0 || function > 2) return bb_fail("bb_math_device: function must be 0 (sincospi), 1 (atan) or 2 (1/x)");
+    if (n <= 0) return 0;
+    BB_CUDA(cudaSetDevice(h->device));
+    bb_math_probe_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(function, x_dev, n, out_dev);
+    h->launches++;
+    BB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int bb_build_distance_table(bb_handle* h, const double* x_ref, int nx, const double* y_ref, int ny,
                                        const double* distance, const double* prior, int nd, double ref_dist,
                                        int phase_marginalization, double* table_out) {

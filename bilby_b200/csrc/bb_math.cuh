@@ -5,7 +5,7 @@
 // (three issue slots per term) and carry full-range / IEEE slow paths.  The versions here keep their coefficients in
 // __constant__ tables (one LDCU.128 per two coefficients) and are specialised for the argument ranges of this path:
 //
-//   bb_sincospi(x)   |x| < 2^30 half turns; argument reduction x = n/2 + r by the 1.5*2^52 shift (two DADDs), minimax
+//   bb_sincospi(x)   |x| < 2^50 half turns (NaN beyond); argument reduction x = n/2 + r by the 1.5*2^52 shift (two DADDs), minimax
 //                    polynomials (7 terms) for sin(pi r), cos(pi r) on |r| <= 1/4 (oracle/tools/make_math_coeffs.py;
 //                    errors 2.5e-18 / 4.7e-17 before rounding)
 //   bb_atan(y)       three-way reduction at tan(pi/8), tan(3 pi/8), one reciprocal, 11-term minimax polynomial
@@ -46,18 +46,22 @@ BB_HD double bb_rcp_pos(double a) {
 #endif
 }
 
-// sin(pi x), cos(pi x)
+// sin(pi x), cos(pi x) for |x| < 2^50 half turns.  Beyond that a double carries no quarter-turn information (and
+// x = inf / nan has none either): the result is NaN, formed by one select on the high word instead of a branch to the
+// library's full-range path (the branch, its convergence barrier and the inlined slow path cost every per-bin loop
+// four issue slots and a good part of its register budget).
 BB_HD void bb_sincospi(double x, double* sn, double* cs) {
 #ifdef __CUDA_ARCH__
-    // huge / inf / nan: library path; |x| >= 2^30 tested on the high word (an integer compare, not a DSETP)
-    if ((__double2hiint(x) & 0x7fffffff) >= 0x41d00000) { sincospi(x, sn, cs); return; }
+    const bool big = (__double2hiint(x) & 0x7fffffff) >= 0x43100000;       // |x| >= 2^50, inf, nan
     const double shift = 6755399441055744.0;                              // 1.5 * 2^52
     const double t = fma(x, 2.0, shift);                                  // low word = nearest integer n of 2x
     const int n = __double2loint(t);
-    const double r = fma(t - shift, -0.5, x);                             // exact, |r| <= 1/4
+    double r = fma(t - shift, -0.5, x);                                   // exact, |r| <= 1/4
+    r = __hiloint2double(big ? 0x7ff80000 : __double2hiint(r), __double2loint(r));
 #else
+    if (!(fabs(x) < 1125899906842624.0)) { *sn = *cs = NAN; return; }
     const double n2 = nearbyint(x + x);
-    const int n = (int)(long long)n2;
+    const int n = (int)(unsigned)(unsigned long long)(long long)n2;
     const double r = x - 0.5 * n2;
 #endif
     const double u = r * r;
@@ -80,6 +84,14 @@ BB_HD void bb_sincospi(double x, double* sn, double* cs) {
     *cs = ((n + 1) & 2) ? -b : b;
 #endif
 }
+
+#ifdef __CUDACC__
+// The same with a branch to the CUDA library for |x| >= 2^30 (round 1's form; see bb_relbin_edge_sample for its one user)
+__device__ __forceinline__ void bb_sincospi_branchy(double x, double* sn, double* cs) {
+    if ((__double2hiint(x) & 0x7fffffff) >= 0x41d00000) { sincospi(x, sn, cs); return; }
+    bb_sincospi(x, sn, cs);
+}
+#endif
 
 // atan(y), any finite y
 BB_HD double bb_atan(double y) {

@@ -389,6 +389,11 @@ int bb_rows_from_unit_cube_device(bb_handle* h, const double* unit_dev, long n, 
                                   void* stream);
 int bb_rows_from_theta_device(bb_handle* h, const double* theta_dev, long n, double* rows_dev, void* stream);
 
+/* The device math layer on arrays (csrc/bb_math.cuh: what the per-bin loops use instead of numpy's sin / cos / arctan
+ * and of IEEE division), exposed so that it can be checked on its own.  function 0: out[2 i], out[2 i + 1] =
+ * sin(pi x_i), cos(pi x_i) (|x| < 2^50, NaN beyond); 1: out[i] = atan(x_i); 2: out[i] = 1 / x_i for normal x_i > 0. */
+int bb_math_device(bb_handle* h, int function, const double* x_dev, long n, double* out_dev, void* stream);
+
 /* Measurement hooks (bench.py).  With profiling enabled the handle brackets every launch of the
  * dominant kernel (K1, the fused inner-product kernel) with CUDA events on the launching stream;
  * bb_profile_read synchronises and returns the summed duration and the number of launches since the
