@@ -438,14 +438,19 @@ static int bb_launch_time_marg_split_t(bb_handle* h, long n, double* out, cudaSt
 
     const long total_blocks = (n + BB_SF_SB - 1) / BB_SF_SB;
     // blocks per chunk: whole multiples of the SM count, large enough that every CTA streams several sample blocks per
-    // launch (8 per SM: 8.19 M eval/s at 1e6 samples, 2 per SM: 7.44 M) but at least ~16 chunks so that the first fill and
-    // the last transform, which run alone, stay a small part of the batch (1e5 samples: 4 per SM, 14 chunks)
-    long bpc = (total_blocks / 16 + h->sm_count - 1) / h->sm_count * h->sm_count;
+    // launch (8 per SM: 8.19 M eval/s at 1e6 samples, 2 per SM: 7.44 M) but at least ~20 chunks so that the first fill and
+    // the last transform, which run alone, stay a small part of the batch (1e5 samples: 3 per SM, 19 chunks; three scratch
+    // buffers, so that a fill never waits for the transform two chunks back: 7.66 -> 7.8 M eval/s, at the edge of the run-to-run noise)
+    long bpc = (total_blocks / 20 + h->sm_count - 1) / h->sm_count * h->sm_count;
     if (bpc < 2L * h->sm_count) bpc = 2L * h->sm_count;
     if (bpc > 8L * h->sm_count) bpc = 8L * h->sm_count;
+    { static const long force = [] { const char* e = getenv("BB_K4_BPC"); return e ? atol(e) : 0L; }();      // experiments
+      if (force > 0) bpc = force * h->sm_count; }
     const int n_chunks = (int)((total_blocks + bpc - 1) / bpc);
     const size_t slots_cap = (size_t)bpc * BB_SF_SB;
-    const size_t need = 2 * slots_cap * (size_t)nfft;
+    // scratch buffers in flight: K4a of chunk c may start once K4b of chunk c - nbuf has drained its buffer
+    static const int nbuf = [] { const char* e = getenv("BB_K4_NBUF"); const int v = e ? atoi(e) : 0; return (v >= 2 && v <= 4) ? v : 3; }();
+    const size_t need = (size_t)nbuf * slots_cap * (size_t)nfft;
     if (need > h->series_cap) {
         cudaFree(h->d_series);
         h->d_series = nullptr;
@@ -453,13 +458,13 @@ static int bb_launch_time_marg_split_t(bb_handle* h, long n, double* out, cudaSt
         BB_CUDA(cudaMalloc(&h->d_series, need * sizeof(double2)));
         h->series_cap = need;
     }
-    if (2 * slots_cap * BB_SF_SLOTREC > h->slotrec_cap) {
+    if ((size_t)nbuf * slots_cap * BB_SF_SLOTREC > h->slotrec_cap) {
         cudaFree(h->d_slotrec);
         h->d_slotrec = nullptr;
         h->slotrec_cap = 0;
-        BB_CUDA(cudaMalloc(&h->d_slotrec, 2 * slots_cap * BB_SF_SLOTREC * sizeof(double)));
-        BB_CUDA(cudaMemset(h->d_slotrec, 0, 2 * slots_cap * BB_SF_SLOTREC * sizeof(double)));
-        h->slotrec_cap = 2 * slots_cap * BB_SF_SLOTREC;
+        BB_CUDA(cudaMalloc(&h->d_slotrec, (size_t)nbuf * slots_cap * BB_SF_SLOTREC * sizeof(double)));
+        BB_CUDA(cudaMemset(h->d_slotrec, 0, (size_t)nbuf * slots_cap * BB_SF_SLOTREC * sizeof(double)));
+        h->slotrec_cap = (size_t)nbuf * slots_cap * BB_SF_SLOTREC;
     }
     if (!h->aux) BB_CUDA(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
     while ((int)h->tm_events.size() < 2 * n_chunks) {
@@ -474,9 +479,9 @@ static int bb_launch_time_marg_split_t(bb_handle* h, long n, double* out, cudaSt
             // blocks j with j * n_chunks + c < total_blocks
             const long nb = (total_blocks - 1 - c) / n_chunks + 1;
             const int n_slots = (int)(nb * BB_SF_SB);
-            double2* buf = h->d_series + (size_t)(c & 1) * slots_cap * nfft;
-            double* srec = h->d_slotrec + (size_t)(c & 1) * slots_cap * BB_SF_SLOTREC;
-            if (c >= 2) BB_CUDA(cudaStreamWaitEvent(st, h->tm_events[2 * (c - 2) + 1], 0));
+            double2* buf = h->d_series + (size_t)(c % nbuf) * slots_cap * nfft;
+            double* srec = h->d_slotrec + (size_t)(c % nbuf) * slots_cap * BB_SF_SLOTREC;
+            if (c >= nbuf) BB_CUDA(cudaStreamWaitEvent(st, h->tm_events[2 * (c - nbuf) + 1], 0));
             // BB_K4_FILL_SMS (experiment): SMs given to K4a; K4b gets the rest (with kernels that fill an SM each, the
             // fill and the transform then run side by side on disjoint SMs instead of sharing every SM)
             static const int fill_sms = [] { const char* e = getenv("BB_K4_FILL_SMS"); return e ? atoi(e) : 0; }();
