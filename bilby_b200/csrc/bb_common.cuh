@@ -100,7 +100,9 @@ struct BBCalGrid {
 };
 
 // calibration factor C = (1 + dA) (2 + i dphi) / (2 - i dphi) = amp1 * (cr + i ci), |cr + i ci| = 1.
-// rec: [4][n] = node amplitudes, their spline coefficients, node phases, their spline coefficients
+// rec: [n][4] = per node (amplitude, its spline coefficient, phase, its spline coefficient): the eight values one bin
+// needs are two neighbouring nodes = 64 contiguous bytes (node-major since round 2: with the four arrays one after the
+// other every load needed its own address, 43 IMADs per row of 32 bins in K4a)
 // spline bin weights: depend only on the frequency and the node grid (calibration.py:368-376)
 struct BBCalW {
     int j;
@@ -118,15 +120,29 @@ BB_HD BBCalW bb_cal_weights(int n, double l0, double inv_delta, double lf) {
     w.d = (w.b * w.b * w.b - w.b) * (1.0 / 6.0);
     return w;
 }
-BB_HD void bb_cal_apply(const double* rec, int n, const BBCalW& w, double* amp1, double* cr, double* ci) {
-    const int j = w.j;
-    const double dA = w.a * rec[j] + w.b * rec[j + 1] + w.c * rec[n + j] + w.d * rec[n + j + 1];
-    const double dP = w.a * rec[2 * n + j] + w.b * rec[2 * n + j + 1] + w.c * rec[3 * n + j] + w.d * rec[3 * n + j + 1];
+BB_HD void bb_cal_finish(double dA, double dP, double* amp1, double* cr, double* ci) {
     const double den = bb_rcp_pos(4.0 + dP * dP);
     *amp1 = 1.0 + dA;
     *cr = (4.0 - dP * dP) * den;
     *ci = 4.0 * dP * den;
 }
+BB_HD void bb_cal_apply(const double* rec, int n, const BBCalW& w, double* amp1, double* cr, double* ci) {
+    const double* r = rec + 4 * w.j;
+    const double dA = w.a * r[0] + w.b * r[4] + w.c * r[1] + w.d * r[5];
+    const double dP = w.a * r[2] + w.b * r[6] + w.c * r[3] + w.d * r[7];
+    bb_cal_finish(dA, dP, amp1, cr, ci);
+}
+#ifdef __CUDACC__
+// the same with four 16-byte loads; rec must be 16-byte aligned (the shared-memory records of K1 and K4a are)
+__device__ __forceinline__ void bb_cal_apply_v(const double* rec, int n, const BBCalW& w, double* amp1, double* cr,
+                                               double* ci) {
+    const double2* r = reinterpret_cast<const double2*>(rec + 4 * w.j);
+    const double2 a0 = r[0], p0 = r[1], a1 = r[2], p1 = r[3];
+    const double dA = w.a * a0.x + w.b * a1.x + w.c * a0.y + w.d * a1.y;
+    const double dP = w.a * p0.x + w.b * p1.x + w.c * p0.y + w.d * p1.y;
+    bb_cal_finish(dA, dP, amp1, cr, ci);
+}
+#endif
 BB_HD void bb_cal_factor(const double* rec, int n, double l0, double inv_delta, double lf, double* amp1,
                          double* cr, double* ci) {
     const BBCalW w = bb_cal_weights(n, l0, inv_delta, lf);

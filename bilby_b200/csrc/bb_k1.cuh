@@ -223,7 +223,7 @@ template <int NDET>
 struct K1State {
     double acc[NDET][3];     // Horner accumulators of conj(h/K) d/S (re, im); sum A^2 / S
     double step[NDET][2];    // R_d = exp(+i pi * 2 dt_d * 32 df)
-    const double* cal;       // CAL: this sample's calibration record [NDET][4][n_points] (shared memory)
+    const double* cal;       // CAL: this sample's calibration record [NDET][n_points][4] (shared memory)
     BBCalGrid grid;
 };
 
@@ -249,7 +249,7 @@ __device__ __forceinline__ void bb_k1_accumulate(K1State<NDET>& st, const TILE& 
             double amp1, cr, ci;
             if (d > 0 && !st.grid.shared)
                 cw = bb_cal_weights(st.grid.n_points, st.grid.l0[d], st.grid.inv_delta[d], tile.lf[i]);
-            bb_cal_apply(st.cal + d * 4 * st.grid.n_points, st.grid.n_points, cw, &amp1, &cr, &ci);
+            bb_cal_apply_v(st.cal + d * 4 * st.grid.n_points, st.grid.n_points, cw, &amp1, &cr, &ci);
             const double tr = amp1 * (wr * cr + wi * ci), ti = amp1 * (wi * cr - wr * ci);
             wr = tr;
             wi = ti;

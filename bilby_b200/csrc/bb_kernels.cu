@@ -298,18 +298,19 @@ __device__ __forceinline__ double bb_warp_sum8(const double* v, int lane) {
 // calibration.py:335-347: spline_coefficients = nodes_to_spline_coefficients . parameters
 __global__ void bb_cal_prologue_kernel(const double* __restrict__ calpar, long n, int n_det, int np,
                                        const double* __restrict__ M, double* __restrict__ calrec) {
-    // one thread per (sample, detector, kind); calpar [n][n_det][2][np] -> calrec [n][n_det][4][np]
+    // one thread per (sample, detector, kind); calpar [n][n_det][2][np] -> calrec [n][n_det][np][4]
+    // (node-major: value and spline coefficient of the amplitude, then of the phase; bb_cal_apply)
     const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n * n_det * 2) return;
     const long sd = t >> 1;
     const int kind = (int)(t & 1);
     const double* p = calpar + (sd * 2 + kind) * np;
-    double* o = calrec + (sd * 4 + 2 * kind) * np;
+    double* o = calrec + sd * 4 * np + 2 * kind;
     for (int i = 0; i < np; ++i) {
-        o[i] = p[i];
+        o[4 * i] = p[i];
         double acc = 0.0;
         for (int j = 0; j < np; ++j) acc += M[i * np + j] * p[j];
-        o[np + i] = acc;
+        o[4 * i + 1] = acc;
     }
 }
 

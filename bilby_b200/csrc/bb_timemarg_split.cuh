@@ -106,7 +106,7 @@ __device__ __forceinline__ void bb_sf_bin(SFState<NDET>& st, const SFTile<NDET>&
             double amp1, cr, ci;
             if (d > 0 && !st.grid.shared)
                 cw = bb_cal_weights(st.grid.n_points, st.grid.l0[d], st.grid.inv_delta[d], tile.lf[i]);
-            bb_cal_apply(st.cal + d * 4 * st.grid.n_points, st.grid.n_points, cw, &amp1, &cr, &ci);
+            bb_cal_apply_v(st.cal + d * 4 * st.grid.n_points, st.grid.n_points, cw, &amp1, &cr, &ci);
             const double qr = amp1 * cr, qi = amp1 * ci;       // conj(C) = amp1 (cr - i ci)
             sr = fma(gr, qr, fma(gi, qi, sr));
             si = fma(gi, qr, fma(-gr, qi, si));
