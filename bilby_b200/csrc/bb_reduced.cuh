@@ -20,13 +20,12 @@
 #ifndef BB_ROQ_CTAS
 #define BB_ROQ_CTAS 4
 #endif
-// K5 leaves the register allocation to ptxas (80 registers for relative binning = 3 CTAs per SM, more for the
-// multi-banded variant, which spills under a 3-CTA bound: 6.2e6 -> 5.3e6 eval/s); BB_RELBIN_CTAS forces a bound for
-// experiments
+// K5: relative binning (CROSS) is held at 3 CTAs per SM (80 registers); the multi-banded variant is left to ptxas
+// (it spills under a 3-CTA bound: 6.2e6 -> 5.3e6 eval/s); BB_RELBIN_CTAS forces a bound for experiments
 #ifdef BB_RELBIN_CTAS
 #define BB_RELBIN_BOUNDS __launch_bounds__(BB_RED_THREADS, BB_RELBIN_CTAS)
 #else
-#define BB_RELBIN_BOUNDS __launch_bounds__(BB_RED_THREADS)
+#define BB_RELBIN_BOUNDS __launch_bounds__(BB_RED_THREADS, CROSS ? 3 : 1)
 #endif
 #define BB_ROQ_WARPS (BB_ROQ_THREADS / 32)
 
@@ -38,8 +37,19 @@ struct BBNodes {
     const double* t3;     // f^(-1/3) = u u
     const double* x3;     // f^(1/3) = (f t) t
     const double* u7;     // f^(-7/6) = u (t t t)
+    // the six columns the kernels read per node (f, t3, x3, u7, lf, q34) a second time in rows of 32 nodes,
+    // blk[row][column][32] (the last node repeated beyond n): one running pointer and immediate offsets per row
+    // instead of six parameter loads and 64-bit index multiplies
+    const double* blk;
     int n;
 };
+#define BB_NB_F 0
+#define BB_NB_T3 32
+#define BB_NB_X3 64
+#define BB_NB_U7 96
+#define BB_NB_LF 128
+#define BB_NB_Q34 160
+#define BB_NB_ROW 192
 
 struct BBRelbinDev {
     BBNodes edges;            // bin edges (relative.py:233 frequency_bin_edges)
@@ -186,31 +196,30 @@ __device__ __forceinline__ void bb_relbin_edge_sample(const double* rec, const d
     // streams hundreds of rows per sample from L2)
     // (only there: with the two rows of a relative-binning sample the extra registers cost more than they hide)
     constexpr bool PREFETCH = !CROSS;
-    const int j0 = lane < ne ? lane : ne - 1;
+    const double* nb = rb.edges.blk + lane;
     double nf = 0.0, nt = 0.0, nx = 0.0, nu7 = 0.0, nlf = 0.0, nq = 0.0;
     if (PREFETCH) {
-        nf = rb.edges.f[j0]; nt = rb.edges.t3[j0]; nx = rb.edges.x3[j0]; nu7 = rb.edges.u7[j0];
-        nlf = rb.edges.lf[j0]; nq = rb.edges.q34[j0];
+        nf = nb[BB_NB_F]; nt = nb[BB_NB_T3]; nx = nb[BB_NB_X3]; nu7 = nb[BB_NB_U7];
+        nlf = nb[BB_NB_LF]; nq = nb[BB_NB_Q34];
     }
-    for (int base = 0; base < ne; base += 32) {
+    for (int base = 0; base < ne; base += 32, nb += BB_NB_ROW) {
         const int j = base + lane;
         const bool more = base + 32 < ne;
         double f, t, x, u7, lfj, q34;
         if (PREFETCH) {
             f = nf; t = nt; x = nx; u7 = nu7; lfj = nlf; q34 = nq;
             if (more) {
-                const int jn = j + 32 < ne ? j + 32 : ne - 1;
-                nf = rb.edges.f[jn];
-                nt = rb.edges.t3[jn];
-                nx = rb.edges.x3[jn];
-                nu7 = rb.edges.u7[jn];
-                nlf = rb.edges.lf[jn];
-                if (APPROX == BB_IMRPHENOMD) nq = rb.edges.q34[jn];
+                const double* nn = nb + BB_NB_ROW;
+                nf = nn[BB_NB_F];
+                nt = nn[BB_NB_T3];
+                nx = nn[BB_NB_X3];
+                nu7 = nn[BB_NB_U7];
+                nlf = nn[BB_NB_LF];
+                if (APPROX == BB_IMRPHENOMD) nq = nn[BB_NB_Q34];
             }
         } else {
-            const int jj = j < ne ? j : ne - 1;
-            f = rb.edges.f[jj]; t = rb.edges.t3[jj]; x = rb.edges.x3[jj]; u7 = rb.edges.u7[jj]; lfj = rb.edges.lf[jj];
-            q34 = (APPROX == BB_IMRPHENOMD) ? rb.edges.q34[jj] : 0.0;
+            f = nb[BB_NB_F]; t = nb[BB_NB_T3]; x = nb[BB_NB_X3]; u7 = nb[BB_NB_U7]; lfj = nb[BB_NB_LF];
+            q34 = (APPROX == BB_IMRPHENOMD) ? nb[BB_NB_Q34] : 0.0;
         }
         double A, ph;
         bb_wave_cols<APPROX>(rec, f, t, x, u7, lfj, q34, &A, &ph);
@@ -391,6 +400,7 @@ bb_roq_kernel(const double* __restrict__ coef, long n, BBRoqDev rq, const double
     unsigned parity = 0;                                     // parity of the next completion of this warp's barrier
     const int nl = rq.lin.n;
     const int n_pass = (nl + 31) / 32;
+    const double* nblk = rq.lin.blk + lane;
     const double ts0 = (double)rq.time_start_index * rq.time_step;
     const double ts1 = (double)(rq.time_start_index + 1) * rq.time_step;
     const double space = ts1 - ts0;                          // samples[1] - samples[0] (roq.py:571)
@@ -405,20 +415,22 @@ bb_roq_kernel(const double* __restrict__ coef, long n, BBRoqDev rq, const double
             double* nxt = slots + (ping ^ 1) * slot_len;
             bb_red_prefetch<CAL>(nxt, nxt + BC_NCOEF, coef, calrec, s + stride, cal_len, lane);
         }
-        // five neighbouring ROQ times per detector (roq.py:509-516, 551-574): first = closest - 2, clipped per index
-        int first[NDET];
-        bool inb[NDET];
-        double ck[NDET][5];
-#pragma unroll
-        for (int d = 0; d < NDET; ++d) {
-            const double ifo_time = rec[BC_DT0] + 0.5 * rec[BC_DET + BC_DSTRIDE * d + 2];
+        // five neighbouring ROQ times per detector (roq.py:509-516, 551-574): first = closest - 2, clipped per index.
+        // Lane d works out detector d (window, interpolation coefficients: four FP64 divisions) and the warp picks the
+        // results up by shuffle, instead of every lane working out every detector.
+        const int dl = lane < NDET ? lane : NDET - 1;
+        int first_m;
+        bool inb_m;
+        double ck_m[5];
+        {
+            const double ifo_time = rec[BC_DT0] + 0.5 * rec[BC_DET + BC_DSTRIDE * dl + 2];
             const double q = floor((ifo_time - ts0) / space);
             const long closest = (long)fmin(fmax(q, -1.0e9), 1.0e9);
-            inb[d] = (closest - 2 >= 0) && (closest + 2 < (long)rq.n_time);
-            first[d] = (int)(closest - 2);
+            inb_m = (closest - 2 >= 0) && (closest + 2 < (long)rq.n_time);
+            first_m = (int)(closest - 2);
             // a = (time_samples[3] - time) / max(time_samples[1] - time_samples[0], 1e-12) on the CLIPPED indices
-            const int i3 = min(max(first[d] + 3, 0), rq.n_time - 1), i1 = min(max(first[d] + 1, 0), rq.n_time - 1),
-                      i0 = min(max(first[d], 0), rq.n_time - 1);
+            const int i3 = min(max(first_m + 3, 0), rq.n_time - 1), i1 = min(max(first_m + 1, 0), rq.n_time - 1),
+                      i0 = min(max(first_m, 0), rq.n_time - 1);
             const double t3 = (double)(rq.time_start_index + i3) * rq.time_step;
             const double t1 = (double)(rq.time_start_index + i1) * rq.time_step;
             const double t0 = (double)(rq.time_start_index + i0) * rq.time_step;
@@ -426,32 +438,39 @@ bb_roq_kernel(const double* __restrict__ coef, long n, BBRoqDev rq, const double
             // The five-sample interpolation (bb_interp5) is linear in the five contractions with REAL coefficients that
             // depend only on the sample's time: the five rows of W are combined first (10 DFMA) and contracted once
             // (4 DFMA) instead of five complex multiply-accumulates (20 DFMA) and 30 running sums per lane.
-            bb_interp5_coeffs(a, ck[d]);
+            bb_interp5_coeffs(a, ck_m);
         }
-        // source of pass 0 per detector and the advance per pass, computed once per sample; the usual case (all five
-        // times of every detector inside the weights) is one branch-free sequence of NDET bulk copies
-        bool all_in = true;
-        const double2* wsrc[NDET];
+        const unsigned inb_mask = __ballot_sync(0xffffffffu, inb_m);
+        const bool all_in = (inb_mask & ((1u << NDET) - 1u)) == ((1u << NDET) - 1u);
+        int first[NDET];
+        double ck[NDET][5];
 #pragma unroll
         for (int d = 0; d < NDET; ++d) {
-            all_in = all_in && inb[d];
-            wsrc[d] = rq.W2 + ((size_t)d * n_pass * rq.n_time + (size_t)max(first[d], 0)) * 32;
+            first[d] = __shfl_sync(0xffffffffu, first_m, d);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) ck[d][k] = __shfl_sync(0xffffffffu, ck_m[k], d);
         }
+        // Source of pass 0 and the advance per pass, computed once per sample.  The usual case (all five times of every
+        // detector inside the weights): lane d issues the one bulk copy of detector d from its own running pointer
+        // (the copy's operands travel through uniform registers, one elected lane at a time, so three lanes with one
+        // copy each are a third of the instructions of one lane with three)
+        const double2* wsrc = rq.W2 + ((size_t)dl * n_pass * rq.n_time + (size_t)max(first_m, 0)) * 32;
+        double2* const wdst = wst + dl * 5 * 32;
         const size_t wstride = (size_t)rq.n_time * 32;
         auto stage_fill = [&](int pass) {
-            if (lane == 0) {
+            if (all_in) {
+                if (lane < NDET) {
+                    if (lane == 0) bb_mbar_expect_tx(bar, (unsigned)(NDET * 5 * 32 * sizeof(double2)));
+                    bb_bulk_g2s(wdst, wsrc, 5 * 32 * sizeof(double2), bar);
+                }
+                wsrc += wstride;
+            } else if (lane == 0) {
                 bb_mbar_expect_tx(bar, (unsigned)(NDET * 5 * 32 * sizeof(double2)));
-                if (all_in) {
-#pragma unroll
-                    for (int d = 0; d < NDET; ++d)
-                        bb_bulk_g2s(wst + d * 5 * 32, wsrc[d] + (size_t)pass * wstride, 5 * 32 * sizeof(double2), bar);
-                } else {
-                    for (int d = 0; d < NDET; ++d) {
-                        const double2* blk = rq.W2 + ((size_t)d * n_pass + pass) * rq.n_time * 32;
-                        for (int k = 0; k < 5; ++k) {
-                            const int i = min(max(first[d] + k, 0), rq.n_time - 1);
-                            bb_bulk_g2s(wst + (d * 5 + k) * 32, blk + (size_t)i * 32, 32 * sizeof(double2), bar);
-                        }
+                for (int d = 0; d < NDET; ++d) {
+                    const double2* blk = rq.W2 + ((size_t)d * n_pass + pass) * rq.n_time * 32;
+                    for (int k = 0; k < 5; ++k) {
+                        const int i = min(max(first[d] + k, 0), rq.n_time - 1);
+                        bb_bulk_g2s(wst + (d * 5 + k) * 32, blk + (size_t)i * 32, 32 * sizeof(double2), bar);
                     }
                 }
             }
@@ -464,13 +483,15 @@ bb_roq_kernel(const double* __restrict__ coef, long n, BBRoqDev rq, const double
 #pragma unroll
         for (int d = 0; d < NDET; ++d) acc[d] = make_double2(0.0, 0.0);
         for (int pass = 0; pass < n_pass; ++pass) {
-            const int j = pass * 32 + lane;
-            double zr0 = 0.0, zi0 = 0.0, lfj = 0.0;
-            if (j < nl) {
-                const double f = rq.lin.f[j];
+            // lanes beyond the last node evaluate the last node again (no branch): their rows of W2 are zero
+            double zr0, zi0, lfj;
+            {
+                const double* nb = nblk + pass * BB_NB_ROW;
+                const double f = nb[BB_NB_F];
                 double A, ph, sn, cs;
-                lfj = rq.lin.lf[j];
-                bb_wave_cols<APPROX>(rec, f, rq.lin.t3[j], rq.lin.x3[j], rq.lin.u7[j], lfj, rq.lin.q34[j], &A, &ph);
+                lfj = nb[BB_NB_LF];
+                bb_wave_cols<APPROX>(rec, f, nb[BB_NB_T3], nb[BB_NB_X3], nb[BB_NB_U7], lfj,
+                                     (APPROX == BB_IMRPHENOMD) ? nb[BB_NB_Q34] : 0.0, &A, &ph);
                 bb_sincospi(ph, &sn, &cs);
                 zr0 = A * cs;                                   // conj(h22) = A e^{+i Phi}
                 zi0 = A * sn;
@@ -514,7 +535,7 @@ bb_roq_kernel(const double* __restrict__ coef, long n, BBRoqDev rq, const double
             if ((lane & 7) == 0 && lane < 24) {
                 const int d = lane >> 3;
                 const double kr = rec[BC_DET + BC_DSTRIDE * d], ki = rec[BC_DET + BC_DSTRIDE * d + 1];
-                const bool in = d == 0 ? inb[0] : (d == 1 ? inb[1] : inb[2]);
+                const bool in = (inb_mask >> d) & 1u;
                 // conj(K) * sum; out of the ROQ time window: d_inner_h += log(False) (roq.py:532-533)
                 o[3 * d] = in ? kr * t8 + ki * im : -INFINITY;
                 o[3 * d + 1] = kr * im - ki * t8;
@@ -532,7 +553,7 @@ bb_roq_kernel(const double* __restrict__ coef, long n, BBRoqDev rq, const double
                 if (lane == 0) {
                     double* o = out + (s * NDET + d) * 3;
                     // conj(K) * sum; out of the ROQ time window: d_inner_h += log(False) (roq.py:532-533)
-                    o[0] = inb[d] ? kr * sr + ki * si : -INFINITY;
+                    o[0] = ((inb_mask >> d) & 1u) ? kr * sr + ki * si : -INFINITY;
                     o[1] = kr * si - ki * sr;
                     o[2] = (rec[BC_STATUS] != 0.0) ? nan("") : hq[d];
                 }

@@ -60,6 +60,15 @@ static int bb_upload_nodes(bb_handle* h, const double* f, int n, BBNodes* out) {
     if (bb_red_upload(h, t3.data(), n, &out->t3)) return 1;
     if (bb_red_upload(h, x3.data(), n, &out->x3)) return 1;
     if (bb_red_upload(h, u7.data(), n, &out->u7)) return 1;
+    const int rows = (n + 31) / 32;
+    std::vector<double> blk((size_t)rows * BB_NB_ROW);
+    for (int i = 0; i < rows * 32; ++i) {
+        const int j = i < n ? i : n - 1;
+        double* b = blk.data() + (size_t)(i / 32) * BB_NB_ROW + (i % 32);
+        b[BB_NB_F] = f[j]; b[BB_NB_T3] = t3[j]; b[BB_NB_X3] = x3[j]; b[BB_NB_U7] = u7[j];
+        b[BB_NB_LF] = lf[j]; b[BB_NB_Q34] = q34[j];
+    }
+    if (bb_red_upload(h, blk.data(), blk.size(), &out->blk)) return 1;
     return 0;
 }
 
