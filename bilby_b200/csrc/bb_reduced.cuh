@@ -20,8 +20,9 @@
 #ifndef BB_ROQ_CTAS
 #define BB_ROQ_CTAS 4
 #endif
-// K5: relative binning (CROSS) is held at 3 CTAs per SM (80 registers); the multi-banded variant is left to ptxas
-// (it spills under a 3-CTA bound: 6.2e6 -> 5.3e6 eval/s); BB_RELBIN_CTAS forces a bound for experiments
+// K5: relative binning (CROSS) is held at 3 CTAs per SM (80 registers); the multi-banded variant is left to ptxas,
+// which takes 164 registers = ONE 8-warp CTA per SM and keeps the next row's tables in flight: 9.3e6 eval/s vs 8.7e6
+// under a 2-CTA bound (126 registers) and 5.3e6 under a 3-CTA bound (spills); BB_RELBIN_CTAS forces a bound for experiments
 #ifdef BB_RELBIN_CTAS
 #define BB_RELBIN_BOUNDS __launch_bounds__(BB_RED_THREADS, BB_RELBIN_CTAS)
 #else
@@ -67,6 +68,9 @@ struct BBRelbinDev {
     const double2* lin_c;     // <d|h> = sum_j lin_c[j] conj(h_j)
     const double* quad_e;     // <h|h> = sum_j quad_e[j] |h_j|^2 + Re(cross_g[j] h_j conj(h_{j-1}))
     const double2* cross_g;
+    // the same three tables in rows of 32 edges, etab[row][det]{lin_c[32], cross_g[32] (relative binning only),
+    // quad_e[32]}: two running pointers and immediate offsets in K5's loop
+    const double* etab;
     int ne_pad;
 };
 
@@ -188,7 +192,7 @@ __device__ __forceinline__ void bb_relbin_sample(const double* rec, const double
 template <int NDET, int APPROX, bool CAL, bool CROSS>
 __device__ __forceinline__ void bb_relbin_edge_sample(const double* rec, const double* cal, const BBCalGrid& grid,
                                                       const BBRelbinDev& rb, int lane, double (*acc)[3]) {
-    const int ne = rb.edges.n, np = rb.ne_pad;
+    const int ne = rb.edges.n;
     double2 carry[NDET];
 #pragma unroll
     for (int d = 0; d < NDET; ++d) carry[d] = make_double2(0.0, 0.0);
@@ -197,13 +201,15 @@ __device__ __forceinline__ void bb_relbin_edge_sample(const double* rec, const d
     // (only there: with the two rows of a relative-binning sample the extra registers cost more than they hide)
     constexpr bool PREFETCH = !CROSS;
     const double* nb = rb.edges.blk + lane;
+    constexpr int ET = CROSS ? 160 : 96;                   // doubles per (row, detector) of etab
+    const double* et = rb.etab + 2 * lane;                 // lin_c (and cross_g 64 doubles on)
+    const double* ee = rb.etab + (CROSS ? 128 : 64) + lane;    // quad_e
     double nf = 0.0, nt = 0.0, nx = 0.0, nu7 = 0.0, nlf = 0.0, nq = 0.0;
     if (PREFETCH) {
         nf = nb[BB_NB_F]; nt = nb[BB_NB_T3]; nx = nb[BB_NB_X3]; nu7 = nb[BB_NB_U7];
         nlf = nb[BB_NB_LF]; nq = nb[BB_NB_Q34];
     }
-    for (int base = 0; base < ne; base += 32, nb += BB_NB_ROW) {
-        const int j = base + lane;
+    for (int base = 0; base < ne; base += 32, nb += BB_NB_ROW, et += NDET * ET, ee += NDET * ET) {
         const bool more = base + 32 < ne;
         double f, t, x, u7, lfj, q34;
         if (PREFETCH) {
@@ -241,12 +247,12 @@ __device__ __forceinline__ void bb_relbin_edge_sample(const double* rec, const d
                 hr = tr;
                 hi = ti;
             }
-            const double2 c = rb.lin_c[(size_t)d * np + j];
-            const double e = rb.quad_e[(size_t)d * np + j];
+            const double2 c = *reinterpret_cast<const double2*>(et + d * ET);
+            const double e = ee[d * ET];
             acc[d][0] = fma(c.x, hr, fma(c.y, hi, acc[d][0]));           // C conj(h)
             acc[d][1] = fma(c.y, hr, fma(-c.x, hi, acc[d][1]));
             if (CROSS) {
-                const double2 g = rb.cross_g[(size_t)d * np + j];
+                const double2 g = *reinterpret_cast<const double2*>(et + d * ET + 64);
                 double lr = __shfl_up_sync(0xffffffffu, hr, 1), li = __shfl_up_sync(0xffffffffu, hi, 1);
                 if (lane == 0) { lr = carry[d].x; li = carry[d].y; }
                 if (more) {

@@ -72,6 +72,26 @@ static int bb_upload_nodes(bb_handle* h, const double* f, int n, BBNodes* out) {
     return 0;
 }
 
+// K5's edge tables in rows of 32 edges: etab[row][det]{lin_c[32] (double2), cross_g[32] (double2, if given), quad_e[32]}
+static int bb_upload_edge_rows(bb_handle* h, int nd, int np, const std::vector<double2>& lc, const std::vector<double>& qe,
+                               const std::vector<double2>* cg, const double** out) {
+    const int et = cg ? 160 : 96, rows = np / 32;
+    std::vector<double> tab((size_t)rows * nd * et, 0.0);
+    for (int d = 0; d < nd; ++d)
+        for (int j = 0; j < np; ++j) {
+            double* t = tab.data() + ((size_t)(j / 32) * nd + d) * et;
+            const int l = j % 32;
+            t[2 * l] = lc[(size_t)d * np + j].x;
+            t[2 * l + 1] = lc[(size_t)d * np + j].y;
+            if (cg) {
+                t[64 + 2 * l] = (*cg)[(size_t)d * np + j].x;
+                t[64 + 2 * l + 1] = (*cg)[(size_t)d * np + j].y;
+            }
+            t[(cg ? 128 : 64) + l] = qe[(size_t)d * np + j];
+        }
+    return bb_red_upload(h, tab.data(), tab.size(), out);
+}
+
 static double2 bb_cinv(double re, double im) {
     // 1 / (re + i im); zero fiducial strain gives inf/nan like the reference's division (relative.py:373)
     const double den = re * re + im * im;
@@ -148,6 +168,7 @@ extern "C" int bb_set_relative_binning(bb_handle* h, int n_edges, const double* 
         if (bb_red_upload(h, lc.data(), lc.size(), &rb->lin_c)) return 1;
         if (bb_red_upload(h, qe.data(), qe.size(), &rb->quad_e)) return 1;
         if (bb_red_upload(h, cg.data(), cg.size(), &rb->cross_g)) return 1;
+        if (bb_upload_edge_rows(h, nd, np, lc, qe, &cg, &rb->etab)) return 1;
         rb->ne_pad = np;
     }
     if (fiducial_grid && bin_inds) {
@@ -200,6 +221,7 @@ extern "C" int bb_set_multiband(bb_handle* h, int n_points, const double* freque
         }
     if (bb_red_upload(h, lc.data(), lc.size(), &rb->lin_c)) return 1;
     if (bb_red_upload(h, qe.data(), qe.size(), &rb->quad_e)) return 1;
+    if (bb_upload_edge_rows(h, nd, np, lc, qe, nullptr, &rb->etab)) return 1;
     rb->ne_pad = np;
     h->rb_fmin = frequencies[0];
     for (int k = 1; k < n_points; ++k) if (frequencies[k] < h->rb_fmin) h->rb_fmin = frequencies[k];
