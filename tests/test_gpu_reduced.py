@@ -34,6 +34,7 @@ def _relbin_product(g, bns, **kw):
     approx = str(g["approximant"])
     wa = dict(waveform_approximant=approx, reference_frequency=50.0, minimum_frequency=20.0)
     oifos = rc.oracle_ifos(g, inj, ocl.lal_binary_neutron_star if bns else ocl.lal_binary_black_hole, wa, lambdas=bns)
+    oifos = oifos[:kw.pop("n_det", len(oifos))]
     ifos = _product_ifos(oifos)
     model = source.lal_binary_neutron_star_relative_binning if bns else source.lal_binary_black_hole_relative_binning
     conv = conversion.convert_to_lal_binary_neutron_star_parameters if bns \
@@ -111,6 +112,24 @@ def test_relative_binning_vs_reference(name, bns):
     assert np.max(np.abs(lnl - g["lnl_distance_phase"]) / _scale(g, g["lnl_distance_phase"])) < RTOL
 
 
+@pytest.mark.parametrize("n_det", [1, 2])
+def test_relative_binning_fewer_detectors_vs_oracle(n_det):
+    """K5 with one and two detectors (row-blocked edge tables are laid out per detector count; plain reductions instead of
+    the nine-sum butterfly) vs the oracle restatement of relative.py:365-430 on the 32 s BNS."""
+    g, _ = rc.load("relbin_bns_32s_H1L1V1")
+    like, draws = _relbin_product(g, True, n_det=n_det)
+    o3, oifos = rc.relbin_oracle(g, True)
+    draws0 = {k: float(v[0]) for k, v in draws.items() if k != "time_jitter"}
+    o = ocr.OracleRelativeBinning(oifos[:n_det], draws0, source_model=ocr.lal_binary_neutron_star_relative_binning,
+                                  waveform_arguments=dict(waveform_approximant=str(g["approximant"]),
+                                                          reference_frequency=50.0, minimum_frequency=20.0))
+    d = {k: v for k, v in draws.items() if k != "time_jitter"}
+    got = like.log_likelihood_ratio_batch(d)
+    ref = np.array([o.log_likelihood_ratio({k: float(v[i]) for k, v in d.items()}) for i in range(len(got))])
+    scale = np.maximum(np.abs(ref), 0.5 * g["optimal_snr_squared"][:, :n_det].sum(axis=1))
+    assert np.max(np.abs(got - ref) / scale) < RTOL
+
+
 def test_relative_binning_time_marginalised_vs_reference():
     from bilby_b200.core.prior import Uniform
     g, _ = rc.load("relbin_bbh_4s_H1L1V1")
@@ -133,6 +152,7 @@ def _roq_product(g, **kw):
     oifos = rc.oracle_ifos(g, inj, ocl.lal_binary_black_hole,
                            dict(waveform_approximant="IMRPhenomD", reference_frequency=20.0, minimum_frequency=20.0),
                            maximum_frequency=fmax)
+    oifos = oifos[:kw.pop("n_det", len(oifos))]
     ifos = _product_ifos(oifos, maximum_frequency=fmax)
     for ifo, snr in zip(ifos, g["optimal_snrs"]):
         ifo.meta_data["optimal_SNR"] = float(snr)      # what inject_signal records (interferometer.py:513)
@@ -182,6 +202,32 @@ def test_roq_vs_reference():
                            extra_priors=dict(phase=Uniform(0, 2 * np.pi, "phase"),
                                              luminosity_distance=PowerLaw(2, 100.0, 5000.0, "luminosity_distance")))
     _close(like.log_likelihood_ratio_batch(d), g["lnl_distance_phase"], scale)
+
+
+@pytest.mark.parametrize("n_det", [1, 2])
+def test_roq_fewer_detectors_vs_oracle(n_det):
+    """K6 with one and two detectors (lane d works out detector d's window: fewer detectors than three take the plain
+    reductions and the last-detector clamp), rows outside the ROQ time window included, vs the oracle (roq.py:467-549)."""
+    import torch
+    g, _ = rc.load("roq_bbh_4s_H1L1V1")
+    like, draws = _roq_product(g, n_det=n_det)
+    _, oifos = rc.roq_oracle(g)
+    o = ocr.OracleROQ(oifos[:n_det], g["linear_matrix"].astype(complex), g["quadratic_matrix"].astype(complex),
+                      g["frequency_nodes_linear"], g["frequency_nodes_quadratic"],
+                      time_prior=ocl.OracleUniform(T_INJ - 0.1, T_INJ + 0.1),
+                      waveform_arguments=dict(waveform_approximant="IMRPhenomD", reference_frequency=20.0),
+                      optimal_snrs=list(g["optimal_snrs"])[:n_det])
+    d = {k: v for k, v in draws.items() if k != "time_jitter"}
+    got = like.log_likelihood_ratio_batch(d)
+    n = len(got)
+    ref = np.array([o.log_likelihood_ratio({k: float(v[i]) for k, v in d.items()}) for i in range(n)])
+    scale = np.maximum(1.0, 0.5 * g["optimal_snr_squared"][:, :n_det].sum(axis=1))
+    _close(got, ref, scale)
+    assert np.isneginf(got[-1]) and np.isneginf(got[-2])
+    snr = like.inner_products_batch(torch.from_numpy(like.pack(d)).cuda()).cpu().numpy()
+    assert snr.shape == (n, n_det, 3)
+    hh = g["optimal_snr_squared"][:, :n_det]
+    assert np.max(np.abs(snr[..., 2] - hh) / hh) < RTOL
 
 
 def test_roq_time_marginalised_vs_reference():
