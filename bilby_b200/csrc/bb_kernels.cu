@@ -197,41 +197,58 @@ __device__ __forceinline__ void bb_wave_cols(const double* c, double f, double t
 // ------------------------------------------------------------------------------------------------
 // K0: prologue
 // ------------------------------------------------------------------------------------------------
-#define BB_K0_THREADS 64
+#define BB_K0_THREADS 64          // samples per CTA
+#ifndef BB_K0_SPLIT
+#define BB_K0_SPLIT 1             // two threads per sample: detector part / waveform part of the record
+#endif
+#define BB_K0_BLOCK (BB_K0_THREADS * (BB_K0_SPLIT ? 2 : 1))
 template <int APPROX>
-__global__ void __launch_bounds__(BB_K0_THREADS) bb_prologue_kernel(const double* __restrict__ params, long n, BBNetwork net,
+__global__ void __launch_bounds__(BB_K0_BLOCK) bb_prologue_kernel(const double* __restrict__ params, long n, BBNetwork net,
                                    BBWaveformConfig wf, double* __restrict__ coef, unsigned* __restrict__ keys,
                                    unsigned* __restrict__ index) {
     // The record is built directly in shared memory (row stride 85 doubles = conflict-free for per-thread access) and
     // leaves with consecutive lanes on consecutive doubles.  A per-thread record is 672 bytes: as a local array it
     // lived in local memory (1.3 KB of extra L1/L2 traffic per sample), and stored double by double from each thread it
     // touched 32 sectors per instruction (lg_throttle-bound, 1.75 x DRAM write amplification, profiles/r1d_k0*).
+    // The 43.5 KB of records cap the SM at 5 CTAs, and one thread per sample left it with 10 warps of one long
+    // dependent chain each: the sky / detector part of the record (antenna patterns, delays, ramp steps) and the
+    // waveform part are independent, so two threads (of different warps) build one record - twice the warps, half the chain.
     __shared__ double stage[BB_K0_THREADS * 85];
     const int tid = threadIdx.x;
-    const long blk0 = (long)blockIdx.x * blockDim.x;
-    const long i = blk0 + tid;
-    const int nrec = (int)min((long)blockDim.x, n - blk0);
+    const int slot = BB_K0_SPLIT ? (tid % BB_K0_THREADS) : tid, role = BB_K0_SPLIT ? (tid / BB_K0_THREADS) : 0;
+    const long blk0 = (long)blockIdx.x * BB_K0_THREADS;
+    const long i = blk0 + slot;
+    const int nrec = (int)min((long)BB_K0_THREADS, n - blk0);
+    double* c = stage + slot * 85;
+    double p[BB_NPARAM];
     if (i < n) {
-        double* c = stage + tid * 85;
-        double p[BB_NPARAM];
 #pragma unroll
         for (int k = 0; k < BB_NPARAM; ++k) p[k] = params[i * BB_NPARAM + k];
-        if (APPROX == BB_IMRPHENOMD) {
+    }
+    if (BB_K0_SPLIT) {
+        if (i < n) for (int k = role; k < BC_NCOEF; k += 2) c[k] = 0.0;
+        __syncthreads();
+    }
+    if (i < n) {
+        if (BB_K0_SPLIT && role == 0) {
+            bb_detector_prologue(p, net, wf, c);
+        } else if (APPROX == BB_IMRPHENOMD) {
             BBQnmTable qnm = {bb_qnm_x, bb_qnm_fring, bb_qnm_fring_d2, bb_qnm_fdamp, bb_qnm_fdamp_d2, BB_QNM_N};
-            bb_phenomd_prologue(p, net, wf, qnm, bb_phenomd_fit, c);
+            bb_phenomd_prologue<!BB_K0_SPLIT>(p, net, wf, qnm, bb_phenomd_fit, c);
         } else {
-            bb_taylorf2_prologue(p, net, wf, c);
-        }
-        if (keys) {
-            // descending active-bin count: blocks of K1 then hold samples of equal length, longest first
-            const unsigned count = (unsigned)(c[BC_KMAX] - c[BC_KMIN]);
-            keys[i] = (1u << 24) - min(count, (1u << 24) - 1u);
-            index[i] = (unsigned)i;
+            bb_taylorf2_prologue<!BB_K0_SPLIT>(p, net, wf, c);
         }
     }
-    __syncthreads();
+    if (BB_K0_SPLIT) __syncthreads();
+    if (i < n && role == 0 && keys) {
+        // descending active-bin count: blocks of K1 then hold samples of equal length, longest first
+        const unsigned count = (unsigned)(c[BC_KMAX] - c[BC_KMIN]);
+        keys[i] = (1u << 24) - min(count, (1u << 24) - 1u);
+        index[i] = (unsigned)i;
+    }
+    if (!BB_K0_SPLIT) __syncthreads();
     double* dst = coef + blk0 * BC_NCOEF;
-    for (int idx = tid; idx < nrec * BC_NCOEF; idx += blockDim.x) {
+    for (int idx = tid; idx < nrec * BC_NCOEF; idx += BB_K0_BLOCK) {
         const int rec = idx / BC_NCOEF, j = idx - rec * BC_NCOEF;
         dst[idx] = stage[rec * 85 + j];
     }
@@ -928,10 +945,10 @@ static int bb_launch_prologue(bb_handle* h, const double* params_dev, long n, cu
     const int threads = BB_K0_THREADS;
     const bool sort = n > BB_K1_SB && h->kind == 0;
     if (wf.approximant == BB_IMRPHENOMD)
-        bb_prologue_kernel<BB_IMRPHENOMD><<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(
+        bb_prologue_kernel<BB_IMRPHENOMD><<<(unsigned)((n + threads - 1) / threads), BB_K0_BLOCK, 0, st>>>(
             params_dev, n, h->net, wf, h->d_coef, sort ? h->d_keys : nullptr, h->d_index);
     else
-        bb_prologue_kernel<BB_TAYLORF2><<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(
+        bb_prologue_kernel<BB_TAYLORF2><<<(unsigned)((n + threads - 1) / threads), BB_K0_BLOCK, 0, st>>>(
             params_dev, n, h->net, wf, h->d_coef, sort ? h->d_keys : nullptr, h->d_index);
     h->launches++;
     BB_CUDA(cudaGetLastError());
@@ -1268,9 +1285,9 @@ extern "C" int bb_frequency_sequence_strain_device(bb_handle* h, const double* p
     wf.f_min = first_frequency;
     wf.add_jitter = 0;
     if (wf.approximant == BB_IMRPHENOMD)
-        bb_prologue_kernel<BB_IMRPHENOMD><<<(unsigned)((n + BB_K0_THREADS - 1) / BB_K0_THREADS), BB_K0_THREADS, 0, st>>>(params_dev, n, h->net, wf, h->d_coef, nullptr, nullptr);
+        bb_prologue_kernel<BB_IMRPHENOMD><<<(unsigned)((n + BB_K0_THREADS - 1) / BB_K0_THREADS), BB_K0_BLOCK, 0, st>>>(params_dev, n, h->net, wf, h->d_coef, nullptr, nullptr);
     else
-        bb_prologue_kernel<BB_TAYLORF2><<<(unsigned)((n + BB_K0_THREADS - 1) / BB_K0_THREADS), BB_K0_THREADS, 0, st>>>(params_dev, n, h->net, wf, h->d_coef, nullptr, nullptr);
+        bb_prologue_kernel<BB_TAYLORF2><<<(unsigned)((n + BB_K0_THREADS - 1) / BB_K0_THREADS), BB_K0_BLOCK, 0, st>>>(params_dev, n, h->net, wf, h->d_coef, nullptr, nullptr);
     h->launches++;
     h->perm_valid = false;
     dim3 grid((n_nodes + 127) / 128, (unsigned)n);

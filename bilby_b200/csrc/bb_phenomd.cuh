@@ -253,6 +253,13 @@ BB_HD double bb_detector_prologue(const double* p, const BBNetwork& net, const B
     return wf.no_time_shift ? 0.0 : tc - net.start_time;
 }
 
+// dt0 alone (the value bb_detector_prologue returns), for the thread that builds the waveform part of a record while its
+// partner builds the detector part (K0)
+BB_HD double bb_prologue_dt0(const double* p, const BBNetwork& net, const BBWaveformConfig& wf) {
+    const double tc = wf.add_jitter ? p[BB_P_GEOCENT_TIME] + p[BB_P_TIME_JITTER] : p[BB_P_GEOCENT_TIME];
+    return wf.no_time_shift ? 0.0 : tc - net.start_time;
+}
+
 // active bin range shared by the approximants: upstream fills i in [int(f_min/df), int(f_max'/df)),
 // the reference then zeroes f < minimum_frequency or f > maximum_frequency (source.py:618-619, 678-679)
 BB_HD void bb_bin_range(const BBNetwork& net, const BBWaveformConfig& wf, double f_max_prime, double* coef) {
@@ -270,15 +277,18 @@ BB_HD void bb_bin_range(const BBNetwork& net, const BBWaveformConfig& wf, double
     coef[BC_KMAX] = k1;
 }
 
+// WHOLE = false: the waveform part only, into a record that is already zero and whose detector part
+// (bb_detector_prologue) another thread writes
+template <bool WHOLE = true>
 BB_HD void bb_phenomd_prologue(const double* p, const BBNetwork& net, const BBWaveformConfig& wf,
                                const BBQnmTable& qnm, const double* fit /* [19][11] */, double* coef) {
-    for (int i = 0; i < BC_NCOEF; ++i) coef[i] = 0.0;
+    if (WHOLE) for (int i = 0; i < BC_NCOEF; ++i) coef[i] = 0.0;
     double m1 = p[BB_P_MASS_1], m2 = p[BB_P_MASS_2], chi1 = p[BB_P_CHI_1], chi2 = p[BB_P_CHI_2];
     if (m2 > m1) { double t = m1; m1 = m2; m2 = t; t = chi1; chi1 = chi2; chi2 = t; }
     const double dist_mpc = p[BB_P_DISTANCE];
     coef[BC_DISTANCE] = dist_mpc;
     coef[BC_JITTER] = p[BB_P_TIME_JITTER];
-    const double dt0 = bb_detector_prologue(p, net, wf, coef);
+    const double dt0 = WHOLE ? bb_detector_prologue(p, net, wf, coef) : bb_prologue_dt0(p, net, wf);
 
     const double M = m1 + m2;
     const double MTSUN = BB_G_SI * BB_MSUN_SI / (BB_C_SI * BB_C_SI * BB_C_SI);

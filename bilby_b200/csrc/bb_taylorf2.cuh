@@ -26,14 +26,15 @@ BB_HD double bb_tf2_series(double v, const double* pv, const double* pvl, const 
     return ph / v5;
 }
 
+template <bool WHOLE = true>      // false: the waveform part only (see bb_phenomd_prologue)
 BB_HD void bb_taylorf2_prologue(const double* p, const BBNetwork& net, const BBWaveformConfig& wf, double* coef) {
-    for (int i = 0; i < BC_NCOEF; ++i) coef[i] = 0.0;
+    if (WHOLE) for (int i = 0; i < BC_NCOEF; ++i) coef[i] = 0.0;
     const double m1 = p[BB_P_MASS_1], m2 = p[BB_P_MASS_2], chi1 = p[BB_P_CHI_1], chi2 = p[BB_P_CHI_2];
     const double lam1 = p[BB_P_LAMBDA_1], lam2 = p[BB_P_LAMBDA_2];
     const double dist_mpc = p[BB_P_DISTANCE];
     coef[BC_DISTANCE] = dist_mpc;
     coef[BC_JITTER] = p[BB_P_TIME_JITTER];
-    const double dt0 = bb_detector_prologue(p, net, wf, coef);
+    const double dt0 = WHOLE ? bb_detector_prologue(p, net, wf, coef) : bb_prologue_dt0(p, net, wf);
     const double M = m1 + m2;
     const double MTSUN = BB_G_SI * BB_MSUN_SI / (BB_C_SI * BB_C_SI * BB_C_SI);
     const double MRSUN = BB_G_SI * BB_MSUN_SI / (BB_C_SI * BB_C_SI);
