@@ -58,12 +58,21 @@ BB_HD double bb_wrap_2pi(double x) {
 }
 
 // F+, Fx for one detector tensor d[9] (row-major) given (ra, dec, psi) and the wrapped GMST
-BB_HD void bb_antenna(const double* d, double ra, double dec, double psi, double gmst_wrapped,
-                      double* fplus, double* fcross) {
+// The six sines and cosines of the sky position and polarisation angle do not depend on the detector: K0 evaluates
+// them once per sample (bb_sky_trig) and every detector contracts its tensor / vertex with them.
+struct BBSkyTrig {
+    double cph, sph, cth, sth, cps, sps;      // phi = ra - gmst, theta = pi/2 - dec, psi
+};
+BB_HD BBSkyTrig bb_sky_trig(double ra, double dec, double psi, double gmst_wrapped) {
     const double phi = ra - gmst_wrapped;
     const double theta = BB_PI / 2 - dec;
-    const double cph = cos(phi), sph = sin(phi), cth = cos(theta), sth = sin(theta);
-    const double cps = cos(psi), sps = sin(psi);
+    BBSkyTrig t;
+    t.cph = cos(phi); t.sph = sin(phi); t.cth = cos(theta); t.sth = sin(theta);
+    t.cps = cos(psi); t.sps = sin(psi);
+    return t;
+}
+BB_HD void bb_antenna_trig(const double* d, const BBSkyTrig& t, double* fplus, double* fcross) {
+    const double cph = t.cph, sph = t.sph, cth = t.cth, sth = t.sth, cps = t.cps, sps = t.sps;
     const double u[3] = {cph * cth, cth * sph, -sth};
     const double v[3] = {-sph, cph, 0.0};
     double m[3], n[3];
@@ -80,15 +89,23 @@ BB_HD void bb_antenna(const double* d, double ra, double dec, double psi, double
     *fplus = fp;
     *fcross = fc;
 }
+BB_HD void bb_antenna(const double* d, double ra, double dec, double psi, double gmst_wrapped,
+                      double* fplus, double* fcross) {
+    const BBSkyTrig t = bb_sky_trig(ra, dec, psi, gmst_wrapped);
+    bb_antenna_trig(d, t, fplus, fcross);
+}
 
 // time delay from geocentre for a detector vertex [m]
+BB_HD double bb_time_delay_trig(const double* vertex, double sth, double cph, double sph, double cth) {
+    const double ox = sth * cph, oy = sth * sph, oz = cth;
+    // omega . (0 - vertex) / c
+    return (ox * (0.0 - vertex[0]) + oy * (0.0 - vertex[1]) + oz * (0.0 - vertex[2])) / BB_C_SI;
+}
 BB_HD double bb_time_delay(const double* vertex, double ra, double dec, double gmst_wrapped) {
     const double phi = ra - gmst_wrapped;
     const double theta = BB_PI / 2 - dec;
     const double sth = sin(theta);
-    const double ox = sth * cos(phi), oy = sth * sin(phi), oz = cos(theta);
-    // omega . (0 - vertex) / c
-    return (ox * (0.0 - vertex[0]) + oy * (0.0 - vertex[1]) + oz * (0.0 - vertex[2])) / BB_C_SI;
+    return bb_time_delay_trig(vertex, sth, cos(phi), sin(phi), cos(theta));
 }
 
 // Detector-based sky frame and detector time reference (bilby/gw/likelihood/base.py:1091-1137

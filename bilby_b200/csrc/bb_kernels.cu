@@ -221,9 +221,19 @@ __global__ void __launch_bounds__(BB_K0_BLOCK) bb_prologue_kernel(const double* 
     const int nrec = (int)min((long)BB_K0_THREADS, n - blk0);
     double* c = stage + slot * 85;
     double p[BB_NPARAM];
-    if (i < n) {
+    {
+        // the CTA's parameter rows are one contiguous piece: consecutive threads fetch consecutive doubles into the
+        // record rows, and every thread then takes its row from shared memory (a thread reading its own 128-byte row
+        // from global memory touches 32 lines per warp instruction and waits for all 16 loads)
+        const double* src = params + blk0 * BB_NPARAM;
+        for (int idx = tid; idx < nrec * BB_NPARAM; idx += BB_K0_BLOCK)
+            stage[(idx / BB_NPARAM) * 85 + (idx % BB_NPARAM)] = src[idx];
+        __syncthreads();
+        if (i < n) {
 #pragma unroll
-        for (int k = 0; k < BB_NPARAM; ++k) p[k] = params[i * BB_NPARAM + k];
+            for (int k = 0; k < BB_NPARAM; ++k) p[k] = c[k];
+        }
+        __syncthreads();
     }
     if (BB_K0_SPLIT) {
         if (i < n) for (int k = role; k < BC_NCOEF; k += 2) c[k] = 0.0;
@@ -247,10 +257,11 @@ __global__ void __launch_bounds__(BB_K0_BLOCK) bb_prologue_kernel(const double* 
         index[i] = (unsigned)i;
     }
     if (!BB_K0_SPLIT) __syncthreads();
+    // warp w writes records w, w + n_warps, ...: consecutive lanes on consecutive doubles, no index division
     double* dst = coef + blk0 * BC_NCOEF;
-    for (int idx = tid; idx < nrec * BC_NCOEF; idx += BB_K0_BLOCK) {
-        const int rec = idx / BC_NCOEF, j = idx - rec * BC_NCOEF;
-        dst[idx] = stage[rec * 85 + j];
+    for (int rec = tid >> 5; rec < nrec; rec += BB_K0_BLOCK / 32) {
+#pragma unroll
+        for (int j = tid & 31; j < BC_NCOEF; j += 32) dst[rec * BC_NCOEF + j] = stage[rec * 85 + j];
     }
 }
 

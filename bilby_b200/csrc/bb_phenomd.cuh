@@ -228,12 +228,20 @@ BB_HD double bb_detector_prologue(const double* p, const BBNetwork& net, const B
     const double gmst_delay = (wf.fixed_antenna_time == 2) ? bb_wrap_2pi(bb_gmst(tc)) : gmst;
     const double cfac = cos(p[BB_P_THETA_JN]);
     const double pfac = 0.5 * (1.0 + cfac * cfac);
+    // sines and cosines of the sky position once per sample, not once per detector (same values: same arguments)
+    const BBSkyTrig sky = bb_sky_trig(p[BB_P_RA], p[BB_P_DEC], p[BB_P_PSI], gmst);
+    double cph_delay = sky.cph, sph_delay = sky.sph;
+    if (wf.fixed_antenna_time == 2) {
+        const double phi_delay = p[BB_P_RA] - gmst_delay;
+        cph_delay = cos(phi_delay);
+        sph_delay = sin(phi_delay);
+    }
     for (int d = 0; d < BB_MAX_DET; ++d) {
         double* cd = coef + BC_DET + BC_DSTRIDE * d;
         if (d < net.n_det) {
             double fp, fc;
-            bb_antenna(net.detector_tensor[d], p[BB_P_RA], p[BB_P_DEC], p[BB_P_PSI], gmst, &fp, &fc);
-            const double delay = bb_time_delay(net.vertex[d], p[BB_P_RA], p[BB_P_DEC], gmst_delay);
+            bb_antenna_trig(net.detector_tensor[d], sky, &fp, &fc);
+            const double delay = bb_time_delay_trig(net.vertex[d], sky.sth, cph_delay, sph_delay, sky.cth);
             // h_det = F+ h+ + Fx hx with h+ = pfac h22, hx = -i cfac h22
             cd[0] = fp * pfac;
             cd[1] = -fc * cfac;

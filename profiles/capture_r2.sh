@@ -20,6 +20,7 @@ k4b) timeout 600 $NCU -k regex:bb_series_fft -s 4 -c 1 -f -o gpurun_out/${tag}_k
 k5) timeout 600 $NCU -k regex:bb_relbin -s 2 -c 1 -f -o gpurun_out/${tag}_k5 python bench_configs.py --config cfg4_relbin --batch 200000 --steps 1 > gpurun_out/${tag}_k5.log 2>&1; export_rep ${tag}_k5 ;;
 k6) timeout 600 $NCU -k regex:bb_roq_kernel -s 2 -c 1 -f -o gpurun_out/${tag}_k6 python bench_configs.py --config cfg4_roq --batch 200000 --steps 1 > gpurun_out/${tag}_k6.log 2>&1; export_rep ${tag}_k6 ;;
 k5mb) timeout 600 $NCU -k regex:bb_relbin -s 2 -c 1 -f -o gpurun_out/${tag}_k5mb python bench_configs.py --config mb --batch 32768 --steps 1 > gpurun_out/${tag}_k5mb.log 2>&1; export_rep ${tag}_k5mb ;;
+k0tf2) timeout 600 $NCU -k regex:bb_prologue -s 4 -c 1 -f -o gpurun_out/${tag}_k0tf2 python bench_configs.py --config cfg4_relbin --batch 1000000 --steps 1 > gpurun_out/${tag}_k0tf2.log 2>&1; export_rep ${tag}_k0tf2 ;;
 k0) timeout 600 $NCU -k regex:bb_prologue -s 2 -c 1 -f -o gpurun_out/${tag}_k0 python bench_configs.py --config cfg1 --batch 1000000 --steps 1 > gpurun_out/${tag}_k0.log 2>&1; export_rep ${tag}_k0 ;;
 esac
 done
