@@ -198,10 +198,17 @@ __device__ __forceinline__ void bb_wave_cols(const double* c, double f, double t
 // K0: prologue
 // ------------------------------------------------------------------------------------------------
 #define BB_K0_THREADS 64          // samples per CTA
-#ifndef BB_K0_SPLIT
-#define BB_K0_SPLIT 1             // two threads per sample: detector part / waveform part of the record
+// two threads per sample (detector part / waveform part of the record) where the two parts are of similar length:
+// TaylorF2.  IMRPhenomD's waveform part is ~3 x the detector part and takes 148 registers: split, half of the 12 resident
+// warps idle at the barrier (configs[1] 52.25 M eval/s); one thread per sample, 10 busy warps: 52.6 M
+#ifndef BB_K0_SPLIT_PD
+#define BB_K0_SPLIT_PD 0
 #endif
+template <int APPROX>
+struct K0Split { static constexpr bool value = (APPROX == BB_TAYLORF2) || BB_K0_SPLIT_PD; };
+#define BB_K0_SPLIT (K0Split<APPROX>::value)
 #define BB_K0_BLOCK (BB_K0_THREADS * (BB_K0_SPLIT ? 2 : 1))
+#define BB_K0_BLOCK_OF(A) (BB_K0_THREADS * (K0Split<A>::value ? 2 : 1))
 template <int APPROX>
 __global__ void __launch_bounds__(BB_K0_BLOCK) bb_prologue_kernel(const double* __restrict__ params, long n, BBNetwork net,
                                    BBWaveformConfig wf, double* __restrict__ coef, unsigned* __restrict__ keys,
@@ -956,10 +963,10 @@ static int bb_launch_prologue(bb_handle* h, const double* params_dev, long n, cu
     const int threads = BB_K0_THREADS;
     const bool sort = n > BB_K1_SB && h->kind == 0;
     if (wf.approximant == BB_IMRPHENOMD)
-        bb_prologue_kernel<BB_IMRPHENOMD><<<(unsigned)((n + threads - 1) / threads), BB_K0_BLOCK, 0, st>>>(
+        bb_prologue_kernel<BB_IMRPHENOMD><<<(unsigned)((n + threads - 1) / threads), BB_K0_BLOCK_OF(BB_IMRPHENOMD), 0, st>>>(
             params_dev, n, h->net, wf, h->d_coef, sort ? h->d_keys : nullptr, h->d_index);
     else
-        bb_prologue_kernel<BB_TAYLORF2><<<(unsigned)((n + threads - 1) / threads), BB_K0_BLOCK, 0, st>>>(
+        bb_prologue_kernel<BB_TAYLORF2><<<(unsigned)((n + threads - 1) / threads), BB_K0_BLOCK_OF(BB_TAYLORF2), 0, st>>>(
             params_dev, n, h->net, wf, h->d_coef, sort ? h->d_keys : nullptr, h->d_index);
     h->launches++;
     BB_CUDA(cudaGetLastError());
@@ -1296,9 +1303,9 @@ extern "C" int bb_frequency_sequence_strain_device(bb_handle* h, const double* p
     wf.f_min = first_frequency;
     wf.add_jitter = 0;
     if (wf.approximant == BB_IMRPHENOMD)
-        bb_prologue_kernel<BB_IMRPHENOMD><<<(unsigned)((n + BB_K0_THREADS - 1) / BB_K0_THREADS), BB_K0_BLOCK, 0, st>>>(params_dev, n, h->net, wf, h->d_coef, nullptr, nullptr);
+        bb_prologue_kernel<BB_IMRPHENOMD><<<(unsigned)((n + BB_K0_THREADS - 1) / BB_K0_THREADS), BB_K0_BLOCK_OF(BB_IMRPHENOMD), 0, st>>>(params_dev, n, h->net, wf, h->d_coef, nullptr, nullptr);
     else
-        bb_prologue_kernel<BB_TAYLORF2><<<(unsigned)((n + BB_K0_THREADS - 1) / BB_K0_THREADS), BB_K0_BLOCK, 0, st>>>(params_dev, n, h->net, wf, h->d_coef, nullptr, nullptr);
+        bb_prologue_kernel<BB_TAYLORF2><<<(unsigned)((n + BB_K0_THREADS - 1) / BB_K0_THREADS), BB_K0_BLOCK_OF(BB_TAYLORF2), 0, st>>>(params_dev, n, h->net, wf, h->d_coef, nullptr, nullptr);
     h->launches++;
     h->perm_valid = false;
     dim3 grid((n_nodes + 127) / 128, (unsigned)n);
